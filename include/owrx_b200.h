@@ -1,0 +1,152 @@
+/*
+ * owrx_b200.h — C ABI of libowrx_b200.so: the B200-native (sm_100a) DSP hot path of OpenWebRX+.
+ *
+ * This is the drop-in boundary.  The reference reaches this arithmetic through the CPython
+ * extension `pycsdr` (un-vendored: luarvique/pycsdr@master wrapping luarvique/csdr@master; pinned
+ * only as python3-csdr >= 0.18.36 in debian/control:22).  Each entry point below names the pycsdr
+ * module(s) / reference call site it replaces.  The repo's `pycsdr/` package binds these symbols
+ * with ctypes so that the reference's unmodified csdr.chain classes run on top.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative OWRX_E_* code
+ * (owrx_last_error() gives a thread-local message); no exceptions cross the ABI; output buffers are
+ * caller-owned; objects are internally synchronised (setters may race with feed/read).
+ * IQ is interleaved float32 (re,im) = pycsdr Format.COMPLEX_FLOAT.  There is NO CPU fallback: every
+ * create call fails with OWRX_E_CUDA when no sm_100-class device is usable.
+ */
+#ifndef OWRX_B200_H
+#define OWRX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OWRX_OK            0
+#define OWRX_E_INVALID    -1   /* bad argument            -> ValueError in the Python shim */
+#define OWRX_E_CUDA       -2   /* CUDA runtime failure    -> RuntimeError                  */
+#define OWRX_E_NOMEM      -3   /* allocation failure      -> MemoryError                   */
+#define OWRX_E_OVERFLOW   -4   /* caller buffer too small -> BufferError                   */
+#define OWRX_E_STATE      -5   /* object stopped / wrong state                             */
+
+const char* owrx_last_error(void);
+const char* owrx_version(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+uint64_t owrx_launch_count(void);
+int owrx_device_count(int* n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Waterfall — replaces the pycsdr chain  Fft -> LogPower|LogAveragePower -> FftSwap -> [FftAdpcm]
+ * built by FftChain (csdr/chain/fft.py:25-49) and driven by SpectrumThread (owrx/fft.py:40-73).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct owrx_wf owrx_wf_t;
+
+#define OWRX_COMPRESSION_NONE  0   /* float32 dB lines, 4*N bytes   (FftSwap output)            */
+#define OWRX_COMPRESSION_ADPCM 1   /* IMA-ADPCM lines, (N+10)/2 B   (FftAdpcm, csdr/chain/fft.py:44) */
+
+/* Fft(size=, every_n_samples=) + LogAveragePower(add_db=, fft_size=, avg_number=) [avg==0: LogPower(add_db=)]
+ * + FftSwap(fft_size=) + optional FftAdpcm(fft_size=).  fft_size: power of two, 256..1048576. */
+int owrx_wf_create(int device, int fft_size, int every_n_samples, int avg_number, float add_db,
+                   int compression, owrx_wf_t** out);
+void owrx_wf_destroy(owrx_wf_t* wf);
+int owrx_wf_set_every_n_samples(owrx_wf_t* wf, int every_n_samples);   /* Fft.setEveryNSamples, csdr/chain/fft.py:55 */
+int owrx_wf_set_avg_number(owrx_wf_t* wf, int avg_number);             /* FftAverager.setFftAverages, csdr/chain/fft.py:12-16 */
+int owrx_wf_set_compression(owrx_wf_t* wf, int compression);           /* FftChain.setCompression, csdr/chain/fft.py:87-96 */
+size_t owrx_wf_line_bytes(const owrx_wf_t* wf);
+
+/* Streaming host path (what the pycsdr shim calls): append n_samples of interleaved IQ from HOST
+ * memory; every completed line is computed on the GPU and queued. */
+int owrx_wf_feed(owrx_wf_t* wf, const float* iq, size_t n_samples);
+/* Pop up to cap_bytes of whole queued lines into out; *n_bytes = bytes written (multiple of line_bytes). */
+int owrx_wf_read(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes);
+
+/* Device-resident batch path: iq_dev holds n_samples complex float32 on the object's device.
+ * Computes every whole line of that record (line l uses frames l*avg..l*avg+avg-1, frame f starts at
+ * sample f*every_n) into out_dev (device; line_bytes each).  db_dev / s16_dev may be NULL; when given
+ * they receive the swapped float32 dB lines (N each) / the quantised int16 lines (N+10 each).
+ * stream: a cudaStream_t (NULL = the object's own stream).  Asynchronous w.r.t. the host. */
+int owrx_wf_process_device(owrx_wf_t* wf, const void* iq_dev, size_t n_samples, void* out_dev,
+                           size_t out_cap_bytes, void* db_dev, void* s16_dev, size_t* n_lines, void* stream);
+/* number of whole lines a record of n_samples yields with the current parameters */
+size_t owrx_wf_lines_for(const owrx_wf_t* wf, size_t n_samples);
+
+/* Stand-alone FftAdpcm encoder stage on the GPU: s16_dev = n_lines x (fft_size+10) int16 (already
+ * quantised and padded), out_dev = n_lines x (fft_size+10)/2 bytes.  State resets per line
+ * (decoder: htdocs/openwebrx.js:1124-1128). */
+int owrx_fft_adpcm_encode_device(int device, const void* s16_dev, int fft_size, size_t n_lines, void* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Channel bank — replaces, for every client attached to one wideband source, the pycsdr chain
+ *   Shift -> FirDecimate -> [FractionalDecimator] -> [Bandpass] -> Squelch      (Selector,
+ *   csdr/chain/selector.py:89-214) followed by the analog demodulator chain
+ *   AmDemod/DcBlock/Agc | FmDemod/Limit/NfmDeemphasis/Agc | FmDemod/Limit/FractionalDecimator/
+ *   WfmDeemphasis | RealPart/Agc   (csdr/chain/analog.py:11-127),
+ * batched: all channels of a bank share ONE pass over the wideband IQ block (owrx/dsp.py:835-837
+ * attaches one reader per client to the same source ring in the reference).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct owrx_bank owrx_bank_t;
+
+#define OWRX_DEMOD_NFM  0   /* NFm: csdr/chain/analog.py:34-52  */
+#define OWRX_DEMOD_AM   1   /* Am:  csdr/chain/analog.py:11-21  */
+#define OWRX_DEMOD_SSB  2   /* Ssb: csdr/chain/analog.py:119-127 */
+#define OWRX_DEMOD_WFM  3   /* WFm: csdr/chain/analog.py:55-116 */
+#define OWRX_DEMOD_NONE 4   /* selector output only (IF samples) */
+
+#define OWRX_AGC_SLOW 0
+#define OWRX_AGC_FAST 1
+
+int owrx_bank_create(int device, double input_rate, owrx_bank_t** out);
+void owrx_bank_destroy(owrx_bank_t* bank);
+
+/* Selector(inputRate, outputRate): csdr/chain/selector.py:89-113 (Decimator math :21-26,37-51). */
+int owrx_bank_add_channel(owrx_bank_t* bank, double output_rate, int* chan);
+int owrx_bank_remove_channel(owrx_bank_t* bank, int chan);
+int owrx_bank_channel_count(const owrx_bank_t* bank);
+/* Shift.setRate(rate), rate = -offset/inputRate: csdr/chain/selector.py:138-140 */
+int owrx_chan_set_shift_rate(owrx_bank_t* bank, int chan, double rate);
+/* Bandpass.setBandpass(lo, hi) in units of the selector output rate; enabled=0 removes the stage:
+ * csdr/chain/selector.py:149-166 */
+int owrx_chan_set_bandpass(owrx_bank_t* bank, int chan, double lo_rate, double hi_rate, int enabled);
+/* Squelch.setSquelchLevel(linear): csdr/chain/selector.py:145-147; default 0 = always open */
+int owrx_chan_set_squelch_level(owrx_bank_t* bank, int chan, float level);
+/* demodulator chain selection (DspManager.setDemodulator, owrx/dsp.py:654-680).
+ * audio_rate/tau only for WFM; agc_profile OWRX_AGC_*; initial_gain/max_gain <= 0 pick the
+ * reference's per-mode values (analog.py:15,39). */
+int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate, double tau, int agc_profile);
+
+/* Streaming host path: one wideband block from HOST memory, shared by every channel. */
+int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples);
+/* Pop queued outputs of one channel (float32 audio after AGC / pre-AGC demod / complex IF). */
+int owrx_chan_read_audio(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n);
+int owrx_chan_read_demod(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n);
+int owrx_chan_read_if(owrx_bank_t* bank, int chan, float* out_iq, size_t cap_samples, size_t* n);
+int owrx_chan_read_power(owrx_bank_t* bank, int chan, float* out, size_t cap, size_t* n);
+/* which optional outputs are materialised for the host (bitmask of OWRX_OUT_*; default AUDIO) */
+#define OWRX_OUT_AUDIO 1
+#define OWRX_OUT_DEMOD 2
+#define OWRX_OUT_IF    4
+#define OWRX_OUT_POWER 8
+int owrx_bank_set_outputs(owrx_bank_t* bank, int mask);
+
+/* Device-resident batch path (bench / embedding): process one wideband block that already lives
+ * in device memory; outputs stay on the device and are NOT queued for the host. */
+int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_samples, void* stream);
+/* samples of audio produced per channel by the last owrx_bank_process_device call */
+int owrx_bank_last_audio_count(const owrx_bank_t* bank, int chan, size_t* n);
+/* device pointer + layout of the last block's audio: element (k, slot) at base[k*stride + slot] */
+int owrx_bank_last_audio_device(const owrx_bank_t* bank, int chan, const float** base, size_t* stride, size_t* slot);
+
+/* per-bank statistics since creation */
+typedef struct {
+    uint64_t input_samples;     /* wideband samples consumed                 */
+    uint64_t channel_samples;   /* sum over channels of wideband samples     */
+    uint64_t kernel_launches;
+    double   device_ms;         /* CUDA-event time of the host-path feeds    */
+} owrx_bank_stats_t;
+int owrx_bank_get_stats(const owrx_bank_t* bank, owrx_bank_stats_t* st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

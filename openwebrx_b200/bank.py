@@ -1,0 +1,144 @@
+"""ChannelBank — all client channels of one wideband source, batched on the GPU.
+
+Host-side mirror of what the reference builds per client: Selector (csdr/chain/selector.py:89-214)
+followed by an analog demodulator chain (csdr/chain/analog.py:11-127); the reference attaches one such
+chain per client to the same source ring (owrx/dsp.py:835-837), here they share one pass over HBM.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .params import shift_rate
+
+_KINDS = {"nfm": N.DEMOD_NFM, "am": N.DEMOD_AM, "usb": N.DEMOD_SSB, "lsb": N.DEMOD_SSB, "ssb": N.DEMOD_SSB,
+          "wfm": N.DEMOD_WFM, "none": N.DEMOD_NONE}
+
+
+def _ptr(obj):
+    if obj is None:
+        return None
+    if hasattr(obj, "data_ptr"):
+        return obj.data_ptr()
+    return int(obj)
+
+
+class Channel:
+    """One client: Selector(inputRate, outputRate) + demodulator. Method names follow Selector's."""
+
+    def __init__(self, bank, cid, output_rate):
+        self.bank = bank
+        self.id = cid
+        self.outputRate = output_rate
+        self.frequencyOffset = 0
+        self.bandpassCutoffs = [None, None]
+
+    def setFrequencyOffset(self, offset):            # csdr/chain/selector.py:132-140
+        self.frequencyOffset = offset
+        N.check(N.lib.owrx_chan_set_shift_rate(self.bank._h, self.id, shift_rate(offset, self.bank.inputRate)))
+
+    def setBandpass(self, low_cut, high_cut):        # csdr/chain/selector.py:159-166
+        self.bandpassCutoffs = [low_cut, high_cut]
+        if low_cut is None or high_cut is None:
+            N.check(N.lib.owrx_chan_set_bandpass(self.bank._h, self.id, 0.0, 0.0, 0))
+        else:
+            N.check(N.lib.owrx_chan_set_bandpass(self.bank._h, self.id, low_cut / self.outputRate,
+                                                 high_cut / self.outputRate, 1))
+
+    def setSquelchLevel(self, level_db):             # csdr/chain/selector.py:142-147
+        N.check(N.lib.owrx_chan_set_squelch_level(self.bank._h, self.id, float(10.0 ** (level_db / 10.0))))
+
+    def setDemodulator(self, kind, audio_rate=48000.0, tau=50e-6, agc_profile="slow"):
+        k = _KINDS[kind] if isinstance(kind, str) else int(kind)
+        prof = N.AGC_FAST if str(agc_profile).lower() == "fast" else N.AGC_SLOW
+        N.check(N.lib.owrx_chan_set_demod(self.bank._h, self.id, k, float(audio_rate), float(tau), prof))
+
+    def _read(self, fn, width=1):
+        chunks = []
+        buf = np.empty(65536 * width, np.float32)
+        while True:
+            n = C.c_size_t()
+            N.check(fn(self.bank._h, self.id, buf.ctypes.data_as(C.c_void_p), 65536, C.byref(n)))
+            if n.value == 0:
+                break
+            chunks.append(buf[:n.value * width].copy())
+        return np.concatenate(chunks) if chunks else np.empty(0, np.float32)
+
+    def read_audio(self):
+        return self._read(N.lib.owrx_chan_read_audio)
+
+    def read_demod(self):
+        return self._read(N.lib.owrx_chan_read_demod)
+
+    def read_if(self):
+        return self._read(N.lib.owrx_chan_read_if, 2).view(np.complex64)
+
+    def read_power(self):
+        return self._read(N.lib.owrx_chan_read_power)
+
+    def last_audio_count(self):
+        n = C.c_size_t()
+        N.check(N.lib.owrx_bank_last_audio_count(self.bank._h, self.id, C.byref(n)))
+        return n.value
+
+    def last_audio_device(self):
+        base, stride, slot = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        N.check(N.lib.owrx_bank_last_audio_device(self.bank._h, self.id, C.byref(base), C.byref(stride), C.byref(slot)))
+        return base.value, stride.value, slot.value
+
+    def remove(self):
+        N.check(N.lib.owrx_bank_remove_channel(self.bank._h, self.id))
+
+
+class ChannelBank:
+    def __init__(self, input_rate, device=0, outputs=N.OUT_AUDIO):
+        self.inputRate = input_rate
+        h = C.c_void_p()
+        N.check(N.lib.owrx_bank_create(device, float(input_rate), C.byref(h)))
+        self._h = h
+        self.channels = []
+        if outputs != N.OUT_AUDIO:
+            self.set_outputs(outputs)
+
+    def set_outputs(self, mask):
+        N.check(N.lib.owrx_bank_set_outputs(self._h, mask))
+
+    def add_channel(self, output_rate, demod="nfm", offset=0, bandpass=None, **demod_kw):
+        cid = C.c_int()
+        N.check(N.lib.owrx_bank_add_channel(self._h, float(output_rate), C.byref(cid)))
+        ch = Channel(self, cid.value, output_rate)
+        ch.setDemodulator(demod, **demod_kw)
+        if offset:
+            ch.setFrequencyOffset(offset)
+        if bandpass is not None:
+            ch.setBandpass(*bandpass)
+        self.channels.append(ch)
+        return ch
+
+    def feed(self, iq):
+        """One wideband block from HOST memory (complex64 numpy array, ideally pinned)."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        N.check(N.lib.owrx_bank_feed(self._h, iq.ctypes.data_as(C.c_void_p), iq.size))
+
+    def feed_ptr(self, host_ptr, n_samples):
+        N.check(N.lib.owrx_bank_feed(self._h, host_ptr, n_samples))
+
+    def process_device(self, iq_dev, n_samples, stream=None):
+        N.check(N.lib.owrx_bank_process_device(self._h, _ptr(iq_dev), n_samples, _ptr(stream)))
+
+    def stats(self):
+        st = N.BankStats()
+        N.check(N.lib.owrx_bank_get_stats(self._h, C.byref(st)))
+        return dict(input_samples=st.input_samples, channel_samples=st.channel_samples,
+                    kernel_launches=st.kernel_launches, device_ms=st.device_ms)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib.owrx_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

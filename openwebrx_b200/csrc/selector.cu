@@ -1,0 +1,1023 @@
+// selector.cu — host side of the channel bank: filter design, per-group stream bookkeeping, launches.
+//
+// Mirrors the parameter math of the reference's Decimator / Selector (csdr/chain/selector.py:21-26,
+// 37-51,115-130,138-140,159-166) and the demodulator wiring of csdr/chain/analog.py:11-127.
+// Filter design follows SURVEY.md Appendix A.1 (double precision, rounded once to float32).
+#include "selector_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+using namespace owrx;
+
+namespace {
+
+// ---------------------------------------------------------------- filter design (A.1)
+int filter_len(double transition)
+{
+    int len = (int)(4.0 / transition);
+    if ((len & 1) == 0) len += 1;
+    return len;
+}
+
+void design_lowpass(std::vector<double>& h, int len, double fc)
+{
+    h.assign((size_t)len, 0.0);
+    const int mid = len / 2;
+    auto win = [](double r) { return 0.54 - 0.46 * cos(2.0 * M_PI * (0.5 + r / 2.0)); };
+    h[mid] = 2.0 * M_PI * fc * win(0.0);
+    for (int i = 1; i <= mid; i++) {
+        const double v = sin(2.0 * M_PI * fc * i) / i * win((double)i / mid);
+        h[mid + i] = v;
+        h[mid - i] = v;
+    }
+    double sum = 0.0;
+    for (double v : h) sum += v;
+    for (double& v : h) v /= sum;
+}
+
+void design_bandpass(std::vector<float2>& out, int len, double lo, double hi)
+{
+    std::vector<double> h;
+    design_lowpass(h, len, (hi - lo) / 2.0);
+    const double centre = (hi + lo) / 2.0;
+    out.resize((size_t)len);
+    for (int i = 0; i < len; i++) {
+        const double ph = 2.0 * M_PI * centre * i;
+        out[i] = make_float2((float)(h[i] * cos(ph)), (float)(h[i] * sin(ph)));
+    }
+}
+
+// NfmDeemphasis taps — spec-defined (upstream tables unrecoverable): frequency-sampled
+// A(f) = 1 (<=400 Hz), 400/f (<=4 kHz), 0 above; Hamming window; unity gain at 400 Hz.
+void design_nfm_deemphasis(std::vector<float>& out, int sample_rate)
+{
+    const int len = sample_rate >= 24000 ? 199 : 79, M = 8192, mid = len / 2;
+    const double fs = sample_rate;
+    std::vector<double> h((size_t)len);
+    for (int n = 0; n < len; n++) {
+        double acc = 0.0;
+        for (int k = 0; k <= M / 2; k++) {
+            const double f = k * fs / M;
+            const double a = f <= 400.0 ? 1.0 : (f <= 4000.0 ? 400.0 / f : 0.0);
+            const double c = (k == 0 || k == M / 2) ? 0.5 : 1.0;
+            acc += c * a * cos(2.0 * M_PI * k * (double)(n - mid) / M);
+        }
+        h[n] = acc * 2.0 / M * (0.54 - 0.46 * cos(2.0 * M_PI * n / (double)(len - 1)));
+    }
+    double g = 0.0;
+    for (int n = 0; n < len; n++) g += h[n] * cos(2.0 * M_PI * 400.0 / fs * (n - mid));
+    out.resize((size_t)len);
+    for (int n = 0; n < len; n++) out[n] = (float)(h[n] / g);
+}
+
+// ---------------------------------------------------------------- stage buffer with history
+// rows of `slots * width` floats; rows [0, fill) hold absolute indices [abs_end - fill, abs_end).
+struct StageBuf {
+    float* d[2] = {nullptr, nullptr};
+    int cur = 0, width = 1, slots = 0;
+    size_t hist = 0, cap_rows = 0, fill = 0;
+    long long abs_end = 0;
+
+    size_t row_floats() const { return (size_t)slots * width; }
+    float* rows(size_t r = 0) const { return d[cur] + r * row_floats(); }
+    float* row_abs(long long a) const { return d[cur] + (size_t)(a - (abs_end - (long long)fill)) * row_floats(); }
+    float* append_ptr() const { return rows(fill); }
+
+    int init(int width_, int slots_, size_t hist_, size_t cap_new)
+    {
+        release();
+        width = width_; slots = slots_; hist = hist_; cap_rows = hist_ + cap_new;
+        for (int b = 0; b < 2; b++) {
+            OWRX_CUDA(cudaMalloc((void**)&d[b], cap_rows * row_floats() * sizeof(float)));
+            OWRX_CUDA(cudaMemset(d[b], 0, cap_rows * row_floats() * sizeof(float)));
+        }
+        cur = 0; fill = hist; abs_end = 0;     // `hist` zero rows precede the stream start
+        return OWRX_OK;
+    }
+    int ensure_new(size_t n_new, cudaStream_t st)
+    {
+        if (fill + n_new <= cap_rows) return OWRX_OK;
+        const size_t ncap = std::max(fill + n_new, cap_rows * 2);
+        for (int b = 0; b < 2; b++) {
+            float* nb = nullptr;
+            OWRX_CUDA(cudaMalloc((void**)&nb, ncap * row_floats() * sizeof(float)));
+            OWRX_CUDA(cudaMemsetAsync(nb, 0, ncap * row_floats() * sizeof(float), st));
+            if (b == cur && fill) OWRX_CUDA(cudaMemcpyAsync(nb, d[b], fill * row_floats() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            OWRX_CUDA(cudaStreamSynchronize(st));
+            cudaFree(d[b]);
+            d[b] = nb;
+        }
+        cap_rows = ncap;
+        return OWRX_OK;
+    }
+    void appended(size_t n) { fill += n; abs_end += (long long)n; }
+    // keep the newest `keep` rows (<= fill) at the front of the other buffer
+    int roll(size_t keep, cudaStream_t st)
+    {
+        keep = std::min(keep, fill);
+        if (keep == fill) return OWRX_OK;
+        if (keep) OWRX_CUDA(cudaMemcpyAsync(d[cur ^ 1], rows(fill - keep), keep * row_floats() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        cur ^= 1;
+        fill = keep;
+        return OWRX_OK;
+    }
+    void release()
+    {
+        for (int b = 0; b < 2; b++) { if (d[b]) cudaFree(d[b]); d[b] = nullptr; }
+        cap_rows = fill = 0;
+    }
+};
+
+struct Chan {
+    int id = -1;
+    int group = -1, slot = -1;
+    double rate = 0.0, phase = 0.0;        // phase (turns) just before the next unconsumed sample
+    bool bp_enabled = false;
+    double bp_lo = 0.0, bp_hi = 0.0;
+    ChanCfg cfg{};
+    std::deque<float> q_audio, q_demod, q_if, q_power;
+    size_t last_audio = 0;
+};
+
+struct Group {
+    double out_rate = 0.0;
+    bool wfm = false;
+    double audio_rate = 0.0, tau = 0.0;
+    int D = 1, T = 1, nseg = 1, nrs = 1, RB = 1;
+    double frac = 1.0;
+    bool has_frac = false;
+    int Tb = 1, sq_len = 1, Td = 1, Tpre = 0;
+    double wfm_rate = 1.0;
+    float alpha = 0.f;
+    int slots = 0;                                   // capacity, multiple of K3_CG
+    std::vector<int> slot_chan;
+    // device tables
+    float* d_taps = nullptr; float* d_deemph = nullptr; float* d_pre = nullptr;
+    double* d_rate = nullptr; double* d_phase = nullptr; float2* d_w = nullptr;
+    float2* d_bp = nullptr; int* d_bp_en = nullptr;
+    ChanCfg* d_cfg = nullptr; ChanState* d_state = nullptr;
+    std::vector<double> h_rate, h_phase; std::vector<float2> h_w;
+    std::vector<int> h_bp_en; std::vector<ChanCfg> h_cfg;
+    bool cfg_dirty = true;
+    // stream position
+    size_t in_off = 0;                               // streaming: offset of the next block in the bank's IQ buffer
+    long long frac_m = 0, wfm_m = 0, sq_abs = 0;
+    StageBuf s1, s2, s3, f1, f1b, f2, f3;
+    float2* d_partial = nullptr; size_t partial_cap = 0;
+    unsigned char* d_gate = nullptr; float* d_power = nullptr; float* d_dcmean = nullptr; float* d_dcprev = nullptr;
+    size_t blocks_cap = 0;
+    long long sq_block_abs = 0;                      // absolute squelch block counter (for report interval)
+    // last run
+    size_t last_audio = 0, last_demod = 0, last_if = 0, last_blocks = 0;
+};
+
+}  // namespace
+
+struct owrx_bank {
+    int device = 0, sm_count = 0;
+    double input_rate = 0.0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    std::vector<std::unique_ptr<Chan>> chans;
+    std::vector<std::unique_ptr<Group>> groups;
+    int out_mask = OWRX_OUT_AUDIO;
+    // streaming wideband buffer
+    float2* d_iq[2] = {nullptr, nullptr};
+    int iq_cur = 0;
+    size_t iq_cap = 0, iq_fill = 0;
+    // pinned staging
+    float* h_stage = nullptr; size_t h_stage_cap = 0;
+    owrx_bank_stats_t stats{};
+};
+
+namespace {
+
+template <typename T> int dev_alloc(T** p, size_t n)
+{
+    *p = nullptr;
+    OWRX_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    OWRX_CUDA(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return OWRX_OK;
+}
+
+void group_release(Group* g)
+{
+    cudaFree(g->d_taps); cudaFree(g->d_deemph); cudaFree(g->d_pre);
+    cudaFree(g->d_rate); cudaFree(g->d_phase); cudaFree(g->d_w);
+    cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state);
+    cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
+    g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1b.release(); g->f2.release(); g->f3.release();
+}
+
+// Decimator._getDecimation + transition/cutoff (csdr/chain/selector.py:21-26,37-51)
+int group_create(owrx_bank* bank, double out_rate, bool wfm, double audio_rate, double tau, int* index)
+{
+    std::unique_ptr<Group> g(new Group());
+    double orate = out_rate;
+    if (orate > bank->input_rate) orate = bank->input_rate;
+    g->out_rate = orate; g->wfm = wfm; g->audio_rate = audio_rate; g->tau = tau;
+    const double d = bank->input_rate / orate;
+    g->D = (int)d;
+    g->frac = (bank->input_rate / g->D) / orate;
+    g->has_frac = g->frac != 1.0;
+    const double transition = 0.15 * (orate / bank->input_rate);
+    const double cutoff = 0.5 * g->D / (bank->input_rate / orate);
+    g->T = filter_len(transition);
+    const int P = (g->T + g->D - 1) / g->D;
+    g->nseg = (P + K3_PP - 1) / K3_PP;
+    g->nrs = (g->D + K3_RBMAX - 1) / K3_RBMAX;
+    g->RB = (g->D + g->nrs - 1) / g->nrs;
+    g->Tb = filter_len(320.0 / orate);                                  // Selector._buildBandpass, selector.py:115-117
+    g->sq_len = std::max(1, (int)(orate / 16));                          // Selector._buildSquelch, selector.py:119-121
+    g->slots = K3_CG;
+    g->slot_chan.assign((size_t)g->slots, -1);
+
+    // FirDecimate taps in polyphase layout [nseg][D][28]
+    std::vector<double> h;
+    design_lowpass(h, g->T, cutoff / g->D);
+    std::vector<float> ht((size_t)g->nseg * g->D * K3_PP, 0.f);
+    for (int t = 0; t < g->T; t++) {
+        const int p = t / g->D, r = t % g->D;
+        ht[((size_t)(p / K3_PP) * g->D + r) * K3_PP + (p % K3_PP)] = (float)h[t];
+    }
+    int rc;
+    if ((rc = dev_alloc(&g->d_taps, ht.size())) != OWRX_OK) return rc;
+    OWRX_CUDA(cudaMemcpy(g->d_taps, ht.data(), ht.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    std::vector<float> de;
+    design_nfm_deemphasis(de, (int)orate);                               // NfmDeemphasis(sampleRate), analog.py:43
+    g->Td = (int)de.size();
+    if ((rc = dev_alloc(&g->d_deemph, de.size())) != OWRX_OK) return rc;
+    OWRX_CUDA(cudaMemcpy(g->d_deemph, de.data(), de.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (wfm) {
+        g->wfm_rate = orate / audio_rate;                                // analog.py:66: 250000.0 / sampleRate
+        g->Tpre = filter_len(0.03);
+        std::vector<double> pre;
+        design_lowpass(pre, g->Tpre, 0.5 / (g->wfm_rate - 0.03));
+        std::vector<float> pf(pre.begin(), pre.end());
+        if ((rc = dev_alloc(&g->d_pre, pf.size())) != OWRX_OK) return rc;
+        OWRX_CUDA(cudaMemcpy(g->d_pre, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const double dt = 1.0 / audio_rate;
+        g->alpha = (float)(dt / (tau + dt));                             // WfmDeemphasis, SURVEY A.11
+    }
+    const size_t S = (size_t)g->slots;
+    if ((rc = dev_alloc(&g->d_rate, S)) || (rc = dev_alloc(&g->d_phase, S)) || (rc = dev_alloc(&g->d_w, S)) ||
+        (rc = dev_alloc(&g->d_bp, S * g->Tb)) || (rc = dev_alloc(&g->d_bp_en, S)) || (rc = dev_alloc(&g->d_cfg, S)) ||
+        (rc = dev_alloc(&g->d_state, S)))
+        return rc;
+    g->h_rate.assign(S, 0.0); g->h_phase.assign(S, 0.0); g->h_w.assign(S, make_float2(1.f, 0.f));
+    g->h_bp_en.assign(S, 0);
+    ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
+    g->h_cfg.assign(S, idle);
+
+    const size_t cap = 4096;
+    if ((rc = g->s1.init(2, g->slots, (size_t)std::max(16, g->Tb), cap)) != OWRX_OK) return rc;
+    if (g->has_frac && (rc = g->s2.init(2, g->slots, (size_t)g->Tb, cap)) != OWRX_OK) return rc;
+    if ((rc = g->s3.init(2, g->slots, (size_t)g->sq_len, cap)) != OWRX_OK) return rc;
+    if ((rc = g->f1.init(1, g->slots, 256, cap)) != OWRX_OK) return rc;
+    if (wfm && (rc = g->f1b.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
+    if ((rc = g->f2.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
+    if ((rc = g->f3.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
+    g->in_off = bank->iq_fill;          // a new group starts with the next incoming sample
+    *index = (int)bank->groups.size();
+    bank->groups.push_back(std::move(g));
+    return OWRX_OK;
+}
+
+int find_group(owrx_bank* bank, double out_rate, bool wfm, double audio_rate, double tau)
+{
+    for (size_t i = 0; i < bank->groups.size(); i++) {
+        Group* g = bank->groups[i].get();
+        if (!g) continue;
+        double orate = std::min(out_rate, bank->input_rate);
+        if (g->out_rate == orate && g->wfm == wfm && (!wfm || (g->audio_rate == audio_rate && g->tau == tau))) return (int)i;
+    }
+    return -1;
+}
+
+void agc_defaults(ChanCfg& c, int kind, int profile)
+{
+    c.kind = kind;
+    c.agc_ref = 0.8f;
+    c.agc_attack = 0.1f;
+    c.agc_decay = profile == OWRX_AGC_FAST ? 0.001f : 0.0001f;
+    c.agc_hang_time = profile == OWRX_AGC_FAST ? 200 : 600;
+    c.agc_max = kind == OWRX_DEMOD_NFM ? 3.0f : 65535.0f;               // NFm: agc.setMaxGain(3), analog.py:39
+    c.active = 1;
+}
+
+float agc_initial_gain(int kind) { return kind == OWRX_DEMOD_AM ? 200.0f : 1.0f; }   // Am: setInitialGain(200), analog.py:15
+
+int place_channel(owrx_bank* bank, Chan* ch, int gi)
+{
+    Group* g = bank->groups[(size_t)gi].get();
+    int slot = -1;
+    for (int s = 0; s < g->slots; s++) if (g->slot_chan[(size_t)s] < 0) { slot = s; break; }
+    if (slot < 0) return fail(OWRX_E_STATE, "group full");     // caller grows before placing
+    g->slot_chan[(size_t)slot] = ch->id;
+    ch->group = gi; ch->slot = slot;
+    ChanState st{};
+    st.agc_gain = agc_initial_gain(ch->cfg.kind);
+    OWRX_CUDA(cudaMemcpy(g->d_state + slot, &st, sizeof(st), cudaMemcpyHostToDevice));
+    g->h_cfg[(size_t)slot] = ch->cfg;
+    g->h_bp_en[(size_t)slot] = 0;
+    g->cfg_dirty = true;
+    return OWRX_OK;
+}
+
+// grow a group's slot capacity by K3_CG, re-laying out every per-slot table and stage buffer
+int group_grow(owrx_bank* bank, Group* g)
+{
+    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    const int os = g->slots, ns = os + K3_CG;
+    auto regrow = [&](auto** p, size_t rows) -> int {
+        using T = typename std::remove_pointer<typename std::remove_pointer<decltype(p)>::type>::type;
+        T* nb = nullptr;
+        int rc = dev_alloc(&nb, rows * (size_t)ns);
+        if (rc != OWRX_OK) return rc;
+        OWRX_CUDA(cudaMemcpy2D(nb, (size_t)ns * sizeof(T), *p, (size_t)os * sizeof(T), (size_t)os * sizeof(T), rows, cudaMemcpyDeviceToDevice));
+        cudaFree(*p);
+        *p = nb;
+        return OWRX_OK;
+    };
+    int rc;
+    if ((rc = regrow(&g->d_rate, 1)) || (rc = regrow(&g->d_phase, 1)) || (rc = regrow(&g->d_w, 1)) ||
+        (rc = regrow(&g->d_bp, (size_t)g->Tb)) || (rc = regrow(&g->d_bp_en, 1)) || (rc = regrow(&g->d_cfg, 1)) ||
+        (rc = regrow(&g->d_state, 1)))
+        return rc;
+    auto regrow_buf = [&](StageBuf& b) -> int {
+        if (!b.d[0]) return OWRX_OK;
+        for (int k = 0; k < 2; k++) {
+            float* nb = nullptr;
+            const size_t orf = (size_t)os * b.width, nrf = (size_t)ns * b.width;
+            int rc2 = dev_alloc(&nb, b.cap_rows * nrf);
+            if (rc2 != OWRX_OK) return rc2;
+            OWRX_CUDA(cudaMemcpy2D(nb, nrf * sizeof(float), b.d[k], orf * sizeof(float), orf * sizeof(float), b.cap_rows, cudaMemcpyDeviceToDevice));
+            cudaFree(b.d[k]);
+            b.d[k] = nb;
+        }
+        b.slots = ns;
+        return OWRX_OK;
+    };
+    if ((rc = regrow_buf(g->s1)) || (rc = regrow_buf(g->s2)) || (rc = regrow_buf(g->s3)) || (rc = regrow_buf(g->f1)) ||
+        (rc = regrow_buf(g->f1b)) || (rc = regrow_buf(g->f2)) || (rc = regrow_buf(g->f3)))
+        return rc;
+    cudaFree(g->d_partial); g->d_partial = nullptr; g->partial_cap = 0;
+    cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
+    g->d_gate = nullptr; g->d_power = nullptr; g->d_dcmean = nullptr; g->d_dcprev = nullptr; g->blocks_cap = 0;
+    g->slots = ns;
+    g->slot_chan.resize((size_t)ns, -1);
+    g->h_rate.resize((size_t)ns, 0.0); g->h_phase.resize((size_t)ns, 0.0); g->h_w.resize((size_t)ns, make_float2(1.f, 0.f));
+    g->h_bp_en.resize((size_t)ns, 0);
+    ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
+    g->h_cfg.resize((size_t)ns, idle);
+    g->cfg_dirty = true;
+    return OWRX_OK;
+}
+
+int upload_bandpass(owrx_bank* bank, Chan* ch)
+{
+    Group* g = bank->groups[(size_t)ch->group].get();
+    g->h_bp_en[(size_t)ch->slot] = ch->bp_enabled ? 1 : 0;
+    g->cfg_dirty = true;
+    if (!ch->bp_enabled) return OWRX_OK;
+    std::vector<float2> taps;
+    design_bandpass(taps, g->Tb, ch->bp_lo, ch->bp_hi);                  // Bandpass.setBandpass, selector.py:159-166
+    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    OWRX_CUDA(cudaMemcpy2D(g->d_bp + ch->slot, (size_t)g->slots * sizeof(float2), taps.data(), sizeof(float2), sizeof(float2),
+                           (size_t)g->Tb, cudaMemcpyHostToDevice));
+    return OWRX_OK;
+}
+
+inline dim3 grid2d(int slots, size_t rows) { return dim3((unsigned)((slots + 31) / 32), (unsigned)((rows + 3) / 4)); }
+const dim3 kBlock2d(32, 4);
+constexpr size_t kRowChunk = 4 * 65535;
+
+// Runs every stage of one group on `n_avail` wideband samples starting at `iq` (device).
+// Returns the number of wideband samples consumed (n_k * D).
+int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_t* consumed)
+{
+    cudaStream_t st = bank->stream;
+    *consumed = 0;
+    g->last_audio = g->last_demod = g->last_if = g->last_blocks = 0;
+    if (n_avail < (size_t)g->T) return OWRX_OK;
+    const size_t n_k = (n_avail - (size_t)g->T) / (size_t)g->D + 1;
+    if (n_k > (size_t)0x7fffffff) return fail(OWRX_E_INVALID, "block too large");
+    const int S = g->slots;
+    int rc;
+
+    // ---- per-launch channel tables
+    for (int s = 0; s < S; s++) {
+        const int cid = g->slot_chan[(size_t)s];
+        if (cid < 0) { g->h_rate[(size_t)s] = 0.0; g->h_phase[(size_t)s] = 0.0; g->h_w[(size_t)s] = make_float2(1.f, 0.f); continue; }
+        Chan* ch = bank->chans[(size_t)cid].get();
+        g->h_rate[(size_t)s] = ch->rate;
+        g->h_phase[(size_t)s] = ch->phase;
+        const double a = 2.0 * M_PI * (ch->rate - floor(ch->rate));
+        g->h_w[(size_t)s] = make_float2((float)cos(a), (float)sin(a));
+    }
+    OWRX_CUDA(cudaMemcpyAsync(g->d_rate, g->h_rate.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+    OWRX_CUDA(cudaMemcpyAsync(g->d_phase, g->h_phase.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+    OWRX_CUDA(cudaMemcpyAsync(g->d_w, g->h_w.data(), (size_t)S * sizeof(float2), cudaMemcpyHostToDevice, st));
+    if (g->cfg_dirty) {
+        OWRX_CUDA(cudaMemcpyAsync(g->d_cfg, g->h_cfg.data(), (size_t)S * sizeof(ChanCfg), cudaMemcpyHostToDevice, st));
+        OWRX_CUDA(cudaMemcpyAsync(g->d_bp_en, g->h_bp_en.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st));
+        g->cfg_dirty = false;
+    }
+
+    // ---- K3: Shift + FirDecimate
+    const int nparts = g->nseg * g->nrs;
+    const int ncg = S / K3_CG;
+    const size_t fixed = (size_t)nparts * ncg;
+    size_t nkr = std::max<size_t>(1, ((size_t)bank->sm_count + fixed - 1) / fixed);
+    nkr = std::min(nkr, n_k);
+    const int KR = (int)((n_k + nkr - 1) / nkr);
+    nkr = (n_k + KR - 1) / KR;
+    const size_t pneed = (size_t)nparts * n_k * S;
+    if (pneed > g->partial_cap) {
+        cudaFree(g->d_partial); g->d_partial = nullptr; g->partial_cap = 0;
+        OWRX_CUDA(cudaMalloc((void**)&g->d_partial, pneed * sizeof(float2)));
+        g->partial_cap = pneed;
+    }
+    if ((rc = g->s1.ensure_new(n_k, st)) != OWRX_OK) return rc;
+    K3Params p;
+    p.iq = iq; p.n_lim = (long long)n_avail; p.taps = g->d_taps;
+    p.ch_rate = g->d_rate; p.ch_phase = g->d_phase; p.ch_w = g->d_w;
+    p.partial = nparts == 1 ? reinterpret_cast<float2*>(g->s1.append_ptr()) : g->d_partial;
+    p.D = g->D; p.nseg = g->nseg; p.nrs = g->nrs; p.RB = g->RB; p.KR = KR; p.n_k = (int)n_k; p.slots = S;
+    const size_t smem = (size_t)g->RB * K3_PP * sizeof(float) + 2 * (size_t)g->RB * sizeof(float2) + 2 * K3_NW * 128 * sizeof(float);
+    OWRX_CUDA(cudaFuncSetAttribute(fir_decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fir_decimate_kernel<<<dim3((unsigned)(nkr * nparts), (unsigned)ncg), K3_NW * 32, smem, st>>>(p);
+    OWRX_LAUNCH_CHECK();
+    bank->stats.kernel_launches++;
+    if (nparts > 1) {
+        const size_t total = n_k * (size_t)S;
+        fir_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g->d_partial, nparts, (int)n_k, S,
+                                                                           reinterpret_cast<float2*>(g->s1.append_ptr()));
+        OWRX_LAUNCH_CHECK();
+        bank->stats.kernel_launches++;
+    }
+    const long long s1_first = g->s1.abs_end;
+    g->s1.appended(n_k);
+    *consumed = n_k * (size_t)g->D;
+
+    // ---- FractionalDecimator (complex)
+    const StageBuf* bp_in = &g->s1;
+    long long bp_first = s1_first;
+    size_t n2 = n_k;
+    if (g->has_frac) {
+        // count outputs m with ceil(5 + m*rate) + 6 < s1.abs_end (same double arithmetic as the kernel)
+        size_t cnt = 0;
+        while (true) {
+            const double where = 5.0 + (double)(g->frac_m + (long long)cnt) * g->frac;
+            if ((long long)ceil(where) + 6 >= g->s1.abs_end) break;
+            cnt++;
+        }
+        n2 = cnt;
+        if ((rc = g->s2.ensure_new(n2, st)) != OWRX_OK) return rc;
+        for (size_t o = 0; o < n2; o += kRowChunk) {
+            const size_t c = std::min(kRowChunk, n2 - o);
+            fracdec_cf_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(
+                reinterpret_cast<const float2*>(g->s1.rows()), g->s1.abs_end - (long long)g->s1.fill, S, nullptr, g->frac,
+                g->frac_m + (long long)o, (int)c, S, reinterpret_cast<float2*>(g->s2.append_ptr()) + o * S);
+            OWRX_LAUNCH_CHECK();
+            bank->stats.kernel_launches++;
+        }
+        bp_first = g->s2.abs_end;
+        g->s2.appended(n2);
+        g->frac_m += (long long)n2;
+        bp_in = &g->s2;
+    }
+
+    // ---- Bandpass -> s3 (selector output / IF)
+    if ((rc = g->s3.ensure_new(n2, st)) != OWRX_OK) return rc;
+    for (size_t o = 0; o < n2; o += kRowChunk) {
+        const size_t c = std::min(kRowChunk, n2 - o);
+        bandpass_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(
+            reinterpret_cast<const float2*>(bp_in->row_abs(bp_first + (long long)o)), S, nullptr, g->d_bp, g->d_bp_en, g->Tb,
+            (int)c, S, reinterpret_cast<float2*>(g->s3.append_ptr()) + o * S);
+        OWRX_LAUNCH_CHECK();
+        bank->stats.kernel_launches++;
+    }
+    const size_t if_row0 = g->s3.fill;
+    g->s3.appended(n2);
+    g->last_if = n2;
+    (void)if_row0;
+
+    // ---- Squelch over whole blocks
+    const size_t pending = (size_t)(g->s3.abs_end - g->sq_abs);
+    const size_t nb = pending / (size_t)g->sq_len;
+    const size_t n4 = nb * (size_t)g->sq_len;
+    g->last_blocks = nb;
+    if (nb) {
+        if (nb > g->blocks_cap) {
+            cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
+            g->blocks_cap = 0;
+            OWRX_CUDA(cudaMalloc((void**)&g->d_gate, nb * (size_t)S));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_power, nb * (size_t)S * sizeof(float)));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_dcmean, nb * (size_t)S * sizeof(float)));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_dcprev, (size_t)S * sizeof(float)));
+            g->blocks_cap = nb;
+        }
+        const float2* sq_in = reinterpret_cast<const float2*>(g->s3.row_abs(g->sq_abs));
+        const int hang_blocks = 2;                                       // hangLength = 2*blockLength, selector.py:124
+        squelch_kernel<<<(S + 127) / 128, 128, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, hang_blocks, g->d_cfg, g->d_state,
+                                                       g->d_gate, g->d_power);
+        OWRX_LAUNCH_CHECK();
+        // ---- demodulator front -> f1
+        if ((rc = g->f1.ensure_new(n4, st)) != OWRX_OK) return rc;
+        for (size_t o = 0; o < n4; o += kRowChunk) {
+            // chunks are multiples of 4 rows but gate lookup uses absolute row / sq_len: pass whole range per chunk
+            const size_t c = std::min(kRowChunk, n4 - o);
+            (void)c;
+        }
+        {
+            // single logical launch split in row chunks that are multiples of sq_len
+            const size_t chunk_rows = std::max<size_t>((size_t)g->sq_len, (kRowChunk / (size_t)g->sq_len) * (size_t)g->sq_len);
+            for (size_t o = 0; o < n4; o += chunk_rows) {
+                const size_t c = std::min(chunk_rows, n4 - o);
+                // FM needs the previous row: for o > 0 it is in the buffer; state is only used at o == 0
+                demod_front_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(sq_in + o * S, S, (int)c, g->sq_len,
+                                                                      g->d_gate + (o / (size_t)g->sq_len) * S, g->d_cfg,
+                                                                      g->d_state, g->f1.append_ptr() + o * S);
+                OWRX_LAUNCH_CHECK();
+                if (o + c < n4) {
+                    // make the carried "last gated sample" right for the next chunk
+                    demod_front_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(sq_in + o * S, S, (int)c, g->sq_len,
+                                                                              g->d_gate + (o / (size_t)g->sq_len) * S, g->d_state);
+                    OWRX_LAUNCH_CHECK();
+                }
+            }
+            demod_front_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(sq_in, S, (int)n4, g->sq_len, g->d_gate, g->d_state);
+            OWRX_LAUNCH_CHECK();
+        }
+        bank->stats.kernel_launches += 3;
+        const long long f1_first = g->f1.abs_end;
+        g->f1.appended(n4);
+        g->sq_abs += (long long)n4;
+
+        size_t n_audio = 0;
+        if (!g->wfm) {
+            // ---- demodulator back: NfmDeemphasis / DcBlock / copy -> f2 (pre-AGC)
+            dc_mean_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)nb), 128, 0, st>>>(g->f1.row_abs(f1_first), S, (int)nb,
+                                                                                        g->sq_len, g->d_cfg, g->d_state,
+                                                                                        g->d_dcmean, g->d_dcprev);
+            OWRX_LAUNCH_CHECK();
+            if ((rc = g->f2.ensure_new(n4, st)) != OWRX_OK) return rc;
+            const size_t chunk_rows = std::max<size_t>((size_t)g->sq_len, (kRowChunk / (size_t)g->sq_len) * (size_t)g->sq_len);
+            for (size_t o = 0; o < n4; o += chunk_rows) {
+                const size_t c = std::min(chunk_rows, n4 - o);
+                demod_back_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(g->f1.row_abs(f1_first + (long long)o), S, (int)c, g->sq_len,
+                                                                     g->d_deemph, g->Td, g->d_cfg,
+                                                                     g->d_dcmean + (o / (size_t)g->sq_len) * S,
+                                                                     o == 0 ? g->d_dcprev : g->d_dcmean + (o / (size_t)g->sq_len - 1) * S,
+                                                                     g->f2.append_ptr() + o * S);
+                OWRX_LAUNCH_CHECK();
+            }
+            dc_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, (int)nb, g->d_cfg, g->d_dcmean, g->d_state);
+            OWRX_LAUNCH_CHECK();
+            bank->stats.kernel_launches += 3;
+            g->f2.appended(n4);
+            n_audio = n4;
+        } else {
+            // ---- WFM: prefiltered fractional decimation to the audio rate, then one-pole de-emphasis
+            size_t cnt = 0;
+            while (true) {
+                const double where = 5.0 + (double)(g->wfm_m + (long long)cnt) * g->wfm_rate;
+                if ((long long)ceil(where) + 6 + (g->Tpre - 1) >= g->f1.abs_end) break;
+                cnt++;
+            }
+            if ((rc = g->f1b.ensure_new(cnt, st)) != OWRX_OK) return rc;
+            if ((rc = g->f2.ensure_new(cnt, st)) != OWRX_OK) return rc;
+            for (size_t o = 0; o < cnt; o += kRowChunk) {
+                const size_t c = std::min(kRowChunk, cnt - o);
+                fracdec_f_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(g->f1.rows(), g->f1.abs_end - (long long)g->f1.fill, S,
+                                                                    g->wfm_rate, g->wfm_m + (long long)o, (int)c, g->d_pre,
+                                                                    g->Tpre, g->f1b.append_ptr() + o * S);
+                OWRX_LAUNCH_CHECK();
+            }
+            if (cnt) {
+                wfm_deemph_kernel<<<(S + 127) / 128, 128, 0, st>>>(g->f1b.append_ptr(), S, (int)cnt, g->alpha, g->d_state,
+                                                                  g->f2.append_ptr());
+                OWRX_LAUNCH_CHECK();
+            }
+            bank->stats.kernel_launches += 2;
+            g->wfm_m += (long long)cnt;
+            g->f2.appended(cnt);
+            n_audio = cnt;
+        }
+        g->last_demod = n_audio;
+        // ---- Agc -> f3
+        if (n_audio) {
+            if ((rc = g->f3.ensure_new(n_audio, st)) != OWRX_OK) return rc;
+            agc_kernel<<<(S + 127) / 128, 128, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+                                                       g->f3.append_ptr());
+            OWRX_LAUNCH_CHECK();
+            bank->stats.kernel_launches++;
+            g->f3.appended(n_audio);
+        }
+        g->last_audio = n_audio;
+    }
+
+    // ---- advance NCO phases
+    for (int s = 0; s < S; s++) {
+        const int cid = g->slot_chan[(size_t)s];
+        if (cid < 0) continue;
+        Chan* ch = bank->chans[(size_t)cid].get();
+        double ph = ch->phase + ch->rate * (double)(*consumed);
+        ch->phase = ph - floor(ph);
+    }
+    return OWRX_OK;
+}
+
+// after outputs were taken: drop f2/f3 rows, keep histories
+int group_roll(owrx_bank* bank, Group* g)
+{
+    cudaStream_t st = bank->stream;
+    int rc;
+    if ((rc = g->s1.roll(g->s1.hist, st)) != OWRX_OK) return rc;
+    if (g->has_frac && (rc = g->s2.roll(g->s2.hist, st)) != OWRX_OK) return rc;
+    if ((rc = g->s3.roll(g->s3.hist, st)) != OWRX_OK) return rc;
+    if ((rc = g->f1.roll(g->f1.hist, st)) != OWRX_OK) return rc;
+    if (g->wfm) g->f1b.roll(0, st);
+    g->f2.roll(0, st);
+    g->f3.roll(0, st);
+    return OWRX_OK;
+}
+
+Chan* get_chan(owrx_bank* bank, int chan)
+{
+    if (!bank || chan < 0 || (size_t)chan >= bank->chans.size()) return nullptr;
+    return bank->chans[(size_t)chan].get();
+}
+
+int ensure_stage(owrx_bank* bank, size_t floats)
+{
+    if (floats <= bank->h_stage_cap) return OWRX_OK;
+    if (bank->h_stage) cudaFreeHost(bank->h_stage);
+    bank->h_stage = nullptr; bank->h_stage_cap = 0;
+    OWRX_CUDA(cudaMallocHost((void**)&bank->h_stage, floats * sizeof(float)));
+    bank->h_stage_cap = floats;
+    return OWRX_OK;
+}
+
+// copy rows [row0, row0+n) of a stage buffer to the host and scatter per channel
+int drain_to_queues(owrx_bank* bank, Group* g, const float* dev_rows, size_t n, int width, int which)
+{
+    if (!n) return OWRX_OK;
+    const size_t floats = n * (size_t)g->slots * width;
+    int rc = ensure_stage(bank, floats);
+    if (rc != OWRX_OK) return rc;
+    OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, dev_rows, floats * sizeof(float), cudaMemcpyDeviceToHost, bank->stream));
+    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    for (int s = 0; s < g->slots; s++) {
+        const int cid = g->slot_chan[(size_t)s];
+        if (cid < 0) continue;
+        Chan* ch = bank->chans[(size_t)cid].get();
+        std::deque<float>& q = which == 0 ? ch->q_audio : (which == 1 ? ch->q_demod : (which == 2 ? ch->q_if : ch->q_power));
+        const float* src = bank->h_stage + (size_t)s * width;
+        const size_t stride = (size_t)g->slots * width;
+        for (size_t i = 0; i < n; i++)
+            for (int w = 0; w < width; w++) q.push_back(src[i * stride + w]);
+    }
+    return OWRX_OK;
+}
+
+int pop_queue(std::deque<float>& q, float* out, size_t cap, size_t* n, size_t unit)
+{
+    size_t take = std::min(cap * unit, q.size());
+    take -= take % unit;
+    std::copy(q.begin(), q.begin() + (ptrdiff_t)take, out);
+    q.erase(q.begin(), q.begin() + (ptrdiff_t)take);
+    *n = take / unit;
+    return OWRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
+{
+    if (!out) return fail(OWRX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!(input_rate > 0.0)) return fail(OWRX_E_INVALID, "input_rate must be positive");
+    int sm = 0, rc = select_device(device, &sm);
+    if (rc != OWRX_OK) return rc;
+    owrx_bank* b = new (std::nothrow) owrx_bank();
+    if (!b) return fail(OWRX_E_NOMEM, "out of host memory");
+    b->device = device; b->sm_count = sm; b->input_rate = input_rate;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e != cudaSuccess) { owrx_bank_destroy(b); return fail(OWRX_E_CUDA, "stream/event create: %s", cudaGetErrorString(e)); }
+    *out = b;
+    return OWRX_OK;
+}
+
+void owrx_bank_destroy(owrx_bank_t* bank)
+{
+    if (!bank) return;
+    cudaSetDevice(bank->device);
+    if (bank->stream) cudaStreamSynchronize(bank->stream);
+    for (auto& g : bank->groups) if (g) group_release(g.get());
+    cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]);
+    if (bank->h_stage) cudaFreeHost(bank->h_stage);
+    if (bank->ev0) cudaEventDestroy(bank->ev0);
+    if (bank->ev1) cudaEventDestroy(bank->ev1);
+    if (bank->stream) cudaStreamDestroy(bank->stream);
+    delete bank;
+}
+
+int owrx_bank_add_channel(owrx_bank_t* bank, double output_rate, int* chan)
+{
+    if (!bank || !chan) return fail(OWRX_E_INVALID, "NULL argument");
+    if (!(output_rate > 0.0)) return fail(OWRX_E_INVALID, "output_rate must be positive");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    int gi = find_group(bank, output_rate, false, 0.0, 0.0), rc;
+    if (gi < 0 && (rc = group_create(bank, output_rate, false, 0.0, 0.0, &gi)) != OWRX_OK) return rc;
+    Group* g = bank->groups[(size_t)gi].get();
+    if (std::find(g->slot_chan.begin(), g->slot_chan.end(), -1) == g->slot_chan.end() && (rc = group_grow(bank, g)) != OWRX_OK) return rc;
+    std::unique_ptr<Chan> ch(new Chan());
+    ch->id = (int)bank->chans.size();
+    agc_defaults(ch->cfg, OWRX_DEMOD_NONE, OWRX_AGC_SLOW);
+    Chan* raw = ch.get();
+    bank->chans.push_back(std::move(ch));
+    if ((rc = place_channel(bank, raw, gi)) != OWRX_OK) return rc;
+    *chan = raw->id;
+    return OWRX_OK;
+}
+
+int owrx_bank_remove_channel(owrx_bank_t* bank, int chan)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    if (ch->group >= 0) {
+        Group* g = bank->groups[(size_t)ch->group].get();
+        g->slot_chan[(size_t)ch->slot] = -1;
+        ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
+        g->h_cfg[(size_t)ch->slot] = idle;
+        g->h_bp_en[(size_t)ch->slot] = 0;
+        g->cfg_dirty = true;
+    }
+    bank->chans[(size_t)chan].reset();
+    return OWRX_OK;
+}
+
+int owrx_bank_channel_count(const owrx_bank_t* bank)
+{
+    if (!bank) return 0;
+    int n = 0;
+    for (auto& c : bank->chans) if (c) n++;
+    return n;
+}
+
+int owrx_chan_set_shift_rate(owrx_bank_t* bank, int chan, double rate)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    ch->rate = rate;
+    return OWRX_OK;
+}
+
+int owrx_chan_set_bandpass(owrx_bank_t* bank, int chan, double lo_rate, double hi_rate, int enabled)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    ch->bp_enabled = enabled != 0; ch->bp_lo = lo_rate; ch->bp_hi = hi_rate;
+    return upload_bandpass(bank, ch);
+}
+
+int owrx_chan_set_squelch_level(owrx_bank_t* bank, int chan, float level)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    ch->cfg.sq_level = level;
+    Group* g = bank->groups[(size_t)ch->group].get();
+    g->h_cfg[(size_t)ch->slot] = ch->cfg;
+    g->cfg_dirty = true;
+    return OWRX_OK;
+}
+
+int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate, double tau, int agc_profile)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    if (kind < OWRX_DEMOD_NFM || kind > OWRX_DEMOD_NONE) return fail(OWRX_E_INVALID, "unknown demodulator %d", kind);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    Group* g = bank->groups[(size_t)ch->group].get();
+    const float level = ch->cfg.sq_level;
+    agc_defaults(ch->cfg, kind, agc_profile);
+    ch->cfg.sq_level = level;
+    const bool wfm = kind == OWRX_DEMOD_WFM;
+    if (wfm && !(audio_rate > 0.0 && tau > 0.0)) return fail(OWRX_E_INVALID, "WFM needs audio_rate and tau");
+    if (wfm != g->wfm || (wfm && (g->audio_rate != audio_rate || g->tau != tau))) {
+        // move to the matching group (WFM channels keep their own lock-step group)
+        const double orate = g->out_rate;
+        g->slot_chan[(size_t)ch->slot] = -1;
+        g->cfg_dirty = true;
+        int gi = find_group(bank, orate, wfm, audio_rate, tau), rc;
+        if (gi < 0 && (rc = group_create(bank, orate, wfm, audio_rate, tau, &gi)) != OWRX_OK) return rc;
+        Group* ng = bank->groups[(size_t)gi].get();
+        if (std::find(ng->slot_chan.begin(), ng->slot_chan.end(), -1) == ng->slot_chan.end() && (rc = group_grow(bank, ng)) != OWRX_OK) return rc;
+        if ((rc = place_channel(bank, ch, gi)) != OWRX_OK) return rc;
+        return upload_bandpass(bank, ch);
+    }
+    // same group: new demodulator chain starts from fresh state (the reference rebuilds the modules)
+    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    ChanState stt{};
+    OWRX_CUDA(cudaMemcpy(&stt, g->d_state + ch->slot, sizeof(stt), cudaMemcpyDeviceToHost));
+    stt.fm_last = make_float2(0.f, 0.f); stt.dc_last = 0.f; stt.iir = 0.f; stt.agc_hang = 0;
+    stt.agc_gain = agc_initial_gain(kind);
+    OWRX_CUDA(cudaMemcpy(g->d_state + ch->slot, &stt, sizeof(stt), cudaMemcpyHostToDevice));
+    g->h_cfg[(size_t)ch->slot] = ch->cfg;
+    g->cfg_dirty = true;
+    return OWRX_OK;
+}
+
+int owrx_bank_set_outputs(owrx_bank_t* bank, int mask)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    bank->out_mask = mask;
+    return OWRX_OK;
+}
+
+int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
+{
+    if (!bank || (!iq && n_samples)) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    cudaStream_t st = bank->stream;
+    bool any = false;
+    for (auto& g : bank->groups) if (g) any = true;
+    if (!any) return OWRX_OK;                         // nobody listening: samples are dropped like an unread ring
+    const size_t need = bank->iq_fill + n_samples;
+    if (need > bank->iq_cap) {
+        const size_t cap = std::max(need, bank->iq_cap * 2);
+        for (int b = 0; b < 2; b++) {
+            float2* nb = nullptr;
+            OWRX_CUDA(cudaMalloc((void**)&nb, cap * sizeof(float2)));
+            if (b == bank->iq_cur && bank->iq_fill)
+                OWRX_CUDA(cudaMemcpyAsync(nb, bank->d_iq[b], bank->iq_fill * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+            OWRX_CUDA(cudaStreamSynchronize(st));
+            cudaFree(bank->d_iq[b]);
+            bank->d_iq[b] = nb;
+        }
+        bank->iq_cap = cap;
+    }
+    float2* buf = bank->d_iq[bank->iq_cur];
+    OWRX_CUDA(cudaEventRecord(bank->ev0, st));
+    OWRX_CUDA(cudaMemcpyAsync(buf + bank->iq_fill, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, st));
+    bank->iq_fill += n_samples;
+    size_t min_off = bank->iq_fill;
+    int rc;
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        size_t consumed = 0;
+        if ((rc = group_run(bank, g, buf + g->in_off, bank->iq_fill - g->in_off, &consumed)) != OWRX_OK) return rc;
+        g->in_off += consumed;
+        min_off = std::min(min_off, g->in_off);
+        int live = 0;
+        for (int cid : g->slot_chan) if (cid >= 0) live++;
+        bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
+    }
+    OWRX_CUDA(cudaEventRecord(bank->ev1, st));
+    // outputs -> host queues
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        if ((bank->out_mask & OWRX_OUT_AUDIO) && (rc = drain_to_queues(bank, g, g->f3.rows(g->f3.fill - g->last_audio), g->last_audio, 1, 0))) return rc;
+        if ((bank->out_mask & OWRX_OUT_DEMOD) && (rc = drain_to_queues(bank, g, g->f2.rows(g->f2.fill - g->last_demod), g->last_demod, 1, 1))) return rc;
+        if ((bank->out_mask & OWRX_OUT_IF) && (rc = drain_to_queues(bank, g, g->s3.rows(g->s3.fill - g->last_if), g->last_if, 2, 2))) return rc;
+        if ((bank->out_mask & OWRX_OUT_POWER) && g->last_blocks) {
+            // reportInterval = measurementsPerSec / readingsPerSec = 4 (selector.py:108-109,126)
+            const size_t nb = g->last_blocks;
+            if ((rc = ensure_stage(bank, nb * (size_t)g->slots)) != OWRX_OK) return rc;
+            OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, g->d_power, nb * (size_t)g->slots * sizeof(float), cudaMemcpyDeviceToHost, st));
+            OWRX_CUDA(cudaStreamSynchronize(st));
+            for (size_t b = 0; b < nb; b++) {
+                if (((g->sq_block_abs + (long long)b) % 4) != 0) continue;
+                for (int s = 0; s < g->slots; s++) {
+                    const int cid = g->slot_chan[(size_t)s];
+                    if (cid >= 0) bank->chans[(size_t)cid]->q_power.push_back(bank->h_stage[b * (size_t)g->slots + s]);
+                }
+            }
+        }
+        g->sq_block_abs += (long long)g->last_blocks;
+        if ((rc = group_roll(bank, g)) != OWRX_OK) return rc;
+    }
+    // drop consumed wideband samples
+    if (min_off > 0) {
+        const size_t tail = bank->iq_fill - min_off;
+        if (tail) OWRX_CUDA(cudaMemcpyAsync(bank->d_iq[bank->iq_cur ^ 1], buf + min_off, tail * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        bank->iq_cur ^= 1;
+        bank->iq_fill = tail;
+        for (auto& gp : bank->groups) if (gp) gp->in_off -= min_off;
+    }
+    OWRX_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, bank->ev0, bank->ev1) == cudaSuccess) bank->stats.device_ms += ms;
+    bank->stats.input_samples += n_samples;
+    return OWRX_OK;
+}
+
+int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_samples, void* stream)
+{
+    if (!bank || !iq_dev) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    cudaStream_t own = bank->stream;
+    if (stream) bank->stream = (cudaStream_t)stream;
+    int rc = OWRX_OK;
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        size_t consumed = 0;
+        // previous block's outputs are dropped; histories stay
+        if ((rc = group_roll(bank, g)) != OWRX_OK) break;
+        if ((rc = group_run(bank, g, (const float2*)iq_dev, n_samples, &consumed)) != OWRX_OK) break;
+        int live = 0;
+        for (int cid : g->slot_chan) if (cid >= 0) live++;
+        bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
+        g->sq_block_abs += (long long)g->last_blocks;
+    }
+    bank->stats.input_samples += n_samples;
+    bank->stream = own;
+    return rc;
+}
+
+int owrx_bank_last_audio_count(const owrx_bank_t* bank, int chan, size_t* n)
+{
+    Chan* ch = get_chan(const_cast<owrx_bank_t*>(bank), chan);
+    if (!ch || !n) return fail(OWRX_E_INVALID, "bad argument");
+    *n = bank->groups[(size_t)ch->group]->last_audio;
+    return OWRX_OK;
+}
+
+int owrx_bank_last_audio_device(const owrx_bank_t* bank, int chan, const float** base, size_t* stride, size_t* slot)
+{
+    Chan* ch = get_chan(const_cast<owrx_bank_t*>(bank), chan);
+    if (!ch || !base || !stride || !slot) return fail(OWRX_E_INVALID, "bad argument");
+    const Group* g = bank->groups[(size_t)ch->group].get();
+    *base = g->f3.rows(g->f3.fill - g->last_audio);
+    *stride = (size_t)g->slots;
+    *slot = (size_t)ch->slot;
+    return OWRX_OK;
+}
+
+int owrx_chan_read_audio(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    return pop_queue(ch->q_audio, out, cap_samples, n, 1);
+}
+
+int owrx_chan_read_demod(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    return pop_queue(ch->q_demod, out, cap_samples, n, 1);
+}
+
+int owrx_chan_read_if(owrx_bank_t* bank, int chan, float* out_iq, size_t cap_samples, size_t* n)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch || !out_iq || !n) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    return pop_queue(ch->q_if, out_iq, cap_samples, n, 2);
+}
+
+int owrx_chan_read_power(owrx_bank_t* bank, int chan, float* out, size_t cap, size_t* n)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    return pop_queue(ch->q_power, out, cap, n, 1);
+}
+
+int owrx_bank_get_stats(const owrx_bank_t* bank, owrx_bank_stats_t* st)
+{
+    if (!bank || !st) return fail(OWRX_E_INVALID, "bad argument");
+    *st = bank->stats;
+    return OWRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,461 @@
+// selector_kernels.cuh — K3/K4/K5: batched Selector front end + analog demodulators on sm_100a.
+//
+// Replaces, for all channels of one decimator group at once, the per-client pycsdr chains
+//   Shift -> FirDecimate -> [FractionalDecimator] -> [Bandpass] -> Squelch   (csdr/chain/selector.py:89-130)
+//   -> AmDemod/DcBlock | FmDemod/Limit/NfmDeemphasis | RealPart | FmDemod/Limit/FractionalDecimator/
+//      WfmDeemphasis -> Agc                                                    (csdr/chain/analog.py:11-127)
+// Arithmetic spec: SURVEY.md Appendix A.6-A.11.
+//
+// Data layout: every low-rate stream is "channel-minor": element (time i, slot s) lives at
+// base[i * slots + s], so a warp's 32 lanes = 32 adjacent channel slots -> fully coalesced, and the
+// sample-serial recurrences (AGC, IIR, squelch hang) run one channel per lane.
+#pragma once
+#include "common.cuh"
+
+namespace owrx {
+
+// ------------------------------------------------------------------------------------------------
+// K3: NCO mix + polyphase FIR decimation, direct form, FP32-FMA bound.
+//   y_c[k] = sum_{t<T} x[kD+t] * e^{j 2 pi (ph_c + rate_c (kD+t+1))} * h[t]
+// Polyphase view: t = pD + r.  A thread owns CN=2 channels (lane <-> channel
+// pair) and 28 rolling accumulators per channel (one per polyphase branch p = output k = j-p of the
+// input block j it is streaming).  Each rotated sample is used for 28 branch FMAs x 2 (re,im); the
+// 28 taps h[pD+r] of one r come from shared memory as 7 broadcast LDS.128.  Warps split the r-range
+// of a block; their partial sums meet in shared memory once per block.
+// ------------------------------------------------------------------------------------------------
+constexpr int K3_NW = 12;        // warps per CTA
+constexpr int K3_CN = 2;         // channels per lane
+constexpr int K3_PP = 28;        // polyphase branches per pass (padded, multiple of 4)
+constexpr int K3_RBMAX = 896;    // max samples of one block (r-range) staged per CTA
+constexpr int K3_CG = 32 * K3_CN;   // channels per CTA
+
+struct K3Params {
+    const float2* iq;        // sample 0 of output 0 of this launch
+    long long n_lim;         // samples readable from iq
+    const float* taps;       // [nseg][D][28]: taps[(ts*D + r)*28 + p'] = h[(ts*28+p')*D + r] (0 beyond T)
+    const double* ch_rate;   // per group slot: Shift rate (turns / sample)
+    const double* ch_phase;  // per group slot: phase (turns) at iq[-1]
+    const float2* ch_w;      // per group slot: e^{j 2 pi rate}
+    float2* partial;         // [nparts = nseg*nrs][n_k][slots]
+    int D, nseg, nrs, RB, KR, n_k, slots;
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+__global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
+{
+    extern __shared__ float4 k3_smem[];
+    float* hs = reinterpret_cast<float*>(k3_smem);                // [RB][28]
+    float2* xs = reinterpret_cast<float2*>(hs + p.RB * K3_PP);    // [2][RB]
+    float* red = reinterpret_cast<float*>(xs + 2 * p.RB);         // [2][NW][128]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bx = blockIdx.x;
+    const int rs = bx % p.nrs; bx /= p.nrs;
+    const int ts = bx % p.nseg;
+    const int kr = bx / p.nseg;
+    const int cg = blockIdx.y;
+    const int part = ts * p.nrs + rs;
+
+    const int r_lo = rs * p.RB;
+    const int rcount = min(p.RB, p.D - r_lo);
+    const int k_lo = kr * p.KR;
+    const int k_hi = min(p.n_k, k_lo + p.KR);
+    if (k_lo >= k_hi || rcount <= 0) return;
+
+    {   // tap slice of this CTA: rcount rows of 28
+        const float4* src = reinterpret_cast<const float4*>(p.taps + ((size_t)ts * p.D + r_lo) * K3_PP);
+        float4* dst = reinterpret_cast<float4*>(hs);
+        for (int i = tid; i < rcount * (K3_PP / 4); i += K3_NW * 32) dst[i] = __ldg(src + i);
+    }
+
+    const int slot0 = cg * K3_CG + lane * K3_CN;
+    const double rate0 = p.ch_rate[slot0], rate1 = p.ch_rate[slot0 + 1];
+    const double ph0 = p.ch_phase[slot0], ph1 = p.ch_phase[slot0 + 1];
+    const float2 w0 = p.ch_w[slot0], w1 = p.ch_w[slot0 + 1];
+
+    const int SL = (rcount + K3_NW - 1) / K3_NW;
+    const int i0 = min(rcount, warp * SL), i1 = min(rcount, i0 + SL);
+
+    float a0r[K3_PP], a0i[K3_PP], a1r[K3_PP], a1i[K3_PP];
+#pragma unroll
+    for (int q = 0; q < K3_PP; q++) { a0r[q] = 0.f; a0i[q] = 0.f; a1r[q] = 0.f; a1i[q] = 0.f; }
+
+    const int j_end = k_hi + K3_PP - 1;     // local block index runs k_lo .. j_end-1
+    auto load_tile = [&](int jl, int buf) {
+        const long long s0 = (long long)(jl + ts * K3_PP) * p.D + r_lo;
+        float2* dst = xs + buf * p.RB;
+        for (int i = tid; i < rcount; i += K3_NW * 32) {
+            const long long s = s0 + i;
+            if (s < p.n_lim) cp_async8(dst + i, p.iq + s);
+            else dst[i] = make_float2(0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+    auto flush = [&](int jl_done, int buf) {
+        // sum the NW warp partials of block jl_done -> output k = jl_done - (PP-1)
+        const int k = jl_done - (K3_PP - 1);
+        if (k >= k_lo && tid < 128) {
+            const float* r = red + buf * (K3_NW * 128) + tid;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < K3_NW; w++) s += r[w * 128];
+            float* out = reinterpret_cast<float*>(p.partial + ((size_t)part * p.n_k + k) * p.slots + cg * K3_CG);
+            out[tid] = s;
+        }
+    };
+
+    load_tile(k_lo, 0);
+    for (int jl = k_lo; jl < j_end; jl++) {
+        const int buf = (jl - k_lo) & 1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (jl + 1 < j_end) load_tile(jl + 1, buf ^ 1);
+        if (jl > k_lo) flush(jl - 1, buf ^ 1);
+
+        if (i0 < i1) {
+            // re-seed both NCOs at the first sample of this warp's slice (double phase -> float sincos)
+            const long long n_rel = (long long)(jl + ts * K3_PP) * p.D + r_lo + i0;
+            double t0 = ph0 + rate0 * (double)(n_rel + 1), t1 = ph1 + rate1 * (double)(n_rel + 1);
+            t0 -= floor(t0); t1 -= floor(t1);
+            float2 q0, q1;
+            sincospif(2.0f * (float)t0, &q0.y, &q0.x);
+            sincospif(2.0f * (float)t1, &q1.y, &q1.x);
+            const float2* xb = xs + buf * p.RB;
+            for (int i = i0; i < i1; i++) {
+                const float2 x = xb[i];
+                const float2 z0 = cmul(x, q0), z1 = cmul(x, q1);
+                q0 = cmul(q0, w0); q1 = cmul(q1, w1);
+                const float4* hrow = reinterpret_cast<const float4*>(hs + i * K3_PP);
+#pragma unroll
+                for (int g = 0; g < K3_PP / 4; g++) {
+                    const float4 h = hrow[g];
+                    a0r[4 * g + 0] = fmaf(z0.x, h.x, a0r[4 * g + 0]); a0i[4 * g + 0] = fmaf(z0.y, h.x, a0i[4 * g + 0]);
+                    a1r[4 * g + 0] = fmaf(z1.x, h.x, a1r[4 * g + 0]); a1i[4 * g + 0] = fmaf(z1.y, h.x, a1i[4 * g + 0]);
+                    a0r[4 * g + 1] = fmaf(z0.x, h.y, a0r[4 * g + 1]); a0i[4 * g + 1] = fmaf(z0.y, h.y, a0i[4 * g + 1]);
+                    a1r[4 * g + 1] = fmaf(z1.x, h.y, a1r[4 * g + 1]); a1i[4 * g + 1] = fmaf(z1.y, h.y, a1i[4 * g + 1]);
+                    a0r[4 * g + 2] = fmaf(z0.x, h.z, a0r[4 * g + 2]); a0i[4 * g + 2] = fmaf(z0.y, h.z, a0i[4 * g + 2]);
+                    a1r[4 * g + 2] = fmaf(z1.x, h.z, a1r[4 * g + 2]); a1i[4 * g + 2] = fmaf(z1.y, h.z, a1i[4 * g + 2]);
+                    a0r[4 * g + 3] = fmaf(z0.x, h.w, a0r[4 * g + 3]); a0i[4 * g + 3] = fmaf(z0.y, h.w, a0i[4 * g + 3]);
+                    a1r[4 * g + 3] = fmaf(z1.x, h.w, a1r[4 * g + 3]); a1i[4 * g + 3] = fmaf(z1.y, h.w, a1i[4 * g + 3]);
+                }
+            }
+        }
+        // emit the oldest branch, roll the accumulators
+        reinterpret_cast<float4*>(red + buf * (K3_NW * 128) + warp * 128)[lane] =
+            make_float4(a0r[K3_PP - 1], a0i[K3_PP - 1], a1r[K3_PP - 1], a1i[K3_PP - 1]);
+#pragma unroll
+        for (int q = K3_PP - 1; q > 0; q--) { a0r[q] = a0r[q - 1]; a0i[q] = a0i[q - 1]; a1r[q] = a1r[q - 1]; a1i[q] = a1i[q - 1]; }
+        a0r[0] = 0.f; a0i[0] = 0.f; a1r[0] = 0.f; a1i[0] = 0.f;
+    }
+    __syncthreads();
+    flush(j_end - 1, (j_end - 1 - k_lo) & 1);
+}
+
+// K3b: sum the tap-segment / r-split partials into the FirDecimate output stream s1[k][slot].
+__global__ void __launch_bounds__(256)
+fir_reduce_kernel(const float2* __restrict__ partial, int nparts, int n_k, int slots, float2* __restrict__ out)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n_k * slots;
+    if (gid >= total) return;
+    float2 s = make_float2(0.f, 0.f);
+    for (int q = 0; q < nparts; q++) {
+        const float2 v = partial[(size_t)q * total + gid];
+        s.x += v.x; s.y += v.y;
+    }
+    out[gid] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 12-point Lagrange coefficients: nodes x_i = i-5 relative to ih, evaluated at -d.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lagrange12(float d, float* c)
+{
+    const float xe = -d;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        float num = 1.0f, den = 1.0f;
+#pragma unroll
+        for (int j = 0; j < 12; j++)
+            if (j != i) { num *= xe - (float)(j - 5); den *= (float)(i - j); }
+        c[i] = num / den;
+    }
+}
+
+// FractionalDecimator(Format.COMPLEX_FLOAT, rate): out[m] for m_abs = m0 + m, where = 5 + m_abs*rate.
+// in: rows of `in_slots` complex, row 0 = absolute index in_abs0; slot map gives the column.
+__global__ void __launch_bounds__(128)
+fracdec_cf_kernel(const float2* __restrict__ in, long long in_abs0, int in_slots, const int* __restrict__ slot_map,
+                  double rate, long long m0, int n_out, int slots, float2* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y * blockDim.y + threadIdx.y;
+    if (s >= slots || m >= n_out) return;
+    const double where = 5.0 + (double)(m0 + m) * rate;
+    const double ihd = ceil(where);
+    float c[12];
+    lagrange12((float)(ihd - where), c);
+    const int col = slot_map ? slot_map[s] : s;
+    const float2* x = in + ((long long)ihd - 5 - in_abs0) * in_slots + col;
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const float2 v = x[(size_t)i * in_slots];
+        re += c[i] * v.x; im += c[i] * v.y;
+    }
+    out[(size_t)m * slots + s] = make_float2(re, im);
+}
+
+// Bandpass: y[i] = sum_t h_s[t] x[i-t] (causal, zero history = zero rows before the stream start).
+// taps: [T][slots] complex, per channel; enabled[s]==0 passes the sample through.
+__global__ void __launch_bounds__(128)
+bandpass_kernel(const float2* __restrict__ in, int in_slots, const int* __restrict__ slot_map,
+                const float2* __restrict__ taps, const int* __restrict__ enabled, int T, int n_out, int slots,
+                float2* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (s >= slots || i >= n_out) return;
+    const int col = slot_map ? slot_map[s] : s;
+    const float2* x = in + (size_t)i * in_slots + col;      // in points at the row of output 0
+    float2 y;
+    if (enabled[s]) {
+        float re = 0.f, im = 0.f;
+        for (int t = 0; t < T; t++) {
+            const float2 h = taps[(size_t)t * slots + s];
+            const float2 v = *(x - (ptrdiff_t)t * in_slots);
+            re += h.x * v.x - h.y * v.y;
+            im += h.x * v.y + h.y * v.x;
+        }
+        y = make_float2(re, im);
+    } else {
+        y = *x;
+    }
+    out[(size_t)i * slots + s] = y;
+}
+
+// per-channel serial state
+struct ChanState {
+    float2 fm_last;     // FmDemod: previous (gated) sample
+    float dc_last;      // DcBlock: previous block mean
+    float iir;          // WfmDeemphasis y[n-1]
+    float agc_gain;
+    int agc_hang;
+    int sq_hang;        // squelch hang counter (blocks)
+    int pad;
+};
+
+struct ChanCfg {
+    int kind;           // OWRX_DEMOD_*
+    float sq_level;     // linear power threshold (0 = open)
+    float agc_ref, agc_attack, agc_decay, agc_max;
+    int agc_hang_time;
+    int active;
+};
+
+// Squelch: one thread per channel walks the new whole blocks in order (hang counter is
+// sequential).  Block power = mean |x|^2 over every `decim`-th sample.
+__global__ void __launch_bounds__(128)
+squelch_kernel(const float2* __restrict__ in, int slots, int n_blocks, int length, int decim, int hang_blocks,
+               const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st, unsigned char* __restrict__ gate,
+               float* __restrict__ power)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    const float level = cfg[s].sq_level;
+    int hang = st[s].sq_hang;
+    for (int b = 0; b < n_blocks; b++) {
+        const float2* x = in + (size_t)b * length * slots + s;
+        float p = 0.f;
+        int cnt = 0;
+        for (int i = 0; i < length; i += decim) {
+            const float2 v = x[(size_t)i * slots];
+            p += v.x * v.x + v.y * v.y;
+            cnt++;
+        }
+        p /= (float)cnt;
+        int open = 0;
+        if (p >= level) { open = 1; hang = hang_blocks; }
+        else if (hang > 0) { open = 1; hang--; }
+        gate[(size_t)b * slots + s] = (unsigned char)open;
+        power[(size_t)b * slots + s] = p;
+    }
+    st[s].sq_hang = hang;
+}
+
+// Demodulator front: gated IF -> AmDemod | FmDemod+Limit | RealPart  (SURVEY A.11).
+// One thread per (sample, slot).  FM needs the previous gated sample: previous row, or the carried
+// state for the first row.  The last row's gated sample is written back by the i == n-1 threads.
+__global__ void __launch_bounds__(128)
+demod_front_kernel(const float2* __restrict__ in, int slots, int n, int length, const unsigned char* __restrict__ gate,
+                   const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st, float* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (s >= slots || i >= n) return;
+    const int kind = cfg[s].kind;
+    float2 x = in[(size_t)i * slots + s];
+    if (!gate[(size_t)(i / length) * slots + s]) x = make_float2(0.f, 0.f);
+    float y = 0.f;
+    if (kind == OWRX_DEMOD_NFM || kind == OWRX_DEMOD_WFM) {
+        float2 pv;
+        if (i == 0) pv = st[s].fm_last;
+        else {
+            pv = in[(size_t)(i - 1) * slots + s];
+            if (!gate[(size_t)((i - 1) / length) * slots + s]) pv = make_float2(0.f, 0.f);
+        }
+        const float K = 0.340447550238101026565118445432744920253753662109375f;
+        const float num = x.x * (x.y - pv.y) - x.y * (x.x - pv.x);
+        const float den = x.x * x.x + x.y * x.y;
+        y = den != 0.f ? K * num / den : 0.f;
+        y = fminf(1.f, fmaxf(-1.f, y));                       // Limit
+    } else if (kind == OWRX_DEMOD_AM) {
+        y = sqrtf(x.x * x.x + x.y * x.y);
+    } else if (kind == OWRX_DEMOD_SSB) {
+        y = x.x;
+    }
+    out[(size_t)i * slots + s] = y;
+}
+
+__global__ void __launch_bounds__(128)
+demod_front_commit_kernel(const float2* __restrict__ in, int slots, int n, int length,
+                          const unsigned char* __restrict__ gate, ChanState* __restrict__ st)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots || n <= 0) return;
+    float2 x = in[(size_t)(n - 1) * slots + s];
+    if (!gate[(size_t)((n - 1) / length) * slots + s]) x = make_float2(0.f, 0.f);
+    st[s].fm_last = x;
+}
+
+// Demodulator back (12 kHz-class groups): NFM -> NfmDeemphasis FIR; AM -> DcBlock (block = squelch
+// block); SSB -> copy.  in points at the row of output 0 and has >= T-1 rows of history before it.
+__global__ void __launch_bounds__(128)
+demod_back_kernel(const float* __restrict__ in, int slots, int n, int length, const float* __restrict__ deemph, int T,
+                  const ChanCfg* __restrict__ cfg, const float* __restrict__ dc_mean, const float* __restrict__ dc_prev,
+                  float* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (s >= slots || i >= n) return;
+    const int kind = cfg[s].kind;
+    const float* x = in + (size_t)i * slots + s;
+    float y;
+    if (kind == OWRX_DEMOD_NFM) {
+        float acc = 0.f;
+        for (int t = 0; t < T; t++) acc += deemph[t] * *(x - (ptrdiff_t)t * slots);
+        y = acc;
+    } else if (kind == OWRX_DEMOD_AM) {
+        const int b = i / length, ib = i % length;
+        const float last = b == 0 ? dc_prev[s] : dc_mean[(size_t)(b - 1) * slots + s];
+        const float avg = dc_mean[(size_t)b * slots + s];
+        y = *x - (last + (avg - last) * ((float)ib / (float)length));
+    } else {
+        y = *x;
+    }
+    out[(size_t)i * slots + s] = y;
+}
+
+// DcBlock block means: one thread per (block, slot); sequential float sum like the oracle.
+__global__ void __launch_bounds__(128)
+dc_mean_kernel(const float* __restrict__ in, int slots, int n_blocks, int length, const ChanCfg* __restrict__ cfg,
+               ChanState* __restrict__ st, float* __restrict__ dc_mean, float* __restrict__ dc_prev)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (s >= slots || b >= n_blocks) return;
+    if (cfg[s].kind != OWRX_DEMOD_AM) { if (b == 0) dc_prev[s] = 0.f; dc_mean[(size_t)b * slots + s] = 0.f; return; }
+    const float* x = in + (size_t)b * length * slots + s;
+    float acc = 0.f;
+    for (int i = 0; i < length; i++) acc += x[(size_t)i * slots];
+    dc_mean[(size_t)b * slots + s] = acc / (float)length;
+    if (b == 0) dc_prev[s] = st[s].dc_last;
+}
+
+__global__ void __launch_bounds__(128)
+dc_commit_kernel(int slots, int n_blocks, const ChanCfg* __restrict__ cfg, const float* __restrict__ dc_mean,
+                 ChanState* __restrict__ st)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots || n_blocks <= 0) return;
+    if (cfg[s].kind == OWRX_DEMOD_AM) st[s].dc_last = dc_mean[(size_t)(n_blocks - 1) * slots + s];
+}
+
+// WFM: FractionalDecimator(Format.FLOAT, rate, prefilter=True): 12-point Lagrange over the
+// forward-looking prefiltered signal v[idx] = sum_t x[idx+t] pre[t]  (SURVEY A.8).
+__global__ void __launch_bounds__(128)
+fracdec_f_kernel(const float* __restrict__ in, long long in_abs0, int slots, double rate, long long m0, int n_out,
+                 const float* __restrict__ pre, int Tpre, float* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y * blockDim.y + threadIdx.y;
+    if (s >= slots || m >= n_out) return;
+    const double where = 5.0 + (double)(m0 + m) * rate;
+    const double ihd = ceil(where);
+    float c[12];
+    lagrange12((float)(ihd - where), c);
+    const float* x = in + ((long long)ihd - 5 - in_abs0) * slots + s;
+    float acc = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) {
+        float v = 0.f;
+        for (int t = 0; t < Tpre; t++) v += x[(size_t)(i + t) * slots] * pre[t];
+        acc += c[i] * v;
+    }
+    out[(size_t)m * slots + s] = acc;
+}
+
+// WfmDeemphasis one-pole IIR, one channel per thread (sample-serial).
+__global__ void __launch_bounds__(128)
+wfm_deemph_kernel(const float* __restrict__ in, int slots, int n, float alpha, ChanState* __restrict__ st,
+                  float* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    float y = st[s].iir;
+    const float om = 1.0f - alpha;
+    for (int i = 0; i < n; i++) {
+        y = alpha * in[(size_t)i * slots + s] + om * y;
+        out[(size_t)i * slots + s] = y;
+    }
+    st[s].iir = y;
+}
+
+// Agc (SPEC-DEFINED), one channel per thread (sample-serial nonlinear recurrence).
+__global__ void __launch_bounds__(128)
+agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st,
+           float* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    const ChanCfg c = cfg[s];
+    if (c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE) {
+        for (int i = 0; i < n; i++) out[(size_t)i * slots + s] = in[(size_t)i * slots + s];
+        return;
+    }
+    float gain = st[s].agc_gain;
+    int hang = st[s].agc_hang;
+    for (int i = 0; i < n; i++) {
+        const float v = in[(size_t)i * slots + s];
+        if (v != 0.f) {
+            const float err = fabsf(v) * gain / c.agc_ref;
+            if (err > 1.f) { gain *= 1.f - c.agc_attack; hang = c.agc_hang_time; }
+            else if (hang > 0) hang--;
+            else gain *= 1.f + c.agc_decay;
+        }
+        gain = fminf(gain, c.agc_max);
+        gain = fmaxf(gain, 0.f);
+        out[(size_t)i * slots + s] = fminf(1.f, fmaxf(-1.f, v * gain));
+    }
+    st[s].agc_gain = gain;
+    st[s].agc_hang = hang;
+}
+
+}  // namespace owrx

@@ -1,0 +1,693 @@
+// waterfall.cu — K1/K2: the waterfall FftChain on sm_100a.
+//
+// Replaces the pycsdr worker chain built by FftChain (reference csdr/chain/fft.py:25-49):
+//   Fft(size, every_n_samples) -> LogAveragePower(add_db, fft_size, avg_number) | LogPower(add_db)
+//   -> FftSwap(fft_size) -> [FftAdpcm(fft_size)]
+// Arithmetic spec: SURVEY.md Appendix A.2-A.5.
+//
+// Kernels (all hand-written, no cuFFT):
+//   wf_colpass_kernel<R0>   four-step column pass for N > 4096 (N = R0 x 4096): window, radix-R0
+//                           butterfly, W_N twiddle, writes the row-major scratch Y.
+//   wf_fft_kernel<LOG2M,..> shared-memory Stockham FFT of M <= 4096 points (radix 16,16,R3) with the
+//                           Hamming window fused into the load and |X|^2 accumulated in REGISTERS over
+//                           the avg frames of a line; one CTA per (line, row, frame-subset).
+//   wf_finalize_kernel      sums the frame-subset partials, 10*log10 + add_db - 10*log10(avg),
+//                           half-swap on store, x100 -> int16 truncation + 10-sample pad.
+//   wf_adpcm_kernel         IMA-ADPCM, state reset per line, low nibble first.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <deque>
+#include <mutex>
+#include <vector>
+
+namespace owrx {
+
+// ------------------------------------------------------------------------------------------------
+// register-resident small DFTs.  After dftR(v) register q holds X[slot<R>(q)].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dft2(float2& a, float2& b)
+{
+    float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d)
+{
+    float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = cmul_mi(csub(b, d));
+    a = cadd(t0, t2);
+    c = csub(t0, t2);
+    b = cadd(t1, t3);
+    d = csub(t1, t3);
+}
+
+template <int R> __device__ __forceinline__ int slot(int q);
+template <> __device__ __forceinline__ int slot<1>(int q) { return q; }
+template <> __device__ __forceinline__ int slot<2>(int q) { return q; }
+template <> __device__ __forceinline__ int slot<4>(int q) { return q; }
+template <> __device__ __forceinline__ int slot<8>(int q) { return (q >> 1) + 4 * (q & 1); }
+template <> __device__ __forceinline__ int slot<16>(int q) { return (q >> 2) + 4 * (q & 3); }
+
+#define OWRX_SQRT1_2 0.70710678118654752440f
+#define OWRX_COS_PI_8 0.92387953251128675613f
+#define OWRX_SIN_PI_8 0.38268343236508977173f
+
+template <int R> __device__ __forceinline__ void dft(float2* v);
+template <> __device__ __forceinline__ void dft<1>(float2*) {}
+template <> __device__ __forceinline__ void dft<2>(float2* v) { dft2(v[0], v[1]); }
+template <> __device__ __forceinline__ void dft<4>(float2* v) { dft4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void dft<8>(float2* v)
+{
+    // n = 2 n1 + n2, m = m1 + 4 m2
+    dft4(v[0], v[2], v[4], v[6]);
+    dft4(v[1], v[3], v[5], v[7]);
+    // v[2 m1 + 1] *= W8^m1
+    v[3] = make_float2((v[3].x + v[3].y) * OWRX_SQRT1_2, (v[3].y - v[3].x) * OWRX_SQRT1_2);
+    v[5] = cmul_mi(v[5]);
+    v[7] = make_float2((v[7].y - v[7].x) * OWRX_SQRT1_2, -(v[7].x + v[7].y) * OWRX_SQRT1_2);
+    dft2(v[0], v[1]);
+    dft2(v[2], v[3]);
+    dft2(v[4], v[5]);
+    dft2(v[6], v[7]);
+}
+template <> __device__ __forceinline__ void dft<16>(float2* v)
+{
+    // n = 4 n1 + n2, m = m1 + 4 m2;  W16^{nm} = W4^{n1 m1} W16^{n2 m1} W4^{n2 m2}
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    const float2 w1 = make_float2(OWRX_COS_PI_8, -OWRX_SIN_PI_8);
+    const float2 w3 = make_float2(OWRX_SIN_PI_8, -OWRX_COS_PI_8);
+    // m1 = 1: exponents 1,2,3
+    v[5] = cmul(v[5], w1);
+    v[6] = make_float2((v[6].x + v[6].y) * OWRX_SQRT1_2, (v[6].y - v[6].x) * OWRX_SQRT1_2);
+    v[7] = cmul(v[7], w3);
+    // m1 = 2: exponents 2,4,6
+    v[9] = make_float2((v[9].x + v[9].y) * OWRX_SQRT1_2, (v[9].y - v[9].x) * OWRX_SQRT1_2);
+    v[10] = cmul_mi(v[10]);
+    v[11] = make_float2((v[11].y - v[11].x) * OWRX_SQRT1_2, -(v[11].x + v[11].y) * OWRX_SQRT1_2);
+    // m1 = 3: exponents 3,6,9
+    v[13] = cmul(v[13], w3);
+    v[14] = make_float2((v[14].y - v[14].x) * OWRX_SQRT1_2, -(v[14].x + v[14].y) * OWRX_SQRT1_2);
+    v[15] = cmul(v[15], make_float2(-OWRX_COS_PI_8, OWRX_SIN_PI_8));
+#pragma unroll
+    for (int m1 = 0; m1 < 4; m1++) dft4(v[4 * m1], v[4 * m1 + 1], v[4 * m1 + 2], v[4 * m1 + 3]);
+}
+
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+struct WfFftParams {
+    const float2* src;       // FROM_IQ: wideband IQ;  else: scratch Y
+    const float* window;     // N floats (FROM_IQ only)
+    const float2* tw2;       // [16][16]   exp(-2 pi i r k / 256)
+    const float2* tw3;       // [R3][256]  exp(-2 pi i r k / M)
+    float* partial;          // [line][subset][N] partial power sums
+    int every_n;             // hop E between frames (FROM_IQ)
+    int frames_per_line;     // avg (or 1)
+    int subsets;             // S frame-subsets per line
+    int r0;                  // four-step rows (1 when FROM_IQ)
+    int n;                   // full FFT size N = r0 * M
+    long long first_frame;   // FROM_IQ: global frame index of line 0 of this launch
+};
+
+// One CTA per (line, row k1, frame subset).  M = 2^LOG2M points, T = M/16 threads.
+template <int LOG2M, bool FROM_IQ>
+__global__ void __launch_bounds__((1 << LOG2M) / 16 < 32 ? 32 : (1 << LOG2M) / 16)
+wf_fft_kernel(WfFftParams p)
+{
+    constexpr int M = 1 << LOG2M;
+    constexpr int T = M / 16;
+    constexpr int R3 = M / 256;
+    constexpr int BUF = M + M / 16;
+    extern __shared__ float2 smem[];
+    float2* bufA = smem;
+    float2* bufB = smem + BUF;
+
+    const int tid = threadIdx.x;
+    const bool active = tid < T;
+    int unit = blockIdx.x;
+    const int subset = unit % p.subsets;
+    unit /= p.subsets;
+    const int k1 = unit % p.r0;
+    const int line = unit / p.r0;
+
+    const int per = (p.frames_per_line + p.subsets - 1) / p.subsets;
+    const int a0 = subset * per;
+    const int a1 = min(p.frames_per_line, a0 + per);
+
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) acc[q] = 0.0f;
+
+    for (int a = a0; a < a1; a++) {
+        float2 v[16];
+        const long long frame = (long long)line * p.frames_per_line + a;
+        if (active) {
+            if (FROM_IQ) {
+                const float2* x = p.src + (p.first_frame + frame) * (long long)p.every_n;
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    float2 s = __ldg(x + tid + r * T);
+                    float w = __ldg(p.window + tid + r * T);
+                    v[r] = make_float2(s.x * w, s.y * w);
+                }
+            } else {
+                const float2* x = p.src + (frame * p.r0 + k1) * (long long)M;
+#pragma unroll
+                for (int r = 0; r < 16; r++) v[r] = __ldg(x + tid + r * T);
+            }
+            // pass 1: radix 16, Ns = 1
+            dft<16>(v);
+#pragma unroll
+            for (int q = 0; q < 16; q++) bufA[pad16(tid * 16 + slot<16>(q))] = v[q];
+        }
+        __syncthreads();
+        if (active) {
+            // pass 2: radix 16, Ns = 16
+            const int k = tid & 15;
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = bufA[pad16(tid + r * T)];
+#pragma unroll
+            for (int r = 1; r < 16; r++) v[r] = cmul(v[r], __ldg(p.tw2 + r * 16 + k));
+            dft<16>(v);
+            if (R3 > 1) {
+                const int base = (tid >> 4) * 256 + k;
+#pragma unroll
+                for (int q = 0; q < 16; q++) bufB[pad16(base + slot<16>(q) * 16)] = v[q];
+            }
+        }
+        if (R3 > 1) {
+            __syncthreads();
+            if (active) {
+                // pass 3: radix R3, Ns = 256; 16/R3 butterflies per thread
+#pragma unroll
+                for (int b = 0; b < 16 / R3; b++) {
+                    const int jb = tid + b * T;
+#pragma unroll
+                    for (int r = 0; r < R3; r++) v[b * R3 + r] = bufB[pad16(jb + r * 256)];
+#pragma unroll
+                    for (int r = 1; r < R3; r++) v[b * R3 + r] = cmul(v[b * R3 + r], __ldg(p.tw3 + r * 256 + jb));
+                    dft<R3>(v + b * R3);
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) acc[q] += v[q].x * v[q].x + v[q].y * v[q].y;
+        }
+    }
+
+    if (active) {
+        float* out = p.partial + ((size_t)line * p.subsets + subset) * (size_t)p.n;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            int bin;
+            if (R3 > 1) {
+                const int b = q / R3, r = q % R3;
+                const int jb = tid + b * T;            // k = jb (< 256), jb >> 8 == 0
+                bin = jb + slot<R3>(r) * 256;
+            } else {
+                bin = tid + slot<16>(q) * 16;          // M == 256
+            }
+            out[(size_t)k1 + (size_t)p.r0 * bin] = acc[q];
+        }
+    }
+}
+
+struct WfColParams {
+    const float2* iq;
+    const float* window;
+    const float2* twn;      // [R0][M] exp(-2 pi i k1 n2 / N)
+    float2* y;              // [frame][R0][M]
+    int every_n;
+    long long first_frame;
+};
+
+template <int R0>
+__global__ void __launch_bounds__(256) wf_colpass_kernel(WfColParams p)
+{
+    constexpr int M = 4096;
+    const int n2 = blockIdx.x * 256 + threadIdx.x;
+    const long long f = blockIdx.y;
+    const float2* x = p.iq + (p.first_frame + f) * (long long)p.every_n;
+    float2 v[R0];
+#pragma unroll
+    for (int n1 = 0; n1 < R0; n1++) {
+        float2 s = __ldg(x + n2 + M * n1);
+        float w = __ldg(p.window + n2 + M * n1);
+        v[n1] = make_float2(s.x * w, s.y * w);
+    }
+    dft<R0>(v);
+    float2* y = p.y + f * (long long)(R0 * M);
+#pragma unroll
+    for (int q = 0; q < R0; q++) {
+        const int k1 = slot<R0>(q);
+        float2 o = v[q];
+        if (k1 > 0) o = cmul(o, __ldg(p.twn + k1 * M + n2));
+        y[k1 * M + n2] = o;
+    }
+}
+
+// sums partials, log, swap, optional quantise.  One thread per output position.
+__global__ void __launch_bounds__(256)
+wf_finalize_kernel(const float* __restrict__ partial, int subsets, int n, float corr, size_t n_lines,
+                   float* __restrict__ db_out, int16_t* __restrict__ s16_out)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_lines * (size_t)n) return;
+    const size_t line = gid / (size_t)n;
+    const int i = (int)(gid % (size_t)n);
+    const int bin = (i + n / 2) & (n - 1);                     // FftSwap: out[i] = in[(i + N/2) mod N]
+    const float* ps = partial + line * (size_t)subsets * (size_t)n + bin;
+    float s = 0.0f;
+    for (int k = 0; k < subsets; k++) s += ps[(size_t)k * n];
+    const float db = 10.0f * log10f(s) + corr;
+    if (db_out) db_out[gid] = db;
+    if (s16_out) {
+        // FftAdpcm quantiser: (int16)(dB * 100), C truncation, clamped
+        float v = db * 100.0f;
+        int q;
+        if (!(v > -32768.0f)) q = -32768;
+        else if (v > 32767.0f) q = 32767;
+        else q = __float2int_rz(v);
+        int16_t* row = s16_out + line * (size_t)(n + 10);
+        row[10 + i] = (int16_t)q;
+        if (i == 0) {
+#pragma unroll
+            for (int k = 0; k < 10; k++) row[k] = (int16_t)q;  // COMPRESS_FFT_PAD_N copies of s[0]
+        }
+    }
+}
+
+// IMA-ADPCM tables — values pinned by the browser decoder, reference htdocs/lib/AudioEngine.js:426-438.
+__constant__ int16_t c_ima_step[89] = {
+    7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45,
+    50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130, 143, 157, 173, 190, 209, 230, 253, 279, 307,
+    337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411, 1552, 1707, 1878, 2066,
+    2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899,
+    15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
+
+__device__ __forceinline__ int ima_encode(int sample, int& index, int& pred, const int* steps)
+{
+    const int st = steps[index];
+    int diff = sample - pred;
+    int code = 0;
+    if (diff < 0) { code = 8; diff = -diff; }
+    int d = st >> 3;
+    if (diff >= st) { code |= 4; diff -= st; d += st; }
+    const int s1 = st >> 1;
+    if (diff >= s1) { code |= 2; diff -= s1; d += s1; }
+    const int s2 = st >> 2;
+    if (diff >= s2) { code |= 1; d += s2; }
+    pred = (code & 8) ? pred - d : pred + d;
+    pred = max(-32768, min(32767, pred));
+    const int c3 = code & 7;
+    index += (c3 < 4) ? -1 : (2 * c3 - 6);
+    index = max(0, min(88, index));
+    return code;
+}
+
+// One thread per line (state is strictly sequential within a line; lines are independent).
+// 32-thread CTAs spread the lines over the SMs.
+__global__ void __launch_bounds__(32)
+wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int n_samples, size_t n_lines)
+{
+    __shared__ int steps[89];
+    for (int i = threadIdx.x; i < 89; i += blockDim.x) steps[i] = c_ima_step[i];
+    __syncthreads();
+    const size_t line = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= n_lines) return;
+    const int16_t* s = s16 + line * (size_t)n_samples;
+    uint8_t* o = out + line * (size_t)(n_samples / 2);
+    int index = 0, pred = 0;
+    for (int i = 0; i + 1 < n_samples; i += 2) {
+        const int lo = ima_encode(s[i], index, pred, steps);
+        const int hi = ima_encode(s[i + 1], index, pred, steps);
+        o[i >> 1] = (uint8_t)(lo | (hi << 4));
+    }
+}
+
+}  // namespace owrx
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace owrx;
+
+struct owrx_wf {
+    int device = 0, sm_count = 0;
+    int n = 0, every_n = 0, avg = 0, compression = 0;
+    float add_db = 0.0f;
+    int m = 0, log2m = 0, r0 = 1;
+    cudaStream_t stream = nullptr;
+    float* d_window = nullptr;
+    float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_twn = nullptr;
+    // scratch
+    float* d_partial = nullptr; size_t partial_cap = 0;
+    float2* d_y = nullptr;      size_t y_cap = 0;
+    int16_t* d_s16 = nullptr;   size_t s16_cap = 0;
+    // streaming
+    float2* d_in = nullptr;     size_t in_cap = 0, in_fill = 0, skip = 0;
+    float2* d_in_alt = nullptr;
+    uint8_t* d_out = nullptr;   size_t out_cap = 0;
+    uint8_t* h_out = nullptr;   size_t h_out_cap = 0;
+    std::deque<std::vector<uint8_t>> queue;
+    std::mutex mu;
+};
+
+static size_t wf_line_bytes(const owrx_wf* wf)
+{
+    return wf->compression == OWRX_COMPRESSION_ADPCM ? (size_t)(wf->n + 10) / 2 : (size_t)wf->n * 4;
+}
+
+static size_t wf_lines_for(const owrx_wf* wf, size_t n_samples)
+{
+    if (wf->every_n <= 0 || n_samples < (size_t)wf->n) return 0;
+    const size_t frames = (n_samples - (size_t)wf->n) / (size_t)wf->every_n + 1;
+    return frames / (size_t)(wf->avg > 0 ? wf->avg : 1);
+}
+
+template <typename T> static int grow(T** ptr, size_t* cap, size_t need)
+{
+    if (need <= *cap) return OWRX_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    OWRX_CUDA(cudaMalloc((void**)ptr, need * sizeof(T)));
+    *cap = need;
+    return OWRX_OK;
+}
+
+template <int LOG2M, bool FROM_IQ> static int launch_fft(const WfFftParams& p, size_t units, cudaStream_t st)
+{
+    constexpr int M = 1 << LOG2M;
+    constexpr int threads = M / 16 < 32 ? 32 : M / 16;
+    const size_t smem = 2 * (size_t)(M + M / 16) * sizeof(float2);
+    OWRX_CUDA(cudaFuncSetAttribute(wf_fft_kernel<LOG2M, FROM_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wf_fft_kernel<LOG2M, FROM_IQ><<<(unsigned)units, threads, smem, st>>>(p);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame, size_t lines, uint8_t* out_dev,
+                        float* db_dev, int16_t* s16_dev, cudaStream_t st)
+{
+    const int fpl = wf->avg > 0 ? wf->avg : 1;
+    const int n = wf->n;
+    // frame subsets: enough CTAs to cover the SMs twice when few lines are in flight
+    int subsets = 1;
+    const size_t base_units = lines * (size_t)wf->r0;
+    if (base_units < (size_t)2 * wf->sm_count)
+        subsets = (int)std::min<size_t>((size_t)std::min(fpl, 8), ((size_t)2 * wf->sm_count + base_units - 1) / base_units);
+    int rc;
+    if ((rc = grow(&wf->d_partial, &wf->partial_cap, lines * (size_t)subsets * (size_t)n)) != OWRX_OK) return rc;
+
+    WfFftParams p;
+    p.window = wf->d_window; p.tw2 = wf->d_tw2; p.tw3 = wf->d_tw3; p.partial = wf->d_partial;
+    p.every_n = wf->every_n; p.frames_per_line = fpl; p.subsets = subsets; p.r0 = wf->r0; p.n = n;
+    const size_t units = lines * (size_t)wf->r0 * (size_t)subsets;
+
+    if (wf->r0 == 1) {
+        p.src = iq_dev; p.first_frame = first_frame;
+        switch (wf->log2m) {
+        case 8:  rc = launch_fft<8, true>(p, units, st); break;
+        case 9:  rc = launch_fft<9, true>(p, units, st); break;
+        case 10: rc = launch_fft<10, true>(p, units, st); break;
+        case 11: rc = launch_fft<11, true>(p, units, st); break;
+        case 12: rc = launch_fft<12, true>(p, units, st); break;
+        default: return fail(OWRX_E_INVALID, "unsupported fft size");
+        }
+        if (rc != OWRX_OK) return rc;
+    } else {
+        const size_t frames = lines * (size_t)fpl;
+        if ((rc = grow(&wf->d_y, &wf->y_cap, frames * (size_t)n)) != OWRX_OK) return rc;
+        WfColParams c;
+        c.iq = iq_dev; c.window = wf->d_window; c.twn = wf->d_twn; c.y = wf->d_y; c.every_n = wf->every_n;
+        c.first_frame = first_frame;
+        dim3 grid(4096 / 256, (unsigned)frames);
+        switch (wf->r0) {
+        case 2:  wf_colpass_kernel<2><<<grid, 256, 0, st>>>(c); break;
+        case 4:  wf_colpass_kernel<4><<<grid, 256, 0, st>>>(c); break;
+        case 8:  wf_colpass_kernel<8><<<grid, 256, 0, st>>>(c); break;
+        case 16: wf_colpass_kernel<16><<<grid, 256, 0, st>>>(c); break;
+        default: return fail(OWRX_E_INVALID, "unsupported fft size");
+        }
+        OWRX_LAUNCH_CHECK();
+        p.src = wf->d_y; p.first_frame = 0;
+        if ((rc = launch_fft<12, false>(p, units, st)) != OWRX_OK) return rc;
+    }
+
+    const bool adpcm = wf->compression == OWRX_COMPRESSION_ADPCM;
+    int16_t* s16 = s16_dev;
+    if (adpcm && !s16) {
+        if ((rc = grow(&wf->d_s16, &wf->s16_cap, lines * (size_t)(n + 10))) != OWRX_OK) return rc;
+        s16 = wf->d_s16;
+    }
+    float* db = db_dev;
+    if (!adpcm && out_dev) db = (float*)out_dev;   // compression "none": the line IS the float32 dB row
+    const float corr = wf->avg > 0 ? wf->add_db - 10.0f * log10f((float)wf->avg) : wf->add_db;
+    const size_t total = lines * (size_t)n;
+    wf_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(wf->d_partial, subsets, n, corr, lines, db,
+                                                                       adpcm ? s16 : nullptr);
+    OWRX_LAUNCH_CHECK();
+    if (!adpcm && db_dev && out_dev && db_dev != (float*)out_dev)
+        OWRX_CUDA(cudaMemcpyAsync(db_dev, out_dev, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (adpcm && out_dev) {
+        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, 0, st>>>(s16, out_dev, n + 10, lines);
+        OWRX_LAUNCH_CHECK();
+    }
+    return OWRX_OK;
+}
+
+static int wf_process(owrx_wf* wf, const float2* iq_dev, size_t n_samples, uint8_t* out_dev, size_t out_cap,
+                      float* db_dev, int16_t* s16_dev, size_t* n_lines, cudaStream_t st)
+{
+    const size_t lines = wf_lines_for(wf, n_samples);
+    const size_t lb = wf_line_bytes(wf);
+    if (out_dev && lines * lb > out_cap) return fail(OWRX_E_OVERFLOW, "output buffer too small: need %zu bytes", lines * lb);
+    const int fpl = wf->avg > 0 ? wf->avg : 1;
+    // chunk so that the four-step scratch stays bounded (<= 256 MiB) and grid.y <= 65535
+    size_t chunk = lines;
+    if (wf->r0 > 1) {
+        const size_t per_line = (size_t)fpl * (size_t)wf->n * sizeof(float2);
+        chunk = std::max<size_t>(1, ((size_t)256 << 20) / per_line);
+        chunk = std::min(chunk, (size_t)65535 / (size_t)fpl > 0 ? (size_t)65535 / (size_t)fpl : 1);
+    }
+    for (size_t l0 = 0; l0 < lines; l0 += chunk) {
+        const size_t lc = std::min(chunk, lines - l0);
+        int rc = wf_run_chunk(wf, iq_dev, (long long)l0 * fpl, lc, out_dev ? out_dev + l0 * lb : nullptr,
+                              db_dev ? db_dev + l0 * (size_t)wf->n : nullptr,
+                              s16_dev ? s16_dev + l0 * (size_t)(wf->n + 10) : nullptr, st);
+        if (rc != OWRX_OK) return rc;
+    }
+    if (n_lines) *n_lines = lines;
+    return OWRX_OK;
+}
+
+static int wf_build_tables(owrx_wf* wf)
+{
+    const int n = wf->n, m = wf->m, r3 = m / 256;
+    std::vector<float> win((size_t)n);
+    for (int i = 0; i < n; i++) win[i] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * i / (double)(n - 1)));
+    std::vector<float2> tw2(256), tw3((size_t)std::max(r3, 1) * 256), twn;
+    for (int r = 0; r < 16; r++)
+        for (int k = 0; k < 16; k++) {
+            double a = -2.0 * M_PI * r * k / 256.0;
+            tw2[r * 16 + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int r = 0; r < r3; r++)
+        for (int k = 0; k < 256; k++) {
+            double a = -2.0 * M_PI * (double)r * k / (double)m;
+            tw3[(size_t)r * 256 + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+    OWRX_CUDA(cudaMalloc((void**)&wf->d_window, win.size() * sizeof(float)));
+    OWRX_CUDA(cudaMalloc((void**)&wf->d_tw2, tw2.size() * sizeof(float2)));
+    OWRX_CUDA(cudaMalloc((void**)&wf->d_tw3, tw3.size() * sizeof(float2)));
+    OWRX_CUDA(cudaMemcpy(wf->d_window, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice));
+    OWRX_CUDA(cudaMemcpy(wf->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    OWRX_CUDA(cudaMemcpy(wf->d_tw3, tw3.data(), tw3.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (wf->r0 > 1) {
+        twn.resize((size_t)n);
+        for (int k1 = 0; k1 < wf->r0; k1++)
+            for (int n2 = 0; n2 < m; n2++) {
+                double a = -2.0 * M_PI * (double)k1 * n2 / (double)n;
+                twn[(size_t)k1 * m + n2] = make_float2((float)cos(a), (float)sin(a));
+            }
+        OWRX_CUDA(cudaMalloc((void**)&wf->d_twn, twn.size() * sizeof(float2)));
+        OWRX_CUDA(cudaMemcpy(wf->d_twn, twn.data(), twn.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    return OWRX_OK;
+}
+
+extern "C" {
+
+int owrx_wf_create(int device, int fft_size, int every_n_samples, int avg_number, float add_db, int compression,
+                   owrx_wf_t** out)
+{
+    if (!out) return fail(OWRX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (fft_size < 256 || fft_size > 65536 || (fft_size & (fft_size - 1)))
+        return fail(OWRX_E_INVALID, "fft_size must be a power of two in [256, 65536], got %d", fft_size);
+    if (every_n_samples < 0 || avg_number < 0) return fail(OWRX_E_INVALID, "negative every_n_samples / avg_number");
+    if (compression != OWRX_COMPRESSION_NONE && compression != OWRX_COMPRESSION_ADPCM)
+        return fail(OWRX_E_INVALID, "unknown compression %d", compression);
+    int sm = 0, rc = select_device(device, &sm);
+    if (rc != OWRX_OK) return rc;
+    owrx_wf* wf = new (std::nothrow) owrx_wf();
+    if (!wf) return fail(OWRX_E_NOMEM, "out of host memory");
+    wf->device = device; wf->sm_count = sm;
+    wf->n = fft_size; wf->every_n = every_n_samples; wf->avg = avg_number; wf->add_db = add_db;
+    wf->compression = compression;
+    if (fft_size <= 4096) { wf->m = fft_size; wf->r0 = 1; } else { wf->m = 4096; wf->r0 = fft_size / 4096; }
+    wf->log2m = 0;
+    while ((1 << wf->log2m) < wf->m) wf->log2m++;
+    cudaError_t e = cudaStreamCreateWithFlags(&wf->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete wf; return fail(OWRX_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    rc = wf_build_tables(wf);
+    if (rc != OWRX_OK) { owrx_wf_destroy(wf); return rc; }
+    *out = wf;
+    return OWRX_OK;
+}
+
+void owrx_wf_destroy(owrx_wf_t* wf)
+{
+    if (!wf) return;
+    cudaSetDevice(wf->device);
+    if (wf->stream) cudaStreamSynchronize(wf->stream);
+    cudaFree(wf->d_window); cudaFree(wf->d_tw2); cudaFree(wf->d_tw3); cudaFree(wf->d_twn);
+    cudaFree(wf->d_partial); cudaFree(wf->d_y); cudaFree(wf->d_s16);
+    cudaFree(wf->d_in); cudaFree(wf->d_in_alt); cudaFree(wf->d_out);
+    if (wf->h_out) cudaFreeHost(wf->h_out);
+    if (wf->stream) cudaStreamDestroy(wf->stream);
+    delete wf;
+}
+
+int owrx_wf_set_every_n_samples(owrx_wf_t* wf, int every_n_samples)
+{
+    if (!wf || every_n_samples < 0) return fail(OWRX_E_INVALID, "bad every_n_samples");
+    std::lock_guard<std::mutex> g(wf->mu);
+    wf->every_n = every_n_samples;
+    return OWRX_OK;
+}
+
+int owrx_wf_set_avg_number(owrx_wf_t* wf, int avg_number)
+{
+    if (!wf || avg_number < 0) return fail(OWRX_E_INVALID, "bad avg_number");
+    std::lock_guard<std::mutex> g(wf->mu);
+    wf->avg = avg_number;
+    return OWRX_OK;
+}
+
+int owrx_wf_set_compression(owrx_wf_t* wf, int compression)
+{
+    if (!wf || (compression != OWRX_COMPRESSION_NONE && compression != OWRX_COMPRESSION_ADPCM))
+        return fail(OWRX_E_INVALID, "bad compression");
+    std::lock_guard<std::mutex> g(wf->mu);
+    if (compression != wf->compression) wf->queue.clear();   // queued lines have the old format
+    wf->compression = compression;
+    return OWRX_OK;
+}
+
+size_t owrx_wf_line_bytes(const owrx_wf_t* wf) { return wf ? wf_line_bytes(wf) : 0; }
+
+size_t owrx_wf_lines_for(const owrx_wf_t* wf, size_t n_samples) { return wf ? wf_lines_for(wf, n_samples) : 0; }
+
+int owrx_wf_process_device(owrx_wf_t* wf, const void* iq_dev, size_t n_samples, void* out_dev, size_t out_cap_bytes,
+                           void* db_dev, void* s16_dev, size_t* n_lines, void* stream)
+{
+    if (!wf || !iq_dev) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(wf->mu);
+    OWRX_CUDA(cudaSetDevice(wf->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : wf->stream;
+    return wf_process(wf, (const float2*)iq_dev, n_samples, (uint8_t*)out_dev, out_cap_bytes, (float*)db_dev,
+                      (int16_t*)s16_dev, n_lines, st);
+}
+
+int owrx_wf_feed(owrx_wf_t* wf, const float* iq, size_t n_samples)
+{
+    if (!wf || (!iq && n_samples)) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(wf->mu);
+    OWRX_CUDA(cudaSetDevice(wf->device));
+    // honour a pending skip (every_n > fft_size leaves a gap after the last consumed frame)
+    if (wf->skip) {
+        const size_t d = std::min(wf->skip, n_samples);
+        iq += 2 * d; n_samples -= d; wf->skip -= d;
+    }
+    if (!n_samples) return OWRX_OK;
+    const size_t need = wf->in_fill + n_samples;
+    if (need > wf->in_cap) {
+        const size_t cap = std::max(need, wf->in_cap * 2);
+        float2* nb = nullptr;
+        OWRX_CUDA(cudaMalloc((void**)&nb, cap * sizeof(float2)));
+        if (wf->in_fill) OWRX_CUDA(cudaMemcpyAsync(nb, wf->d_in, wf->in_fill * sizeof(float2), cudaMemcpyDeviceToDevice, wf->stream));
+        OWRX_CUDA(cudaStreamSynchronize(wf->stream));
+        cudaFree(wf->d_in); cudaFree(wf->d_in_alt);
+        wf->d_in = nb; wf->d_in_alt = nullptr; wf->in_cap = cap;
+        OWRX_CUDA(cudaMalloc((void**)&wf->d_in_alt, cap * sizeof(float2)));
+    }
+    OWRX_CUDA(cudaMemcpyAsync(wf->d_in + wf->in_fill, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, wf->stream));
+    wf->in_fill += n_samples;
+    const size_t lines = wf_lines_for(wf, wf->in_fill);
+    if (!lines) { OWRX_CUDA(cudaStreamSynchronize(wf->stream)); return OWRX_OK; }
+    const size_t lb = wf_line_bytes(wf);
+    if (lines * lb > wf->out_cap) {
+        cudaFree(wf->d_out); wf->d_out = nullptr; wf->out_cap = 0;
+        OWRX_CUDA(cudaMalloc((void**)&wf->d_out, lines * lb));
+        wf->out_cap = lines * lb;
+    }
+    if (lines * lb > wf->h_out_cap) {
+        if (wf->h_out) cudaFreeHost(wf->h_out);
+        wf->h_out = nullptr; wf->h_out_cap = 0;
+        OWRX_CUDA(cudaMallocHost((void**)&wf->h_out, lines * lb));
+        wf->h_out_cap = lines * lb;
+    }
+    size_t got = 0;
+    int rc = wf_process(wf, wf->d_in, wf->in_fill, wf->d_out, wf->out_cap, nullptr, nullptr, &got, wf->stream);
+    if (rc != OWRX_OK) return rc;
+    OWRX_CUDA(cudaMemcpyAsync(wf->h_out, wf->d_out, got * lb, cudaMemcpyDeviceToHost, wf->stream));
+    // carry the unconsumed tail to the front of the alternate buffer
+    const size_t fpl = (size_t)(wf->avg > 0 ? wf->avg : 1);
+    const size_t consumed = got * fpl * (size_t)wf->every_n;
+    if (consumed >= wf->in_fill) {
+        wf->skip = consumed - wf->in_fill;
+        wf->in_fill = 0;
+    } else {
+        const size_t tail = wf->in_fill - consumed;
+        OWRX_CUDA(cudaMemcpyAsync(wf->d_in_alt, wf->d_in + consumed, tail * sizeof(float2), cudaMemcpyDeviceToDevice, wf->stream));
+        std::swap(wf->d_in, wf->d_in_alt);
+        wf->in_fill = tail;
+    }
+    OWRX_CUDA(cudaStreamSynchronize(wf->stream));
+    for (size_t l = 0; l < got; l++) wf->queue.emplace_back(wf->h_out + l * lb, wf->h_out + (l + 1) * lb);
+    return OWRX_OK;
+}
+
+int owrx_wf_read(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes)
+{
+    if (!wf || !out || !n_bytes) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(wf->mu);
+    size_t o = 0;
+    while (!wf->queue.empty() && o + wf->queue.front().size() <= cap_bytes) {
+        memcpy((uint8_t*)out + o, wf->queue.front().data(), wf->queue.front().size());
+        o += wf->queue.front().size();
+        wf->queue.pop_front();
+    }
+    *n_bytes = o;
+    if (o == 0 && !wf->queue.empty()) return fail(OWRX_E_OVERFLOW, "buffer smaller than one line");
+    return OWRX_OK;
+}
+
+int owrx_fft_adpcm_encode_device(int device, const void* s16_dev, int fft_size, size_t n_lines, void* out_dev, void* stream)
+{
+    if (!s16_dev || !out_dev || fft_size <= 0 || (fft_size & 1)) return fail(OWRX_E_INVALID, "bad argument");
+    int rc = select_device(device, nullptr);
+    if (rc != OWRX_OK) return rc;
+    if (!n_lines) return OWRX_OK;
+    wf_adpcm_kernel<<<(unsigned)((n_lines + 31) / 32), 32, 0, (cudaStream_t)stream>>>((const int16_t*)s16_dev, (uint8_t*)out_dev,
+                                                                                   fft_size + 10, n_lines);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+}  // extern "C"
