@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native OpenWebRX+ DSP hot path.
+
+Metric (BASELINE.json): channel-MS/s = wideband input MS/s x concurrent client channels, measured on
+BASELINE config 2: "Selector DDC + NFM/AM/USB demod: 10 MS/s wideband, 64 concurrent 12 kHz client
+channels on 1xB200".  A step = one pass of the hot path (Shift -> FirDecimate -> FractionalDecimator ->
+Bandpass -> Squelch -> demod -> AGC for all 64 channels) over one synthetic IQ block.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (N > 1: under torchrun, weak scaling:
+                                                           #   64 channels per GPU, IQ block broadcast over NCCL)
+  python bench.py --impl reference ...                     # the CPU chain (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric through
+the public host API (owrx_bank_feed from pinned host memory + audio read-back); `roofline` describes the
+dominant kernel (K3: NCO mix + polyphase FIR decimation); `waterfall` reports the FftChain half of the
+hot path (BASELINE config 1 shape) from its own timed loop; `cpu_baseline` the oracle on host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 10_000_000           # config 2 wideband rate
+OUT_RATE = 12000
+CH_PER_GPU = 64
+BLOCK = 1 << 24           # samples per step: 134 MB of complex64 > the 126 MB L2
+WF_FS, WF_N, WF_FPS, WF_OV = 2_400_000, 4096, 9, 0.3     # config 1 (waterfall)
+METRIC = "channel-MS/s (input MS/s x clients) + waterfall FFT frames/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured"
+        except Exception:
+            pass
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]            # samples under load = upper half
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def channel_plan(rank, n_ch):
+    from openwebrx_b200.synth import carrier_plan
+    return carrier_plan(64, FS, seed=20260101 + rank)[:n_ch] if n_ch <= 64 else carrier_plan(n_ch, FS, seed=20260101 + rank)
+
+
+def synth_iq_torch(n, fs, carriers, device, seed=20260101):
+    """Same signal model as openwebrx_b200.synth.make_iq, generated on the GPU (plumbing, untimed)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    x = torch.empty(n, 2, device=device, dtype=torch.float32)
+    chunk = 1 << 21
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        t = (torch.arange(s, e, device=device, dtype=torch.float64)) / fs
+        re = 1e-3 * torch.randn(e - s, device=device, generator=g, dtype=torch.float32)
+        im = 1e-3 * torch.randn(e - s, device=device, generator=g, dtype=torch.float32)
+        for c in carriers:
+            f, a, kind = c["offset"], c["amp"], c["kind"]
+            if kind == "am":
+                env = a * (1.0 + 0.5 * torch.cos(2 * np.pi * 1000.0 * t)) / 1.5
+                ph = 2 * np.pi * ((f * t) % 1.0)
+                re += (env * torch.cos(ph)).float(); im += (env * torch.sin(ph)).float()
+            elif kind == "nfm":
+                ph = 2 * np.pi * ((f * t) % 1.0) + 2.5 * torch.sin(2 * np.pi * 1000.0 * t)
+                re += (a * torch.cos(ph)).float(); im += (a * torch.sin(ph)).float()
+            else:
+                for df in (700.0, 1900.0):
+                    ph = 2 * np.pi * (((f + df) * t) % 1.0)
+                    re += (0.5 * a * torch.cos(ph)).float(); im += (0.5 * a * torch.sin(ph)).float()
+        x[s:e, 0] = re; x[s:e, 1] = im
+    return x
+
+
+def cpu_chain_rate(carriers, seconds_budget, n_samples, threads):
+    """Times the oracle port of the per-client chain (one chain per client, one pass per stage — the
+    reference's structure) on `threads` host threads.  Returns (channel-MS/s, channels run, wall s)."""
+    import oracle
+    from openwebrx_b200.synth import BANDPASS, make_iq
+    kind = {"nfm": oracle.DEMOD_NFM, "am": oracle.DEMOD_AM, "usb": oracle.DEMOD_SSB}
+    iq = make_iq(n_samples, FS, carriers[:8], seed=1)
+    oracle.lib()
+
+    def one(c):
+        oracle.client_chain_run(iq, FS, OUT_RATE, c["offset"], BANDPASS[c["kind"]], kind[c["kind"]], fast_shift=True)
+
+    t0 = time.perf_counter(); one(carriers[0]); t1 = time.perf_counter() - t0
+    per_thread = max(1, int(seconds_budget / max(t1, 1e-3)))
+    done = [0] * threads
+
+    def worker(i):
+        for k in range(per_thread):
+            one(carriers[(i + k) % len(carriers)])
+            done[i] += 1
+
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths: t.start()
+    for t in ths: t.join()
+    wall = time.perf_counter() - t0
+    total = sum(done)
+    return total * n_samples / wall / 1e6, total, wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  pycsdr/libcsdr are not in the
+    reference tree and cannot be built, so this times the oracle port (cpu_baseline.kind
+    "port") with all host threads, on the same config / metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    carriers = channel_plan(0, CH_PER_GPU)
+    n_samples = 1 << 20
+    vals, ms = [], []
+    for step in range(args.warmup + args.steps):
+        v, total, wall = cpu_chain_rate(carriers, 1.0, n_samples, threads)
+        if step >= args.warmup:
+            vals.append(v); ms.append(wall * 1e3)
+    value = float(np.mean(vals)) if vals else 0.0
+    sample = "%d threads x oracle client chains (10 MS/s -> 12 kHz NFM/AM/USB) over %d-sample records, ~1 s per step" % (threads, n_samples)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "channel-MS/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(ms)) if ms else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: Selector DDC + NFM/AM/USB demod, 10 MS/s wideband, 64 x 12 kHz channels", "cpu": True},
+            "cpu_baseline": {"value": value, "unit": "channel-MS/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "channel-MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openwebrx_b200 import ChannelBank, Waterfall, _native as N, fftchain_params
+    from openwebrx_b200.synth import BANDPASS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, sm_max, peak_src = load_peaks()
+
+    # ---- channels: 64 per GPU, channel c tunes to carrier c (1/3 AM, 1/3 NFM, 1/3 USB)
+    carriers = channel_plan(0, CH_PER_GPU)          # the wideband signal (same on every rank: it is broadcast)
+    my_plan = carriers                              # each rank tunes its own 64 clients to those carriers
+    bank = ChannelBank(FS, device=local)
+    chans = []
+    for i, c in enumerate(my_plan):
+        off = c["offset"] + (rank * 7) % 50          # ranks tune slightly differently: no shared work
+        chans.append(bank.add_channel(OUT_RATE, demod=c["kind"], offset=off, bandpass=BANDPASS[c["kind"]]))
+    D, T = 833, 22223
+    n_k = (BLOCK - T) // D + 1
+    consumed = n_k * D
+
+    # ---- synthetic wideband block, resident in HBM (rank 0 generates; others receive it by broadcast)
+    iq = synth_iq_torch(BLOCK, FS, carriers, dev) if rank == 0 else torch.empty(BLOCK, 2, device=dev, dtype=torch.float32)
+    if world > 1:
+        dist.broadcast(iq, 0)
+    bcast_buf = [iq, torch.empty_like(iq)] if world > 1 else [iq]
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step(i):
+        if world > 1:
+            # the hop: rank 0's block reaches every GPU over NVLink (NCCL broadcast), then each GPU runs its channels
+            src = bcast_buf[i & 1]
+            if rank == 0 and src is not iq:
+                src.copy_(iq, non_blocking=True)
+            dist.broadcast(src, 0)
+            bank.process_device(src, BLOCK, stream=sp)
+        else:
+            bank.process_device(iq, BLOCK, stream=sp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    bank.profile(True)
+    bank.profile_read(reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = N.lib.owrx_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = N.lib.owrx_launch_count() - launches0
+    k3_ms, k3_n = bank.profile_read(reset=True)
+    bank.profile(False)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * CH_PER_GPU * consumed / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e: public host API, pinned host input, H2D + audio D2H inside the timed region
+    h_iq = torch.empty(BLOCK, 2, dtype=torch.float32).pin_memory()
+    h_iq.copy_(iq)
+    bank2 = ChannelBank(FS, device=local)
+    ch2 = [bank2.add_channel(OUT_RATE, demod=c["kind"], offset=c["offset"], bandpass=BANDPASS[c["kind"]]) for c in my_plan]
+    hp = h_iq.data_ptr()
+
+    def e2e_step():
+        if world > 1:
+            # rank 0 uploads, NCCL carries the block to the other GPUs, every rank returns its audio to the host
+            if rank == 0:
+                iq.copy_(h_iq, non_blocking=True)
+            dist.broadcast(iq, 0)
+            bank2.process_device(iq, BLOCK, stream=sp)
+            base, stride, _ = ch2[0].last_audio_device()
+            n_a = ch2[0].last_audio_count()
+            torch.cuda.synchronize()
+            return n_a
+        bank2.feed_ptr(hp, BLOCK)
+        return None
+
+    for i in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    for c in ch2:
+        c.read_audio()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    n_audio = sum(len(c.read_audio()) for c in ch2) if world == 1 else 0
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_consumed = (BLOCK // D) * D                   # the streaming path carries the FIR tail between blocks
+    e2e_value = world * CH_PER_GPU * e2e_consumed / (e2e_ms * 1e-3) / 1e6
+    d2h = (n_audio // e2e_steps) * 4 if world == 1 else CH_PER_GPU * (n_k // 750) * 750 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- waterfall half of the hot path (config 1 shape), own timed loop on this GPU
+    wf_stats = bench_waterfall(torch, dev, hbm_peak)
+
+    # ---- roofline of the dominant kernel (K3)
+    k3_avg_s = (k3_ms / max(k3_n, 1)) * 1e-3
+    algo_bytes = 8.0 * BLOCK + 8.0 * CH_PER_GPU * n_k            # IQ read once + complex IF written (per launch)
+    achieved = algo_bytes / k3_avg_s / 1e9 if k3_avg_s > 0 else 0.0
+    flops = CH_PER_GPU * float(consumed) * (8.0 + 4.0 * T / D)    # C*Nin*(8 + 4T/D)
+    f_obs = (clk or {}).get("sm_mhz") or sm_max
+    fp32_peak = 148 * 128 * 2 * f_obs * 1e6 / 1e12
+    fp32_ach = flops / k3_avg_s / 1e12 if k3_avg_s > 0 else 0.0
+
+    # ---- CPU baseline beside it (bounded sample, rank 0 only, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, total, wall = cpu_chain_rate(carriers, 2.0, 1 << 20, threads)
+        cpu = {"value": v, "unit": "channel-MS/s", "cores": threads, "kind": "port",
+               "sample": "%d oracle client chains (C2 shape) over 2^20-sample records on %d threads, %.1f s wall" % (total, threads, wall)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "channel-MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: Selector DDC + NFM/AM/USB demod, 10 MS/s wideband, %d x 12 kHz channels per GPU" % CH_PER_GPU,
+                   "channels_total": world * CH_PER_GPU, "block_samples": BLOCK, "decimation": D, "fir_taps": T,
+                   "l2": "input block 134 MB > 126 MB L2; no flush needed", "parallelism": "channels sharded x%d, IQ block NCCL-broadcast" % world if world > 1 else "1 GPU",
+                   "realtime_factor": value / (FS / 1e6 * CH_PER_GPU * world)},
+        "e2e": {"value": e2e_value, "unit": "channel-MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"kernel": "fir_decimate_kernel (K3: NCO mix + polyphase FIR decimate, 64 ch)", "bound": "hbm", "achieved": achieved,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms": k3_avg_s * 1e3, "kernel_share_of_step": (k3_ms / args.steps) / ms_step if ms_step > 0 else None,
+                     "note": "direct-form DDC is FP32-FMA bound by construction (SURVEY 8d): see roofline_fp32"},
+        "roofline_fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
+                          "peak_def": "148 SM x 128 lanes x 2 x observed SM clock (%.0f MHz)" % f_obs},
+        "waterfall": wf_stats,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_waterfall(torch, dev, hbm_peak, lines=592, steps=5):
+    from openwebrx_b200 import Waterfall, fftchain_params
+    avg, every_n = fftchain_params(WF_FS, WF_N, WF_OV, WF_FPS)
+    n = every_n * avg * lines + WF_N                      # 592 lines = 1.27 GB of IQ, far beyond L2
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    iq = 1e-3 * torch.randn(n, 2, device=dev, generator=g, dtype=torch.float32)
+    tt = torch.arange(n, device=dev, dtype=torch.float32)
+    iq[:, 0] += 0.3 * torch.cos(0.7 * tt); iq[:, 1] += 0.3 * torch.sin(0.7 * tt)
+    del tt
+    wf = Waterfall(WF_FS, WF_N, WF_OV, WF_FPS, "adpcm", device=dev.index or 0)
+    out = torch.empty(lines * wf.line_bytes, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    for _ in range(3):
+        wf.process_device(iq, n, out, out.numel(), stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        got = wf.process_device(iq, n, out, out.numel(), stream=st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    unique = 8.0 * ((avg - 1) * every_n + WF_N) + wf.line_bytes      # 8*U + out per line
+    gbs = unique * got / (ms * 1e-3) / 1e9
+    return {"workload": "C1: 2.4 MS/s, 4096-pt, 9 fps, overlap 0.3 -> avg 93, hop 2867, ADPCM", "lines_per_s": got / (ms * 1e-3),
+            "ffts_per_s": got * avg / (ms * 1e-3), "realtime_factor": got / (ms * 1e-3) / 9.0, "ms_per_batch": ms, "lines_per_batch": int(got),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "note": "whole FftChain (fft + finalize + adpcm launches) vs algorithmic bytes"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -146,6 +146,12 @@ typedef struct {
 } owrx_bank_stats_t;
 int owrx_bank_get_stats(const owrx_bank_t* bank, owrx_bank_stats_t* st);
 
+/* Optional per-kernel timing of the dominant kernel (K3: NCO mix + FIR decimation): when enabled a
+ * CUDA event pair brackets every K3 launch on the launching stream; owrx_bank_profile_read waits for
+ * the recorded events and returns the accumulated device time and launch count. */
+int owrx_bank_profile(owrx_bank_t* bank, int enable);
+int owrx_bank_profile_read(owrx_bank_t* bank, double* k3_ms, uint64_t* k3_launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,8 @@ SIGNATURES = {
     "owrx_bank_last_audio_count": (_i, [_vp, _i, _psz]),
     "owrx_bank_last_audio_device": (_i, [_vp, _i, _pp, _psz, _psz]),
     "owrx_bank_get_stats": (_i, [_vp, C.POINTER(BankStats)]),
+    "owrx_bank_profile": (_i, [_vp, _i]),
+    "owrx_bank_profile_read": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -132,6 +132,14 @@ class ChannelBank:
         return dict(input_samples=st.input_samples, channel_samples=st.channel_samples,
                     kernel_launches=st.kernel_launches, device_ms=st.device_ms)
 
+    def profile(self, enable=True):
+        N.check(N.lib.owrx_bank_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self, reset=True):
+        ms, n = C.c_double(), C.c_uint64()
+        N.check(N.lib.owrx_bank_profile_read(self._h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
     def close(self):
         if getattr(self, "_h", None):
             N.lib.owrx_bank_destroy(self._h)

@@ -195,6 +195,12 @@ struct owrx_bank {
     // pinned staging
     float* h_stage = nullptr; size_t h_stage_cap = 0;
     owrx_bank_stats_t stats{};
+    // optional per-kernel timing of K3 (CUDA events on the launching stream)
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    double prof_k3_ms = 0.0;
+    uint64_t prof_k3_launches = 0;
 };
 
 namespace {
@@ -454,8 +460,22 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     p.D = g->D; p.nseg = g->nseg; p.nrs = g->nrs; p.RB = g->RB; p.KR = KR; p.n_k = (int)n_k; p.slots = S;
     const size_t smem = (size_t)g->RB * K3_PP * sizeof(float) + 2 * (size_t)g->RB * sizeof(float2) + 2 * K3_NW * 128 * sizeof(float);
     OWRX_CUDA(cudaFuncSetAttribute(fir_decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (bank->profile) {
+        if (bank->prof_used == bank->prof_events.size()) {
+            cudaEvent_t a, b;
+            OWRX_CUDA(cudaEventCreate(&a));
+            OWRX_CUDA(cudaEventCreate(&b));
+            bank->prof_events.emplace_back(a, b);
+        }
+        pe0 = bank->prof_events[bank->prof_used].first;
+        pe1 = bank->prof_events[bank->prof_used].second;
+        bank->prof_used++;
+        OWRX_CUDA(cudaEventRecord(pe0, st));
+    }
     fir_decimate_kernel<<<dim3((unsigned)(nkr * nparts), (unsigned)ncg), K3_NW * 32, smem, st>>>(p);
     OWRX_LAUNCH_CHECK();
+    if (pe1) OWRX_CUDA(cudaEventRecord(pe1, st));
     bank->stats.kernel_launches++;
     if (nparts > 1) {
         const size_t total = n_k * (size_t)S;
@@ -732,6 +752,7 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     if (bank->h_stage) cudaFreeHost(bank->h_stage);
     if (bank->ev0) cudaEventDestroy(bank->ev0);
     if (bank->ev1) cudaEventDestroy(bank->ev1);
+    for (auto& pe : bank->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (bank->stream) cudaStreamDestroy(bank->stream);
     delete bank;
 }
@@ -1011,6 +1032,33 @@ int owrx_chan_read_power(owrx_bank_t* bank, int chan, float* out, size_t cap, si
     if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(bank->mu);
     return pop_queue(ch->q_power, out, cap, n, 1);
+}
+
+int owrx_bank_profile(owrx_bank_t* bank, int enable)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    bank->profile = enable != 0;
+    return OWRX_OK;
+}
+
+int owrx_bank_profile_read(owrx_bank_t* bank, double* k3_ms, uint64_t* k3_launches, int reset)
+{
+    if (!bank || !k3_ms || !k3_launches) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    for (size_t i = 0; i < bank->prof_used; i++) {
+        OWRX_CUDA(cudaEventSynchronize(bank->prof_events[i].second));
+        float ms = 0.f;
+        OWRX_CUDA(cudaEventElapsedTime(&ms, bank->prof_events[i].first, bank->prof_events[i].second));
+        bank->prof_k3_ms += ms;
+        bank->prof_k3_launches++;
+    }
+    bank->prof_used = 0;
+    *k3_ms = bank->prof_k3_ms;
+    *k3_launches = bank->prof_k3_launches;
+    if (reset) { bank->prof_k3_ms = 0.0; bank->prof_k3_launches = 0; }
+    return OWRX_OK;
 }
 
 int owrx_bank_get_stats(const owrx_bank_t* bank, owrx_bank_stats_t* st)
