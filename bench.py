@@ -214,8 +214,12 @@ def run_ours(args):
     if world > 1:
         dist.broadcast(iq, 0)
     bcast_buf = [iq, torch.empty_like(iq)] if world > 1 else [iq]
-    stream = torch.cuda.current_stream()
+    # a created (non-default) stream: the C ABI treats a NULL handle as "use the object's own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     def step(i):
         if world > 1:
@@ -364,6 +368,8 @@ def bench_waterfall(torch, dev, hbm_peak, lines=592, steps=5):
     wf = Waterfall(WF_FS, WF_N, WF_OV, WF_FPS, "adpcm", device=dev.index or 0)
     out = torch.empty(lines * wf.line_bytes, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream()
+    assert st.cuda_stream != 0
+    torch.cuda.synchronize()
     for _ in range(3):
         wf.process_device(iq, n, out, out.numel(), stream=st.cuda_stream)
     torch.cuda.synchronize()

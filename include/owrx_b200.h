@@ -46,7 +46,7 @@ typedef struct owrx_wf owrx_wf_t;
 #define OWRX_COMPRESSION_ADPCM 1   /* IMA-ADPCM lines, (N+10)/2 B   (FftAdpcm, csdr/chain/fft.py:44) */
 
 /* Fft(size=, every_n_samples=) + LogAveragePower(add_db=, fft_size=, avg_number=) [avg==0: LogPower(add_db=)]
- * + FftSwap(fft_size=) + optional FftAdpcm(fft_size=).  fft_size: power of two, 256..1048576. */
+ * + FftSwap(fft_size=) + optional FftAdpcm(fft_size=).  fft_size: power of two, 256..65536. */
 int owrx_wf_create(int device, int fft_size, int every_n_samples, int avg_number, float add_db,
                    int compression, owrx_wf_t** out);
 void owrx_wf_destroy(owrx_wf_t* wf);
@@ -65,7 +65,8 @@ int owrx_wf_read(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes);
  * Computes every whole line of that record (line l uses frames l*avg..l*avg+avg-1, frame f starts at
  * sample f*every_n) into out_dev (device; line_bytes each).  db_dev / s16_dev may be NULL; when given
  * they receive the swapped float32 dB lines (N each) / the quantised int16 lines (N+10 each).
- * stream: a cudaStream_t (NULL = the object's own stream).  Asynchronous w.r.t. the host. */
+ * stream: a cudaStream_t; NULL selects the object's own non-blocking stream (so the legacy default
+ * stream cannot be named here: pass a created stream to order against other work).  Asynchronous. */
 int owrx_wf_process_device(owrx_wf_t* wf, const void* iq_dev, size_t n_samples, void* out_dev,
                            size_t out_cap_bytes, void* db_dev, void* s16_dev, size_t* n_lines, void* stream);
 /* number of whole lines a record of n_samples yields with the current parameters */
@@ -101,6 +102,32 @@ void owrx_bank_destroy(owrx_bank_t* bank);
 
 /* Selector(inputRate, outputRate): csdr/chain/selector.py:89-113 (Decimator math :21-26,37-51). */
 int owrx_bank_add_channel(owrx_bank_t* bank, double output_rate, int* chan);
+
+/* The same channel described by the exact arguments the reference's chain classes pass to the
+ * pycsdr module constructors (what the pycsdr shim sees):
+ *   FirDecimate(decimation, transition, cutoff)                    csdr/chain/selector.py:29
+ *   FractionalDecimator(Format.COMPLEX_FLOAT, fraction)            csdr/chain/selector.py:33   (1.0 = absent)
+ *   Bandpass(transition=bp_transition, use_fft=True)               csdr/chain/selector.py:115-117
+ *   Squelch(Format.COMPLEX_FLOAT, length=squelch_length, decimation=5, hangLength=2*length, ...)  :119-130
+ *   NfmDeemphasis(deemph_rate)                                     csdr/chain/analog.py:43
+ *   FractionalDecimator(Format.FLOAT, wfm_decimation, prefilter=True), WfmDeemphasis(wfm_audio_rate, wfm_tau)
+ *                                                                  csdr/chain/analog.py:66-67  (wfm != 0 only) */
+typedef struct {
+    int    decimation;
+    double transition;
+    double cutoff;
+    double fraction;
+    double bp_transition;
+    int    squelch_length;
+    int    deemph_rate;
+    int    wfm;
+    double wfm_decimation;
+    int    wfm_audio_rate;
+    double wfm_tau;
+} owrx_chan_spec_t;
+int owrx_bank_add_channel_ex(owrx_bank_t* bank, const owrx_chan_spec_t* spec, int* chan);
+/* Agc.setProfile / setInitialGain / setMaxGain (csdr/chain/analog.py:13-15,37-39,121-122); gains <= 0 keep the current value */
+int owrx_chan_set_agc(owrx_bank_t* bank, int chan, int profile, float initial_gain, float max_gain);
 int owrx_bank_remove_channel(owrx_bank_t* bank, int chan);
 int owrx_bank_channel_count(const owrx_bank_t* bank);
 /* Shift.setRate(rate), rate = -offset/inputRate: csdr/chain/selector.py:138-140 */
@@ -122,6 +149,17 @@ int owrx_chan_read_audio(owrx_bank_t* bank, int chan, float* out, size_t cap_sam
 int owrx_chan_read_demod(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n);
 int owrx_chan_read_if(owrx_bank_t* bank, int chan, float* out_iq, size_t cap_samples, size_t* n);
 int owrx_chan_read_power(owrx_bank_t* bank, int chan, float* out, size_t cap, size_t* n);
+/* Client audio tail, run on the GPU after the AGC:
+ *   OWRX_AUDIO_F32   none (float32 audio via owrx_chan_read_audio)
+ *   OWRX_AUDIO_S16   Convert(Format.FLOAT, Format.SHORT)                      csdr/chain/clientaudio.py:12
+ *   OWRX_AUDIO_ADPCM Convert + AdpcmEncoder(sync=True)                        csdr/chain/clientaudio.py:34
+ * S16 / ADPCM bytes are popped with owrx_chan_read_bytes (little-endian int16, or the SYNC-framed stream
+ * the browser decodes: htdocs/lib/AudioEngine.js:449-491). */
+#define OWRX_AUDIO_F32   0
+#define OWRX_AUDIO_S16   1
+#define OWRX_AUDIO_ADPCM 2
+int owrx_chan_set_audio_format(owrx_bank_t* bank, int chan, int format);
+int owrx_chan_read_bytes(owrx_bank_t* bank, int chan, void* out, size_t cap_bytes, size_t* n);
 /* which optional outputs are materialised for the host (bitmask of OWRX_OUT_*; default AUDIO) */
 #define OWRX_OUT_AUDIO 1
 #define OWRX_OUT_DEMOD 2

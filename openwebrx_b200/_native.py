@@ -15,6 +15,13 @@ COMPRESSION_NONE, COMPRESSION_ADPCM = 0, 1
 DEMOD_NFM, DEMOD_AM, DEMOD_SSB, DEMOD_WFM, DEMOD_NONE = 0, 1, 2, 3, 4
 AGC_SLOW, AGC_FAST = 0, 1
 OUT_AUDIO, OUT_DEMOD, OUT_IF, OUT_POWER = 1, 2, 4, 8
+AUDIO_F32, AUDIO_S16, AUDIO_ADPCM = 0, 1, 2
+
+
+class ChanSpec(C.Structure):
+    _fields_ = [("decimation", C.c_int), ("transition", C.c_double), ("cutoff", C.c_double), ("fraction", C.c_double),
+                ("bp_transition", C.c_double), ("squelch_length", C.c_int), ("deemph_rate", C.c_int), ("wfm", C.c_int),
+                ("wfm_decimation", C.c_double), ("wfm_audio_rate", C.c_int), ("wfm_tau", C.c_double)]
 
 
 class BankStats(C.Structure):
@@ -52,6 +59,8 @@ SIGNATURES = {
     "owrx_bank_create": (_i, [_i, _d, _pp]),
     "owrx_bank_destroy": (None, [_vp]),
     "owrx_bank_add_channel": (_i, [_vp, _d, C.POINTER(_i)]),
+    "owrx_bank_add_channel_ex": (_i, [_vp, C.POINTER(ChanSpec), C.POINTER(_i)]),
+    "owrx_chan_set_agc": (_i, [_vp, _i, _i, _f, _f]),
     "owrx_bank_remove_channel": (_i, [_vp, _i]),
     "owrx_bank_channel_count": (_i, [_vp]),
     "owrx_chan_set_shift_rate": (_i, [_vp, _i, _d]),
@@ -64,6 +73,8 @@ SIGNATURES = {
     "owrx_chan_read_if": (_i, [_vp, _i, _vp, _sz, _psz]),
     "owrx_chan_read_power": (_i, [_vp, _i, _vp, _sz, _psz]),
     "owrx_bank_set_outputs": (_i, [_vp, _i]),
+    "owrx_chan_set_audio_format": (_i, [_vp, _i, _i]),
+    "owrx_chan_read_bytes": (_i, [_vp, _i, _vp, _sz, _psz]),
     "owrx_bank_process_device": (_i, [_vp, _vp, _sz, _vp]),
     "owrx_bank_last_audio_count": (_i, [_vp, _i, _psz]),
     "owrx_bank_last_audio_device": (_i, [_vp, _i, _pp, _psz, _psz]),

@@ -64,6 +64,22 @@ class Channel:
             chunks.append(buf[:n.value * width].copy())
         return np.concatenate(chunks) if chunks else np.empty(0, np.float32)
 
+    def setAudioFormat(self, fmt):
+        """'f32' | 's16' (Convert FLOAT->SHORT) | 'adpcm' (Convert + AdpcmEncoder(sync=True)); csdr/chain/clientaudio.py"""
+        code = {"f32": N.AUDIO_F32, "s16": N.AUDIO_S16, "adpcm": N.AUDIO_ADPCM}[fmt]
+        N.check(N.lib.owrx_chan_set_audio_format(self.bank._h, self.id, code))
+
+    def read_bytes(self):
+        chunks = []
+        buf = np.empty(1 << 16, np.uint8)
+        while True:
+            n = C.c_size_t()
+            N.check(N.lib.owrx_chan_read_bytes(self.bank._h, self.id, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n)))
+            if n.value == 0:
+                break
+            chunks.append(buf[:n.value].copy())
+        return np.concatenate(chunks) if chunks else np.empty(0, np.uint8)
+
     def read_audio(self):
         return self._read(N.lib.owrx_chan_read_audio)
 

@@ -141,14 +141,17 @@ struct Chan {
     bool bp_enabled = false;
     double bp_lo = 0.0, bp_hi = 0.0;
     ChanCfg cfg{};
+    owrx_chan_spec_t spec{};
+    float agc_initial = 1.0f;
+    int audio_fmt = OWRX_AUDIO_F32;
     std::deque<float> q_audio, q_demod, q_if, q_power;
+    std::vector<unsigned char> q_bytes;
     size_t last_audio = 0;
 };
 
 struct Group {
-    double out_rate = 0.0;
+    owrx_chan_spec_t spec{};
     bool wfm = false;
-    double audio_rate = 0.0, tau = 0.0;
     int D = 1, T = 1, nseg = 1, nrs = 1, RB = 1;
     double frac = 1.0;
     bool has_frac = false;
@@ -175,6 +178,12 @@ struct Group {
     long long sq_block_abs = 0;                      // absolute squelch block counter (for report interval)
     // last run
     size_t last_audio = 0, last_demod = 0, last_if = 0, last_blocks = 0;
+    // client audio tail (Convert / AdpcmEncoder)
+    std::vector<int> h_tail_mode;
+    int* d_tail_mode = nullptr; TailState* d_tail = nullptr; int* d_tail_count = nullptr;
+    int16_t* d_tail_s16 = nullptr; unsigned char* d_tail_bytes = nullptr;
+    size_t tail_rows_cap = 0; int tail_cap = 0;
+    bool any_tail = false, tail_ran = false;
 };
 
 }  // namespace
@@ -219,29 +228,66 @@ void group_release(Group* g)
     cudaFree(g->d_rate); cudaFree(g->d_phase); cudaFree(g->d_w);
     cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state);
     cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
+    cudaFree(g->d_tail_mode); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
     g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1b.release(); g->f2.release(); g->f3.release();
 }
 
-// Decimator._getDecimation + transition/cutoff (csdr/chain/selector.py:21-26,37-51)
-int group_create(owrx_bank* bank, double out_rate, bool wfm, double audio_rate, double tau, int* index)
+// Selector / Decimator parameter math (csdr/chain/selector.py:21-26,37-51,115-126): the spec a plain
+// Selector(inputRate, outputRate) hands to pycsdr.
+owrx_chan_spec_t spec_from_rates(double input_rate, double output_rate)
 {
+    owrx_chan_spec_t sp{};
+    double orate = output_rate > input_rate ? input_rate : output_rate;
+    const double d = input_rate / orate;
+    sp.decimation = (int)d;
+    sp.fraction = (input_rate / sp.decimation) / orate;
+    sp.transition = 0.15 * (orate / input_rate);
+    sp.cutoff = 0.5 * sp.decimation / (input_rate / orate);
+    sp.bp_transition = 320.0 / orate;                                  // Selector._buildBandpass, selector.py:115-117
+    sp.squelch_length = std::max(1, (int)(orate / 16));                // Selector._buildSquelch, selector.py:119-121
+    sp.deemph_rate = (int)orate;                                       // NfmDeemphasis(sampleRate), analog.py:43
+    return sp;
+}
+
+bool spec_equal(const owrx_chan_spec_t& a, const owrx_chan_spec_t& b)
+{
+    return a.decimation == b.decimation && a.transition == b.transition && a.cutoff == b.cutoff && a.fraction == b.fraction &&
+           a.bp_transition == b.bp_transition && a.squelch_length == b.squelch_length && a.deemph_rate == b.deemph_rate &&
+           a.wfm == b.wfm && (!a.wfm || (a.wfm_decimation == b.wfm_decimation && a.wfm_audio_rate == b.wfm_audio_rate && a.wfm_tau == b.wfm_tau));
+}
+
+int spec_validate(const owrx_chan_spec_t& sp)
+{
+    if (sp.decimation < 1) return fail(OWRX_E_INVALID, "decimation must be >= 1");
+    if (!(sp.transition > 0.0 && sp.transition < 2.0)) return fail(OWRX_E_INVALID, "bad FirDecimate transition %g", sp.transition);
+    if (!(sp.cutoff > 0.0)) return fail(OWRX_E_INVALID, "bad FirDecimate cutoff %g", sp.cutoff);
+    if (!(sp.fraction >= 1.0)) return fail(OWRX_E_INVALID, "fraction must be >= 1");
+    if (!(sp.bp_transition > 0.0 && sp.bp_transition < 2.0)) return fail(OWRX_E_INVALID, "bad Bandpass transition %g", sp.bp_transition);
+    if (sp.squelch_length < 1) return fail(OWRX_E_INVALID, "bad Squelch length");
+    if (sp.deemph_rate < 1) return fail(OWRX_E_INVALID, "bad de-emphasis rate");
+    if (sp.wfm && !(sp.wfm_decimation > 1.03 && sp.wfm_audio_rate > 0 && sp.wfm_tau > 0.0)) return fail(OWRX_E_INVALID, "bad WFM parameters");
+    return OWRX_OK;
+}
+
+int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
+{
+    int vrc = spec_validate(sp);
+    if (vrc != OWRX_OK) return vrc;
     std::unique_ptr<Group> g(new Group());
-    double orate = out_rate;
-    if (orate > bank->input_rate) orate = bank->input_rate;
-    g->out_rate = orate; g->wfm = wfm; g->audio_rate = audio_rate; g->tau = tau;
-    const double d = bank->input_rate / orate;
-    g->D = (int)d;
-    g->frac = (bank->input_rate / g->D) / orate;
+    g->spec = sp;
+    const bool wfm = sp.wfm != 0;
+    g->wfm = wfm;
+    g->D = sp.decimation;
+    g->frac = sp.fraction;
     g->has_frac = g->frac != 1.0;
-    const double transition = 0.15 * (orate / bank->input_rate);
-    const double cutoff = 0.5 * g->D / (bank->input_rate / orate);
-    g->T = filter_len(transition);
+    const double cutoff = sp.cutoff;
+    g->T = filter_len(sp.transition);
     const int P = (g->T + g->D - 1) / g->D;
     g->nseg = (P + K3_PP - 1) / K3_PP;
     g->nrs = (g->D + K3_RBMAX - 1) / K3_RBMAX;
     g->RB = (g->D + g->nrs - 1) / g->nrs;
-    g->Tb = filter_len(320.0 / orate);                                  // Selector._buildBandpass, selector.py:115-117
-    g->sq_len = std::max(1, (int)(orate / 16));                          // Selector._buildSquelch, selector.py:119-121
+    g->Tb = filter_len(sp.bp_transition);
+    g->sq_len = sp.squelch_length;
     g->slots = K3_CG;
     g->slot_chan.assign((size_t)g->slots, -1);
 
@@ -258,26 +304,28 @@ int group_create(owrx_bank* bank, double out_rate, bool wfm, double audio_rate, 
     OWRX_CUDA(cudaMemcpy(g->d_taps, ht.data(), ht.size() * sizeof(float), cudaMemcpyHostToDevice));
 
     std::vector<float> de;
-    design_nfm_deemphasis(de, (int)orate);                               // NfmDeemphasis(sampleRate), analog.py:43
+    design_nfm_deemphasis(de, sp.deemph_rate);                           // NfmDeemphasis(sampleRate), analog.py:43
     g->Td = (int)de.size();
     if ((rc = dev_alloc(&g->d_deemph, de.size())) != OWRX_OK) return rc;
     OWRX_CUDA(cudaMemcpy(g->d_deemph, de.data(), de.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (wfm) {
-        g->wfm_rate = orate / audio_rate;                                // analog.py:66: 250000.0 / sampleRate
+        g->wfm_rate = sp.wfm_decimation;                                 // analog.py:66: 250000.0 / sampleRate
         g->Tpre = filter_len(0.03);
         std::vector<double> pre;
         design_lowpass(pre, g->Tpre, 0.5 / (g->wfm_rate - 0.03));
         std::vector<float> pf(pre.begin(), pre.end());
         if ((rc = dev_alloc(&g->d_pre, pf.size())) != OWRX_OK) return rc;
         OWRX_CUDA(cudaMemcpy(g->d_pre, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice));
-        const double dt = 1.0 / audio_rate;
-        g->alpha = (float)(dt / (tau + dt));                             // WfmDeemphasis, SURVEY A.11
+        const double dt = 1.0 / (double)sp.wfm_audio_rate;
+        g->alpha = (float)(dt / (sp.wfm_tau + dt));                      // WfmDeemphasis, SURVEY A.11
     }
     const size_t S = (size_t)g->slots;
     if ((rc = dev_alloc(&g->d_rate, S)) || (rc = dev_alloc(&g->d_phase, S)) || (rc = dev_alloc(&g->d_w, S)) ||
         (rc = dev_alloc(&g->d_bp, S * g->Tb)) || (rc = dev_alloc(&g->d_bp_en, S)) || (rc = dev_alloc(&g->d_cfg, S)) ||
-        (rc = dev_alloc(&g->d_state, S)))
+        (rc = dev_alloc(&g->d_state, S)) || (rc = dev_alloc(&g->d_tail_mode, S)) || (rc = dev_alloc(&g->d_tail, S)) ||
+        (rc = dev_alloc(&g->d_tail_count, S)))
         return rc;
+    g->h_tail_mode.assign(S, 0);
     g->h_rate.assign(S, 0.0); g->h_phase.assign(S, 0.0); g->h_w.assign(S, make_float2(1.f, 0.f));
     g->h_bp_en.assign(S, 0);
     ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
@@ -297,13 +345,11 @@ int group_create(owrx_bank* bank, double out_rate, bool wfm, double audio_rate, 
     return OWRX_OK;
 }
 
-int find_group(owrx_bank* bank, double out_rate, bool wfm, double audio_rate, double tau)
+int find_group(owrx_bank* bank, const owrx_chan_spec_t& sp)
 {
     for (size_t i = 0; i < bank->groups.size(); i++) {
         Group* g = bank->groups[i].get();
-        if (!g) continue;
-        double orate = std::min(out_rate, bank->input_rate);
-        if (g->out_rate == orate && g->wfm == wfm && (!wfm || (g->audio_rate == audio_rate && g->tau == tau))) return (int)i;
+        if (g && spec_equal(g->spec, sp)) return (int)i;
     }
     return -1;
 }
@@ -330,10 +376,13 @@ int place_channel(owrx_bank* bank, Chan* ch, int gi)
     g->slot_chan[(size_t)slot] = ch->id;
     ch->group = gi; ch->slot = slot;
     ChanState st{};
-    st.agc_gain = agc_initial_gain(ch->cfg.kind);
+    st.agc_gain = ch->agc_initial;
     OWRX_CUDA(cudaMemcpy(g->d_state + slot, &st, sizeof(st), cudaMemcpyHostToDevice));
     g->h_cfg[(size_t)slot] = ch->cfg;
     g->h_bp_en[(size_t)slot] = 0;
+    g->h_tail_mode[(size_t)slot] = ch->audio_fmt;
+    TailState tl{0, 0, 1001, 0, 0};
+    OWRX_CUDA(cudaMemcpy(g->d_tail + slot, &tl, sizeof(tl), cudaMemcpyHostToDevice));
     g->cfg_dirty = true;
     return OWRX_OK;
 }
@@ -356,8 +405,11 @@ int group_grow(owrx_bank* bank, Group* g)
     int rc;
     if ((rc = regrow(&g->d_rate, 1)) || (rc = regrow(&g->d_phase, 1)) || (rc = regrow(&g->d_w, 1)) ||
         (rc = regrow(&g->d_bp, (size_t)g->Tb)) || (rc = regrow(&g->d_bp_en, 1)) || (rc = regrow(&g->d_cfg, 1)) ||
-        (rc = regrow(&g->d_state, 1)))
+        (rc = regrow(&g->d_state, 1)) || (rc = regrow(&g->d_tail_mode, 1)) || (rc = regrow(&g->d_tail, 1)) ||
+        (rc = regrow(&g->d_tail_count, 1)))
         return rc;
+    cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
+    g->d_tail_s16 = nullptr; g->d_tail_bytes = nullptr; g->tail_rows_cap = 0; g->tail_cap = 0;
     auto regrow_buf = [&](StageBuf& b) -> int {
         if (!b.d[0]) return OWRX_OK;
         for (int k = 0; k < 2; k++) {
@@ -382,6 +434,7 @@ int group_grow(owrx_bank* bank, Group* g)
     g->slot_chan.resize((size_t)ns, -1);
     g->h_rate.resize((size_t)ns, 0.0); g->h_phase.resize((size_t)ns, 0.0); g->h_w.resize((size_t)ns, make_float2(1.f, 0.f));
     g->h_bp_en.resize((size_t)ns, 0);
+    g->h_tail_mode.resize((size_t)ns, 0);
     ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
     g->h_cfg.resize((size_t)ns, idle);
     g->cfg_dirty = true;
@@ -435,6 +488,9 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     if (g->cfg_dirty) {
         OWRX_CUDA(cudaMemcpyAsync(g->d_cfg, g->h_cfg.data(), (size_t)S * sizeof(ChanCfg), cudaMemcpyHostToDevice, st));
         OWRX_CUDA(cudaMemcpyAsync(g->d_bp_en, g->h_bp_en.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st));
+        OWRX_CUDA(cudaMemcpyAsync(g->d_tail_mode, g->h_tail_mode.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st));
+        g->any_tail = false;
+        for (int m : g->h_tail_mode) if (m) g->any_tail = true;
         g->cfg_dirty = false;
     }
 
@@ -642,6 +698,23 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
             OWRX_LAUNCH_CHECK();
             bank->stats.kernel_launches++;
             g->f3.appended(n_audio);
+            g->tail_ran = false;
+            if (g->any_tail) {
+                // ---- client audio tail: Convert(FLOAT, SHORT) [+ AdpcmEncoder(sync=True)]
+                const int cap = (int)(n_audio / 2 + 8 * (n_audio / 2002 + 2) + 16);
+                if (n_audio > g->tail_rows_cap || cap > g->tail_cap) {
+                    cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
+                    g->d_tail_s16 = nullptr; g->d_tail_bytes = nullptr; g->tail_rows_cap = 0; g->tail_cap = 0;
+                    OWRX_CUDA(cudaMalloc((void**)&g->d_tail_s16, n_audio * (size_t)S * sizeof(int16_t)));
+                    OWRX_CUDA(cudaMalloc((void**)&g->d_tail_bytes, (size_t)cap * S));
+                    g->tail_rows_cap = n_audio; g->tail_cap = cap;
+                }
+                audio_tail_kernel<<<(S + 63) / 64, 64, 0, st>>>(g->f3.rows(g->f3.fill - n_audio), S, (int)n_audio, g->d_tail_mode,
+                                                               g->d_tail, g->d_tail_s16, g->d_tail_bytes, g->d_tail_count, g->tail_cap);
+                OWRX_LAUNCH_CHECK();
+                bank->stats.kernel_launches++;
+                g->tail_ran = true;
+            }
         }
         g->last_audio = n_audio;
     }
@@ -710,6 +783,36 @@ int drain_to_queues(owrx_bank* bank, Group* g, const float* dev_rows, size_t n, 
     return OWRX_OK;
 }
 
+// client audio tail -> per-channel byte queues (int16 LE samples, or the ADPCM stream)
+int drain_tail(owrx_bank* bank, Group* g)
+{
+    const size_t n = g->last_audio, S = (size_t)g->slots;
+    const size_t s16_floats = (n * S * sizeof(int16_t) + 3) / 4, byte_floats = ((size_t)g->tail_cap * S + 3) / 4;
+    int rc = ensure_stage(bank, s16_floats + byte_floats + S);
+    if (rc != OWRX_OK) return rc;
+    int16_t* h16 = reinterpret_cast<int16_t*>(bank->h_stage);
+    unsigned char* hb = reinterpret_cast<unsigned char*>(bank->h_stage + s16_floats);
+    int* hc = reinterpret_cast<int*>(bank->h_stage + s16_floats + byte_floats);
+    OWRX_CUDA(cudaMemcpyAsync(h16, g->d_tail_s16, n * S * sizeof(int16_t), cudaMemcpyDeviceToHost, bank->stream));
+    OWRX_CUDA(cudaMemcpyAsync(hb, g->d_tail_bytes, (size_t)g->tail_cap * S, cudaMemcpyDeviceToHost, bank->stream));
+    OWRX_CUDA(cudaMemcpyAsync(hc, g->d_tail_count, S * sizeof(int), cudaMemcpyDeviceToHost, bank->stream));
+    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    for (size_t s = 0; s < S; s++) {
+        const int cid = g->slot_chan[s];
+        if (cid < 0) continue;
+        Chan* ch = bank->chans[(size_t)cid].get();
+        if (ch->audio_fmt == OWRX_AUDIO_S16) {
+            const size_t o = ch->q_bytes.size();
+            ch->q_bytes.resize(o + n * 2);
+            int16_t* dst = reinterpret_cast<int16_t*>(ch->q_bytes.data() + o);
+            for (size_t i = 0; i < n; i++) dst[i] = h16[i * S + s];
+        } else if (ch->audio_fmt == OWRX_AUDIO_ADPCM) {
+            ch->q_bytes.insert(ch->q_bytes.end(), hb + s * (size_t)g->tail_cap, hb + s * (size_t)g->tail_cap + hc[s]);
+        }
+    }
+    return OWRX_OK;
+}
+
 int pop_queue(std::deque<float>& q, float* out, size_t cap, size_t* n, size_t unit)
 {
     size_t take = std::min(cap * unit, q.size());
@@ -757,24 +860,36 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     delete bank;
 }
 
-int owrx_bank_add_channel(owrx_bank_t* bank, double output_rate, int* chan)
+static int add_channel_spec(owrx_bank_t* bank, const owrx_chan_spec_t& sp, int* chan)
 {
-    if (!bank || !chan) return fail(OWRX_E_INVALID, "NULL argument");
-    if (!(output_rate > 0.0)) return fail(OWRX_E_INVALID, "output_rate must be positive");
     std::lock_guard<std::mutex> lk(bank->mu);
     OWRX_CUDA(cudaSetDevice(bank->device));
-    int gi = find_group(bank, output_rate, false, 0.0, 0.0), rc;
-    if (gi < 0 && (rc = group_create(bank, output_rate, false, 0.0, 0.0, &gi)) != OWRX_OK) return rc;
+    int gi = find_group(bank, sp), rc;
+    if (gi < 0 && (rc = group_create(bank, sp, &gi)) != OWRX_OK) return rc;
     Group* g = bank->groups[(size_t)gi].get();
     if (std::find(g->slot_chan.begin(), g->slot_chan.end(), -1) == g->slot_chan.end() && (rc = group_grow(bank, g)) != OWRX_OK) return rc;
     std::unique_ptr<Chan> ch(new Chan());
     ch->id = (int)bank->chans.size();
-    agc_defaults(ch->cfg, OWRX_DEMOD_NONE, OWRX_AGC_SLOW);
+    ch->spec = sp;
+    agc_defaults(ch->cfg, sp.wfm ? OWRX_DEMOD_WFM : OWRX_DEMOD_NONE, OWRX_AGC_SLOW);
     Chan* raw = ch.get();
     bank->chans.push_back(std::move(ch));
     if ((rc = place_channel(bank, raw, gi)) != OWRX_OK) return rc;
     *chan = raw->id;
     return OWRX_OK;
+}
+
+int owrx_bank_add_channel(owrx_bank_t* bank, double output_rate, int* chan)
+{
+    if (!bank || !chan) return fail(OWRX_E_INVALID, "NULL argument");
+    if (!(output_rate > 0.0)) return fail(OWRX_E_INVALID, "output_rate must be positive");
+    return add_channel_spec(bank, spec_from_rates(bank->input_rate, output_rate), chan);
+}
+
+int owrx_bank_add_channel_ex(owrx_bank_t* bank, const owrx_chan_spec_t* spec, int* chan)
+{
+    if (!bank || !chan || !spec) return fail(OWRX_E_INVALID, "NULL argument");
+    return add_channel_spec(bank, *spec, chan);
 }
 
 int owrx_bank_remove_channel(owrx_bank_t* bank, int chan)
@@ -788,6 +903,7 @@ int owrx_bank_remove_channel(owrx_bank_t* bank, int chan)
         ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
         g->h_cfg[(size_t)ch->slot] = idle;
         g->h_bp_en[(size_t)ch->slot] = 0;
+        g->h_tail_mode[(size_t)ch->slot] = 0;
         g->cfg_dirty = true;
     }
     bank->chans[(size_t)chan].reset();
@@ -844,15 +960,27 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
     const float level = ch->cfg.sq_level;
     agc_defaults(ch->cfg, kind, agc_profile);
     ch->cfg.sq_level = level;
+    ch->agc_initial = agc_initial_gain(kind);
     const bool wfm = kind == OWRX_DEMOD_WFM;
     if (wfm && !(audio_rate > 0.0 && tau > 0.0)) return fail(OWRX_E_INVALID, "WFM needs audio_rate and tau");
-    if (wfm != g->wfm || (wfm && (g->audio_rate != audio_rate || g->tau != tau))) {
+    owrx_chan_spec_t sp = ch->spec;
+    sp.wfm = wfm ? 1 : 0;
+    if (wfm) {
+        // WFm chain (analog.py:55-67): FractionalDecimator(FLOAT, IF rate / audio rate, prefilter=True) + WfmDeemphasis
+        const double if_rate = bank->input_rate / sp.decimation / sp.fraction;
+        sp.wfm_decimation = if_rate / audio_rate;
+        sp.wfm_audio_rate = (int)audio_rate;
+        sp.wfm_tau = tau;
+    }
+    if (!spec_equal(sp, g->spec)) {
         // move to the matching group (WFM channels keep their own lock-step group)
-        const double orate = g->out_rate;
+        int vrc = spec_validate(sp);
+        if (vrc != OWRX_OK) return vrc;
         g->slot_chan[(size_t)ch->slot] = -1;
         g->cfg_dirty = true;
-        int gi = find_group(bank, orate, wfm, audio_rate, tau), rc;
-        if (gi < 0 && (rc = group_create(bank, orate, wfm, audio_rate, tau, &gi)) != OWRX_OK) return rc;
+        ch->spec = sp;
+        int gi = find_group(bank, sp), rc;
+        if (gi < 0 && (rc = group_create(bank, sp, &gi)) != OWRX_OK) return rc;
         Group* ng = bank->groups[(size_t)gi].get();
         if (std::find(ng->slot_chan.begin(), ng->slot_chan.end(), -1) == ng->slot_chan.end() && (rc = group_grow(bank, ng)) != OWRX_OK) return rc;
         if ((rc = place_channel(bank, ch, gi)) != OWRX_OK) return rc;
@@ -863,10 +991,66 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
     ChanState stt{};
     OWRX_CUDA(cudaMemcpy(&stt, g->d_state + ch->slot, sizeof(stt), cudaMemcpyDeviceToHost));
     stt.fm_last = make_float2(0.f, 0.f); stt.dc_last = 0.f; stt.iir = 0.f; stt.agc_hang = 0;
-    stt.agc_gain = agc_initial_gain(kind);
+    stt.agc_gain = ch->agc_initial;
     OWRX_CUDA(cudaMemcpy(g->d_state + ch->slot, &stt, sizeof(stt), cudaMemcpyHostToDevice));
     g->h_cfg[(size_t)ch->slot] = ch->cfg;
     g->cfg_dirty = true;
+    return OWRX_OK;
+}
+
+int owrx_chan_set_agc(owrx_bank_t* bank, int chan, int profile, float initial_gain, float max_gain)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    Group* g = bank->groups[(size_t)ch->group].get();
+    ch->cfg.agc_decay = profile == OWRX_AGC_FAST ? 0.001f : 0.0001f;
+    ch->cfg.agc_hang_time = profile == OWRX_AGC_FAST ? 200 : 600;
+    if (max_gain > 0.f) ch->cfg.agc_max = max_gain;
+    if (initial_gain > 0.f) {
+        ch->agc_initial = initial_gain;
+        OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+        ChanState stt{};
+        OWRX_CUDA(cudaMemcpy(&stt, g->d_state + ch->slot, sizeof(stt), cudaMemcpyDeviceToHost));
+        stt.agc_gain = initial_gain;
+        OWRX_CUDA(cudaMemcpy(g->d_state + ch->slot, &stt, sizeof(stt), cudaMemcpyHostToDevice));
+    }
+    g->h_cfg[(size_t)ch->slot] = ch->cfg;
+    g->cfg_dirty = true;
+    return OWRX_OK;
+}
+
+int owrx_chan_set_audio_format(owrx_bank_t* bank, int chan, int format)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    if (format != OWRX_AUDIO_F32 && format != OWRX_AUDIO_S16 && format != OWRX_AUDIO_ADPCM) return fail(OWRX_E_INVALID, "unknown audio format %d", format);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    Group* g = bank->groups[(size_t)ch->group].get();
+    if (format != ch->audio_fmt) {
+        // a new AdpcmEncoder starts from reset state and announces it with a SYNC block
+        OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+        TailState tl{0, 0, 1001, 0, 0};
+        OWRX_CUDA(cudaMemcpy(g->d_tail + ch->slot, &tl, sizeof(tl), cudaMemcpyHostToDevice));
+        ch->q_bytes.clear();
+    }
+    ch->audio_fmt = format;
+    g->h_tail_mode[(size_t)ch->slot] = format;
+    g->cfg_dirty = true;
+    return OWRX_OK;
+}
+
+int owrx_chan_read_bytes(owrx_bank_t* bank, int chan, void* out, size_t cap_bytes, size_t* n)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    const size_t take = std::min(cap_bytes, ch->q_bytes.size());
+    memcpy(out, ch->q_bytes.data(), take);
+    ch->q_bytes.erase(ch->q_bytes.begin(), ch->q_bytes.begin() + (ptrdiff_t)take);
+    *n = take;
     return OWRX_OK;
 }
 
@@ -924,6 +1108,7 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
         Group* g = gp.get();
         if (!g) continue;
         if ((bank->out_mask & OWRX_OUT_AUDIO) && (rc = drain_to_queues(bank, g, g->f3.rows(g->f3.fill - g->last_audio), g->last_audio, 1, 0))) return rc;
+        if (g->any_tail && g->tail_ran && g->last_audio && (rc = drain_tail(bank, g)) != OWRX_OK) return rc;
         if ((bank->out_mask & OWRX_OUT_DEMOD) && (rc = drain_to_queues(bank, g, g->f2.rows(g->f2.fill - g->last_demod), g->last_demod, 1, 1))) return rc;
         if ((bank->out_mask & OWRX_OUT_IF) && (rc = drain_to_queues(bank, g, g->s3.rows(g->s3.fill - g->last_if), g->last_if, 2, 2))) return rc;
         if ((bank->out_mask & OWRX_OUT_POWER) && g->last_blocks) {

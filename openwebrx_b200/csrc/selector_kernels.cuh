@@ -458,4 +458,83 @@ agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __rest
     st[s].agc_hang = hang;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Client audio tail: Convert(FLOAT -> SHORT) [+ AdpcmEncoder(sync=True)], reference
+// csdr/chain/clientaudio.py:12,34.  Wire format pinned by the browser decoder
+// (htdocs/lib/AudioEngine.js:449-491): "SYNC", int16 LE step index, int16 LE predictor, then 1001
+// data bytes, low nibble first.  One channel per thread; the codec state is sample-serial.
+// ------------------------------------------------------------------------------------------------
+struct TailState {
+    int index, pred, since_sync, have_lo, lo;
+};
+
+__constant__ int16_t c_ima_step_audio[89] = {
+    7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45,
+    50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130, 143, 157, 173, 190, 209, 230, 253, 279, 307,
+    337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411, 1552, 1707, 1878, 2066,
+    2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899,
+    15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
+
+__device__ __forceinline__ int ima_encode_audio(int sample, int& index, int& pred, const int* steps)
+{
+    const int st = steps[index];
+    int diff = sample - pred;
+    int code = 0;
+    if (diff < 0) { code = 8; diff = -diff; }
+    int d = st >> 3;
+    if (diff >= st) { code |= 4; diff -= st; d += st; }
+    const int s1 = st >> 1;
+    if (diff >= s1) { code |= 2; diff -= s1; d += s1; }
+    const int s2 = st >> 2;
+    if (diff >= s2) { code |= 1; d += s2; }
+    pred = (code & 8) ? pred - d : pred + d;
+    pred = max(-32768, min(32767, pred));
+    const int c3 = code & 7;
+    index += (c3 < 4) ? -1 : (2 * c3 - 6);
+    index = max(0, min(88, index));
+    return code;
+}
+
+// mode[s]: 0 = float only, 1 = int16, 2 = int16 + ADPCM with SYNC framing
+__global__ void __launch_bounds__(64)
+audio_tail_kernel(const float* __restrict__ in, int slots, int n, const int* __restrict__ mode, TailState* __restrict__ ts,
+                  int16_t* __restrict__ s16_out, unsigned char* __restrict__ bytes_out, int* __restrict__ count_out, int cap)
+{
+    __shared__ int steps[89];
+    for (int i = threadIdx.x; i < 89; i += blockDim.x) steps[i] = c_ima_step_audio[i];
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    const int md = mode[s];
+    if (md == 0) { count_out[s] = 0; return; }
+    TailState t = ts[s];
+    unsigned char* o = bytes_out + (size_t)s * cap;
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        float v = in[(size_t)i * slots + s] * 32767.0f;                  // Convert(FLOAT, SHORT), SURVEY A.12
+        const int q = v > 32767.0f ? 32767 : (v < -32768.0f ? -32768 : __float2int_rz(v));
+        s16_out[(size_t)i * slots + s] = (int16_t)q;
+        if (md == 2) {
+            if (!t.have_lo) {
+                if (t.since_sync == 1001) {
+                    o[cnt++] = 'S'; o[cnt++] = 'Y'; o[cnt++] = 'N'; o[cnt++] = 'C';
+                    o[cnt++] = (unsigned char)(t.index & 0xff); o[cnt++] = (unsigned char)((t.index >> 8) & 0xff);
+                    o[cnt++] = (unsigned char)(t.pred & 0xff);  o[cnt++] = (unsigned char)((t.pred >> 8) & 0xff);
+                    t.since_sync = 0;
+                }
+                t.lo = ima_encode_audio(q, t.index, t.pred, steps);
+                t.have_lo = 1;
+            } else {
+                const int hi = ima_encode_audio(q, t.index, t.pred, steps);
+                o[cnt++] = (unsigned char)(t.lo | (hi << 4));
+                t.have_lo = 0;
+                t.since_sync++;
+            }
+        }
+    }
+    ts[s] = t;
+    count_out[s] = cnt;
+}
+
 }  // namespace owrx
