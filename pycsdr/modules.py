@@ -87,6 +87,12 @@ class Reader:
         return self._buffer._format
 
     def read(self):
+        """next write unit.  Frame granularity is preserved: every Writer.write() surfaces as exactly one
+        read() result, because the reference forwards one read() as one WebSocket message and the browser
+        decodes each FFT message as exactly one line (owrx/fft.py:70-73, htdocs/openwebrx.js:1124-1131)."""
+        return self._read(False)
+
+    def _read(self, everything):
         b = self._buffer
         with b._cond:
             while not self._stopped and self._pos >= b._end:
@@ -96,8 +102,12 @@ class Reader:
             if self._pos < b._start:          # overrun: a slow reader loses the oldest data (ring semantics)
                 self._pos = b._start
             first = self._pos - b._start
-            chunks = [b._chunks[i] for i in range(first, len(b._chunks))]
-            self._pos = b._end
+            if everything:
+                chunks = [b._chunks[i] for i in range(first, len(b._chunks))]
+                self._pos = b._end
+            else:
+                chunks = [b._chunks[first]]
+                self._pos += 1
             b._trim()
         if len(chunks) == 1:
             return memoryview(chunks[0])
@@ -874,7 +884,7 @@ class _SourceRunner(threading.Thread):
         N = None
         idle = 0
         while True:
-            data = self.reader.read()
+            data = self.reader._read(True)      # the runner batches everything that has arrived into one GPU pass
             if data is None:
                 break
             try:

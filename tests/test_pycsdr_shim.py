@@ -21,10 +21,11 @@ def test_buffer_multi_reader_and_stop():
     r1, r2 = b.getReader(), b.getReader()
     b.write(b"\x01\x02\x03\x04")
     b.write(bytearray(b"\x05\x06\x07\x08"))
-    d1 = r1.read()
+    d1 = r1._read(True)                                 # internal: everything that has arrived
     assert bytes(d1) == b"\x01\x02\x03\x04\x05\x06\x07\x08" and len(d1) == 8
     assert b"\x02" + d1 == b"\x02" + bytes(d1) and d1.tobytes()[:2] == b"\x01\x02"       # owrx/connection.py:475 usage
-    assert bytes(r2.read()) == bytes(d1)                # independent cursor
+    assert bytes(r2.read()) == b"\x01\x02\x03\x04"    # independent cursor; public read() = one write unit
+    assert bytes(r2.read()) == b"\x05\x06\x07\x08"
     r3 = b.getReader()                                  # late reader only sees new data
     got = []
     t = threading.Thread(target=lambda: got.append(r3.read()))
