@@ -48,6 +48,21 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
+// Blackwell packed FP32: fma.rn.f32x2 -> SASS FFMA2 (two FMAs per issue slot; a scalar operand is
+// broadcast by the hardware).  Accumulators of adjacent polyphase branches (p, p+1) share a 64-bit
+// register pair, the tap pair comes straight out of the LDS.128, and the rotated sample component is
+// the broadcast scalar: no register-bank conflict between the two fresh operands (both are aligned
+// even/odd pairs) and half the issue slots of the scalar FFMA stream.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(f32x2& c, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }
+
 __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
 {
     extern __shared__ float4 k3_smem[];
@@ -83,9 +98,10 @@ __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
     const int SL = (rcount + K3_NW - 1) / K3_NW;
     const int i0 = min(rcount, warp * SL), i1 = min(rcount, i0 + SL);
 
-    float a0r[K3_PP], a0i[K3_PP], a1r[K3_PP], a1i[K3_PP];
+    // pair j holds branches (2j, 2j+1)
+    f32x2 a0r[K3_PP / 2], a0i[K3_PP / 2], a1r[K3_PP / 2], a1i[K3_PP / 2];
 #pragma unroll
-    for (int q = 0; q < K3_PP; q++) { a0r[q] = 0.f; a0i[q] = 0.f; a1r[q] = 0.f; a1i[q] = 0.f; }
+    for (int q = 0; q < K3_PP / 2; q++) { a0r[q] = 0ull; a0i[q] = 0ull; a1r[q] = 0ull; a1i[q] = 0ull; }
 
     const int j_end = k_hi + K3_PP - 1;     // local block index runs k_lo .. j_end-1
     auto load_tile = [&](int jl, int buf) {
@@ -128,31 +144,71 @@ __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
             sincospif(2.0f * (float)t0, &q0.y, &q0.x);
             sincospif(2.0f * (float)t1, &q1.y, &q1.x);
             const float2* xb = xs + buf * p.RB;
-            for (int i = i0; i < i1; i++) {
-                const float2 x = xb[i];
-                const float2 z0 = cmul(x, q0), z1 = cmul(x, q1);
-                q0 = cmul(q0, w0); q1 = cmul(q1, w1);
-                const float4* hrow = reinterpret_cast<const float4*>(hs + i * K3_PP);
+#define K3_GROUP(G, H)                                                                                  \
+    {                                                                                                   \
+        const f32x2 hlo = pk2(H.x, H.y), hhi = pk2(H.z, H.w);                                           \
+        ffma2(a0r[2 * G], z0x, hlo); ffma2(a0r[2 * G + 1], z0x, hhi);                                   \
+        ffma2(a0i[2 * G], z0y, hlo); ffma2(a0i[2 * G + 1], z0y, hhi);                                   \
+        ffma2(a1r[2 * G], z1x, hlo); ffma2(a1r[2 * G + 1], z1x, hhi);                                   \
+        ffma2(a1i[2 * G], z1y, hlo); ffma2(a1i[2 * G + 1], z1y, hhi);                                   \
+    }
+#define K3_ROTATE()                                                                                     \
+    const float2 x = xb[i];                                                                             \
+    const float2 z0 = cmul(x, q0), z1 = cmul(x, q1);                                                    \
+    q0 = cmul(q0, w0); q1 = cmul(q1, w1);                                                               \
+    const f32x2 z0x = pk2(z0.x, z0.x), z0y = pk2(z0.y, z0.y), z1x = pk2(z1.x, z1.x), z1y = pk2(z1.y, z1.y);
+            // branches p' that still feed an output of this CTA's range: [jl-(k_hi-1), jl-k_lo] (clamped)
+            const int g_lo = max(0, jl - (k_hi - 1)) >> 2, g_hi = min(K3_PP - 1, jl - k_lo) >> 2;
+            if (g_lo == 0 && g_hi == K3_PP / 4 - 1) {
+                // steady state: all 28 branches live
+#pragma unroll 1
+                for (int i = i0; i < i1; i++) {
+                    K3_ROTATE()
+                    const float4* hrow = reinterpret_cast<const float4*>(hs + i * K3_PP);
 #pragma unroll
-                for (int g = 0; g < K3_PP / 4; g++) {
-                    const float4 h = hrow[g];
-                    a0r[4 * g + 0] = fmaf(z0.x, h.x, a0r[4 * g + 0]); a0i[4 * g + 0] = fmaf(z0.y, h.x, a0i[4 * g + 0]);
-                    a1r[4 * g + 0] = fmaf(z1.x, h.x, a1r[4 * g + 0]); a1i[4 * g + 0] = fmaf(z1.y, h.x, a1i[4 * g + 0]);
-                    a0r[4 * g + 1] = fmaf(z0.x, h.y, a0r[4 * g + 1]); a0i[4 * g + 1] = fmaf(z0.y, h.y, a0i[4 * g + 1]);
-                    a1r[4 * g + 1] = fmaf(z1.x, h.y, a1r[4 * g + 1]); a1i[4 * g + 1] = fmaf(z1.y, h.y, a1i[4 * g + 1]);
-                    a0r[4 * g + 2] = fmaf(z0.x, h.z, a0r[4 * g + 2]); a0i[4 * g + 2] = fmaf(z0.y, h.z, a0i[4 * g + 2]);
-                    a1r[4 * g + 2] = fmaf(z1.x, h.z, a1r[4 * g + 2]); a1i[4 * g + 2] = fmaf(z1.y, h.z, a1i[4 * g + 2]);
-                    a0r[4 * g + 3] = fmaf(z0.x, h.w, a0r[4 * g + 3]); a0i[4 * g + 3] = fmaf(z0.y, h.w, a0i[4 * g + 3]);
-                    a1r[4 * g + 3] = fmaf(z1.x, h.w, a1r[4 * g + 3]); a1i[4 * g + 3] = fmaf(z1.y, h.w, a1i[4 * g + 3]);
+                    for (int g = 0; g < K3_PP / 4; g++) {
+                        const float4 h = hrow[g];
+                        K3_GROUP(g, h)
+                    }
+                }
+            } else {
+                // head / tail of the output range: skip the branch groups whose outputs lie outside it
+#pragma unroll 1
+                for (int i = i0; i < i1; i++) {
+                    K3_ROTATE()
+                    const float4* hrow = reinterpret_cast<const float4*>(hs + i * K3_PP);
+#pragma unroll
+                    for (int g = 0; g < K3_PP / 4; g++) {
+                        if (g >= g_lo && g <= g_hi) {
+                            const float4 h = hrow[g];
+                            K3_GROUP(g, h)
+                        }
+                    }
                 }
             }
+#undef K3_GROUP
+#undef K3_ROTATE
         }
         // emit the oldest branch, roll the accumulators
-        reinterpret_cast<float4*>(red + buf * (K3_NW * 128) + warp * 128)[lane] =
-            make_float4(a0r[K3_PP - 1], a0i[K3_PP - 1], a1r[K3_PP - 1], a1i[K3_PP - 1]);
-#pragma unroll
-        for (int q = K3_PP - 1; q > 0; q--) { a0r[q] = a0r[q - 1]; a0i[q] = a0i[q - 1]; a1r[q] = a1r[q - 1]; a1i[q] = a1i[q - 1]; }
-        a0r[0] = 0.f; a0i[0] = 0.f; a1r[0] = 0.f; a1i[0] = 0.f;
+        {
+            float lo, e0, e1, e2, e3;
+            upk2(a0r[K3_PP / 2 - 1], lo, e0); upk2(a0i[K3_PP / 2 - 1], lo, e1);
+            upk2(a1r[K3_PP / 2 - 1], lo, e2); upk2(a1i[K3_PP / 2 - 1], lo, e3);
+            reinterpret_cast<float4*>(red + buf * (K3_NW * 128) + warp * 128)[lane] = make_float4(e0, e1, e2, e3);
+        }
+        // branch p of the next block is branch p-1 of this one: shift every pair by one float
+#define K3_ROLL(A)                                                                                      \
+    {                                                                                                   \
+        float plo, phi, clo, chi;                                                                       \
+        _Pragma("unroll") for (int q = K3_PP / 2 - 1; q > 0; q--) {                                     \
+            upk2(A[q], clo, chi); upk2(A[q - 1], plo, phi);                                             \
+            A[q] = pk2(phi, clo);                                                                       \
+        }                                                                                               \
+        upk2(A[0], clo, chi);                                                                           \
+        A[0] = pk2(0.f, clo);                                                                           \
+    }
+        K3_ROLL(a0r) K3_ROLL(a0i) K3_ROLL(a1r) K3_ROLL(a1i)
+#undef K3_ROLL
     }
     __syncthreads();
     flush(j_end - 1, (j_end - 1 - k_lo) & 1);

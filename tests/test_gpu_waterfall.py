@@ -33,14 +33,13 @@ def _truth_db(iq, n, every_n, avg, add_db=-70.0):
 
 
 def _assert_db_parity(db, ref_db, truth):
-    """0.01 dB on every bin the float32 oracle itself resolves (|oracle - float64| <= 0.003 dB); on the
-    ill-conditioned rest (deep nulls of single / barely averaged frames, where float32 FFTs of ANY
-    ordering disagree) the GPU must be no further from the float64 truth than 3x the oracle is."""
-    err_or = np.abs(ref_db - truth)
-    good = err_or <= 0.003
+    """0.01 dB on every well-conditioned bin (not in a deep null: within 10 dB of the line's median); in the
+    deep nulls of single / barely averaged frames float32 FFTs of ANY butterfly ordering disagree, so there
+    the GPU must simply be no further from the float64 truth than 3x the float32 oracle is."""
+    good = truth >= (np.median(truth, axis=1, keepdims=True) - 10.0)
     assert good.mean() > 0.8
     assert np.abs(db - ref_db)[good].max() <= DB_TOL
-    assert np.abs(db - truth).max() <= max(DB_TOL, 3.0 * err_or.max())
+    assert np.abs(db - truth).max() <= max(DB_TOL, 3.0 * np.abs(ref_db - truth).max())
 
 
 def _decode_none(lines, n):
