@@ -498,11 +498,13 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     const int nparts = g->nseg * g->nrs;
     const int ncg = S / K3_CG;
     const size_t fixed = (size_t)nparts * ncg;
-    size_t nkr = std::max<size_t>(1, ((size_t)bank->sm_count + fixed - 1) / fixed);
-    nkr = std::min(nkr, n_k);
-    const int KR = (int)((n_k + nkr - 1) / nkr);
-    nkr = (n_k + KR - 1) / KR;
-    const size_t pneed = (size_t)nparts * n_k * S;
+    // input-stationary ranges of JB blocks (>= 28 so that an output straddles at most two ranges)
+    const size_t n_blocks = n_k + K3_PP - 1;
+    size_t n_ranges = std::max<size_t>(1, ((size_t)bank->sm_count + fixed - 1) / fixed);
+    n_ranges = std::min(n_ranges, std::max<size_t>(1, n_blocks / K3_PP));
+    const int JB = (int)((n_blocks + n_ranges - 1) / n_ranges);
+    n_ranges = (n_blocks + JB - 1) / JB;
+    const size_t pneed = (size_t)nparts * n_k * S + (size_t)nparts * n_ranges * (K3_PP - 1) * S;
     if (pneed > g->partial_cap) {
         cudaFree(g->d_partial); g->d_partial = nullptr; g->partial_cap = 0;
         OWRX_CUDA(cudaMalloc((void**)&g->d_partial, pneed * sizeof(float2)));
@@ -512,8 +514,9 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     K3Params p;
     p.iq = iq; p.n_lim = (long long)n_avail; p.taps = g->d_taps;
     p.ch_rate = g->d_rate; p.ch_phase = g->d_phase; p.ch_w = g->d_w;
-    p.partial = nparts == 1 ? reinterpret_cast<float2*>(g->s1.append_ptr()) : g->d_partial;
-    p.D = g->D; p.nseg = g->nseg; p.nrs = g->nrs; p.RB = g->RB; p.KR = KR; p.n_k = (int)n_k; p.slots = S;
+    p.partial = g->d_partial;
+    p.side = g->d_partial + (size_t)nparts * n_k * S;
+    p.D = g->D; p.nseg = g->nseg; p.nrs = g->nrs; p.RB = g->RB; p.JB = JB; p.n_blocks = (int)n_blocks; p.n_k = (int)n_k; p.slots = S;
     const size_t smem = (size_t)g->RB * K3_PP * sizeof(float) + 2 * (size_t)g->RB * sizeof(float2) + 2 * K3_NW * 128 * sizeof(float);
     OWRX_CUDA(cudaFuncSetAttribute(fir_decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -529,13 +532,13 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
         bank->prof_used++;
         OWRX_CUDA(cudaEventRecord(pe0, st));
     }
-    fir_decimate_kernel<<<dim3((unsigned)(nkr * nparts), (unsigned)ncg), K3_NW * 32, smem, st>>>(p);
+    fir_decimate_kernel<<<dim3((unsigned)(n_ranges * nparts), (unsigned)ncg), K3_NW * 32, smem, st>>>(p);
     OWRX_LAUNCH_CHECK();
     if (pe1) OWRX_CUDA(cudaEventRecord(pe1, st));
     bank->stats.kernel_launches++;
-    if (nparts > 1) {
+    {
         const size_t total = n_k * (size_t)S;
-        fir_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g->d_partial, nparts, (int)n_k, S,
+        fir_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.side, nparts, (int)n_ranges, JB, (int)n_k, S,
                                                                            reinterpret_cast<float2*>(g->s1.append_ptr()));
         OWRX_LAUNCH_CHECK();
         bank->stats.kernel_launches++;

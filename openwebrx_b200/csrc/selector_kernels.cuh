@@ -23,7 +23,7 @@ namespace owrx {
 // 28 taps h[pD+r] of one r come from shared memory as 7 broadcast LDS.128.  Warps split the r-range
 // of a block; their partial sums meet in shared memory once per block.
 // ------------------------------------------------------------------------------------------------
-constexpr int K3_NW = 12;        // warps per CTA
+constexpr int K3_NW = 12;        // warps per CTA (3 per scheduler)
 constexpr int K3_CN = 2;         // channels per lane
 constexpr int K3_PP = 28;        // polyphase branches per pass (padded, multiple of 4)
 constexpr int K3_RBMAX = 896;    // max samples of one block (r-range) staged per CTA
@@ -36,8 +36,9 @@ struct K3Params {
     const double* ch_rate;   // per group slot: Shift rate (turns / sample)
     const double* ch_phase;  // per group slot: phase (turns) at iq[-1]
     const float2* ch_w;      // per group slot: e^{j 2 pi rate}
-    float2* partial;         // [nparts = nseg*nrs][n_k][slots]
-    int D, nseg, nrs, RB, KR, n_k, slots;
+    float2* partial;         // [nparts = nseg*nrs][n_k][slots]: complete outputs and range-tail partial sums
+    float2* side;            // [nparts][n_ranges][27][slots]: range-head partial sums (outputs owned by the previous range)
+    int D, nseg, nrs, RB, JB, n_blocks, n_k, slots;
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
@@ -63,6 +64,12 @@ __device__ __forceinline__ f32x2 pk2(float lo, float hi)
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ void ffma2(f32x2& c, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }
 
+// Work decomposition: INPUT-stationary.  The launch covers n_blocks = n_k + 27 input blocks of D samples;
+// CTA (range r, tap segment ts, r-split rs, channel group cg) streams blocks [r*JB, (r+1)*JB) and keeps,
+// per channel, 28 rolling accumulators: accumulator p of block j belongs to output k = j - p.  Every FMA
+// feeds some output (no warm-up waste): outputs whose 28 blocks straddle a range boundary get one
+// partial sum from each of the two ranges (`partial` from the earlier one, `side` from the later one)
+// and fir_reduce_kernel adds them.
 __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
 {
     extern __shared__ float4 k3_smem[];
@@ -74,15 +81,16 @@ __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
     int bx = blockIdx.x;
     const int rs = bx % p.nrs; bx /= p.nrs;
     const int ts = bx % p.nseg;
-    const int kr = bx / p.nseg;
+    const int range = bx / p.nseg;
     const int cg = blockIdx.y;
     const int part = ts * p.nrs + rs;
+    const int n_ranges = (p.n_blocks + p.JB - 1) / p.JB;
 
     const int r_lo = rs * p.RB;
     const int rcount = min(p.RB, p.D - r_lo);
-    const int k_lo = kr * p.KR;
-    const int k_hi = min(p.n_k, k_lo + p.KR);
-    if (k_lo >= k_hi || rcount <= 0) return;
+    const int jb0 = range * p.JB;
+    const int jb1 = min(p.n_blocks, jb0 + p.JB);
+    if (jb0 >= jb1 || rcount <= 0) return;
 
     {   // tap slice of this CTA: rcount rows of 28
         const float4* src = reinterpret_cast<const float4*>(p.taps + ((size_t)ts * p.D + r_lo) * K3_PP);
@@ -103,7 +111,6 @@ __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
 #pragma unroll
     for (int q = 0; q < K3_PP / 2; q++) { a0r[q] = 0ull; a0i[q] = 0ull; a1r[q] = 0ull; a1i[q] = 0ull; }
 
-    const int j_end = k_hi + K3_PP - 1;     // local block index runs k_lo .. j_end-1
     auto load_tile = [&](int jl, int buf) {
         const long long s0 = (long long)(jl + ts * K3_PP) * p.D + r_lo;
         float2* dst = xs + buf * p.RB;
@@ -114,89 +121,20 @@ __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
         }
         cp_async_commit();
     };
+    // sum the NW warp partials that completed after block jl_done -> output k = jl_done - 27
     auto flush = [&](int jl_done, int buf) {
-        // sum the NW warp partials of block jl_done -> output k = jl_done - (PP-1)
         const int k = jl_done - (K3_PP - 1);
-        if (k >= k_lo && tid < 128) {
-            const float* r = red + buf * (K3_NW * 128) + tid;
-            float s = 0.f;
+        if (k < 0 || k >= p.n_k || tid >= 128) return;
+        const float* r = red + buf * (K3_NW * 128) + tid;
+        float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < K3_NW; w++) s += r[w * 128];
-            float* out = reinterpret_cast<float*>(p.partial + ((size_t)part * p.n_k + k) * p.slots + cg * K3_CG);
-            out[tid] = s;
-        }
+        for (int w = 0; w < K3_NW; w++) s += r[w * 128];
+        float* out;
+        if (k >= jb0) out = reinterpret_cast<float*>(p.partial + ((size_t)part * p.n_k + k) * p.slots + cg * K3_CG);
+        else out = reinterpret_cast<float*>(p.side + (((size_t)part * n_ranges + range) * (K3_PP - 1) + (k - (jb0 - (K3_PP - 1)))) * p.slots + cg * K3_CG);
+        out[tid] = s;
     };
-
-    load_tile(k_lo, 0);
-    for (int jl = k_lo; jl < j_end; jl++) {
-        const int buf = (jl - k_lo) & 1;
-        cp_async_wait_all();
-        __syncthreads();
-        if (jl + 1 < j_end) load_tile(jl + 1, buf ^ 1);
-        if (jl > k_lo) flush(jl - 1, buf ^ 1);
-
-        if (i0 < i1) {
-            // re-seed both NCOs at the first sample of this warp's slice (double phase -> float sincos)
-            const long long n_rel = (long long)(jl + ts * K3_PP) * p.D + r_lo + i0;
-            double t0 = ph0 + rate0 * (double)(n_rel + 1), t1 = ph1 + rate1 * (double)(n_rel + 1);
-            t0 -= floor(t0); t1 -= floor(t1);
-            float2 q0, q1;
-            sincospif(2.0f * (float)t0, &q0.y, &q0.x);
-            sincospif(2.0f * (float)t1, &q1.y, &q1.x);
-            const float2* xb = xs + buf * p.RB;
-#define K3_GROUP(G, H)                                                                                  \
-    {                                                                                                   \
-        const f32x2 hlo = pk2(H.x, H.y), hhi = pk2(H.z, H.w);                                           \
-        ffma2(a0r[2 * G], z0x, hlo); ffma2(a0r[2 * G + 1], z0x, hhi);                                   \
-        ffma2(a0i[2 * G], z0y, hlo); ffma2(a0i[2 * G + 1], z0y, hhi);                                   \
-        ffma2(a1r[2 * G], z1x, hlo); ffma2(a1r[2 * G + 1], z1x, hhi);                                   \
-        ffma2(a1i[2 * G], z1y, hlo); ffma2(a1i[2 * G + 1], z1y, hhi);                                   \
-    }
-#define K3_ROTATE()                                                                                     \
-    const float2 x = xb[i];                                                                             \
-    const float2 z0 = cmul(x, q0), z1 = cmul(x, q1);                                                    \
-    q0 = cmul(q0, w0); q1 = cmul(q1, w1);                                                               \
-    const f32x2 z0x = pk2(z0.x, z0.x), z0y = pk2(z0.y, z0.y), z1x = pk2(z1.x, z1.x), z1y = pk2(z1.y, z1.y);
-            // branches p' that still feed an output of this CTA's range: [jl-(k_hi-1), jl-k_lo] (clamped)
-            const int g_lo = max(0, jl - (k_hi - 1)) >> 2, g_hi = min(K3_PP - 1, jl - k_lo) >> 2;
-            if (g_lo == 0 && g_hi == K3_PP / 4 - 1) {
-                // steady state: all 28 branches live
-#pragma unroll 1
-                for (int i = i0; i < i1; i++) {
-                    K3_ROTATE()
-                    const float4* hrow = reinterpret_cast<const float4*>(hs + i * K3_PP);
-#pragma unroll
-                    for (int g = 0; g < K3_PP / 4; g++) {
-                        const float4 h = hrow[g];
-                        K3_GROUP(g, h)
-                    }
-                }
-            } else {
-                // head / tail of the output range: skip the branch groups whose outputs lie outside it
-#pragma unroll 1
-                for (int i = i0; i < i1; i++) {
-                    K3_ROTATE()
-                    const float4* hrow = reinterpret_cast<const float4*>(hs + i * K3_PP);
-#pragma unroll
-                    for (int g = 0; g < K3_PP / 4; g++) {
-                        if (g >= g_lo && g <= g_hi) {
-                            const float4 h = hrow[g];
-                            K3_GROUP(g, h)
-                        }
-                    }
-                }
-            }
-#undef K3_GROUP
-#undef K3_ROTATE
-        }
-        // emit the oldest branch, roll the accumulators
-        {
-            float lo, e0, e1, e2, e3;
-            upk2(a0r[K3_PP / 2 - 1], lo, e0); upk2(a0i[K3_PP / 2 - 1], lo, e1);
-            upk2(a1r[K3_PP / 2 - 1], lo, e2); upk2(a1i[K3_PP / 2 - 1], lo, e3);
-            reinterpret_cast<float4*>(red + buf * (K3_NW * 128) + warp * 128)[lane] = make_float4(e0, e1, e2, e3);
-        }
-        // branch p of the next block is branch p-1 of this one: shift every pair by one float
+    // emit the oldest branch (p = 27) into the cross-warp reduction buffer, then age every branch by one block
 #define K3_ROLL(A)                                                                                      \
     {                                                                                                   \
         float plo, phi, clo, chi;                                                                       \
@@ -207,26 +145,89 @@ __global__ void __launch_bounds__(K3_NW * 32, 1) fir_decimate_kernel(K3Params p)
         upk2(A[0], clo, chi);                                                                           \
         A[0] = pk2(0.f, clo);                                                                           \
     }
+    auto emit_and_roll = [&](int buf) {
+        float lo, e0, e1, e2, e3;
+        upk2(a0r[K3_PP / 2 - 1], lo, e0); upk2(a0i[K3_PP / 2 - 1], lo, e1);
+        upk2(a1r[K3_PP / 2 - 1], lo, e2); upk2(a1i[K3_PP / 2 - 1], lo, e3);
+        reinterpret_cast<float4*>(red + buf * (K3_NW * 128) + warp * 128)[lane] = make_float4(e0, e1, e2, e3);
         K3_ROLL(a0r) K3_ROLL(a0i) K3_ROLL(a1r) K3_ROLL(a1i)
-#undef K3_ROLL
+    };
+
+    load_tile(jb0, 0);
+    for (int jl = jb0; jl < jb1; jl++) {
+        const int buf = (jl - jb0) & 1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (jl + 1 < jb1) load_tile(jl + 1, buf ^ 1);
+        if (jl > jb0) flush(jl - 1, buf ^ 1);
+
+        if (i0 < i1) {
+            // re-seed both NCOs at the first sample of this warp's slice (double phase -> float sincos)
+            const long long n_rel = (long long)(jl + ts * K3_PP) * p.D + r_lo + i0;
+            double t0 = ph0 + rate0 * (double)(n_rel + 1), t1 = ph1 + rate1 * (double)(n_rel + 1);
+            t0 -= floor(t0); t1 -= floor(t1);
+            float2 q0, q1;
+            sincospif(2.0f * (float)t0, &q0.y, &q0.x);
+            sincospif(2.0f * (float)t1, &q1.y, &q1.x);
+            const float2* xb = xs + buf * p.RB;
+#pragma unroll 1
+            for (int i = i0; i < i1; i++) {
+                const float2 x = xb[i];
+                const float2 z0 = cmul(x, q0), z1 = cmul(x, q1);
+                q0 = cmul(q0, w0); q1 = cmul(q1, w1);
+                const f32x2 z0x = pk2(z0.x, z0.x), z0y = pk2(z0.y, z0.y), z1x = pk2(z1.x, z1.x), z1y = pk2(z1.y, z1.y);
+                const float4* hrow = reinterpret_cast<const float4*>(hs + i * K3_PP);
+#pragma unroll
+                for (int g = 0; g < K3_PP / 4; g++) {
+                    const float4 h = hrow[g];
+                    const f32x2 hlo = pk2(h.x, h.y), hhi = pk2(h.z, h.w);
+                    ffma2(a0r[2 * g], z0x, hlo); ffma2(a0r[2 * g + 1], z0x, hhi);
+                    ffma2(a0i[2 * g], z0y, hlo); ffma2(a0i[2 * g + 1], z0y, hhi);
+                    ffma2(a1r[2 * g], z1x, hlo); ffma2(a1r[2 * g + 1], z1x, hhi);
+                    ffma2(a1i[2 * g], z1y, hlo); ffma2(a1i[2 * g + 1], z1y, hhi);
+                }
+            }
+        }
+        emit_and_roll(buf);
     }
+    // drain: the 27 younger branches are the range-tail partial sums of outputs jb1-27 .. jb1-1
+    int buf = (jb1 - jb0) & 1;
     __syncthreads();
-    flush(j_end - 1, (j_end - 1 - k_lo) & 1);
+    flush(jb1 - 1, buf ^ 1);
+    for (int d = 1; d < K3_PP; d++) {
+        emit_and_roll(buf);
+        __syncthreads();
+        flush(jb1 - 1 + d, buf);
+        buf ^= 1;
+    }
+#undef K3_ROLL
 }
 
-// K3b: sum the tap-segment / r-split partials into the FirDecimate output stream s1[k][slot].
+// K3b: sum the tap-segment / r-split partials and the range-head partial sums into the FirDecimate
+// output stream s1[k][slot].
 __global__ void __launch_bounds__(256)
-fir_reduce_kernel(const float2* __restrict__ partial, int nparts, int n_k, int slots, float2* __restrict__ out)
+fir_reduce_kernel(const float2* __restrict__ partial, const float2* __restrict__ side, int nparts, int n_ranges, int JB, int n_k,
+                  int slots, float2* __restrict__ out)
 {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)n_k * slots;
     if (gid >= total) return;
-    float2 s = make_float2(0.f, 0.f);
+    const int k = (int)(gid / slots), s = (int)(gid % slots);
+    float2 acc = make_float2(0.f, 0.f);
     for (int q = 0; q < nparts; q++) {
         const float2 v = partial[(size_t)q * total + gid];
-        s.x += v.x; s.y += v.y;
+        acc.x += v.x; acc.y += v.y;
     }
-    out[gid] = s;
+    // is k one of the 27 outputs just below a range start?  range = ceil-ish((k + 27) / JB)
+    const int range = (k + (K3_PP - 1)) / JB;
+    const int h = k - (range * JB - (K3_PP - 1));
+    if (range >= 1 && range < n_ranges && h >= 0 && h < K3_PP - 1) {
+        for (int q = 0; q < nparts; q++) {
+            const float2 v = side[(((size_t)q * n_ranges + range) * (K3_PP - 1) + h) * slots + s];
+            acc.x += v.x; acc.y += v.y;
+        }
+    }
+    out[gid] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------
