@@ -607,8 +607,9 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
         }
         const float2* sq_in = reinterpret_cast<const float2*>(g->s3.row_abs(g->sq_abs));
         const int hang_blocks = 2;                                       // hangLength = 2*blockLength, selector.py:124
-        squelch_kernel<<<(S + 127) / 128, 128, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, hang_blocks, g->d_cfg, g->d_state,
-                                                       g->d_gate, g->d_power);
+        squelch_power_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)nb), 128, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, g->d_power);
+        OWRX_LAUNCH_CHECK();
+        squelch_gate_kernel<<<(S + 127) / 128, 128, 0, st>>>(g->d_power, S, (int)nb, hang_blocks, g->d_cfg, g->d_state, g->d_gate);
         OWRX_LAUNCH_CHECK();
         // ---- demodulator front -> f1
         if ((rc = g->f1.ensure_new(n4, st)) != OWRX_OK) return rc;
@@ -683,7 +684,7 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
                 OWRX_LAUNCH_CHECK();
             }
             if (cnt) {
-                wfm_deemph_kernel<<<(S + 127) / 128, 128, 0, st>>>(g->f1b.append_ptr(), S, (int)cnt, g->alpha, g->d_state,
+                wfm_deemph_kernel<<<(S + 31) / 32, 32, 0, st>>>(g->f1b.append_ptr(), S, (int)cnt, g->alpha, g->d_state,
                                                                   g->f2.append_ptr());
                 OWRX_LAUNCH_CHECK();
             }
@@ -696,7 +697,7 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
         // ---- Agc -> f3
         if (n_audio) {
             if ((rc = g->f3.ensure_new(n_audio, st)) != OWRX_OK) return rc;
-            agc_kernel<<<(S + 127) / 128, 128, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+            agc_kernel<<<(S + 31) / 32, 32, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
                                                        g->f3.append_ptr());
             OWRX_LAUNCH_CHECK();
             bank->stats.kernel_launches++;

@@ -317,32 +317,40 @@ struct ChanCfg {
     int active;
 };
 
-// Squelch: one thread per channel walks the new whole blocks in order (hang counter is
-// sequential).  Block power = mean |x|^2 over every `decim`-th sample.
+// Squelch.  Block power = mean |x|^2 over every `decim`-th sample: one thread per (block, slot),
+// independent loads.  The gate (threshold + hang counter, sequential over blocks) is a second tiny kernel.
 __global__ void __launch_bounds__(128)
-squelch_kernel(const float2* __restrict__ in, int slots, int n_blocks, int length, int decim, int hang_blocks,
-               const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st, unsigned char* __restrict__ gate,
-               float* __restrict__ power)
+squelch_power_kernel(const float2* __restrict__ in, int slots, int n_blocks, int length, int decim, float* __restrict__ power)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (s >= slots || b >= n_blocks) return;
+    const float2* x = in + (size_t)b * length * slots + s;
+    float p = 0.f;
+    int cnt = 0;
+#pragma unroll 8
+    for (int i = 0; i < length; i += decim) {
+        const float2 v = x[(size_t)i * slots];
+        p += v.x * v.x + v.y * v.y;
+        cnt++;
+    }
+    power[(size_t)b * slots + s] = p / (float)cnt;
+}
+
+__global__ void __launch_bounds__(128)
+squelch_gate_kernel(const float* __restrict__ power, int slots, int n_blocks, int hang_blocks, const ChanCfg* __restrict__ cfg,
+                    ChanState* __restrict__ st, unsigned char* __restrict__ gate)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= slots) return;
     const float level = cfg[s].sq_level;
     int hang = st[s].sq_hang;
     for (int b = 0; b < n_blocks; b++) {
-        const float2* x = in + (size_t)b * length * slots + s;
-        float p = 0.f;
-        int cnt = 0;
-        for (int i = 0; i < length; i += decim) {
-            const float2 v = x[(size_t)i * slots];
-            p += v.x * v.x + v.y * v.y;
-            cnt++;
-        }
-        p /= (float)cnt;
+        const float p = power[(size_t)b * slots + s];
         int open = 0;
         if (p >= level) { open = 1; hang = hang_blocks; }
         else if (hang > 0) { open = 1; hang--; }
         gate[(size_t)b * slots + s] = (unsigned char)open;
-        power[(size_t)b * slots + s] = p;
     }
     st[s].sq_hang = hang;
 }
@@ -469,8 +477,13 @@ fracdec_f_kernel(const float* __restrict__ in, long long in_abs0, int slots, dou
     out[(size_t)m * slots + s] = acc;
 }
 
-// WfmDeemphasis one-pole IIR, one channel per thread (sample-serial).
-__global__ void __launch_bounds__(128)
+// Sample-serial recurrences run one channel per lane.  A lane's samples sit `slots` floats apart, so a
+// warp-wide load of one time step is coalesced; SER_TT time steps are fetched as independent loads
+// into registers (and the next tile is prefetched) before the dependent chain runs over them.
+constexpr int SER_TT = 16;
+
+// WfmDeemphasis one-pole IIR.
+__global__ void __launch_bounds__(32)
 wfm_deemph_kernel(const float* __restrict__ in, int slots, int n, float alpha, ChanState* __restrict__ st,
                   float* __restrict__ out)
 {
@@ -478,43 +491,79 @@ wfm_deemph_kernel(const float* __restrict__ in, int slots, int n, float alpha, C
     if (s >= slots) return;
     float y = st[s].iir;
     const float om = 1.0f - alpha;
-    for (int i = 0; i < n; i++) {
-        y = alpha * in[(size_t)i * slots + s] + om * y;
-        out[(size_t)i * slots + s] = y;
+    float cur[SER_TT], nxt[SER_TT];
+#pragma unroll
+    for (int t = 0; t < SER_TT; t++) nxt[t] = t < n ? in[(size_t)t * slots + s] : 0.f;
+    for (int i0 = 0; i0 < n; i0 += SER_TT) {
+#pragma unroll
+        for (int t = 0; t < SER_TT; t++) cur[t] = nxt[t];
+#pragma unroll
+        for (int t = 0; t < SER_TT; t++) {
+            const int i = i0 + SER_TT + t;
+            nxt[t] = i < n ? in[(size_t)i * slots + s] : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < SER_TT; t++) {
+            y = alpha * cur[t] + om * y;
+            if (i0 + t < n) out[(size_t)(i0 + t) * slots + s] = y; else y = y;
+            cur[t] = y;
+        }
     }
-    st[s].iir = y;
+    // the loop above over-runs the recurrence on padded zeros in the last tile: recompute the carried state exactly
+    if (n > 0) st[s].iir = out[(size_t)(n - 1) * slots + s];
 }
 
-// Agc (SPEC-DEFINED), one channel per thread (sample-serial nonlinear recurrence).
-__global__ void __launch_bounds__(128)
+// Agc (SPEC-DEFINED).  The gain recurrence is evaluated speculatively: both candidate gains
+// are formed while the envelope comparison resolves, so the dependent chain is mul -> select per sample.
+__global__ void __launch_bounds__(32)
 agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st,
            float* __restrict__ out)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= slots) return;
     const ChanCfg c = cfg[s];
-    if (c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE) {
-        for (int i = 0; i < n; i++) out[(size_t)i * slots + s] = in[(size_t)i * slots + s];
-        return;
-    }
+    const bool bypass = c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE;
     float gain = st[s].agc_gain;
     int hang = st[s].agc_hang;
-    for (int i = 0; i < n; i++) {
-        const float v = in[(size_t)i * slots + s];
-        if (v != 0.f) {
-            const float err = fabsf(v) * gain / c.agc_ref;
-            if (err > 1.f) { gain *= 1.f - c.agc_attack; hang = c.agc_hang_time; }
-            else if (hang > 0) hang--;
-            else gain *= 1.f + c.agc_decay;
+    const float dn = 1.f - c.agc_attack, up = 1.f + c.agc_decay;
+    float cur[SER_TT], nxt[SER_TT];
+#pragma unroll
+    for (int t = 0; t < SER_TT; t++) nxt[t] = t < n ? in[(size_t)t * slots + s] : 0.f;
+    for (int i0 = 0; i0 < n; i0 += SER_TT) {
+#pragma unroll
+        for (int t = 0; t < SER_TT; t++) cur[t] = nxt[t];
+#pragma unroll
+        for (int t = 0; t < SER_TT; t++) {
+            const int i = i0 + SER_TT + t;
+            nxt[t] = i < n ? in[(size_t)i * slots + s] : 0.f;
         }
-        gain = fminf(gain, c.agc_max);
-        gain = fmaxf(gain, 0.f);
-        out[(size_t)i * slots + s] = fminf(1.f, fmaxf(-1.f, v * gain));
+        if (!bypass) {
+#pragma unroll
+            for (int t = 0; t < SER_TT; t++) {
+                const float v = cur[t];
+                // padded zeros leave the state untouched (v == 0 is skipped by the algorithm itself)
+                if (v != 0.f) {
+                    const float err = fabsf(v) * gain / c.agc_ref;
+                    const float g_dn = gain * dn;
+                    const float g_up = gain * up;
+                    if (err > 1.f) { gain = g_dn; hang = c.agc_hang_time; }
+                    else if (hang > 0) hang--;
+                    else gain = g_up;
+                }
+                gain = fminf(gain, c.agc_max);
+                gain = fmaxf(gain, 0.f);
+                cur[t] = fminf(1.f, fmaxf(-1.f, v * gain));
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < SER_TT; t++)
+            if (i0 + t < n) out[(size_t)(i0 + t) * slots + s] = cur[t];
     }
-    st[s].agc_gain = gain;
-    st[s].agc_hang = hang;
+    if (!bypass) {
+        st[s].agc_gain = gain;
+        st[s].agc_hang = hang;
+    }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Client audio tail: Convert(FLOAT -> SHORT) [+ AdpcmEncoder(sync=True)], reference

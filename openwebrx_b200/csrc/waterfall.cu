@@ -288,9 +288,14 @@ __constant__ int16_t c_ima_step[89] = {
     2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899,
     15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
 
-__device__ __forceinline__ int ima_encode(int sample, int& index, int& pred, const int* steps)
+// One IMA-ADPCM step.  `st` is the step of the current index (carried in a register); the
+// steps of all five possible successor indices are fetched from shared memory while the quantiser's
+// compare chain resolves, so no table lookup sits on the sample-to-sample dependency chain.
+__device__ __forceinline__ int ima_encode(int sample, int& index, int& pred, int& st, const int* steps)
 {
-    const int st = steps[index];
+    const int c0 = steps[max(index - 1, 0)];
+    const int c1 = steps[min(index + 2, 88)], c2 = steps[min(index + 4, 88)];
+    const int c3 = steps[min(index + 6, 88)], c4 = steps[min(index + 8, 88)];
     int diff = sample - pred;
     int code = 0;
     if (diff < 0) { code = 8; diff = -diff; }
@@ -302,29 +307,49 @@ __device__ __forceinline__ int ima_encode(int sample, int& index, int& pred, con
     if (diff >= s2) { code |= 1; d += s2; }
     pred = (code & 8) ? pred - d : pred + d;
     pred = max(-32768, min(32767, pred));
-    const int c3 = code & 7;
-    index += (c3 < 4) ? -1 : (2 * c3 - 6);
-    index = max(0, min(88, index));
+    const int m = code & 7;
+    index = max(0, min(88, index + ((m < 4) ? -1 : (2 * m - 6))));
+    st = (m < 4) ? c0 : ((m & 2) ? ((m & 1) ? c4 : c3) : ((m & 1) ? c2 : c1));
     return code;
 }
 
-// One thread per line (state is strictly sequential within a line; lines are independent).
-// 32-thread CTAs spread the lines over the SMs.
+// FftAdpcm encoder, warp-cooperative: a warp owns 32 lines (one per lane: the codec state is strictly
+// sequential within a line, lines are independent and reset per line).  Each iteration the warp stages a
+// 64-sample chunk of all 32 lines through shared memory with coalesced 128-byte row loads, every lane
+// encodes its own line's chunk from (conflict-free, padded) shared memory, and the 32 output bytes per
+// line leave through shared memory as one 32-byte sector per line.
+constexpr int ADPCM_CH = 64;
 __global__ void __launch_bounds__(32)
 wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int n_samples, size_t n_lines)
 {
     __shared__ int steps[89];
-    for (int i = threadIdx.x; i < 89; i += blockDim.x) steps[i] = c_ima_step[i];
-    __syncthreads();
-    const size_t line = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (line >= n_lines) return;
-    const int16_t* s = s16 + line * (size_t)n_samples;
-    uint8_t* o = out + line * (size_t)(n_samples / 2);
-    int index = 0, pred = 0;
-    for (int i = 0; i + 1 < n_samples; i += 2) {
-        const int lo = ima_encode(s[i], index, pred, steps);
-        const int hi = ima_encode(s[i + 1], index, pred, steps);
-        o[i >> 1] = (uint8_t)(lo | (hi << 4));
+    __shared__ unsigned tile[32][ADPCM_CH / 2 + 1];
+    __shared__ unsigned char otile[32][ADPCM_CH / 2 + 4];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 89; i += 32) steps[i] = c_ima_step[i];
+    __syncwarp();
+    const size_t line0 = (size_t)blockIdx.x * 32;
+    const int nl = (int)min((size_t)32, n_lines - line0);
+    int index = 0, pred = 0, st = 7;
+    for (int c0 = 0; c0 < n_samples; c0 += ADPCM_CH) {
+        const int valid = min(ADPCM_CH, n_samples - c0);          // even
+        for (int l = 0; l < nl; l++)
+            if (2 * lane < valid)
+                tile[l][lane] = *reinterpret_cast<const unsigned*>(s16 + (line0 + l) * (size_t)n_samples + c0 + 2 * lane);
+        __syncwarp();
+        if (lane < nl) {
+#pragma unroll 4
+            for (int w = 0; w < valid / 2; w++) {
+                const unsigned v = tile[lane][w];
+                const int lo = ima_encode((int)(short)(v & 0xffffu), index, pred, st, steps);
+                const int hi = ima_encode((int)(short)(v >> 16), index, pred, st, steps);
+                otile[lane][w] = (unsigned char)(lo | (hi << 4));
+            }
+        }
+        __syncwarp();
+        for (int l = 0; l < nl; l++)
+            if (lane < valid / 2) out[(line0 + l) * (size_t)(n_samples / 2) + c0 / 2 + lane] = otile[l][lane];
+        __syncwarp();
     }
 }
 
