@@ -170,6 +170,10 @@ int owrx_bank_set_outputs(owrx_bank_t* bank, int mask);
 /* Device-resident batch path (bench / embedding): process one wideband block that already lives
  * in device memory; outputs stay on the device and are NOT queued for the host. */
 int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_samples, void* stream);
+/* Pipelined device path: the low-rate stages of block i run on the bank's side stream while the K3 pass of
+ * block i+1 runs on the caller's stream.  owrx_bank_join makes `stream` wait for everything issued so far. */
+int owrx_bank_set_pipelined(owrx_bank_t* bank, int enable);
+int owrx_bank_join(owrx_bank_t* bank, void* stream);
 /* samples of audio produced per channel by the last owrx_bank_process_device call */
 int owrx_bank_last_audio_count(const owrx_bank_t* bank, int chan, size_t* n);
 /* device pointer + layout of the last block's audio: element (k, slot) at base[k*stride + slot] */

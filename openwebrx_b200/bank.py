@@ -148,6 +148,12 @@ class ChannelBank:
         return dict(input_samples=st.input_samples, channel_samples=st.channel_samples,
                     kernel_launches=st.kernel_launches, device_ms=st.device_ms)
 
+    def set_pipelined(self, enable=True):
+        N.check(N.lib.owrx_bank_set_pipelined(self._h, 1 if enable else 0))
+
+    def join(self, stream=None):
+        N.check(N.lib.owrx_bank_join(self._h, _ptr(stream)))
+
     def profile(self, enable=True):
         N.check(N.lib.owrx_bank_profile(self._h, 1 if enable else 0))
 

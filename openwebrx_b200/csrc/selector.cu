@@ -134,6 +134,28 @@ struct StageBuf {
     }
 };
 
+// flat FIFO of floats: one bulk append per feed, bulk pop
+struct FQ {
+    std::vector<float> v;
+    size_t off = 0;
+    size_t size() const { return v.size() - off; }
+    void push(const float* p, size_t n)
+    {
+        if (off && off >= v.size() / 2) { v.erase(v.begin(), v.begin() + (ptrdiff_t)off); off = 0; }
+        v.insert(v.end(), p, p + n);
+    }
+    void push_back(float x) { v.push_back(x); }
+    size_t pop(float* out, size_t max_floats, size_t unit)
+    {
+        size_t take = std::min(max_floats, size());
+        take -= take % unit;
+        std::copy(v.begin() + (ptrdiff_t)off, v.begin() + (ptrdiff_t)(off + take), out);
+        off += take;
+        if (off == v.size()) { v.clear(); off = 0; }
+        return take;
+    }
+};
+
 struct Chan {
     int id = -1;
     int group = -1, slot = -1;
@@ -144,7 +166,7 @@ struct Chan {
     owrx_chan_spec_t spec{};
     float agc_initial = 1.0f;
     int audio_fmt = OWRX_AUDIO_F32;
-    std::deque<float> q_audio, q_demod, q_if, q_power;
+    FQ q_audio, q_demod, q_if, q_power;
     std::vector<unsigned char> q_bytes;
     size_t last_audio = 0;
 };
@@ -178,6 +200,8 @@ struct Group {
     long long sq_block_abs = 0;                      // absolute squelch block counter (for report interval)
     // last run
     size_t last_audio = 0, last_demod = 0, last_if = 0, last_blocks = 0;
+    size_t pend_rows = 0;                            // FirDecimate rows appended to s1 since the last tail pass
+    long long pend_first = 0;
     // client audio tail (Convert / AdpcmEncoder)
     std::vector<int> h_tail_mode;
     int* d_tail_mode = nullptr; TailState* d_tail = nullptr; int* d_tail_count = nullptr;
@@ -201,9 +225,16 @@ struct owrx_bank {
     float2* d_iq[2] = {nullptr, nullptr};
     int iq_cur = 0;
     size_t iq_cap = 0, iq_fill = 0;
-    // pinned staging
+    // pinned staging + device transpose scratch for the output drain
     float* h_stage = nullptr; size_t h_stage_cap = 0;
+    float* d_xpose = nullptr; size_t d_xpose_cap = 0;
     owrx_bank_stats_t stats{};
+    // H2D copy stream for the chunked host path; side stream + events for the pipelined device path
+    cudaStream_t copy_stream = nullptr, side_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    cudaEvent_t fir_done = nullptr, tail_done[2] = {nullptr, nullptr};
+    bool pipelined = false;
+    unsigned long long calls = 0;
     // optional per-kernel timing of K3 (CUDA events on the launching stream)
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -328,7 +359,7 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     g->h_tail_mode.assign(S, 0);
     g->h_rate.assign(S, 0.0); g->h_phase.assign(S, 0.0); g->h_w.assign(S, make_float2(1.f, 0.f));
     g->h_bp_en.assign(S, 0);
-    ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
+    ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f; idle.agc_thr = 0.8f;
     g->h_cfg.assign(S, idle);
 
     const size_t cap = 4096;
@@ -363,6 +394,10 @@ void agc_defaults(ChanCfg& c, int kind, int profile)
     c.agc_hang_time = profile == OWRX_AGC_FAST ? 200 : 600;
     c.agc_max = kind == OWRX_DEMOD_NFM ? 3.0f : 65535.0f;               // NFm: agc.setMaxGain(3), analog.py:39
     c.active = 1;
+    // exact threshold form of "abs(v)*gain/ref > 1": the largest a with (float)(a / ref) <= 1
+    float a = c.agc_ref;
+    while (a / c.agc_ref <= 1.0f) a = nextafterf(a, INFINITY);
+    c.agc_thr = nextafterf(a, 0.0f);
 }
 
 float agc_initial_gain(int kind) { return kind == OWRX_DEMOD_AM ? 200.0f : 1.0f; }   // Am: setInitialGain(200), analog.py:15
@@ -435,7 +470,7 @@ int group_grow(owrx_bank* bank, Group* g)
     g->h_rate.resize((size_t)ns, 0.0); g->h_phase.resize((size_t)ns, 0.0); g->h_w.resize((size_t)ns, make_float2(1.f, 0.f));
     g->h_bp_en.resize((size_t)ns, 0);
     g->h_tail_mode.resize((size_t)ns, 0);
-    ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
+    ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f; idle.agc_thr = 0.8f;
     g->h_cfg.resize((size_t)ns, idle);
     g->cfg_dirty = true;
     return OWRX_OK;
@@ -459,13 +494,13 @@ inline dim3 grid2d(int slots, size_t rows) { return dim3((unsigned)((slots + 31)
 const dim3 kBlock2d(32, 4);
 constexpr size_t kRowChunk = 4 * 65535;
 
-// Runs every stage of one group on `n_avail` wideband samples starting at `iq` (device).
+// K3 pass of one group over `n_avail` wideband samples starting at `iq` (device), on stream `st`:
+// Shift + FirDecimate for every channel, appended to s1.  May be called several times (chunked host
+// feeds) before group_tail runs the remaining stages over all pending rows.
 // Returns the number of wideband samples consumed (n_k * D).
-int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_t* consumed)
+int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_t* consumed, cudaStream_t st)
 {
-    cudaStream_t st = bank->stream;
     *consumed = 0;
-    g->last_audio = g->last_demod = g->last_if = g->last_blocks = 0;
     if (n_avail < (size_t)g->T) return OWRX_OK;
     const size_t n_k = (n_avail - (size_t)g->T) / (size_t)g->D + 1;
     if (n_k > (size_t)0x7fffffff) return fail(OWRX_E_INVALID, "block too large");
@@ -543,9 +578,32 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
         OWRX_LAUNCH_CHECK();
         bank->stats.kernel_launches++;
     }
-    const long long s1_first = g->s1.abs_end;
+    if (g->pend_rows == 0) g->pend_first = g->s1.abs_end;
     g->s1.appended(n_k);
+    g->pend_rows += n_k;
     *consumed = n_k * (size_t)g->D;
+
+    // ---- advance NCO phases
+    for (int s = 0; s < S; s++) {
+        const int cid = g->slot_chan[(size_t)s];
+        if (cid < 0) continue;
+        Chan* ch = bank->chans[(size_t)cid].get();
+        double ph = ch->phase + ch->rate * (double)(*consumed);
+        ch->phase = ph - floor(ph);
+    }
+    return OWRX_OK;
+}
+
+// Every stage after FirDecimate, over the s1 rows appended since the last call, on stream `st`.
+int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
+{
+    g->last_audio = g->last_demod = g->last_if = g->last_blocks = 0;
+    const size_t n_k = g->pend_rows;
+    const long long s1_first = g->pend_first;
+    g->pend_rows = 0;
+    if (!n_k) return OWRX_OK;
+    const int S = g->slots;
+    int rc;
 
     // ---- FractionalDecimator (complex)
     const StageBuf* bp_in = &g->s1;
@@ -723,23 +781,15 @@ int group_run(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
         g->last_audio = n_audio;
     }
 
-    // ---- advance NCO phases
-    for (int s = 0; s < S; s++) {
-        const int cid = g->slot_chan[(size_t)s];
-        if (cid < 0) continue;
-        Chan* ch = bank->chans[(size_t)cid].get();
-        double ph = ch->phase + ch->rate * (double)(*consumed);
-        ch->phase = ph - floor(ph);
-    }
     return OWRX_OK;
 }
 
 // after outputs were taken: drop f2/f3 rows, keep histories
-int group_roll(owrx_bank* bank, Group* g)
+int group_roll_s1(Group* g, cudaStream_t st) { return g->s1.roll(g->s1.hist, st); }
+
+int group_roll_rest(Group* g, cudaStream_t st)
 {
-    cudaStream_t st = bank->stream;
     int rc;
-    if ((rc = g->s1.roll(g->s1.hist, st)) != OWRX_OK) return rc;
     if (g->has_frac && (rc = g->s2.roll(g->s2.hist, st)) != OWRX_OK) return rc;
     if ((rc = g->s3.roll(g->s3.hist, st)) != OWRX_OK) return rc;
     if ((rc = g->f1.roll(g->f1.hist, st)) != OWRX_OK) return rc;
@@ -765,24 +815,32 @@ int ensure_stage(owrx_bank* bank, size_t floats)
     return OWRX_OK;
 }
 
-// copy rows [row0, row0+n) of a stage buffer to the host and scatter per channel
+// rows [n][slots] of `width`-float elements -> channel-major [slots][n] on the device, one D2H copy, then
+// one contiguous append per channel
 int drain_to_queues(owrx_bank* bank, Group* g, const float* dev_rows, size_t n, int width, int which)
 {
     if (!n) return OWRX_OK;
     const size_t floats = n * (size_t)g->slots * width;
     int rc = ensure_stage(bank, floats);
     if (rc != OWRX_OK) return rc;
-    OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, dev_rows, floats * sizeof(float), cudaMemcpyDeviceToHost, bank->stream));
+    if (floats > bank->d_xpose_cap) {
+        cudaFree(bank->d_xpose); bank->d_xpose = nullptr; bank->d_xpose_cap = 0;
+        OWRX_CUDA(cudaMalloc((void**)&bank->d_xpose, floats * sizeof(float)));
+        bank->d_xpose_cap = floats;
+    }
+    const dim3 grid((unsigned)((g->slots + 31) / 32), (unsigned)((n + 31) / 32));
+    if (width == 1) transpose_kernel<float><<<grid, dim3(32, 8), 0, bank->stream>>>(dev_rows, g->slots, n, bank->d_xpose);
+    else transpose_kernel<float2><<<grid, dim3(32, 8), 0, bank->stream>>>(reinterpret_cast<const float2*>(dev_rows), g->slots, n,
+                                                                         reinterpret_cast<float2*>(bank->d_xpose));
+    OWRX_LAUNCH_CHECK();
+    OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, bank->d_xpose, floats * sizeof(float), cudaMemcpyDeviceToHost, bank->stream));
     OWRX_CUDA(cudaStreamSynchronize(bank->stream));
     for (int s = 0; s < g->slots; s++) {
         const int cid = g->slot_chan[(size_t)s];
         if (cid < 0) continue;
         Chan* ch = bank->chans[(size_t)cid].get();
-        std::deque<float>& q = which == 0 ? ch->q_audio : (which == 1 ? ch->q_demod : (which == 2 ? ch->q_if : ch->q_power));
-        const float* src = bank->h_stage + (size_t)s * width;
-        const size_t stride = (size_t)g->slots * width;
-        for (size_t i = 0; i < n; i++)
-            for (int w = 0; w < width; w++) q.push_back(src[i * stride + w]);
+        FQ& q = which == 0 ? ch->q_audio : (which == 1 ? ch->q_demod : (which == 2 ? ch->q_if : ch->q_power));
+        q.push(bank->h_stage + (size_t)s * n * width, n * width);
     }
     return OWRX_OK;
 }
@@ -817,13 +875,9 @@ int drain_tail(owrx_bank* bank, Group* g)
     return OWRX_OK;
 }
 
-int pop_queue(std::deque<float>& q, float* out, size_t cap, size_t* n, size_t unit)
+int pop_queue(FQ& q, float* out, size_t cap, size_t* n, size_t unit)
 {
-    size_t take = std::min(cap * unit, q.size());
-    take -= take % unit;
-    std::copy(q.begin(), q.begin() + (ptrdiff_t)take, out);
-    q.erase(q.begin(), q.begin() + (ptrdiff_t)take);
-    *n = take / unit;
+    *n = q.pop(out, cap * unit, unit) / unit;
     return OWRX_OK;
 }
 
@@ -842,8 +896,13 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (!b) return fail(OWRX_E_NOMEM, "out of host memory");
     b->device = device; b->sm_count = sm; b->input_rate = input_rate;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fir_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->tail_done[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->tail_done[1], cudaEventDisableTiming);
     if (e != cudaSuccess) { owrx_bank_destroy(b); return fail(OWRX_E_CUDA, "stream/event create: %s", cudaGetErrorString(e)); }
     *out = b;
     return OWRX_OK;
@@ -853,9 +912,15 @@ void owrx_bank_destroy(owrx_bank_t* bank)
 {
     if (!bank) return;
     cudaSetDevice(bank->device);
-    if (bank->stream) cudaStreamSynchronize(bank->stream);
+    cudaDeviceSynchronize();
     for (auto& g : bank->groups) if (g) group_release(g.get());
-    cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]);
+    cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]); cudaFree(bank->d_xpose);
+    for (cudaEvent_t e : bank->chunk_events) cudaEventDestroy(e);
+    if (bank->fir_done) cudaEventDestroy(bank->fir_done);
+    if (bank->tail_done[0]) cudaEventDestroy(bank->tail_done[0]);
+    if (bank->tail_done[1]) cudaEventDestroy(bank->tail_done[1]);
+    if (bank->copy_stream) cudaStreamDestroy(bank->copy_stream);
+    if (bank->side_stream) cudaStreamDestroy(bank->side_stream);
     if (bank->h_stage) cudaFreeHost(bank->h_stage);
     if (bank->ev0) cudaEventDestroy(bank->ev0);
     if (bank->ev1) cudaEventDestroy(bank->ev1);
@@ -904,7 +969,7 @@ int owrx_bank_remove_channel(owrx_bank_t* bank, int chan)
     if (ch->group >= 0) {
         Group* g = bank->groups[(size_t)ch->group].get();
         g->slot_chan[(size_t)ch->slot] = -1;
-        ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f;
+        ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f; idle.agc_thr = 0.8f;
         g->h_cfg[(size_t)ch->slot] = idle;
         g->h_bp_en[(size_t)ch->slot] = 0;
         g->h_tail_mode[(size_t)ch->slot] = 0;
@@ -1066,6 +1131,35 @@ int owrx_bank_set_outputs(owrx_bank_t* bank, int mask)
     return OWRX_OK;
 }
 
+// host -> queues for one group after its tail pass
+static int group_drain(owrx_bank* bank, Group* g)
+{
+    cudaStream_t st = bank->stream;
+    int rc;
+    if ((bank->out_mask & OWRX_OUT_AUDIO) && (rc = drain_to_queues(bank, g, g->f3.rows(g->f3.fill - g->last_audio), g->last_audio, 1, 0))) return rc;
+    if (g->any_tail && g->tail_ran && g->last_audio && (rc = drain_tail(bank, g)) != OWRX_OK) return rc;
+    if ((bank->out_mask & OWRX_OUT_DEMOD) && (rc = drain_to_queues(bank, g, g->f2.rows(g->f2.fill - g->last_demod), g->last_demod, 1, 1))) return rc;
+    if ((bank->out_mask & OWRX_OUT_IF) && (rc = drain_to_queues(bank, g, g->s3.rows(g->s3.fill - g->last_if), g->last_if, 2, 2))) return rc;
+    if ((bank->out_mask & OWRX_OUT_POWER) && g->last_blocks) {
+        // reportInterval = measurementsPerSec / readingsPerSec = 4 (selector.py:108-109,126)
+        const size_t nb = g->last_blocks;
+        if ((rc = ensure_stage(bank, nb * (size_t)g->slots)) != OWRX_OK) return rc;
+        OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, g->d_power, nb * (size_t)g->slots * sizeof(float), cudaMemcpyDeviceToHost, st));
+        OWRX_CUDA(cudaStreamSynchronize(st));
+        for (size_t b = 0; b < nb; b++) {
+            if (((g->sq_block_abs + (long long)b) % 4) != 0) continue;
+            for (int s = 0; s < g->slots; s++) {
+                const int cid = g->slot_chan[(size_t)s];
+                if (cid >= 0) bank->chans[(size_t)cid]->q_power.push_back(bank->h_stage[b * (size_t)g->slots + s]);
+            }
+        }
+    }
+    g->sq_block_abs += (long long)g->last_blocks;
+    return OWRX_OK;
+}
+
+// Host path.  The block is uploaded in chunks on a copy stream; the K3 pass of chunk c runs while chunk
+// c+1 is still crossing PCIe.  The low-rate stages run once over everything the chunks produced.
 int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
 {
     if (!bank || (!iq && n_samples)) return fail(OWRX_E_INVALID, "NULL argument");
@@ -1091,47 +1185,50 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     }
     float2* buf = bank->d_iq[bank->iq_cur];
     OWRX_CUDA(cudaEventRecord(bank->ev0, st));
-    OWRX_CUDA(cudaMemcpyAsync(buf + bank->iq_fill, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, st));
+    // chunks of ~4 M samples keep K3 at a full wave of CTAs; small feeds are a single chunk
+    const size_t chunk = (size_t)1 << 22;
+    const size_t n_chunks = std::max<size_t>(1, (n_samples + chunk - 1) / chunk);
+    while (bank->chunk_events.size() < n_chunks) {
+        cudaEvent_t e;
+        OWRX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        bank->chunk_events.push_back(e);
+    }
+    // the copy stream must not overwrite the buffer before earlier work on `st` (carry copy) is done
+    OWRX_CUDA(cudaEventRecord(bank->fir_done, st));
+    OWRX_CUDA(cudaStreamWaitEvent(bank->copy_stream, bank->fir_done, 0));
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t o = c * chunk, len = std::min(chunk, n_samples - o);
+        if (len) OWRX_CUDA(cudaMemcpyAsync(buf + bank->iq_fill + o, iq + 2 * o, len * sizeof(float2), cudaMemcpyHostToDevice, bank->copy_stream));
+        OWRX_CUDA(cudaEventRecord(bank->chunk_events[c], bank->copy_stream));
+    }
+    int rc;
+    const size_t fill0 = bank->iq_fill;
+    for (auto& gp : bank->groups) if (gp) { if ((rc = group_roll_s1(gp.get(), st)) != OWRX_OK) return rc; }
+    for (size_t c = 0; c < n_chunks; c++) {
+        OWRX_CUDA(cudaStreamWaitEvent(st, bank->chunk_events[c], 0));
+        const size_t avail = fill0 + std::min(n_samples, (c + 1) * chunk);
+        for (auto& gp : bank->groups) {
+            Group* g = gp.get();
+            if (!g) continue;
+            size_t consumed = 0;
+            if ((rc = group_fir(bank, g, buf + g->in_off, avail - g->in_off, &consumed, st)) != OWRX_OK) return rc;
+            g->in_off += consumed;
+            int live = 0;
+            for (int cid : g->slot_chan) if (cid >= 0) live++;
+            bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
+        }
+    }
     bank->iq_fill += n_samples;
     size_t min_off = bank->iq_fill;
-    int rc;
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
         if (!g) continue;
-        size_t consumed = 0;
-        if ((rc = group_run(bank, g, buf + g->in_off, bank->iq_fill - g->in_off, &consumed)) != OWRX_OK) return rc;
-        g->in_off += consumed;
         min_off = std::min(min_off, g->in_off);
-        int live = 0;
-        for (int cid : g->slot_chan) if (cid >= 0) live++;
-        bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
+        if ((rc = group_roll_rest(g, st)) != OWRX_OK) return rc;
+        if ((rc = group_tail(bank, g, st)) != OWRX_OK) return rc;
     }
     OWRX_CUDA(cudaEventRecord(bank->ev1, st));
-    // outputs -> host queues
-    for (auto& gp : bank->groups) {
-        Group* g = gp.get();
-        if (!g) continue;
-        if ((bank->out_mask & OWRX_OUT_AUDIO) && (rc = drain_to_queues(bank, g, g->f3.rows(g->f3.fill - g->last_audio), g->last_audio, 1, 0))) return rc;
-        if (g->any_tail && g->tail_ran && g->last_audio && (rc = drain_tail(bank, g)) != OWRX_OK) return rc;
-        if ((bank->out_mask & OWRX_OUT_DEMOD) && (rc = drain_to_queues(bank, g, g->f2.rows(g->f2.fill - g->last_demod), g->last_demod, 1, 1))) return rc;
-        if ((bank->out_mask & OWRX_OUT_IF) && (rc = drain_to_queues(bank, g, g->s3.rows(g->s3.fill - g->last_if), g->last_if, 2, 2))) return rc;
-        if ((bank->out_mask & OWRX_OUT_POWER) && g->last_blocks) {
-            // reportInterval = measurementsPerSec / readingsPerSec = 4 (selector.py:108-109,126)
-            const size_t nb = g->last_blocks;
-            if ((rc = ensure_stage(bank, nb * (size_t)g->slots)) != OWRX_OK) return rc;
-            OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, g->d_power, nb * (size_t)g->slots * sizeof(float), cudaMemcpyDeviceToHost, st));
-            OWRX_CUDA(cudaStreamSynchronize(st));
-            for (size_t b = 0; b < nb; b++) {
-                if (((g->sq_block_abs + (long long)b) % 4) != 0) continue;
-                for (int s = 0; s < g->slots; s++) {
-                    const int cid = g->slot_chan[(size_t)s];
-                    if (cid >= 0) bank->chans[(size_t)cid]->q_power.push_back(bank->h_stage[b * (size_t)g->slots + s]);
-                }
-            }
-        }
-        g->sq_block_abs += (long long)g->last_blocks;
-        if ((rc = group_roll(bank, g)) != OWRX_OK) return rc;
-    }
+    for (auto& gp : bank->groups) if (gp && (rc = group_drain(bank, gp.get())) != OWRX_OK) return rc;
     // drop consumed wideband samples
     if (min_off > 0) {
         const size_t tail = bank->iq_fill - min_off;
@@ -1147,29 +1244,70 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     return OWRX_OK;
 }
 
+// Device-resident path.  With owrx_bank_set_pipelined(bank, 1) the low-rate stages of block i run on
+// the bank's side stream while the K3 pass of block i+1 runs on the caller's stream; owrx_bank_join
+// makes a stream wait for everything issued so far.
 int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_samples, void* stream)
 {
     if (!bank || !iq_dev) return fail(OWRX_E_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(bank->mu);
     OWRX_CUDA(cudaSetDevice(bank->device));
-    cudaStream_t own = bank->stream;
-    if (stream) bank->stream = (cudaStream_t)stream;
+    cudaStream_t sa = stream ? (cudaStream_t)stream : bank->stream;
+    cudaStream_t sb = bank->pipelined ? bank->side_stream : sa;
+    const int par = (int)(bank->calls & 1);
     int rc = OWRX_OK;
+    if (bank->pipelined) {
+        // s1 ping-pong: this block's K3 writes the buffer the tail of two blocks ago was reading
+        OWRX_CUDA(cudaStreamWaitEvent(sa, bank->tail_done[par], 0));
+    }
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
         if (!g) continue;
         size_t consumed = 0;
-        // previous block's outputs are dropped; histories stay
-        if ((rc = group_roll(bank, g)) != OWRX_OK) break;
-        if ((rc = group_run(bank, g, (const float2*)iq_dev, n_samples, &consumed)) != OWRX_OK) break;
+        if (g->cfg_dirty && bank->pipelined) OWRX_CUDA(cudaStreamSynchronize(sb));
+        if ((rc = group_roll_s1(g, sa)) != OWRX_OK) return rc;
+        if ((rc = group_fir(bank, g, (const float2*)iq_dev, n_samples, &consumed, sa)) != OWRX_OK) return rc;
         int live = 0;
         for (int cid : g->slot_chan) if (cid >= 0) live++;
         bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
+    }
+    if (bank->pipelined) {
+        OWRX_CUDA(cudaEventRecord(bank->fir_done, sa));
+        OWRX_CUDA(cudaStreamWaitEvent(sb, bank->fir_done, 0));
+    }
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        // previous block's outputs are dropped; histories stay
+        if ((rc = group_roll_rest(g, sb)) != OWRX_OK) return rc;
+        if ((rc = group_tail(bank, g, sb)) != OWRX_OK) return rc;
         g->sq_block_abs += (long long)g->last_blocks;
     }
+    if (bank->pipelined) OWRX_CUDA(cudaEventRecord(bank->tail_done[par], sb));   // awaited by the call after next
+    bank->calls++;
     bank->stats.input_samples += n_samples;
-    bank->stream = own;
     return rc;
+}
+
+int owrx_bank_set_pipelined(owrx_bank_t* bank, int enable)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    OWRX_CUDA(cudaDeviceSynchronize());
+    bank->pipelined = enable != 0;
+    return OWRX_OK;
+}
+
+int owrx_bank_join(owrx_bank_t* bank, void* stream)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    cudaStream_t sa = stream ? (cudaStream_t)stream : bank->stream;
+    OWRX_CUDA(cudaStreamWaitEvent(sa, bank->tail_done[0], 0));
+    OWRX_CUDA(cudaStreamWaitEvent(sa, bank->tail_done[1], 0));
+    return OWRX_OK;
 }
 
 int owrx_bank_last_audio_count(const owrx_bank_t* bank, int chan, size_t* n)

@@ -315,6 +315,7 @@ struct ChanCfg {
     float agc_ref, agc_attack, agc_decay, agc_max;
     int agc_hang_time;
     int active;
+    float agc_thr;      // largest float a with fl(a / agc_ref) <= 1: "err > 1" <=> abs(v)*gain > agc_thr, exactly
 };
 
 // Squelch.  Block power = mean |x|^2 over every `decim`-th sample: one thread per (block, slot),
@@ -538,20 +539,18 @@ agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __rest
             nxt[t] = i < n ? in[(size_t)i * slots + s] : 0.f;
         }
         if (!bypass) {
+            // branch-free (lanes are different channels: any branch here would diverge every sample)
 #pragma unroll
             for (int t = 0; t < SER_TT; t++) {
                 const float v = cur[t];
-                // padded zeros leave the state untouched (v == 0 is skipped by the algorithm itself)
-                if (v != 0.f) {
-                    const float err = fabsf(v) * gain / c.agc_ref;
-                    const float g_dn = gain * dn;
-                    const float g_up = gain * up;
-                    if (err > 1.f) { gain = g_dn; hang = c.agc_hang_time; }
-                    else if (hang > 0) hang--;
-                    else gain = g_up;
-                }
-                gain = fminf(gain, c.agc_max);
-                gain = fmaxf(gain, 0.f);
+                const bool nz = v != 0.f;                               // zeros are skipped by the algorithm itself
+                const bool att = nz && (fabsf(v) * gain > c.agc_thr);   // == (fabsf(v) * gain / ref > 1)
+                const bool idle = !nz || (!att && hang > 0);
+                const float g_dn = fmaxf(fminf(gain * dn, c.agc_max), 0.f);
+                const float g_up = fmaxf(fminf(gain * up, c.agc_max), 0.f);
+                const float g_id = fmaxf(fminf(gain, c.agc_max), 0.f);
+                hang = att ? c.agc_hang_time : ((nz && hang > 0) ? hang - 1 : hang);
+                gain = att ? g_dn : (idle ? g_id : g_up);
                 cur[t] = fminf(1.f, fmaxf(-1.f, v * gain));
             }
         }
@@ -562,6 +561,26 @@ agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __rest
     if (!bypass) {
         st[s].agc_gain = gain;
         st[s].agc_hang = hang;
+    }
+}
+
+// [n][slots] -> [slots][n] (output drain: one contiguous run per channel for the host)
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int slots, size_t n, T* __restrict__ out)
+{
+    __shared__ T tile[32][33];
+    const int s0 = blockIdx.x * 32;
+    const size_t i0 = (size_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const size_t i = i0 + r;
+        const int sl = s0 + threadIdx.x;
+        if (i < n && sl < slots) tile[r][threadIdx.x] = in[i * slots + sl];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int sl = s0 + r;
+        const size_t i = i0 + threadIdx.x;
+        if (i < n && sl < slots) out[(size_t)sl * n + i] = tile[threadIdx.x][r];
     }
 }
 
