@@ -535,7 +535,8 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     const size_t fixed = (size_t)nparts * ncg;
     // input-stationary ranges of JB blocks (>= 28 so that an output straddles at most two ranges)
     const size_t n_blocks = n_k + K3_PP - 1;
-    size_t n_ranges = std::max<size_t>(1, ((size_t)bank->sm_count + fixed - 1) / fixed);
+    const size_t sms = (size_t)bank->sm_count - (bank->pipelined ? 1 : 0);
+    size_t n_ranges = std::max<size_t>(1, sms / fixed);
     n_ranges = std::min(n_ranges, std::max<size_t>(1, n_blocks / K3_PP));
     const int JB = (int)((n_blocks + n_ranges - 1) / n_ranges);
     n_ranges = (n_blocks + JB - 1) / JB;
@@ -752,6 +753,20 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
             n_audio = cnt;
         }
         g->last_demod = n_audio;
+        g->last_audio = n_audio;
+    }
+    return OWRX_OK;
+}
+
+// The sample-serial end of the chain (Agc, then the client audio tail) over the rows group_tail produced.
+// One warp per 32 channels: negligible resources, so it may run on a side stream beside the next K3 pass.
+int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
+{
+    const int S = g->slots;
+    const size_t n_audio = g->last_audio;
+    int rc;
+    g->tail_ran = false;
+    {
         // ---- Agc -> f3
         if (n_audio) {
             if ((rc = g->f3.ensure_new(n_audio, st)) != OWRX_OK) return rc;
@@ -760,7 +775,6 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
             OWRX_LAUNCH_CHECK();
             bank->stats.kernel_launches++;
             g->f3.appended(n_audio);
-            g->tail_ran = false;
             if (g->any_tail) {
                 // ---- client audio tail: Convert(FLOAT, SHORT) [+ AdpcmEncoder(sync=True)]
                 const int cap = (int)(n_audio / 2 + 8 * (n_audio / 2002 + 2) + 16);
@@ -778,9 +792,7 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
                 g->tail_ran = true;
             }
         }
-        g->last_audio = n_audio;
     }
-
     return OWRX_OK;
 }
 
@@ -1226,6 +1238,7 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
         min_off = std::min(min_off, g->in_off);
         if ((rc = group_roll_rest(g, st)) != OWRX_OK) return rc;
         if ((rc = group_tail(bank, g, st)) != OWRX_OK) return rc;
+        if ((rc = group_tail_serial(bank, g, st)) != OWRX_OK) return rc;
     }
     OWRX_CUDA(cudaEventRecord(bank->ev1, st));
     for (auto& gp : bank->groups) if (gp && (rc = group_drain(bank, gp.get())) != OWRX_OK) return rc;
@@ -1244,9 +1257,9 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     return OWRX_OK;
 }
 
-// Device-resident path.  With owrx_bank_set_pipelined(bank, 1) the low-rate stages of block i run on
-// the bank's side stream while the K3 pass of block i+1 runs on the caller's stream; owrx_bank_join
-// makes a stream wait for everything issued so far.
+// Device-resident path.  With owrx_bank_set_pipelined(bank, 1) the sample-serial stages of block i (Agc,
+// audio tail: one warp per 32 channels) run on the bank's side stream beside the K3 pass of block i+1,
+// which then leaves one SM free for them; owrx_bank_join makes a stream wait for everything issued so far.
 int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_samples, void* stream)
 {
     if (!bank || !iq_dev) return fail(OWRX_E_INVALID, "NULL argument");
@@ -1271,17 +1284,21 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         for (int cid : g->slot_chan) if (cid >= 0) live++;
         bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
     }
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        // previous block's outputs are dropped; histories stay
+        if ((rc = group_roll_rest(g, sa)) != OWRX_OK) return rc;
+        if ((rc = group_tail(bank, g, sa)) != OWRX_OK) return rc;
+        g->sq_block_abs += (long long)g->last_blocks;
+    }
     if (bank->pipelined) {
         OWRX_CUDA(cudaEventRecord(bank->fir_done, sa));
         OWRX_CUDA(cudaStreamWaitEvent(sb, bank->fir_done, 0));
     }
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
-        if (!g) continue;
-        // previous block's outputs are dropped; histories stay
-        if ((rc = group_roll_rest(g, sb)) != OWRX_OK) return rc;
-        if ((rc = group_tail(bank, g, sb)) != OWRX_OK) return rc;
-        g->sq_block_abs += (long long)g->last_blocks;
+        if (g && (rc = group_tail_serial(bank, g, sb)) != OWRX_OK) return rc;
     }
     if (bank->pipelined) OWRX_CUDA(cudaEventRecord(bank->tail_done[par], sb));   // awaited by the call after next
     bank->calls++;

@@ -479,88 +479,125 @@ fracdec_f_kernel(const float* __restrict__ in, long long in_abs0, int slots, dou
 }
 
 // Sample-serial recurrences run one channel per lane.  A lane's samples sit `slots` floats apart, so a
-// warp-wide load of one time step is coalesced; SER_TT time steps are fetched as independent loads
-// into registers (and the next tile is prefetched) before the dependent chain runs over them.
+// warp-wide access to one time step is coalesced.  The input is streamed through a per-warp shared
+// memory ring with cp.async, SER_STAGES-1 tiles of SER_TT time steps ahead of the dependent chain, so
+// the only latency left on the chain is the arithmetic itself.  Each lane only ever reads the column
+// it loaded itself: no barrier is needed.
 constexpr int SER_TT = 16;
+constexpr int SER_STAGES = 6;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct SerialFeed {
+    float (*ring)[SER_TT][32];
+    const float* in;
+    int slots, n, s, lane, nt;
+    __device__ void issue(int tile) const
+    {
+        if (tile < nt) {
+#pragma unroll
+            for (int t = 0; t < SER_TT; t++) {
+                const int i = tile * SER_TT + t;
+                if (i < n) cp_async4(&ring[tile % SER_STAGES][t][lane], in + (size_t)i * slots + s);
+            }
+        }
+        cp_async_commit();
+    }
+};
 
 // WfmDeemphasis one-pole IIR.
 __global__ void __launch_bounds__(32)
 wfm_deemph_kernel(const float* __restrict__ in, int slots, int n, float alpha, ChanState* __restrict__ st,
                   float* __restrict__ out)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= slots) return;
+    __shared__ float ring[SER_STAGES][SER_TT][32];
+    const int lane = threadIdx.x;
+    const int s = min(blockIdx.x * 32 + lane, slots - 1);
     float y = st[s].iir;
     const float om = 1.0f - alpha;
-    float cur[SER_TT], nxt[SER_TT];
+    SerialFeed f{ring, in, slots, n, s, lane, (n + SER_TT - 1) / SER_TT};
+    for (int k = 0; k < SER_STAGES - 1; k++) f.issue(k);
+    for (int tile = 0; tile < f.nt; tile++) {
+        f.issue(tile + SER_STAGES - 1);
+        cp_async_wait<SER_STAGES - 1>();
+        const int cnt = min(SER_TT, n - tile * SER_TT);
+        float v[SER_TT];
 #pragma unroll
-    for (int t = 0; t < SER_TT; t++) nxt[t] = t < n ? in[(size_t)t * slots + s] : 0.f;
-    for (int i0 = 0; i0 < n; i0 += SER_TT) {
+        for (int t = 0; t < SER_TT; t++) v[t] = t < cnt ? ring[tile % SER_STAGES][t][lane] : 0.f;
+        if (cnt == SER_TT) {
 #pragma unroll
-        for (int t = 0; t < SER_TT; t++) cur[t] = nxt[t];
-#pragma unroll
-        for (int t = 0; t < SER_TT; t++) {
-            const int i = i0 + SER_TT + t;
-            nxt[t] = i < n ? in[(size_t)i * slots + s] : 0.f;
+            for (int t = 0; t < SER_TT; t++) { y = alpha * v[t] + om * y; v[t] = y; }
+        } else {
+            for (int t = 0; t < cnt; t++) { y = alpha * v[t] + om * y; v[t] = y; }
         }
+        float* o = out + (size_t)tile * SER_TT * slots + s;
 #pragma unroll
-        for (int t = 0; t < SER_TT; t++) {
-            y = alpha * cur[t] + om * y;
-            if (i0 + t < n) out[(size_t)(i0 + t) * slots + s] = y; else y = y;
-            cur[t] = y;
-        }
+        for (int t = 0; t < SER_TT; t++)
+            if (t < cnt) o[(size_t)t * slots] = v[t];
     }
-    // the loop above over-runs the recurrence on padded zeros in the last tile: recompute the carried state exactly
-    if (n > 0) st[s].iir = out[(size_t)(n - 1) * slots + s];
+    st[s].iir = y;
 }
 
-// Agc (SPEC-DEFINED).  The gain recurrence is evaluated speculatively: both candidate gains
-// are formed while the envelope comparison resolves, so the dependent chain is mul -> select per sample.
+// Agc (SPEC-DEFINED).  Branch-free (lanes are different channels: a branch would diverge on
+// every sample); all three candidate gains are formed while the envelope comparison resolves, so the
+// sample-to-sample dependency is multiply -> compare -> select.
+struct AgcRun {
+    float gain, dn, up, thr, gmax;
+    int hang, hang_time;
+    __device__ __forceinline__ float step(float v)
+    {
+        const bool nz = v != 0.f;                           // zeros are skipped by the algorithm itself
+        const bool att = nz && (fabsf(v) * gain > thr);     // == (fabsf(v) * gain / ref > 1), exactly
+        const bool idle = !nz || (!att && hang > 0);
+        const float g_dn = fmaxf(fminf(gain * dn, gmax), 0.f);
+        const float g_up = fmaxf(fminf(gain * up, gmax), 0.f);
+        const float g_id = fmaxf(fminf(gain, gmax), 0.f);
+        hang = att ? hang_time : ((nz && hang > 0) ? hang - 1 : hang);
+        gain = att ? g_dn : (idle ? g_id : g_up);
+        return fminf(1.f, fmaxf(-1.f, v * gain));
+    }
+};
+
 __global__ void __launch_bounds__(32)
 agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st,
            float* __restrict__ out)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= slots) return;
+    __shared__ float ring[SER_STAGES][SER_TT][32];
+    const int lane = threadIdx.x;
+    const int s = min(blockIdx.x * 32 + lane, slots - 1);
     const ChanCfg c = cfg[s];
     const bool bypass = c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE;
-    float gain = st[s].agc_gain;
-    int hang = st[s].agc_hang;
-    const float dn = 1.f - c.agc_attack, up = 1.f + c.agc_decay;
-    float cur[SER_TT], nxt[SER_TT];
+    AgcRun a{st[s].agc_gain, 1.f - c.agc_attack, 1.f + c.agc_decay, c.agc_thr, c.agc_max, st[s].agc_hang, c.agc_hang_time};
+    SerialFeed f{ring, in, slots, n, s, lane, (n + SER_TT - 1) / SER_TT};
+    for (int k = 0; k < SER_STAGES - 1; k++) f.issue(k);
+    for (int tile = 0; tile < f.nt; tile++) {
+        f.issue(tile + SER_STAGES - 1);
+        cp_async_wait<SER_STAGES - 1>();
+        const int cnt = min(SER_TT, n - tile * SER_TT);
+        float v[SER_TT];
 #pragma unroll
-    for (int t = 0; t < SER_TT; t++) nxt[t] = t < n ? in[(size_t)t * slots + s] : 0.f;
-    for (int i0 = 0; i0 < n; i0 += SER_TT) {
-#pragma unroll
-        for (int t = 0; t < SER_TT; t++) cur[t] = nxt[t];
-#pragma unroll
-        for (int t = 0; t < SER_TT; t++) {
-            const int i = i0 + SER_TT + t;
-            nxt[t] = i < n ? in[(size_t)i * slots + s] : 0.f;
-        }
+        for (int t = 0; t < SER_TT; t++) v[t] = t < cnt ? ring[tile % SER_STAGES][t][lane] : 0.f;
         if (!bypass) {
-            // branch-free (lanes are different channels: any branch here would diverge every sample)
+            if (cnt == SER_TT) {
 #pragma unroll
-            for (int t = 0; t < SER_TT; t++) {
-                const float v = cur[t];
-                const bool nz = v != 0.f;                               // zeros are skipped by the algorithm itself
-                const bool att = nz && (fabsf(v) * gain > c.agc_thr);   // == (fabsf(v) * gain / ref > 1)
-                const bool idle = !nz || (!att && hang > 0);
-                const float g_dn = fmaxf(fminf(gain * dn, c.agc_max), 0.f);
-                const float g_up = fmaxf(fminf(gain * up, c.agc_max), 0.f);
-                const float g_id = fmaxf(fminf(gain, c.agc_max), 0.f);
-                hang = att ? c.agc_hang_time : ((nz && hang > 0) ? hang - 1 : hang);
-                gain = att ? g_dn : (idle ? g_id : g_up);
-                cur[t] = fminf(1.f, fmaxf(-1.f, v * gain));
+                for (int t = 0; t < SER_TT; t++) v[t] = a.step(v[t]);
+            } else {
+                for (int t = 0; t < cnt; t++) v[t] = a.step(v[t]);
             }
         }
+        float* o = out + (size_t)tile * SER_TT * slots + s;
 #pragma unroll
         for (int t = 0; t < SER_TT; t++)
-            if (i0 + t < n) out[(size_t)(i0 + t) * slots + s] = cur[t];
+            if (t < cnt) o[(size_t)t * slots] = v[t];
     }
     if (!bypass) {
-        st[s].agc_gain = gain;
-        st[s].agc_hang = hang;
+        st[s].agc_gain = a.gain;
+        st[s].agc_hang = a.hang;
     }
 }
 
