@@ -11,7 +11,9 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 SO = os.path.join(HERE, "libowrx_b200.so")
-SOURCES = ["core.cu", "waterfall.cu", "selector.cu"]
+SOURCES = ["core.cu", "waterfall.cu", "selector.cu", "k3_fir.cu"]
+# per-file extra flags: K3's FFMA2 loop is scheduled better by ptxas -O1 (see k3_fir.cu)
+EXTRA_FLAGS = {"k3_fir.cu": ["-Xptxas", "-O1"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
@@ -42,7 +44,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -6,7 +6,9 @@
 #include "selector_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <deque>
 #include <map>
 #include <memory>
@@ -200,6 +202,8 @@ struct Group {
     long long sq_block_abs = 0;                      // absolute squelch block counter (for report interval)
     // last run
     size_t last_audio = 0, last_demod = 0, last_if = 0, last_blocks = 0;
+    size_t pass_audio = 0;                           // audio rows produced by the last tail pass
+    size_t feed_blocks = 0;                          // squelch blocks processed so far in this feed
     size_t pend_rows = 0;                            // FirDecimate rows appended to s1 since the last tail pass
     long long pend_first = 0;
     // client audio tail (Convert / AdpcmEncoder)
@@ -233,7 +237,8 @@ struct owrx_bank {
     cudaStream_t copy_stream = nullptr, side_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t fir_done = nullptr, tail_done[2] = {nullptr, nullptr};
-    bool pipelined = false;
+    bool pipelined = false, reserve_sm = false;
+    std::vector<cudaEvent_t> fir_events;
     unsigned long long calls = 0;
     // optional per-kernel timing of K3 (CUDA events on the launching stream)
     bool profile = false;
@@ -520,14 +525,6 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     OWRX_CUDA(cudaMemcpyAsync(g->d_rate, g->h_rate.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     OWRX_CUDA(cudaMemcpyAsync(g->d_phase, g->h_phase.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     OWRX_CUDA(cudaMemcpyAsync(g->d_w, g->h_w.data(), (size_t)S * sizeof(float2), cudaMemcpyHostToDevice, st));
-    if (g->cfg_dirty) {
-        OWRX_CUDA(cudaMemcpyAsync(g->d_cfg, g->h_cfg.data(), (size_t)S * sizeof(ChanCfg), cudaMemcpyHostToDevice, st));
-        OWRX_CUDA(cudaMemcpyAsync(g->d_bp_en, g->h_bp_en.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st));
-        OWRX_CUDA(cudaMemcpyAsync(g->d_tail_mode, g->h_tail_mode.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st));
-        g->any_tail = false;
-        for (int m : g->h_tail_mode) if (m) g->any_tail = true;
-        g->cfg_dirty = false;
-    }
 
     // ---- K3: Shift + FirDecimate
     const int nparts = g->nseg * g->nrs;
@@ -535,7 +532,7 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     const size_t fixed = (size_t)nparts * ncg;
     // input-stationary ranges of JB blocks (>= 28 so that an output straddles at most two ranges)
     const size_t n_blocks = n_k + K3_PP - 1;
-    const size_t sms = (size_t)bank->sm_count - (bank->pipelined ? 1 : 0);
+    const size_t sms = (size_t)bank->sm_count - (bank->reserve_sm ? 1 : 0);
     size_t n_ranges = std::max<size_t>(1, sms / fixed);
     n_ranges = std::min(n_ranges, std::max<size_t>(1, n_blocks / K3_PP));
     const int JB = (int)((n_blocks + n_ranges - 1) / n_ranges);
@@ -554,7 +551,6 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     p.side = g->d_partial + (size_t)nparts * n_k * S;
     p.D = g->D; p.nseg = g->nseg; p.nrs = g->nrs; p.RB = g->RB; p.JB = JB; p.n_blocks = (int)n_blocks; p.n_k = (int)n_k; p.slots = S;
     const size_t smem = (size_t)g->RB * K3_PP * sizeof(float) + 2 * (size_t)g->RB * sizeof(float2) + 2 * K3_NW * 128 * sizeof(float);
-    OWRX_CUDA(cudaFuncSetAttribute(fir_decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (bank->profile) {
         if (bank->prof_used == bank->prof_events.size()) {
@@ -568,8 +564,7 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
         bank->prof_used++;
         OWRX_CUDA(cudaEventRecord(pe0, st));
     }
-    fir_decimate_kernel<<<dim3((unsigned)(n_ranges * nparts), (unsigned)ncg), K3_NW * 32, smem, st>>>(p);
-    OWRX_LAUNCH_CHECK();
+    if ((rc = launch_fir_decimate(p, dim3((unsigned)(n_ranges * nparts), (unsigned)ncg), smem, st)) != OWRX_OK) return rc;
     if (pe1) OWRX_CUDA(cudaEventRecord(pe1, st));
     bank->stats.kernel_launches++;
     {
@@ -598,7 +593,7 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
 // Every stage after FirDecimate, over the s1 rows appended since the last call, on stream `st`.
 int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
 {
-    g->last_audio = g->last_demod = g->last_if = g->last_blocks = 0;
+    g->pass_audio = 0;
     const size_t n_k = g->pend_rows;
     const long long s1_first = g->pend_first;
     g->pend_rows = 0;
@@ -646,29 +641,26 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
     }
     const size_t if_row0 = g->s3.fill;
     g->s3.appended(n2);
-    g->last_if = n2;
+    g->last_if += n2;
     (void)if_row0;
 
     // ---- Squelch over whole blocks
     const size_t pending = (size_t)(g->s3.abs_end - g->sq_abs);
     const size_t nb = pending / (size_t)g->sq_len;
     const size_t n4 = nb * (size_t)g->sq_len;
-    g->last_blocks = nb;
+    g->last_blocks += nb;
     if (nb) {
-        if (nb > g->blocks_cap) {
-            cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
-            g->blocks_cap = 0;
-            OWRX_CUDA(cudaMalloc((void**)&g->d_gate, nb * (size_t)S));
-            OWRX_CUDA(cudaMalloc((void**)&g->d_power, nb * (size_t)S * sizeof(float)));
-            OWRX_CUDA(cudaMalloc((void**)&g->d_dcmean, nb * (size_t)S * sizeof(float)));
-            OWRX_CUDA(cudaMalloc((void**)&g->d_dcprev, (size_t)S * sizeof(float)));
-            g->blocks_cap = nb;
-        }
+        if (g->feed_blocks + nb > g->blocks_cap) return fail(OWRX_E_STATE, "squelch scratch under-provisioned");
+        // per-block scratch of this pass sits behind the blocks of earlier passes of the same feed
+        unsigned char* const d_gate = g->d_gate + g->feed_blocks * (size_t)S;
+        float* const d_power = g->d_power + g->feed_blocks * (size_t)S;
+        float* const d_dcmean = g->d_dcmean + g->feed_blocks * (size_t)S;
+        g->feed_blocks += nb;
         const float2* sq_in = reinterpret_cast<const float2*>(g->s3.row_abs(g->sq_abs));
         const int hang_blocks = 2;                                       // hangLength = 2*blockLength, selector.py:124
-        squelch_power_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)nb), 128, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, g->d_power);
+        squelch_power_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)nb), 128, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, d_power);
         OWRX_LAUNCH_CHECK();
-        squelch_gate_kernel<<<(S + 127) / 128, 128, 0, st>>>(g->d_power, S, (int)nb, hang_blocks, g->d_cfg, g->d_state, g->d_gate);
+        squelch_gate_kernel<<<(S + 127) / 128, 128, 0, st>>>(d_power, S, (int)nb, hang_blocks, g->d_cfg, g->d_state, d_gate);
         OWRX_LAUNCH_CHECK();
         // ---- demodulator front -> f1
         if ((rc = g->f1.ensure_new(n4, st)) != OWRX_OK) return rc;
@@ -684,17 +676,17 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
                 const size_t c = std::min(chunk_rows, n4 - o);
                 // FM needs the previous row: for o > 0 it is in the buffer; state is only used at o == 0
                 demod_front_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(sq_in + o * S, S, (int)c, g->sq_len,
-                                                                      g->d_gate + (o / (size_t)g->sq_len) * S, g->d_cfg,
+                                                                      d_gate + (o / (size_t)g->sq_len) * S, g->d_cfg,
                                                                       g->d_state, g->f1.append_ptr() + o * S);
                 OWRX_LAUNCH_CHECK();
                 if (o + c < n4) {
                     // make the carried "last gated sample" right for the next chunk
                     demod_front_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(sq_in + o * S, S, (int)c, g->sq_len,
-                                                                              g->d_gate + (o / (size_t)g->sq_len) * S, g->d_state);
+                                                                              d_gate + (o / (size_t)g->sq_len) * S, g->d_state);
                     OWRX_LAUNCH_CHECK();
                 }
             }
-            demod_front_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(sq_in, S, (int)n4, g->sq_len, g->d_gate, g->d_state);
+            demod_front_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(sq_in, S, (int)n4, g->sq_len, d_gate, g->d_state);
             OWRX_LAUNCH_CHECK();
         }
         bank->stats.kernel_launches += 3;
@@ -707,7 +699,7 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
             // ---- demodulator back: NfmDeemphasis / DcBlock / copy -> f2 (pre-AGC)
             dc_mean_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)nb), 128, 0, st>>>(g->f1.row_abs(f1_first), S, (int)nb,
                                                                                         g->sq_len, g->d_cfg, g->d_state,
-                                                                                        g->d_dcmean, g->d_dcprev);
+                                                                                        d_dcmean, g->d_dcprev);
             OWRX_LAUNCH_CHECK();
             if ((rc = g->f2.ensure_new(n4, st)) != OWRX_OK) return rc;
             const size_t chunk_rows = std::max<size_t>((size_t)g->sq_len, (kRowChunk / (size_t)g->sq_len) * (size_t)g->sq_len);
@@ -715,12 +707,12 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
                 const size_t c = std::min(chunk_rows, n4 - o);
                 demod_back_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(g->f1.row_abs(f1_first + (long long)o), S, (int)c, g->sq_len,
                                                                      g->d_deemph, g->Td, g->d_cfg,
-                                                                     g->d_dcmean + (o / (size_t)g->sq_len) * S,
-                                                                     o == 0 ? g->d_dcprev : g->d_dcmean + (o / (size_t)g->sq_len - 1) * S,
+                                                                     d_dcmean + (o / (size_t)g->sq_len) * S,
+                                                                     o == 0 ? g->d_dcprev : d_dcmean + (o / (size_t)g->sq_len - 1) * S,
                                                                      g->f2.append_ptr() + o * S);
                 OWRX_LAUNCH_CHECK();
             }
-            dc_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, (int)nb, g->d_cfg, g->d_dcmean, g->d_state);
+            dc_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, (int)nb, g->d_cfg, d_dcmean, g->d_state);
             OWRX_LAUNCH_CHECK();
             bank->stats.kernel_launches += 3;
             g->f2.appended(n4);
@@ -752,8 +744,9 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
             g->f2.appended(cnt);
             n_audio = cnt;
         }
-        g->last_demod = n_audio;
-        g->last_audio = n_audio;
+        g->last_demod += n_audio;
+        g->last_audio += n_audio;
+        g->pass_audio = n_audio;
     }
     return OWRX_OK;
 }
@@ -763,9 +756,8 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
 int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
 {
     const int S = g->slots;
-    const size_t n_audio = g->last_audio;
+    const size_t n_audio = g->pass_audio;
     int rc;
-    g->tail_ran = false;
     {
         // ---- Agc -> f3
         if (n_audio) {
@@ -776,17 +768,12 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
             bank->stats.kernel_launches++;
             g->f3.appended(n_audio);
             if (g->any_tail) {
-                // ---- client audio tail: Convert(FLOAT, SHORT) [+ AdpcmEncoder(sync=True)]
-                const int cap = (int)(n_audio / 2 + 8 * (n_audio / 2002 + 2) + 16);
-                if (n_audio > g->tail_rows_cap || cap > g->tail_cap) {
-                    cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
-                    g->d_tail_s16 = nullptr; g->d_tail_bytes = nullptr; g->tail_rows_cap = 0; g->tail_cap = 0;
-                    OWRX_CUDA(cudaMalloc((void**)&g->d_tail_s16, n_audio * (size_t)S * sizeof(int16_t)));
-                    OWRX_CUDA(cudaMalloc((void**)&g->d_tail_bytes, (size_t)cap * S));
-                    g->tail_rows_cap = n_audio; g->tail_cap = cap;
-                }
+                // ---- client audio tail: Convert(FLOAT, SHORT) [+ AdpcmEncoder(sync=True)]; appends behind earlier passes
+                const size_t row0 = g->last_audio - n_audio;
+                if (g->last_audio > g->tail_rows_cap) return fail(OWRX_E_STATE, "audio tail scratch under-provisioned");
                 audio_tail_kernel<<<(S + 63) / 64, 64, 0, st>>>(g->f3.rows(g->f3.fill - n_audio), S, (int)n_audio, g->d_tail_mode,
-                                                               g->d_tail, g->d_tail_s16, g->d_tail_bytes, g->d_tail_count, g->tail_cap);
+                                                               g->d_tail, g->d_tail_s16 + row0 * (size_t)S, g->d_tail_bytes,
+                                                               g->d_tail_count, g->tail_cap);
                 OWRX_LAUNCH_CHECK();
                 bank->stats.kernel_launches++;
                 g->tail_ran = true;
@@ -796,18 +783,68 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
     return OWRX_OK;
 }
 
-// after outputs were taken: drop f2/f3 rows, keep histories
-int group_roll_s1(Group* g, cudaStream_t st) { return g->s1.roll(g->s1.hist, st); }
-
-int group_roll_rest(Group* g, cudaStream_t st)
+// Start of a feed / device block: drop the previous outputs (histories stay), reset the per-feed counters and
+// provision every buffer for up to `rows` new FirDecimate outputs so that nothing reallocates while the
+// streams overlap.
+int group_begin_feed(owrx_bank* bank, Group* g, size_t rows, cudaStream_t st_fir, cudaStream_t st_tail)
 {
+    const int S = g->slots;
     int rc;
-    if (g->has_frac && (rc = g->s2.roll(g->s2.hist, st)) != OWRX_OK) return rc;
-    if ((rc = g->s3.roll(g->s3.hist, st)) != OWRX_OK) return rc;
-    if ((rc = g->f1.roll(g->f1.hist, st)) != OWRX_OK) return rc;
-    if (g->wfm) g->f1b.roll(0, st);
-    g->f2.roll(0, st);
-    g->f3.roll(0, st);
+    if (g->cfg_dirty) {
+        // retune / re-filter / mode change since the last block: per-channel tables are consumed by kernels on
+        // both streams, so quiesce the device before replacing them
+        OWRX_CUDA(cudaDeviceSynchronize());
+        OWRX_CUDA(cudaMemcpy(g->d_cfg, g->h_cfg.data(), (size_t)S * sizeof(ChanCfg), cudaMemcpyHostToDevice));
+        OWRX_CUDA(cudaMemcpy(g->d_bp_en, g->h_bp_en.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
+        OWRX_CUDA(cudaMemcpy(g->d_tail_mode, g->h_tail_mode.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
+        g->any_tail = false;
+        for (int m : g->h_tail_mode) if (m) g->any_tail = true;
+        g->cfg_dirty = false;
+    }
+    const size_t blocks = rows / (size_t)g->sq_len + 2;
+    const size_t low = rows + (size_t)g->sq_len + 64;           // rows any low-rate stage can append in one feed
+    if ((rc = g->s1.roll(g->s1.hist, st_fir)) != OWRX_OK) return rc;
+    if (g->has_frac && (rc = g->s2.roll(g->s2.hist, st_tail)) != OWRX_OK) return rc;
+    if ((rc = g->s3.roll(g->s3.hist, st_tail)) != OWRX_OK) return rc;
+    if ((rc = g->f1.roll(g->f1.hist, st_tail)) != OWRX_OK) return rc;
+    if (g->wfm) g->f1b.roll(0, st_tail);
+    g->f2.roll(0, st_tail);
+    g->f3.roll(0, st_tail);
+    g->last_audio = g->last_demod = g->last_if = g->last_blocks = 0;
+    g->pass_audio = 0; g->feed_blocks = 0; g->tail_ran = false;
+    const bool grow = g->s1.fill + rows > g->s1.cap_rows || (g->has_frac && g->s2.fill + low > g->s2.cap_rows) ||
+                      g->s3.fill + low > g->s3.cap_rows || g->f1.fill + low > g->f1.cap_rows || low > g->f2.cap_rows ||
+                      low > g->f3.cap_rows || (g->wfm && low > g->f1b.cap_rows) || blocks > g->blocks_cap ||
+                      (g->any_tail && low > g->tail_rows_cap);
+    if (grow) {
+        OWRX_CUDA(cudaDeviceSynchronize());
+        if ((rc = g->s1.ensure_new(rows, st_fir)) != OWRX_OK) return rc;
+        if (g->has_frac && (rc = g->s2.ensure_new(low, st_tail)) != OWRX_OK) return rc;
+        if ((rc = g->s3.ensure_new(low, st_tail)) != OWRX_OK) return rc;
+        if ((rc = g->f1.ensure_new(low, st_tail)) != OWRX_OK) return rc;
+        if (g->wfm && (rc = g->f1b.ensure_new(low, st_tail)) != OWRX_OK) return rc;
+        if ((rc = g->f2.ensure_new(low, st_tail)) != OWRX_OK) return rc;
+        if ((rc = g->f3.ensure_new(low, st_tail)) != OWRX_OK) return rc;
+        if (blocks > g->blocks_cap) {
+            cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
+            g->d_gate = nullptr; g->d_power = nullptr; g->d_dcmean = nullptr; g->d_dcprev = nullptr; g->blocks_cap = 0;
+            OWRX_CUDA(cudaMalloc((void**)&g->d_gate, blocks * (size_t)S));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_power, blocks * (size_t)S * sizeof(float)));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_dcmean, blocks * (size_t)S * sizeof(float)));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_dcprev, (size_t)S * sizeof(float)));
+            g->blocks_cap = blocks;
+        }
+        if (g->any_tail && low > g->tail_rows_cap) {
+            const int cap = (int)(low / 2 + 8 * (low / 2002 + 2) + 16);
+            cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
+            g->d_tail_s16 = nullptr; g->d_tail_bytes = nullptr; g->tail_rows_cap = 0; g->tail_cap = 0;
+            OWRX_CUDA(cudaMalloc((void**)&g->d_tail_s16, low * (size_t)S * sizeof(int16_t)));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_tail_bytes, (size_t)cap * S));
+            g->tail_rows_cap = low; g->tail_cap = cap;
+        }
+        OWRX_CUDA(cudaDeviceSynchronize());
+    }
+    if (g->any_tail) OWRX_CUDA(cudaMemsetAsync(g->d_tail_count, 0, (size_t)S * sizeof(int), st_tail));
     return OWRX_OK;
 }
 
@@ -928,6 +965,7 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     for (auto& g : bank->groups) if (g) group_release(g.get());
     cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]); cudaFree(bank->d_xpose);
     for (cudaEvent_t e : bank->chunk_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : bank->fir_events) cudaEventDestroy(e);
     if (bank->fir_done) cudaEventDestroy(bank->fir_done);
     if (bank->tail_done[0]) cudaEventDestroy(bank->tail_done[0]);
     if (bank->tail_done[1]) cudaEventDestroy(bank->tail_done[1]);
@@ -1178,6 +1216,11 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     std::lock_guard<std::mutex> lk(bank->mu);
     OWRX_CUDA(cudaSetDevice(bank->device));
     cudaStream_t st = bank->stream;
+    static const bool trace = getenv("OWRX_TRACE") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace) fprintf(stderr, "[owrx feed] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
+    };
     bool any = false;
     for (auto& g : bank->groups) if (g) any = true;
     if (!any) return OWRX_OK;                         // nobody listening: samples are dropped like an unread ring
@@ -1215,7 +1258,25 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     }
     int rc;
     const size_t fill0 = bank->iq_fill;
-    for (auto& gp : bank->groups) if (gp) { if ((rc = group_roll_s1(gp.get(), st)) != OWRX_OK) return rc; }
+    // with several chunks the low-rate stages of chunk c run on the side stream beside the K3 pass of chunk c+1
+    const bool overlap = n_chunks > 1;
+    cudaStream_t tails = overlap ? bank->side_stream : st;
+    bank->reserve_sm = overlap;
+    if (overlap) {
+        OWRX_CUDA(cudaEventRecord(bank->fir_done, st));
+        OWRX_CUDA(cudaStreamWaitEvent(tails, bank->fir_done, 0));
+    }
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        const size_t rows = (fill0 + n_samples - g->in_off) / (size_t)g->D + 1;
+        if ((rc = group_begin_feed(bank, g, rows, st, tails)) != OWRX_OK) return rc;
+    }
+    while (bank->fir_events.size() < n_chunks) {
+        cudaEvent_t e;
+        OWRX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        bank->fir_events.push_back(e);
+    }
     for (size_t c = 0; c < n_chunks; c++) {
         OWRX_CUDA(cudaStreamWaitEvent(st, bank->chunk_events[c], 0));
         const size_t avail = fill0 + std::min(n_samples, (c + 1) * chunk);
@@ -1229,19 +1290,30 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
             for (int cid : g->slot_chan) if (cid >= 0) live++;
             bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
         }
+        if (overlap) {
+            OWRX_CUDA(cudaEventRecord(bank->fir_events[c], st));
+            OWRX_CUDA(cudaStreamWaitEvent(tails, bank->fir_events[c], 0));
+        }
+        for (auto& gp : bank->groups) {
+            Group* g = gp.get();
+            if (!g) continue;
+            if ((rc = group_tail(bank, g, tails)) != OWRX_OK) return rc;
+            if ((rc = group_tail_serial(bank, g, tails)) != OWRX_OK) return rc;
+        }
+    }
+    bank->reserve_sm = false;
+    if (overlap) {
+        OWRX_CUDA(cudaEventRecord(bank->fir_done, tails));
+        OWRX_CUDA(cudaStreamWaitEvent(st, bank->fir_done, 0));
     }
     bank->iq_fill += n_samples;
     size_t min_off = bank->iq_fill;
-    for (auto& gp : bank->groups) {
-        Group* g = gp.get();
-        if (!g) continue;
-        min_off = std::min(min_off, g->in_off);
-        if ((rc = group_roll_rest(g, st)) != OWRX_OK) return rc;
-        if ((rc = group_tail(bank, g, st)) != OWRX_OK) return rc;
-        if ((rc = group_tail_serial(bank, g, st)) != OWRX_OK) return rc;
-    }
+    for (auto& gp : bank->groups) if (gp) min_off = std::min(min_off, gp->in_off);
     OWRX_CUDA(cudaEventRecord(bank->ev1, st));
+    lap("launched");
+    if (trace) { cudaStreamSynchronize(st); lap("gpu done"); }
     for (auto& gp : bank->groups) if (gp && (rc = group_drain(bank, gp.get())) != OWRX_OK) return rc;
+    lap("drained");
     // drop consumed wideband samples
     if (min_off > 0) {
         const size_t tail = bank->iq_fill - min_off;
@@ -1251,6 +1323,7 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
         for (auto& gp : bank->groups) if (gp) gp->in_off -= min_off;
     }
     OWRX_CUDA(cudaStreamSynchronize(st));
+    lap("end");
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, bank->ev0, bank->ev1) == cudaSuccess) bank->stats.device_ms += ms;
     bank->stats.input_samples += n_samples;
@@ -1273,12 +1346,13 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         // s1 ping-pong: this block's K3 writes the buffer the tail of two blocks ago was reading
         OWRX_CUDA(cudaStreamWaitEvent(sa, bank->tail_done[par], 0));
     }
+    bank->reserve_sm = bank->pipelined;
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
         if (!g) continue;
         size_t consumed = 0;
-        if (g->cfg_dirty && bank->pipelined) OWRX_CUDA(cudaStreamSynchronize(sb));
-        if ((rc = group_roll_s1(g, sa)) != OWRX_OK) return rc;
+        // previous block's outputs are dropped; histories stay
+        if ((rc = group_begin_feed(bank, g, n_samples / (size_t)g->D + 1, sa, sa)) != OWRX_OK) return rc;
         if ((rc = group_fir(bank, g, (const float2*)iq_dev, n_samples, &consumed, sa)) != OWRX_OK) return rc;
         int live = 0;
         for (int cid : g->slot_chan) if (cid >= 0) live++;
@@ -1287,8 +1361,6 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
         if (!g) continue;
-        // previous block's outputs are dropped; histories stay
-        if ((rc = group_roll_rest(g, sa)) != OWRX_OK) return rc;
         if ((rc = group_tail(bank, g, sa)) != OWRX_OK) return rc;
         g->sq_block_abs += (long long)g->last_blocks;
     }
@@ -1300,6 +1372,7 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         Group* g = gp.get();
         if (g && (rc = group_tail_serial(bank, g, sb)) != OWRX_OK) return rc;
     }
+    bank->reserve_sm = false;
     if (bank->pipelined) OWRX_CUDA(cudaEventRecord(bank->tail_done[par], sb));   // awaited by the call after next
     bank->calls++;
     bank->stats.input_samples += n_samples;
