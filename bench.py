@@ -187,6 +187,7 @@ def run_ours(args):
     import torch.distributed as dist
     from openwebrx_b200 import ChannelBank, Waterfall, _native as N, fftchain_params
     from openwebrx_b200.synth import BANDPASS
+    from openwebrx_b200.sharding import broadcast_block
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,7 +228,7 @@ def run_ours(args):
             src = bcast_buf[i & 1]
             if rank == 0 and src is not iq:
                 src.copy_(iq, non_blocking=True)
-            dist.broadcast(src, 0)
+            broadcast_block(src, 0)
             bank.process_device(src, BLOCK, stream=sp)
         else:
             bank.process_device(iq, BLOCK, stream=sp)
@@ -275,39 +276,45 @@ def run_ours(args):
     ch2 = [bank2.add_channel(OUT_RATE, demod=c["kind"], offset=c["offset"], bandpass=BANDPASS[c["kind"]]) for c in my_plan]
     hp = h_iq.data_ptr()
 
+    audio_buf = np.empty(1 << 17, np.float32)
+
     def e2e_step():
+        """one block through the public host API: H2D of the block from pinned memory, the whole chain, audio D2H and
+        the per-channel read a consumer does (owrx_chan_read_audio into a caller buffer)"""
         if world > 1:
             # rank 0 uploads, NCCL carries the block to the other GPUs, every rank returns its audio to the host
             if rank == 0:
                 iq.copy_(h_iq, non_blocking=True)
-            dist.broadcast(iq, 0)
+            broadcast_block(iq, 0)
             bank2.process_device(iq, BLOCK, stream=sp)
-            base, stride, _ = ch2[0].last_audio_device()
-            n_a = ch2[0].last_audio_count()
-            torch.cuda.synchronize()
-            return n_a
+            bank2.drain()
+            got = 0
+            for c in ch2:
+                got += c.read_audio_into(audio_buf)
+            return got
         bank2.feed_ptr(hp, BLOCK)
-        return None
+        got = 0
+        for c in ch2:
+            got += c.read_audio_into(audio_buf)
+        return got
 
-    for i in range(max(1, min(args.warmup, 2))):
+    for i in range(max(1, min(args.warmup, 3))):
         e2e_step()
-    for c in ch2:
-        c.read_audio()
     barrier()
     e2e_steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
+    n_audio = 0
     for i in range(e2e_steps):
-        e2e_step()
+        n_audio += e2e_step()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    n_audio = sum(len(c.read_audio()) for c in ch2) if world == 1 else 0
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_consumed = (BLOCK // D) * D                   # the streaming path carries the FIR tail between blocks
     e2e_value = world * CH_PER_GPU * e2e_consumed / (e2e_ms * 1e-3) / 1e6
-    d2h = (n_audio // e2e_steps) * 4 if world == 1 else CH_PER_GPU * (n_k // 750) * 750 * 4
+    d2h = (n_audio // e2e_steps) * 4
 
     if rank != 0:
         if world > 1:

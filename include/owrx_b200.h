@@ -174,6 +174,9 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
  * block i+1 runs on the caller's stream.  owrx_bank_join makes `stream` wait for everything issued so far. */
 int owrx_bank_set_pipelined(owrx_bank_t* bank, int enable);
 int owrx_bank_join(owrx_bank_t* bank, void* stream);
+/* Copy the outputs of the last owrx_bank_process_device call into the per-channel host queues (D2H), so that
+ * owrx_chan_read_* pops them exactly as after owrx_bank_feed.  Synchronous. */
+int owrx_bank_drain(owrx_bank_t* bank);
 /* samples of audio produced per channel by the last owrx_bank_process_device call */
 int owrx_bank_last_audio_count(const owrx_bank_t* bank, int chan, size_t* n);
 /* device pointer + layout of the last block's audio: element (k, slot) at base[k*stride + slot] */

@@ -83,6 +83,12 @@ class Channel:
     def read_audio(self):
         return self._read(N.lib.owrx_chan_read_audio)
 
+    def read_audio_into(self, buf):
+        """pop queued float32 audio into a caller-owned numpy buffer; returns the sample count"""
+        n = C.c_size_t()
+        N.check(N.lib.owrx_chan_read_audio(self.bank._h, self.id, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n)))
+        return n.value
+
     def read_demod(self):
         return self._read(N.lib.owrx_chan_read_demod)
 
@@ -153,6 +159,10 @@ class ChannelBank:
 
     def join(self, stream=None):
         N.check(N.lib.owrx_bank_join(self._h, _ptr(stream)))
+
+    def drain(self):
+        """D2H of the last process_device block into the host queues (then read_audio etc. pop it)"""
+        N.check(N.lib.owrx_bank_drain(self._h))
 
     def profile(self, enable=True):
         N.check(N.lib.owrx_bank_profile(self._h, 1 if enable else 0))

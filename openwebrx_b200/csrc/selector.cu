@@ -236,7 +236,7 @@ struct owrx_bank {
     // H2D copy stream for the chunked host path; side stream + events for the pipelined device path
     cudaStream_t copy_stream = nullptr, side_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
-    cudaEvent_t fir_done = nullptr, tail_done[2] = {nullptr, nullptr};
+    cudaEvent_t fir_done = nullptr, tail_done[2] = {nullptr, nullptr}, dev_done = nullptr;
     bool pipelined = false, reserve_sm = false;
     std::vector<cudaEvent_t> fir_events;
     unsigned long long calls = 0;
@@ -950,6 +950,7 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fir_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->dev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->tail_done[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->tail_done[1], cudaEventDisableTiming);
     if (e != cudaSuccess) { owrx_bank_destroy(b); return fail(OWRX_E_CUDA, "stream/event create: %s", cudaGetErrorString(e)); }
@@ -967,6 +968,7 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     for (cudaEvent_t e : bank->chunk_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->fir_events) cudaEventDestroy(e);
     if (bank->fir_done) cudaEventDestroy(bank->fir_done);
+    if (bank->dev_done) cudaEventDestroy(bank->dev_done);
     if (bank->tail_done[0]) cudaEventDestroy(bank->tail_done[0]);
     if (bank->tail_done[1]) cudaEventDestroy(bank->tail_done[1]);
     if (bank->copy_stream) cudaStreamDestroy(bank->copy_stream);
@@ -1374,9 +1376,33 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
     }
     bank->reserve_sm = false;
     if (bank->pipelined) OWRX_CUDA(cudaEventRecord(bank->tail_done[par], sb));   // awaited by the call after next
+    OWRX_CUDA(cudaEventRecord(bank->dev_done, sa));
     bank->calls++;
     bank->stats.input_samples += n_samples;
     return rc;
+}
+
+// Device path + host outputs: copy what the last owrx_bank_process_device call produced into the per-channel
+// host queues (the same queues owrx_bank_feed fills), so owrx_chan_read_* can pop it.
+int owrx_bank_drain(owrx_bank_t* bank)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    cudaStream_t st = bank->stream;
+    OWRX_CUDA(cudaStreamWaitEvent(st, bank->dev_done, 0));
+    OWRX_CUDA(cudaStreamWaitEvent(st, bank->tail_done[0], 0));
+    OWRX_CUDA(cudaStreamWaitEvent(st, bank->tail_done[1], 0));
+    int rc;
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        const long long blocks = (long long)g->last_blocks;
+        g->sq_block_abs -= blocks;                   // group_drain re-adds it (power report phase)
+        if ((rc = group_drain(bank, g)) != OWRX_OK) return rc;
+    }
+    OWRX_CUDA(cudaStreamSynchronize(st));
+    return OWRX_OK;
 }
 
 int owrx_bank_set_pipelined(owrx_bank_t* bank, int enable)

@@ -76,6 +76,42 @@ def test_c2_shape_fractional(gpu):
         _check(ch, _oracle_chain(iq, fs, out, car), min_len=1500)
 
 
+def test_c3_shape_r_split(gpu):
+    # 61.44 MS/s -> 12 kHz: D = 5120, T = 136533 (BASELINE config 3 shape): the D-sample block is split over
+    # 6 CTAs (r-splits) whose partial sums meet in fir_reduce_kernel
+    fs, out = 61.44e6, 12000
+    cars = carrier_plan(2, fs, seed=28)
+    n = 136533 + 5120 * (750 + 40)
+    iq = make_iq(n, fs, cars, seed=28)
+    bank, chans = _setup(fs, out, cars, 2)
+    bank.feed(iq)
+    for ch, car in chans:
+        _check(ch, _oracle_chain(iq, fs, out, car), min_len=750)
+
+
+def test_device_path_matches_host_path(gpu):
+    # owrx_bank_process_device (+ pipelined side stream) + owrx_bank_drain == owrx_bank_feed
+    import torch
+    fs, out = 2.4e6, 12000
+    cars = carrier_plan(3, fs, seed=29)
+    n = 5333 + 200 * (750 * 2 + 10)
+    iq = make_iq(n, fs, cars, seed=29)
+    bank, chans = _setup(fs, out, cars, 3)
+    bank.feed(iq)
+    want = [(ch.read_if(), ch.read_demod(), ch.read_audio()) for ch, _ in chans]
+    bank2, chans2 = _setup(fs, out, cars, 3)
+    bank2.set_pipelined(True)
+    d_iq = torch.from_numpy(iq.view(np.float32)).cuda()
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    bank2.process_device(d_iq, n, stream=st.cuda_stream)
+    bank2.drain()
+    for (ch, _), (w_if, w_dm, w_au) in zip(chans2, want):
+        assert np.array_equal(ch.read_if(), w_if)
+        assert np.array_equal(ch.read_demod(), w_dm)
+        assert np.array_equal(ch.read_audio(), w_au)
+
+
 def test_streaming_ragged_equals_one_shot(gpu):
     fs, out = 2.4e6, 12000
     cars = carrier_plan(3, fs, seed=23)
