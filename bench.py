@@ -253,7 +253,8 @@ def run_ours(args):
     iq = synth_iq_torch(BLOCK, FS, carriers, dev) if rank == 0 else torch.empty(BLOCK, 2, device=dev, dtype=torch.float32)
     if world > 1:
         dist.broadcast(iq, 0)
-    bcast_buf = [iq, torch.empty_like(iq)] if world > 1 else [iq]
+    iq_src = iq
+    bcast_buf = [torch.empty_like(iq), torch.empty_like(iq)] if world > 1 else [iq]
     # a created (non-default) stream: the C ABI treats a NULL handle as "use the object's own stream"
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.synchronize()
@@ -261,14 +262,23 @@ def run_ours(args):
     sp = stream.cuda_stream
     assert sp != 0
 
+    pending = [None]
+
+    def issue_broadcast(i):
+        # the hop: rank 0's block reaches every GPU over NVLink (NCCL broadcast).  Issued one block ahead on NCCL's own
+        # stream, so the transfer of block i+1 overlaps the K3 pass of block i (double-buffered).
+        buf = bcast_buf[i & 1]
+        if rank == 0:
+            buf.copy_(iq_src, non_blocking=True)        # "fresh" samples from the ingest side
+        pending[0] = broadcast_block(buf, 0, async_op=True)
+
     def step(i):
         if world > 1:
-            # the hop: rank 0's block reaches every GPU over NVLink (NCCL broadcast), then each GPU runs its channels
-            src = bcast_buf[i & 1]
-            if rank == 0 and src is not iq:
-                src.copy_(iq, non_blocking=True)
-            broadcast_block(src, 0)
-            bank.process_device(src, BLOCK, stream=sp)
+            if pending[0] is None:
+                issue_broadcast(i)
+            pending[0].wait()                            # current stream waits for block i
+            issue_broadcast(i + 1)
+            bank.process_device(bcast_buf[i & 1], BLOCK, stream=sp)
         else:
             bank.process_device(iq, BLOCK, stream=sp)
 
