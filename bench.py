@@ -429,13 +429,16 @@ def bench_waterfall(torch, dev, hbm_peak, lines=592, steps=5):
     st = torch.cuda.current_stream()
     assert st.cuda_stream != 0
     torch.cuda.synchronize()
+    wf.set_pipelined(True)        # ADPCM of batch i on the side stream beside the FFT pass of batch i+1
     for _ in range(3):
         wf.process_device(iq, n, out, out.numel(), stream=st.cuda_stream)
+    wf.join(st.cuda_stream)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for _ in range(steps):
         got = wf.process_device(iq, n, out, out.numel(), stream=st.cuda_stream)
+    wf.join(st.cuda_stream)
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps

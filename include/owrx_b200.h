@@ -69,6 +69,10 @@ int owrx_wf_read(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes);
  * stream cannot be named here: pass a created stream to order against other work).  Asynchronous. */
 int owrx_wf_process_device(owrx_wf_t* wf, const void* iq_dev, size_t n_samples, void* out_dev,
                            size_t out_cap_bytes, void* db_dev, void* s16_dev, size_t* n_lines, void* stream);
+/* Pipelined device path: the FftAdpcm encoder of batch i (latency-bound: one warp per 32 lines) runs on a
+ * high-priority side stream beside the FFT pass of batch i+1.  owrx_wf_join makes `stream` wait for it. */
+int owrx_wf_set_pipelined(owrx_wf_t* wf, int enable);
+int owrx_wf_join(owrx_wf_t* wf, void* stream);
 /* number of whole lines a record of n_samples yields with the current parameters */
 size_t owrx_wf_lines_for(const owrx_wf_t* wf, size_t n_samples);
 

@@ -55,6 +55,8 @@ SIGNATURES = {
     "owrx_wf_read": (_i, [_vp, _vp, _sz, _psz]),
     "owrx_wf_process_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _psz, _vp]),
     "owrx_wf_lines_for": (_sz, [_vp, _sz]),
+    "owrx_wf_set_pipelined": (_i, [_vp, _i]),
+    "owrx_wf_join": (_i, [_vp, _vp]),
     "owrx_fft_adpcm_encode_device": (_i, [_i, _vp, _i, _sz, _vp, _vp]),
     "owrx_bank_create": (_i, [_i, _d, _pp]),
     "owrx_bank_destroy": (None, [_vp]),

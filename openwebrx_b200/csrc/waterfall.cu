@@ -113,7 +113,7 @@ struct WfFftParams {
 
 // One CTA per (line, row k1, frame subset).  M = 2^LOG2M points, T = M/16 threads.
 template <int LOG2M, bool FROM_IQ>
-__global__ void __launch_bounds__((1 << LOG2M) / 16 < 32 ? 32 : (1 << LOG2M) / 16)
+__global__ void __launch_bounds__((1 << LOG2M) / 16 < 32 ? 32 : (1 << LOG2M) / 16, LOG2M >= 11 ? 2 : 1)
 wf_fft_kernel(WfFftParams p)
 {
     constexpr int M = 1 << LOG2M;
@@ -123,6 +123,9 @@ wf_fft_kernel(WfFftParams p)
     extern __shared__ float2 smem[];
     float2* bufA = smem;
     float2* bufB = smem + BUF;
+    // |X|^2 accumulators live in shared memory (slot q of thread t at accS[q*T + t]: conflict-free), which keeps
+    // the kernel under 128 registers so that two CTAs share an SM and cover each other's barriers and load latency
+    float* accS = reinterpret_cast<float*>(smem + 2 * BUF);
 
     const int tid = threadIdx.x;
     const bool active = tid < T;
@@ -136,9 +139,10 @@ wf_fft_kernel(WfFftParams p)
     const int a0 = subset * per;
     const int a1 = min(p.frames_per_line, a0 + per);
 
-    float acc[16];
+    if (active) {
 #pragma unroll
-    for (int q = 0; q < 16; q++) acc[q] = 0.0f;
+        for (int q = 0; q < 16; q++) accS[q * T + tid] = 0.0f;
+    }
 
     for (int a = a0; a < a1; a++) {
         float2 v[16];
@@ -194,7 +198,7 @@ wf_fft_kernel(WfFftParams p)
         }
         if (active) {
 #pragma unroll
-            for (int q = 0; q < 16; q++) acc[q] += v[q].x * v[q].x + v[q].y * v[q].y;
+            for (int q = 0; q < 16; q++) accS[q * T + tid] += v[q].x * v[q].x + v[q].y * v[q].y;
         }
     }
 
@@ -210,7 +214,7 @@ wf_fft_kernel(WfFftParams p)
             } else {
                 bin = tid + slot<16>(q) * 16;          // M == 256
             }
-            out[(size_t)k1 + (size_t)p.r0 * bin] = acc[q];
+            out[(size_t)k1 + (size_t)p.r0 * bin] = accS[q * T + tid];
         }
     }
 }
@@ -288,67 +292,103 @@ __constant__ int16_t c_ima_step[89] = {
     2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899,
     15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
 
-// One IMA-ADPCM step.  `st` is the step of the current index (carried in a register); the
-// steps of all five possible successor indices are fetched from shared memory while the quantiser's
-// compare chain resolves, so no table lookup sits on the sample-to-sample dependency chain.
-__device__ __forceinline__ int ima_encode(int sample, int& index, int& pred, int& st, const int* steps)
+// One IMA-ADPCM step.  `st` is the step of the current index (carried in a register).  The steps
+// of the five possible successor indices come from ONE 16-byte shared-memory entry per index, fetched while
+// the quantiser's compare chain resolves, so no table lookup sits on the sample-to-sample dependency chain.
+//   cand[i] = { step[max(i-1,0)] | step[min(i+2,88)] << 16,  step[min(i+4,88)] | step[min(i+6,88)] << 16,  step[min(i+8,88)], - }
+__device__ __forceinline__ int ima_encode(int sample, int& index, int& pred, int& st, const uint4* cand)
 {
-    const int c0 = steps[max(index - 1, 0)];
-    const int c1 = steps[min(index + 2, 88)], c2 = steps[min(index + 4, 88)];
-    const int c3 = steps[min(index + 6, 88)], c4 = steps[min(index + 8, 88)];
+    const uint4 c = cand[index];
     int diff = sample - pred;
+    const int neg = diff < 0;
+    diff = abs(diff);
     int code = 0;
-    if (diff < 0) { code = 8; diff = -diff; }
     int d = st >> 3;
-    if (diff >= st) { code |= 4; diff -= st; d += st; }
+    if (diff >= st) { code = 4; diff -= st; d += st; }
     const int s1 = st >> 1;
     if (diff >= s1) { code |= 2; diff -= s1; d += s1; }
     const int s2 = st >> 2;
     if (diff >= s2) { code |= 1; d += s2; }
-    pred = (code & 8) ? pred - d : pred + d;
-    pred = max(-32768, min(32767, pred));
-    const int m = code & 7;
-    index = max(0, min(88, index + ((m < 4) ? -1 : (2 * m - 6))));
-    st = (m < 4) ? c0 : ((m & 2) ? ((m & 1) ? c4 : c3) : ((m & 1) ? c2 : c1));
-    return code;
+    pred = max(-32768, min(32767, neg ? pred - d : pred + d));
+    // successor: index-1 for code < 4, else index + 2*(code-3); the matching step is field f of the entry
+    const int f = max(code - 3, 0);
+    index = max(0, min(88, index + (code < 4 ? -1 : 2 * code - 6)));
+    const unsigned w = f < 2 ? c.x : (f < 4 ? c.y : c.z);
+    st = (int)((w >> ((f & 1) << 4)) & 0xffffu);
+    return code | (neg << 3);
 }
 
 // FftAdpcm encoder, warp-cooperative: a warp owns 32 lines (one per lane: the codec state is strictly
 // sequential within a line, lines are independent and reset per line).  Each iteration the warp stages a
-// 64-sample chunk of all 32 lines through shared memory with coalesced 128-byte row loads, every lane
-// encodes its own line's chunk from (conflict-free, padded) shared memory, and the 32 output bytes per
-// line leave through shared memory as one 32-byte sector per line.
+// 64-sample chunk of all 32 lines through shared memory with coalesced 128-byte row loads (cp.async, one chunk
+// ahead of the encoder), every lane encodes its own line's chunk from padded (conflict-free) shared memory, and
+// the 32 output bytes per line leave through shared memory as one 32-byte sector per line.
 constexpr int ADPCM_CH = 64;
 __global__ void __launch_bounds__(32)
 wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int n_samples, size_t n_lines)
 {
-    __shared__ int steps[89];
-    __shared__ unsigned tile[32][ADPCM_CH / 2 + 1];
-    __shared__ unsigned char otile[32][ADPCM_CH / 2 + 4];
+    __shared__ uint4 cand[89];
+    __shared__ unsigned tile[2][32][ADPCM_CH / 2 + 1];
+    __shared__ unsigned otile[32][ADPCM_CH / 8 + 1];
     const int lane = threadIdx.x;
-    for (int i = lane; i < 89; i += 32) steps[i] = c_ima_step[i];
-    __syncwarp();
+    for (int i = lane; i < 89; i += 32) {
+        const unsigned c0 = c_ima_step[max(i - 1, 0)], c1 = c_ima_step[min(i + 2, 88)], c2 = c_ima_step[min(i + 4, 88)];
+        const unsigned c3 = c_ima_step[min(i + 6, 88)], c4 = c_ima_step[min(i + 8, 88)];
+        cand[i] = make_uint4(c0 | (c1 << 16), c2 | (c3 << 16), c4, 0u);
+    }
     const size_t line0 = (size_t)blockIdx.x * 32;
     const int nl = (int)min((size_t)32, n_lines - line0);
+    const int n_chunks = (n_samples + ADPCM_CH - 1) / ADPCM_CH;
+    auto stage = [&](int chunk, int buf) {
+        const int c0 = chunk * ADPCM_CH;
+        if (chunk < n_chunks && c0 + 2 * lane < n_samples) {
+            for (int l = 0; l < nl; l++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[buf][l][lane]);
+                const int16_t* src = s16 + (line0 + l) * (size_t)n_samples + c0 + 2 * lane;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    stage(0, 0);
+    __syncwarp();
     int index = 0, pred = 0, st = 7;
-    for (int c0 = 0; c0 < n_samples; c0 += ADPCM_CH) {
+    for (int chunk = 0; chunk < n_chunks; chunk++) {
+        const int buf = chunk & 1;
+        const int c0 = chunk * ADPCM_CH;
         const int valid = min(ADPCM_CH, n_samples - c0);          // even
-        for (int l = 0; l < nl; l++)
-            if (2 * lane < valid)
-                tile[l][lane] = *reinterpret_cast<const unsigned*>(s16 + (line0 + l) * (size_t)n_samples + c0 + 2 * lane);
+        stage(chunk + 1, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;\n" ::);
         __syncwarp();
         if (lane < nl) {
-#pragma unroll 4
-            for (int w = 0; w < valid / 2; w++) {
-                const unsigned v = tile[lane][w];
-                const int lo = ima_encode((int)(short)(v & 0xffffu), index, pred, st, steps);
-                const int hi = ima_encode((int)(short)(v >> 16), index, pred, st, steps);
-                otile[lane][w] = (unsigned char)(lo | (hi << 4));
+            for (int w4 = 0; w4 < valid / 8; w4++) {
+                unsigned packed = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned v = tile[buf][lane][4 * w4 + k];
+                    const int lo = ima_encode((int)(short)(v & 0xffffu), index, pred, st, cand);
+                    const int hi = ima_encode((int)(short)(v >> 16), index, pred, st, cand);
+                    packed |= (unsigned)(lo | (hi << 4)) << (8 * k);
+                }
+                otile[lane][w4] = packed;
+            }
+            // trailing samples of the last chunk (valid is even, not necessarily a multiple of 8)
+            const int done = (valid / 8) * 8;
+            if (done < valid) {
+                unsigned packed = 0;
+                for (int k = 0; k < (valid - done) / 2; k++) {
+                    const unsigned v = tile[buf][lane][done / 2 + k];
+                    const int lo = ima_encode((int)(short)(v & 0xffffu), index, pred, st, cand);
+                    const int hi = ima_encode((int)(short)(v >> 16), index, pred, st, cand);
+                    packed |= (unsigned)(lo | (hi << 4)) << (8 * k);
+                }
+                otile[lane][valid / 8] = packed;
             }
         }
         __syncwarp();
+        const unsigned char* ob = reinterpret_cast<const unsigned char*>(&otile[0][0]);
         for (int l = 0; l < nl; l++)
-            if (lane < valid / 2) out[(line0 + l) * (size_t)(n_samples / 2) + c0 / 2 + lane] = otile[l][lane];
+            if (lane < valid / 2) out[(line0 + l) * (size_t)(n_samples / 2) + c0 / 2 + lane] = ob[l * (ADPCM_CH / 8 + 1) * 4 + lane];
         __syncwarp();
     }
 }
@@ -372,6 +412,13 @@ struct owrx_wf {
     float* d_partial = nullptr; size_t partial_cap = 0;
     float2* d_y = nullptr;      size_t y_cap = 0;
     int16_t* d_s16 = nullptr;   size_t s16_cap = 0;
+    // pipelined mode: the (latency-bound, one warp per 32 lines) ADPCM pass of batch i runs on a high-priority side
+    // stream beside the FFT pass of batch i+1; the int16 scratch is double-buffered
+    bool pipelined = false;
+    cudaStream_t side = nullptr;
+    int16_t* d_s16_alt = nullptr; size_t s16_alt_cap = 0;
+    cudaEvent_t fin_done = nullptr, adpcm_done[2] = {nullptr, nullptr};
+    int s16_cur = 0;
     // streaming
     float2* d_in = nullptr;     size_t in_cap = 0, in_fill = 0, skip = 0;
     float2* d_in_alt = nullptr;
@@ -408,7 +455,7 @@ template <int LOG2M, bool FROM_IQ> static int launch_fft(const WfFftParams& p, s
 {
     constexpr int M = 1 << LOG2M;
     constexpr int threads = M / 16 < 32 ? 32 : M / 16;
-    const size_t smem = 2 * (size_t)(M + M / 16) * sizeof(float2);
+    const size_t smem = 2 * (size_t)(M + M / 16) * sizeof(float2) + (size_t)M * sizeof(float);
     OWRX_CUDA(cudaFuncSetAttribute(wf_fft_kernel<LOG2M, FROM_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wf_fft_kernel<LOG2M, FROM_IQ><<<(unsigned)units, threads, smem, st>>>(p);
     OWRX_LAUNCH_CHECK();
@@ -466,9 +513,18 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
     const bool adpcm = wf->compression == OWRX_COMPRESSION_ADPCM;
     int16_t* s16 = s16_dev;
     if (adpcm && !s16) {
-        if ((rc = grow(&wf->d_s16, &wf->s16_cap, lines * (size_t)(n + 10))) != OWRX_OK) return rc;
-        s16 = wf->d_s16;
+        const bool alt = wf->pipelined && wf->s16_cur;
+        if (wf->pipelined) {
+            // the encoder of two batches ago was reading this buffer (growing it would also free it under the encoder)
+            OWRX_CUDA(cudaStreamWaitEvent(st, wf->adpcm_done[wf->s16_cur], 0));
+            if (lines * (size_t)(n + 10) > (alt ? wf->s16_alt_cap : wf->s16_cap)) OWRX_CUDA(cudaStreamSynchronize(wf->side));
+        }
+        if ((rc = alt ? grow(&wf->d_s16_alt, &wf->s16_alt_cap, lines * (size_t)(n + 10))
+                      : grow(&wf->d_s16, &wf->s16_cap, lines * (size_t)(n + 10))) != OWRX_OK)
+            return rc;
+        s16 = alt ? wf->d_s16_alt : wf->d_s16;
     }
+    const bool side_adpcm = adpcm && out_dev && wf->pipelined && !s16_dev;
     float* db = db_dev;
     if (!adpcm && out_dev) db = (float*)out_dev;   // compression "none": the line IS the float32 dB row
     const float corr = wf->avg > 0 ? wf->add_db - 10.0f * log10f((float)wf->avg) : wf->add_db;
@@ -479,8 +535,18 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
     if (!adpcm && db_dev && out_dev && db_dev != (float*)out_dev)
         OWRX_CUDA(cudaMemcpyAsync(db_dev, out_dev, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (adpcm && out_dev) {
-        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, 0, st>>>(s16, out_dev, n + 10, lines);
+        cudaStream_t sa = st;
+        if (side_adpcm) {
+            OWRX_CUDA(cudaEventRecord(wf->fin_done, st));
+            OWRX_CUDA(cudaStreamWaitEvent(wf->side, wf->fin_done, 0));
+            sa = wf->side;
+        }
+        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, 0, sa>>>(s16, out_dev, n + 10, lines);
         OWRX_LAUNCH_CHECK();
+        if (side_adpcm) {
+            OWRX_CUDA(cudaEventRecord(wf->adpcm_done[wf->s16_cur], sa));
+            wf->s16_cur ^= 1;
+        }
     }
     return OWRX_OK;
 }
@@ -568,6 +634,12 @@ int owrx_wf_create(int device, int fft_size, int every_n_samples, int avg_number
     wf->log2m = 0;
     while ((1 << wf->log2m) < wf->m) wf->log2m++;
     cudaError_t e = cudaStreamCreateWithFlags(&wf->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&wf->side, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&wf->fin_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&wf->adpcm_done[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&wf->adpcm_done[1], cudaEventDisableTiming);
     if (e != cudaSuccess) { delete wf; return fail(OWRX_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     rc = wf_build_tables(wf);
     if (rc != OWRX_OK) { owrx_wf_destroy(wf); return rc; }
@@ -581,7 +653,12 @@ void owrx_wf_destroy(owrx_wf_t* wf)
     cudaSetDevice(wf->device);
     if (wf->stream) cudaStreamSynchronize(wf->stream);
     cudaFree(wf->d_window); cudaFree(wf->d_tw2); cudaFree(wf->d_tw3); cudaFree(wf->d_twn);
-    cudaFree(wf->d_partial); cudaFree(wf->d_y); cudaFree(wf->d_s16);
+    cudaDeviceSynchronize();
+    cudaFree(wf->d_partial); cudaFree(wf->d_y); cudaFree(wf->d_s16); cudaFree(wf->d_s16_alt);
+    if (wf->fin_done) cudaEventDestroy(wf->fin_done);
+    if (wf->adpcm_done[0]) cudaEventDestroy(wf->adpcm_done[0]);
+    if (wf->adpcm_done[1]) cudaEventDestroy(wf->adpcm_done[1]);
+    if (wf->side) cudaStreamDestroy(wf->side);
     cudaFree(wf->d_in); cudaFree(wf->d_in_alt); cudaFree(wf->d_out);
     if (wf->h_out) cudaFreeHost(wf->h_out);
     if (wf->stream) cudaStreamDestroy(wf->stream);
@@ -700,6 +777,27 @@ int owrx_wf_read(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes)
     }
     *n_bytes = o;
     if (o == 0 && !wf->queue.empty()) return fail(OWRX_E_OVERFLOW, "buffer smaller than one line");
+    return OWRX_OK;
+}
+
+int owrx_wf_set_pipelined(owrx_wf_t* wf, int enable)
+{
+    if (!wf) return fail(OWRX_E_INVALID, "NULL waterfall");
+    std::lock_guard<std::mutex> g(wf->mu);
+    OWRX_CUDA(cudaSetDevice(wf->device));
+    OWRX_CUDA(cudaDeviceSynchronize());
+    wf->pipelined = enable != 0;
+    return OWRX_OK;
+}
+
+int owrx_wf_join(owrx_wf_t* wf, void* stream)
+{
+    if (!wf) return fail(OWRX_E_INVALID, "NULL waterfall");
+    std::lock_guard<std::mutex> g(wf->mu);
+    OWRX_CUDA(cudaSetDevice(wf->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : wf->stream;
+    OWRX_CUDA(cudaStreamWaitEvent(st, wf->adpcm_done[0], 0));
+    OWRX_CUDA(cudaStreamWaitEvent(st, wf->adpcm_done[1], 0));
     return OWRX_OK;
 }
 

@@ -104,6 +104,12 @@ class Waterfall:
                                              _ptr(s16_dev), C.byref(n), _ptr(stream)))
         return n.value
 
+    def set_pipelined(self, enable=True):
+        N.check(N.lib.owrx_wf_set_pipelined(self._h, 1 if enable else 0))
+
+    def join(self, stream=None):
+        N.check(N.lib.owrx_wf_join(self._h, _ptr(stream)))
+
     def close(self):
         if getattr(self, "_h", None):
             N.lib.owrx_wf_destroy(self._h)
