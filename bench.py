@@ -47,6 +47,18 @@ def load_peaks():
     return 6650.0, 1965.0, "fallback"
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json);
+    valid for this bench's block size / channel count only."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
+        if d.get("block_samples") == BLOCK and d.get("channels") == CH_PER_GPU:
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every few ms from a
     thread (the main thread sits in cudaStreamSynchronize with the GIL released); nvidia-smi -lms as fallback."""
@@ -402,7 +414,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"kernel": "fir_decimate_kernel (K3: NCO mix + polyphase FIR decimate, 64 ch)", "bound": "hbm", "achieved": achieved,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": load_traffic("fir_decimate_kernel"), "peak_source": peak_src,
                      "kernel_ms": k3_avg_s * 1e3, "kernel_share_of_step": (k3_ms / args.steps) / ms_step if ms_step > 0 else None,
                      "note": "direct-form DDC is FP32-FMA bound by construction (SURVEY 8d): see roofline_fp32"},
         "roofline_fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
