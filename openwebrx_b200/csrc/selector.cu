@@ -368,8 +368,9 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     g->h_cfg.assign(S, idle);
 
     const size_t cap = 4096;
-    if ((rc = g->s1.init(2, g->slots, (size_t)std::max(16, g->Tb), cap)) != OWRX_OK) return rc;
-    if (g->has_frac && (rc = g->s2.init(2, g->slots, (size_t)g->Tb, cap)) != OWRX_OK) return rc;
+    // band-pass input history: Tb-1 taps back, plus the register-blocked kernel's window overshoot (2*BP_RB + padding of T)
+    if ((rc = g->s1.init(2, g->slots, (size_t)(g->Tb + 3 * BP_RB), cap)) != OWRX_OK) return rc;
+    if (g->has_frac && (rc = g->s2.init(2, g->slots, (size_t)(g->Tb + 3 * BP_RB), cap)) != OWRX_OK) return rc;
     if ((rc = g->s3.init(2, g->slots, (size_t)g->sq_len, cap)) != OWRX_OK) return rc;
     if ((rc = g->f1.init(1, g->slots, 256, cap)) != OWRX_OK) return rc;
     if (wfm && (rc = g->f1b.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
@@ -631,9 +632,9 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
 
     // ---- Bandpass -> s3 (selector output / IF)
     if ((rc = g->s3.ensure_new(n2, st)) != OWRX_OK) return rc;
-    for (size_t o = 0; o < n2; o += kRowChunk) {
-        const size_t c = std::min(kRowChunk, n2 - o);
-        bandpass_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(
+    for (size_t o = 0; o < n2; o += kRowChunk * BP_RB) {
+        const size_t c = std::min(kRowChunk * BP_RB, n2 - o);
+        bandpass_kernel<<<grid2d(S, (c + BP_RB - 1) / BP_RB), kBlock2d, 0, st>>>(
             reinterpret_cast<const float2*>(bp_in->row_abs(bp_first + (long long)o)), S, nullptr, g->d_bp, g->d_bp_en, g->Tb,
             (int)c, S, reinterpret_cast<float2*>(g->s3.append_ptr()) + o * S);
         OWRX_LAUNCH_CHECK();

@@ -122,32 +122,60 @@ fracdec_cf_kernel(const float2* __restrict__ in, long long in_abs0, int in_slots
     out[(size_t)m * slots + s] = make_float2(re, im);
 }
 
-// Bandpass: y[i] = sum_t h_s[t] x[i-t] (causal, zero history = zero rows before the stream start).
-// taps: [T][slots] complex, per channel; enabled[s]==0 passes the sample through.
+// Bandpass: y[i] = sum_t h_s[t] x[i-t] (causal, zero history = zero rows before the stream start) — the linear
+// convolution the reference's FFT overlap-add computes.  taps: [T][slots] complex, per channel;
+// enabled[s]==0 passes the sample through.  Register-blocked direct form: a thread owns BP_RB consecutive outputs
+// of one channel (lane <-> channel, so tap and sample loads are coalesced) and slides a 2*BP_RB-1 sample window
+// through registers: per BP_RB taps it loads BP_RB taps + BP_RB samples and issues 4*BP_RB^2 FMAs.
+constexpr int BP_RB = 8;
 __global__ void __launch_bounds__(128)
 bandpass_kernel(const float2* __restrict__ in, int in_slots, const int* __restrict__ slot_map,
                 const float2* __restrict__ taps, const int* __restrict__ enabled, int T, int n_out, int slots,
                 float2* __restrict__ out)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (s >= slots || i >= n_out) return;
+    const int i0 = (blockIdx.y * blockDim.y + threadIdx.y) * BP_RB;
+    if (s >= slots || i0 >= n_out) return;
     const int col = slot_map ? slot_map[s] : s;
-    const float2* x = in + (size_t)i * in_slots + col;      // in points at the row of output 0
-    float2 y;
-    if (enabled[s]) {
-        float re = 0.f, im = 0.f;
-        for (int t = 0; t < T; t++) {
-            const float2 h = taps[(size_t)t * slots + s];
-            const float2 v = *(x - (ptrdiff_t)t * in_slots);
-            re += h.x * v.x - h.y * v.y;
-            im += h.x * v.y + h.y * v.x;
-        }
-        y = make_float2(re, im);
-    } else {
-        y = *x;
+    const float2* x = in + col;                          // x[i * in_slots] is sample i of this channel (row 0 = output 0)
+    if (!enabled[s]) {
+#pragma unroll
+        for (int j = 0; j < BP_RB; j++)
+            if (i0 + j < n_out) out[(size_t)(i0 + j) * slots + s] = x[(ptrdiff_t)(i0 + j) * in_slots];
+        return;
     }
-    out[(size_t)i * slots + s] = y;
+    float2 acc[BP_RB];
+#pragma unroll
+    for (int j = 0; j < BP_RB; j++) acc[j] = make_float2(0.f, 0.f);
+    // window xw[k] = x[b - (BP_RB-1) + k], b = i0 - t0; only indices up to i0+BP_RB-1 ever carry weight, and rows past the
+    // last valid output are never read: clamp the row index (their accumulators are discarded)
+    const int last = n_out - 1;
+    float2 xw[2 * BP_RB - 1];
+#pragma unroll
+    for (int k = 0; k < 2 * BP_RB - 1; k++) xw[k] = x[(ptrdiff_t)min(i0 - (BP_RB - 1) + k, last) * in_slots];
+    for (int t0 = 0; t0 < T; t0 += BP_RB) {
+        float2 h[BP_RB];
+#pragma unroll
+        for (int u = 0; u < BP_RB; u++) h[u] = t0 + u < T ? taps[(size_t)(t0 + u) * slots + s] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < BP_RB; u++) {
+#pragma unroll
+            for (int j = 0; j < BP_RB; j++) {
+                const float2 v = xw[BP_RB - 1 + j - u];
+                acc[j].x = fmaf(h[u].x, v.x, acc[j].x); acc[j].x = fmaf(-h[u].y, v.y, acc[j].x);
+                acc[j].y = fmaf(h[u].x, v.y, acc[j].y); acc[j].y = fmaf(h[u].y, v.x, acc[j].y);
+            }
+        }
+        // slide the window BP_RB samples into the past
+#pragma unroll
+        for (int k = 2 * BP_RB - 2; k >= BP_RB; k--) xw[k] = xw[k - BP_RB];
+        const int b = i0 - t0 - BP_RB;
+#pragma unroll
+        for (int k = 0; k < BP_RB; k++) xw[k] = x[(ptrdiff_t)(b - (BP_RB - 1) + k) * in_slots];
+    }
+#pragma unroll
+    for (int j = 0; j < BP_RB; j++)
+        if (i0 + j < n_out) out[(size_t)(i0 + j) * slots + s] = acc[j];
 }
 
 // per-channel serial state

@@ -510,44 +510,18 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
         if ((rc = launch_fft<12, false>(p, units, st)) != OWRX_OK) return rc;
     }
 
+    // finalize: log / swap / quantise.  The ADPCM encoder runs once per batch (wf_process), not per chunk:
+    // its run time is the serial latency of ONE line however many lines are in flight.
     const bool adpcm = wf->compression == OWRX_COMPRESSION_ADPCM;
-    int16_t* s16 = s16_dev;
-    if (adpcm && !s16) {
-        const bool alt = wf->pipelined && wf->s16_cur;
-        if (wf->pipelined) {
-            // the encoder of two batches ago was reading this buffer (growing it would also free it under the encoder)
-            OWRX_CUDA(cudaStreamWaitEvent(st, wf->adpcm_done[wf->s16_cur], 0));
-            if (lines * (size_t)(n + 10) > (alt ? wf->s16_alt_cap : wf->s16_cap)) OWRX_CUDA(cudaStreamSynchronize(wf->side));
-        }
-        if ((rc = alt ? grow(&wf->d_s16_alt, &wf->s16_alt_cap, lines * (size_t)(n + 10))
-                      : grow(&wf->d_s16, &wf->s16_cap, lines * (size_t)(n + 10))) != OWRX_OK)
-            return rc;
-        s16 = alt ? wf->d_s16_alt : wf->d_s16;
-    }
-    const bool side_adpcm = adpcm && out_dev && wf->pipelined && !s16_dev;
     float* db = db_dev;
     if (!adpcm && out_dev) db = (float*)out_dev;   // compression "none": the line IS the float32 dB row
     const float corr = wf->avg > 0 ? wf->add_db - 10.0f * log10f((float)wf->avg) : wf->add_db;
     const size_t total = lines * (size_t)n;
     wf_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(wf->d_partial, subsets, n, corr, lines, db,
-                                                                       adpcm ? s16 : nullptr);
+                                                                       adpcm ? s16_dev : nullptr);
     OWRX_LAUNCH_CHECK();
     if (!adpcm && db_dev && out_dev && db_dev != (float*)out_dev)
         OWRX_CUDA(cudaMemcpyAsync(db_dev, out_dev, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (adpcm && out_dev) {
-        cudaStream_t sa = st;
-        if (side_adpcm) {
-            OWRX_CUDA(cudaEventRecord(wf->fin_done, st));
-            OWRX_CUDA(cudaStreamWaitEvent(wf->side, wf->fin_done, 0));
-            sa = wf->side;
-        }
-        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, 0, sa>>>(s16, out_dev, n + 10, lines);
-        OWRX_LAUNCH_CHECK();
-        if (side_adpcm) {
-            OWRX_CUDA(cudaEventRecord(wf->adpcm_done[wf->s16_cur], sa));
-            wf->s16_cur ^= 1;
-        }
-    }
     return OWRX_OK;
 }
 
@@ -565,12 +539,43 @@ static int wf_process(owrx_wf* wf, const float2* iq_dev, size_t n_samples, uint8
         chunk = std::max<size_t>(1, ((size_t)256 << 20) / per_line);
         chunk = std::min(chunk, (size_t)65535 / (size_t)fpl > 0 ? (size_t)65535 / (size_t)fpl : 1);
     }
+    const bool adpcm = wf->compression == OWRX_COMPRESSION_ADPCM;
+    const int n = wf->n;
+    int16_t* s16 = s16_dev;
+    int rc;
+    const bool side_adpcm = adpcm && out_dev && wf->pipelined && !s16_dev;
+    if (adpcm && !s16 && lines) {
+        const bool alt = wf->pipelined && wf->s16_cur;
+        if (wf->pipelined) {
+            // the encoder of two batches ago was reading this buffer (growing it would also free it under the encoder)
+            OWRX_CUDA(cudaStreamWaitEvent(st, wf->adpcm_done[wf->s16_cur], 0));
+            if (lines * (size_t)(n + 10) > (alt ? wf->s16_alt_cap : wf->s16_cap)) OWRX_CUDA(cudaStreamSynchronize(wf->side));
+        }
+        if ((rc = alt ? grow(&wf->d_s16_alt, &wf->s16_alt_cap, lines * (size_t)(n + 10))
+                      : grow(&wf->d_s16, &wf->s16_cap, lines * (size_t)(n + 10))) != OWRX_OK)
+            return rc;
+        s16 = alt ? wf->d_s16_alt : wf->d_s16;
+    }
     for (size_t l0 = 0; l0 < lines; l0 += chunk) {
         const size_t lc = std::min(chunk, lines - l0);
-        int rc = wf_run_chunk(wf, iq_dev, (long long)l0 * fpl, lc, out_dev ? out_dev + l0 * lb : nullptr,
-                              db_dev ? db_dev + l0 * (size_t)wf->n : nullptr,
-                              s16_dev ? s16_dev + l0 * (size_t)(wf->n + 10) : nullptr, st);
+        rc = wf_run_chunk(wf, iq_dev, (long long)l0 * fpl, lc, out_dev ? out_dev + l0 * lb : nullptr,
+                          db_dev ? db_dev + l0 * (size_t)wf->n : nullptr,
+                          s16 ? s16 + l0 * (size_t)(wf->n + 10) : nullptr, st);
         if (rc != OWRX_OK) return rc;
+    }
+    if (adpcm && out_dev && lines) {
+        cudaStream_t sa = st;
+        if (side_adpcm) {
+            OWRX_CUDA(cudaEventRecord(wf->fin_done, st));
+            OWRX_CUDA(cudaStreamWaitEvent(wf->side, wf->fin_done, 0));
+            sa = wf->side;
+        }
+        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, 0, sa>>>(s16, out_dev, n + 10, lines);
+        OWRX_LAUNCH_CHECK();
+        if (side_adpcm) {
+            OWRX_CUDA(cudaEventRecord(wf->adpcm_done[wf->s16_cur], sa));
+            wf->s16_cur ^= 1;
+        }
     }
     if (n_lines) *n_lines = lines;
     return OWRX_OK;
