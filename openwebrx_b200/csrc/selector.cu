@@ -195,7 +195,7 @@ struct Group {
     // stream position
     size_t in_off = 0;                               // streaming: offset of the next block in the bank's IQ buffer
     long long frac_m = 0, wfm_m = 0, sq_abs = 0;
-    StageBuf s1, s2, s3, f1, f1b, f2, f3;
+    StageBuf s1, s2, s3, f1, f1p, f1b, f2, f3;
     float2* d_partial = nullptr; size_t partial_cap = 0;
     unsigned char* d_gate = nullptr; float* d_power = nullptr; float* d_dcmean = nullptr; float* d_dcprev = nullptr;
     size_t blocks_cap = 0;
@@ -265,7 +265,7 @@ void group_release(Group* g)
     cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state);
     cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     cudaFree(g->d_tail_mode); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
-    g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1b.release(); g->f2.release(); g->f3.release();
+    g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1p.release(); g->f1b.release(); g->f2.release(); g->f3.release();
 }
 
 // Selector / Decimator parameter math (csdr/chain/selector.py:21-26,37-51,115-126): the spec a plain
@@ -295,7 +295,7 @@ bool spec_equal(const owrx_chan_spec_t& a, const owrx_chan_spec_t& b)
 int spec_validate(const owrx_chan_spec_t& sp)
 {
     if (sp.decimation < 1) return fail(OWRX_E_INVALID, "decimation must be >= 1");
-    if (!(sp.transition > 0.0 && sp.transition < 2.0)) return fail(OWRX_E_INVALID, "bad FirDecimate transition %g", sp.transition);
+    if (!(sp.transition > 0.0 && sp.transition <= 4.0)) return fail(OWRX_E_INVALID, "bad FirDecimate transition %g", sp.transition);
     if (!(sp.cutoff > 0.0)) return fail(OWRX_E_INVALID, "bad FirDecimate cutoff %g", sp.cutoff);
     if (!(sp.fraction >= 1.0)) return fail(OWRX_E_INVALID, "fraction must be >= 1");
     if (!(sp.bp_transition > 0.0 && sp.bp_transition < 2.0)) return fail(OWRX_E_INVALID, "bad Bandpass transition %g", sp.bp_transition);
@@ -373,6 +373,7 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     if (g->has_frac && (rc = g->s2.init(2, g->slots, (size_t)(g->Tb + 3 * BP_RB), cap)) != OWRX_OK) return rc;
     if ((rc = g->s3.init(2, g->slots, (size_t)g->sq_len, cap)) != OWRX_OK) return rc;
     if ((rc = g->f1.init(1, g->slots, 256, cap)) != OWRX_OK) return rc;
+    if (wfm && (rc = g->f1p.init(1, g->slots, 32, cap)) != OWRX_OK) return rc;
     if (wfm && (rc = g->f1b.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
     if ((rc = g->f2.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
     if ((rc = g->f3.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
@@ -465,7 +466,7 @@ int group_grow(owrx_bank* bank, Group* g)
         b.slots = ns;
         return OWRX_OK;
     };
-    if ((rc = regrow_buf(g->s1)) || (rc = regrow_buf(g->s2)) || (rc = regrow_buf(g->s3)) || (rc = regrow_buf(g->f1)) ||
+    if ((rc = regrow_buf(g->s1)) || (rc = regrow_buf(g->s2)) || (rc = regrow_buf(g->s3)) || (rc = regrow_buf(g->f1)) || (rc = regrow_buf(g->f1p)) ||
         (rc = regrow_buf(g->f1b)) || (rc = regrow_buf(g->f2)) || (rc = regrow_buf(g->f3)))
         return rc;
     cudaFree(g->d_partial); g->d_partial = nullptr; g->partial_cap = 0;
@@ -719,20 +720,34 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
             g->f2.appended(n4);
             n_audio = n4;
         } else {
-            // ---- WFM: prefiltered fractional decimation to the audio rate, then one-pole de-emphasis
+            // ---- WFM: prefilter (133-tap LPF, once per input index) -> 12-point Lagrange to the audio rate -> de-emphasis
+            const long long v_end = g->f1.abs_end - (long long)(g->Tpre - 1);      // prefilter looks Tpre-1 samples ahead
+            const size_t nv = v_end > g->f1p.abs_end ? (size_t)(v_end - g->f1p.abs_end) : 0;
+            if (nv) {
+                if ((rc = g->f1p.ensure_new(nv, st)) != OWRX_OK) return rc;
+                const float* src = g->f1.row_abs(g->f1p.abs_end);
+                const int last_row = (int)(g->f1.abs_end - 1 - g->f1p.abs_end);
+                for (size_t o = 0; o < nv; o += kRowChunk * BP_RB) {
+                    const size_t c = std::min(kRowChunk * BP_RB, nv - o);
+                    fir_fwd_f_kernel<<<grid2d(S, (c + BP_RB - 1) / BP_RB), kBlock2d, 0, st>>>(src + o * S, S, (int)c, last_row - (int)o, g->d_pre,
+                                                                                           g->Tpre, g->f1p.append_ptr() + o * S);
+                    OWRX_LAUNCH_CHECK();
+                }
+                g->f1p.appended(nv);
+            }
             size_t cnt = 0;
             while (true) {
                 const double where = 5.0 + (double)(g->wfm_m + (long long)cnt) * g->wfm_rate;
-                if ((long long)ceil(where) + 6 + (g->Tpre - 1) >= g->f1.abs_end) break;
+                if ((long long)ceil(where) + 6 >= g->f1p.abs_end) break;
                 cnt++;
             }
             if ((rc = g->f1b.ensure_new(cnt, st)) != OWRX_OK) return rc;
             if ((rc = g->f2.ensure_new(cnt, st)) != OWRX_OK) return rc;
             for (size_t o = 0; o < cnt; o += kRowChunk) {
                 const size_t c = std::min(kRowChunk, cnt - o);
-                fracdec_f_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(g->f1.rows(), g->f1.abs_end - (long long)g->f1.fill, S,
-                                                                    g->wfm_rate, g->wfm_m + (long long)o, (int)c, g->d_pre,
-                                                                    g->Tpre, g->f1b.append_ptr() + o * S);
+                fracdec_f_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(g->f1p.rows(), g->f1p.abs_end - (long long)g->f1p.fill, S,
+                                                                    g->wfm_rate, g->wfm_m + (long long)o, (int)c, nullptr, 0,
+                                                                    g->f1b.append_ptr() + o * S);
                 OWRX_LAUNCH_CHECK();
             }
             if (cnt) {
@@ -808,14 +823,14 @@ int group_begin_feed(owrx_bank* bank, Group* g, size_t rows, cudaStream_t st_fir
     if (g->has_frac && (rc = g->s2.roll(g->s2.hist, st_tail)) != OWRX_OK) return rc;
     if ((rc = g->s3.roll(g->s3.hist, st_tail)) != OWRX_OK) return rc;
     if ((rc = g->f1.roll(g->f1.hist, st_tail)) != OWRX_OK) return rc;
-    if (g->wfm) g->f1b.roll(0, st_tail);
+    if (g->wfm) { g->f1b.roll(0, st_tail); if ((rc = g->f1p.roll(g->f1p.hist, st_tail)) != OWRX_OK) return rc; }
     g->f2.roll(0, st_tail);
     g->f3.roll(0, st_tail);
     g->last_audio = g->last_demod = g->last_if = g->last_blocks = 0;
     g->pass_audio = 0; g->feed_blocks = 0; g->tail_ran = false;
     const bool grow = g->s1.fill + rows > g->s1.cap_rows || (g->has_frac && g->s2.fill + low > g->s2.cap_rows) ||
                       g->s3.fill + low > g->s3.cap_rows || g->f1.fill + low > g->f1.cap_rows || low > g->f2.cap_rows ||
-                      low > g->f3.cap_rows || (g->wfm && low > g->f1b.cap_rows) || blocks > g->blocks_cap ||
+                      low > g->f3.cap_rows || (g->wfm && (low > g->f1b.cap_rows || g->f1p.fill + low > g->f1p.cap_rows)) || blocks > g->blocks_cap ||
                       (g->any_tail && low > g->tail_rows_cap);
     if (grow) {
         OWRX_CUDA(cudaDeviceSynchronize());
@@ -824,6 +839,7 @@ int group_begin_feed(owrx_bank* bank, Group* g, size_t rows, cudaStream_t st_fir
         if ((rc = g->s3.ensure_new(low, st_tail)) != OWRX_OK) return rc;
         if ((rc = g->f1.ensure_new(low, st_tail)) != OWRX_OK) return rc;
         if (g->wfm && (rc = g->f1b.ensure_new(low, st_tail)) != OWRX_OK) return rc;
+        if (g->wfm && (rc = g->f1p.ensure_new(low, st_tail)) != OWRX_OK) return rc;
         if ((rc = g->f2.ensure_new(low, st_tail)) != OWRX_OK) return rc;
         if ((rc = g->f3.ensure_new(low, st_tail)) != OWRX_OK) return rc;
         if (blocks > g->blocks_cap) {

@@ -334,6 +334,41 @@ dc_commit_kernel(int slots, int n_blocks, const ChanCfg* __restrict__ cfg, const
     if (cfg[s].kind == OWRX_DEMOD_AM) st[s].dc_last = dc_mean[(size_t)(n_blocks - 1) * slots + s];
 }
 
+// Forward-looking real FIR with taps shared by all channels: v[i] = sum_t x[i+t] pre[t] — the prefilter of
+// FractionalDecimator(FLOAT, prefilter=True) evaluated once per input index instead of 12 times per output.
+// Register-blocked like bandpass_kernel; rows past `last_row` are never weighted by a non-zero tap and are clamped.
+__global__ void __launch_bounds__(128)
+fir_fwd_f_kernel(const float* __restrict__ in, int slots, int n_out, int last_row, const float* __restrict__ pre, int T,
+                 float* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = (blockIdx.y * blockDim.y + threadIdx.y) * BP_RB;
+    if (s >= slots || i0 >= n_out) return;
+    const float* x = in + s;
+    float acc[BP_RB];
+#pragma unroll
+    for (int j = 0; j < BP_RB; j++) acc[j] = 0.f;
+    float xw[2 * BP_RB - 1];                            // xw[k] = x[i0 + t0 + k]
+#pragma unroll
+    for (int k = 0; k < 2 * BP_RB - 1; k++) xw[k] = x[(size_t)min(i0 + k, last_row) * slots];
+    for (int t0 = 0; t0 < T; t0 += BP_RB) {
+        float h[BP_RB];
+#pragma unroll
+        for (int u = 0; u < BP_RB; u++) h[u] = t0 + u < T ? __ldg(pre + t0 + u) : 0.f;
+#pragma unroll
+        for (int u = 0; u < BP_RB; u++)
+#pragma unroll
+            for (int j = 0; j < BP_RB; j++) acc[j] = fmaf(h[u], xw[j + u], acc[j]);
+#pragma unroll
+        for (int k = 0; k < BP_RB - 1; k++) xw[k] = xw[k + BP_RB];
+#pragma unroll
+        for (int k = BP_RB - 1; k < 2 * BP_RB - 1; k++) xw[k] = x[(size_t)min(i0 + t0 + BP_RB + k, last_row) * slots];
+    }
+#pragma unroll
+    for (int j = 0; j < BP_RB; j++)
+        if (i0 + j < n_out) out[(size_t)(i0 + j) * slots + s] = acc[j];
+}
+
 // WFM: FractionalDecimator(Format.FLOAT, rate, prefilter=True): 12-point Lagrange over the
 // forward-looking prefiltered signal v[idx] = sum_t x[idx+t] pre[t]  (SURVEY A.8).
 __global__ void __launch_bounds__(128)
@@ -351,8 +386,13 @@ fracdec_f_kernel(const float* __restrict__ in, long long in_abs0, int slots, dou
     float acc = 0.f;
 #pragma unroll 1
     for (int i = 0; i < 12; i++) {
-        float v = 0.f;
-        for (int t = 0; t < Tpre; t++) v += x[(size_t)(i + t) * slots] * pre[t];
+        float v;
+        if (Tpre > 0) {
+            v = 0.f;
+            for (int t = 0; t < Tpre; t++) v += x[(size_t)(i + t) * slots] * pre[t];
+        } else {
+            v = x[(size_t)i * slots];        // input already prefiltered (fir_fwd_f_kernel)
+        }
         acc += c[i] * v;
     }
     out[(size_t)m * slots + s] = acc;

@@ -688,10 +688,19 @@ class _ChannelPlan:
         """returns dict describing the chain or None if it is not (yet) a complete, supported client chain"""
         i = 0
         d = {}
-        if not isinstance(chain[0], Shift) or len(chain) < 2 or not isinstance(chain[1], FirDecimate):
+        if not isinstance(chain[0], Shift) or len(chain) < 2:
             return None
-        d["shift"], d["fir"] = chain[0], chain[1]
-        i = 2
+        d["shift"] = chain[0]
+        if isinstance(chain[1], FirDecimate):
+            d["fir"] = chain[1]
+            i = 2
+        elif isinstance(chain[1], Bandpass):
+            # SecondarySelector: Shift -> Bandpass at the same rate (csdr/chain/selector.py:217-226): a channel with
+            # decimation 1 and a one-tap (identity) FirDecimate
+            d["fir"] = None
+            i = 1
+        else:
+            return None
         d["frac"] = None
         if i < len(chain) and isinstance(chain[i], FractionalDecimator) and chain[i].format is Format.COMPLEX_FLOAT:
             d["frac"] = chain[i]; i += 1
@@ -810,9 +819,10 @@ class _SourceRunner(threading.Thread):
     def _update_channel(self, N, head, d, links):
         fir, frac, bp, sq = d["fir"], d["frac"], d["bandpass"], d["squelch"]
         sp = N.ChanSpec()
-        sp.decimation = fir.decimation
-        sp.transition = fir.transition
-        sp.cutoff = fir.cutoff
+        if fir is not None:
+            sp.decimation, sp.transition, sp.cutoff = fir.decimation, fir.transition, fir.cutoff
+        else:
+            sp.decimation, sp.transition, sp.cutoff = 1, 4.0, 0.5          # filter length odd(int(4/4)) = 1: identity
         sp.fraction = frac.rate if frac is not None else 1.0
         sp.bp_transition = bp.transition if bp is not None else 0.05
         sp.squelch_length = sq.length if sq is not None else 750
