@@ -200,6 +200,24 @@ int owrx_bank_get_stats(const owrx_bank_t* bank, owrx_bank_stats_t* st);
  * the recorded events and returns the accumulated device time and launch count. */
 int owrx_bank_profile(owrx_bank_t* bank, int enable);
 int owrx_bank_profile_read(owrx_bank_t* bank, double* k3_ms, uint64_t* k3_launches, int reset);
+/* per kernel kind: ms[OWRX_PROF_KINDS], launches[OWRX_PROF_KINDS] */
+#define OWRX_PROF_K3_DIRECT   0   /* fir_decimate_kernel: direct-form NCO mix + polyphase FIR                 */
+#define OWRX_PROF_FC_FORWARD  1   /* fc_forward_kernel: shared per-branch forward FFTs                        */
+#define OWRX_PROF_FC_CONTRACT 2   /* fc_contract_kernel: per-channel spectral contraction over the branches   */
+#define OWRX_PROF_FC_INVERSE  3   /* fc_inverse_kernel: per-channel inverse FFT + post-rotation               */
+#define OWRX_PROF_KINDS       4
+int owrx_bank_profile_read_ex(owrx_bank_t* bank, double* ms, uint64_t* launches, int reset);
+
+/* How Shift + FirDecimate (csdr/chain/selector.py:29,95) is evaluated.  Both forms compute the same sums
+ * (float32 rounding differs at the 1e-6 level):
+ *   OWRX_FIR_DIRECT    direct-form polyphase FIR, 2T/D FMA per input sample per channel (K3)
+ *   OWRX_FIR_FASTCONV  polyphase fast convolution: one shared forward FFT pass + a per-channel spectral contraction,
+ *                      ~4.5 FMA per input sample per channel (K3F); needs decimation >= 8
+ *   OWRX_FIR_AUTO      (default) fast convolution for feeds that yield >= 64 outputs per channel, direct otherwise */
+#define OWRX_FIR_AUTO     0
+#define OWRX_FIR_DIRECT   1
+#define OWRX_FIR_FASTCONV 2
+int owrx_bank_set_fir_mode(owrx_bank_t* bank, int mode);
 
 #ifdef __cplusplus
 }

@@ -86,7 +86,11 @@ SIGNATURES = {
     "owrx_bank_get_stats": (_i, [_vp, C.POINTER(BankStats)]),
     "owrx_bank_profile": (_i, [_vp, _i]),
     "owrx_bank_profile_read": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
+    "owrx_bank_profile_read_ex": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
+    "owrx_bank_set_fir_mode": (_i, [_vp, _i]),
 }
+PROF_KINDS = ("k3_direct", "fc_forward", "fc_contract", "fc_inverse")
+FIR_MODES = {"auto": 0, "direct": 1, "fastconv": 2}
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here = header/library mismatch: fail loudly

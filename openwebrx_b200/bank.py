@@ -172,6 +172,17 @@ class ChannelBank:
         N.check(N.lib.owrx_bank_profile_read(self._h, C.byref(ms), C.byref(n), 1 if reset else 0))
         return ms.value, n.value
 
+    def profile_read_ex(self, reset=True):
+        """{kind: (ms, launches)} per kernel kind (direct K3 / fast-convolution forward, contract, inverse)"""
+        k = len(N.PROF_KINDS)
+        ms, n = (C.c_double * k)(), (C.c_uint64 * k)()
+        N.check(N.lib.owrx_bank_profile_read_ex(self._h, ms, n, 1 if reset else 0))
+        return {name: (ms[i], n[i]) for i, name in enumerate(N.PROF_KINDS)}
+
+    def set_fir_mode(self, mode="auto"):
+        """how Shift + FirDecimate is evaluated: "auto" | "direct" (K3) | "fastconv" (K3F)"""
+        N.check(N.lib.owrx_bank_set_fir_mode(self._h, N.FIR_MODES[mode] if isinstance(mode, str) else int(mode)))
+
     def close(self):
         if getattr(self, "_h", None):
             N.lib.owrx_bank_destroy(self._h)

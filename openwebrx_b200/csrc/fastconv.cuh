@@ -1,0 +1,40 @@
+// fastconv.cuh — K3F: Shift + FirDecimate of every client channel as a polyphase fast convolution.
+//
+// Same arithmetic contract as K3 (selector_kernels.cuh / SURVEY Appendix A.6-A.7):
+//   y_c[k] = sum_{t<T} x[kD+t] * e^{j 2 pi (ph_c + rate_c (kD+t+1))} * h[t]
+//          = e^{j 2 pi (ph_c + rate_c (kD+1))} * z_c[k],   z_c[k] = sum_t g_c[t] x[kD+t],  g_c[t] = h[t] e^{j 2 pi rate_c t}
+// With t = D s + r (polyphase branch r, s < P = ceil(T/D)) and x_r[a] = x[D a + r]:
+//   z_c[k] = sum_{r<D} sum_{s<P} g_c[D s + r] x_r[k + s]
+// i.e. D short correlations at the OUTPUT rate.  Each is evaluated with M-point FFTs (overlap-save, block of
+// M branch samples -> Kb = M-P+1 outputs):
+//   F_b[q][r]   = FFT_M over a of x[(b Kb + a) D + r]                    (shared by ALL channels)        fc_forward_kernel
+//   Z_b[q][c]   = sum_r F_b[q][r] * Tab[q][r][c]                         (dense contraction, K = D)      fc_contract_kernel
+//   z_c[bKb+m]  = (1/M) IFFT_M over q of Z_b[q][c],  m < Kb, then the post-rotation                    fc_inverse_kernel
+//   Tab[q][r][c] = sum_s g_c[D s + r] e^{+j 2 pi q s / M}                (rebuilt when a channel retunes) fc_table_kernel
+// Exact (no bin slicing: every alias of the decimation is carried by the per-branch FFTs), works for any D, and
+// costs 4 M/Kb ~ 4.5 FMA per input sample per channel instead of the direct form's 2 T/D ~ 53.
+#pragma once
+#include "common.cuh"
+
+namespace owrx {
+
+constexpr int FC_M = 256;        // branch FFT size
+constexpr int FC_KC = 32;        // contraction chunk (branches per pipeline stage); D is padded to a multiple
+constexpr int FC_CG = 64;        // channel slots per contraction CTA
+
+struct FcShape {
+    int D, T, P, Kb, Dp, slots;
+};
+
+// rebuild the table columns of `n` slots: slot_list[i], rate_list[i] (device arrays)
+int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, float2* d_tab,
+                    cudaStream_t st);
+// F[q][b][r] for blocks b < B of the stream starting at iq (sample 0 = first tap of output 0)
+int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float2* d_F, cudaStream_t st);
+int fc_launch_contract(const FcShape& sh, const float2* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, cudaStream_t st);
+// out[(k0 + b Kb + m) * slots + c] for k0 + b Kb + m < n_k; phases are relative to iq[-1] of the whole call
+int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
+                      float2* out, cudaStream_t st);
+int fc_init_tables();
+
+}  // namespace owrx

@@ -4,6 +4,7 @@
 // 37-51,115-130,138-140,159-166) and the demodulator wiring of csdr/chain/analog.py:11-127.
 // Filter design follows SURVEY.md Appendix A.1 (double precision, rounded once to float32).
 #include "selector_kernels.cuh"
+#include "fastconv.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -212,6 +213,14 @@ struct Group {
     int16_t* d_tail_s16 = nullptr; unsigned char* d_tail_bytes = nullptr;
     size_t tail_rows_cap = 0; int tail_cap = 0;
     bool any_tail = false, tail_ran = false;
+    // K3F fast-convolution channeliser (fastconv.cuh): tables are built lazily on the first eligible pass
+    bool fc_ok = false;
+    FcShape fc{};
+    float* d_fc_h = nullptr; float2* d_fc_tab = nullptr; float2* d_fc_F = nullptr; float2* d_fc_Z = nullptr;
+    int* d_fc_slots = nullptr; double* d_fc_rates = nullptr;
+    size_t fc_blocks_cap = 0;
+    std::vector<double> fc_tab_rate;                 // per slot: Shift rate its table column was built for (NaN = none)
+    std::vector<float> fc_taps;                      // h[t] rounded to float (same values K3 uses)
 };
 
 }  // namespace
@@ -243,9 +252,11 @@ struct owrx_bank {
     // optional per-kernel timing of K3 (CUDA events on the launching stream)
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<int> prof_tags;
     size_t prof_used = 0;
-    double prof_k3_ms = 0.0;
-    uint64_t prof_k3_launches = 0;
+    double prof_ms[OWRX_PROF_KINDS] = {0.0, 0.0, 0.0, 0.0};
+    uint64_t prof_launches[OWRX_PROF_KINDS] = {0, 0, 0, 0};
+    int fir_mode = OWRX_FIR_AUTO;
 };
 
 namespace {
@@ -265,6 +276,7 @@ void group_release(Group* g)
     cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state);
     cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     cudaFree(g->d_tail_mode); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
+    cudaFree(g->d_fc_h); cudaFree(g->d_fc_tab); cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates);
     g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1p.release(); g->f1b.release(); g->f2.release(); g->f3.release();
 }
 
@@ -335,6 +347,10 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
         const int p = t / g->D, r = t % g->D;
         ht[((size_t)(p / K3_PP) * g->D + r) * K3_PP + (p % K3_PP)] = (float)h[t];
     }
+    g->fc_taps.resize((size_t)g->T);
+    for (int t = 0; t < g->T; t++) g->fc_taps[(size_t)t] = (float)h[t];
+    g->fc = FcShape{g->D, g->T, P, FC_M - P + 1, (g->D + FC_KC - 1) / FC_KC * FC_KC, g->slots};
+    g->fc_ok = g->D >= 8 && P <= FC_M / 4;
     int rc;
     if ((rc = dev_alloc(&g->d_taps, ht.size())) != OWRX_OK) return rc;
     OWRX_CUDA(cudaMemcpy(g->d_taps, ht.data(), ht.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -472,6 +488,11 @@ int group_grow(owrx_bank* bank, Group* g)
     cudaFree(g->d_partial); g->d_partial = nullptr; g->partial_cap = 0;
     cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     g->d_gate = nullptr; g->d_power = nullptr; g->d_dcmean = nullptr; g->d_dcprev = nullptr; g->blocks_cap = 0;
+    // fast-convolution tables are laid out per slot count: rebuild lazily
+    cudaFree(g->d_fc_tab); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates);
+    g->d_fc_tab = nullptr; g->d_fc_Z = nullptr; g->d_fc_slots = nullptr; g->d_fc_rates = nullptr;
+    g->fc.slots = ns;
+    g->fc_tab_rate.clear();
     g->slots = ns;
     g->slot_chan.resize((size_t)ns, -1);
     g->h_rate.resize((size_t)ns, 0.0); g->h_phase.resize((size_t)ns, 0.0); g->h_w.resize((size_t)ns, make_float2(1.f, 0.f));
@@ -501,6 +522,104 @@ inline dim3 grid2d(int slots, size_t rows) { return dim3((unsigned)((slots + 31)
 const dim3 kBlock2d(32, 4);
 constexpr size_t kRowChunk = 4 * 65535;
 
+// optional CUDA-event bracket around a kernel of kind `tag` (OWRX_PROF_*) on its launching stream
+int prof_mark(owrx_bank* bank, int tag, cudaStream_t st, bool begin)
+{
+    if (!bank->profile) return OWRX_OK;
+    if (begin) {
+        if (bank->prof_used == bank->prof_events.size()) {
+            cudaEvent_t a, b;
+            OWRX_CUDA(cudaEventCreate(&a));
+            OWRX_CUDA(cudaEventCreate(&b));
+            bank->prof_events.emplace_back(a, b);
+            bank->prof_tags.push_back(tag);
+        }
+        bank->prof_tags[bank->prof_used] = tag;
+        OWRX_CUDA(cudaEventRecord(bank->prof_events[bank->prof_used].first, st));
+    } else {
+        OWRX_CUDA(cudaEventRecord(bank->prof_events[bank->prof_used].second, st));
+        bank->prof_used++;
+    }
+    return OWRX_OK;
+}
+
+// K3F: Shift + FirDecimate of one group by polyphase fast convolution (fastconv.cuh); same outputs as the direct
+// K3 pass.  `iq`, `n_avail`, the d_rate/d_phase tables and s1 capacity are already set up by group_fir.
+int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_t n_k, cudaStream_t st)
+{
+    const int S = g->slots;
+    int rc;
+    FcShape& sh = g->fc;
+    if (!g->d_fc_h) {
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_h, g->fc_taps.size() * sizeof(float)));
+        OWRX_CUDA(cudaMemcpyAsync(g->d_fc_h, g->fc_taps.data(), g->fc_taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (!g->d_fc_tab) {
+        // zero-fill on `st` (a non-blocking stream: a legacy-stream cudaMemset would not be ordered before the table kernel)
+        const size_t tab_bytes = (size_t)FC_M * sh.Dp * S * sizeof(float2);
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_tab, tab_bytes));
+        OWRX_CUDA(cudaMemsetAsync(g->d_fc_tab, 0, tab_bytes, st));
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_slots, (size_t)S * sizeof(int)));
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_rates, (size_t)S * sizeof(double)));
+        g->fc_tab_rate.assign((size_t)S, NAN);
+    }
+    // ---- (re)build the table columns of retuned / new channels
+    {
+        std::vector<int> sl;
+        std::vector<double> rt;
+        for (int s = 0; s < S; s++) {
+            const int cid = g->slot_chan[(size_t)s];
+            if (cid < 0) continue;
+            const double r = bank->chans[(size_t)cid]->rate;
+            if (g->fc_tab_rate[(size_t)s] == r) continue;
+            g->fc_tab_rate[(size_t)s] = r;
+            sl.push_back(s);
+            rt.push_back(r);
+        }
+        if (!sl.empty()) {
+            // the staging arrays may still be read by an earlier table launch on another stream: order on the device
+            OWRX_CUDA(cudaMemcpyAsync(g->d_fc_slots, sl.data(), sl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            OWRX_CUDA(cudaMemcpyAsync(g->d_fc_rates, rt.data(), rt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            OWRX_CUDA(cudaStreamSynchronize(st));                     // pageable sources: safe to drop the vectors
+            if ((rc = fc_launch_table(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tab, st)) != OWRX_OK) return rc;
+            bank->stats.kernel_launches++;
+        }
+    }
+    // ---- scratch for up to Bmax blocks per pass
+    const size_t blocks_total = (n_k + (size_t)sh.Kb - 1) / (size_t)sh.Kb;
+    const size_t per_block = (size_t)FC_M * sh.Dp * sizeof(float2);
+    const size_t Bmax = std::max<size_t>(1, std::min<size_t>(4096, ((size_t)256 << 20) / per_block));
+    const size_t need = std::min(blocks_total, Bmax);
+    if (need > g->fc_blocks_cap) {
+        OWRX_CUDA(cudaStreamSynchronize(st));
+        cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z);
+        g->d_fc_F = nullptr; g->d_fc_Z = nullptr; g->fc_blocks_cap = 0;
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_F, need * per_block));
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, need * (size_t)FC_M * S * sizeof(float2)));
+        g->fc_blocks_cap = need;
+    }
+    if (!g->d_fc_Z) {
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, g->fc_blocks_cap * (size_t)FC_M * S * sizeof(float2)));
+    }
+    float2* out = reinterpret_cast<float2*>(g->s1.append_ptr());
+    for (size_t b0 = 0; b0 < blocks_total; b0 += Bmax) {
+        const int B = (int)std::min(Bmax, blocks_total - b0);
+        const size_t s_off = b0 * (size_t)sh.Kb * (size_t)sh.D;
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, true)) != OWRX_OK) return rc;
+        if ((rc = fc_launch_forward(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_F, st)) != OWRX_OK) return rc;
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, false)) != OWRX_OK) return rc;
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, true)) != OWRX_OK) return rc;
+        if ((rc = fc_launch_contract(sh, g->d_fc_F, g->d_fc_tab, B, g->d_fc_Z, bank->sm_count, st)) != OWRX_OK) return rc;
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, false)) != OWRX_OK) return rc;
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, true)) != OWRX_OK) return rc;
+        if ((rc = fc_launch_inverse(sh, g->d_fc_Z, B, g->d_rate, g->d_phase, (long long)(b0 * (size_t)sh.Kb), (long long)n_k, out, st)) != OWRX_OK)
+            return rc;
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, false)) != OWRX_OK) return rc;
+        bank->stats.kernel_launches += 3;
+    }
+    return OWRX_OK;
+}
+
 // K3 pass of one group over `n_avail` wideband samples starting at `iq` (device), on stream `st`:
 // Shift + FirDecimate for every channel, appended to s1.  May be called several times (chunked host
 // feeds) before group_tail runs the remaining stages over all pending rows.
@@ -528,6 +647,11 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     OWRX_CUDA(cudaMemcpyAsync(g->d_phase, g->h_phase.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     OWRX_CUDA(cudaMemcpyAsync(g->d_w, g->h_w.data(), (size_t)S * sizeof(float2), cudaMemcpyHostToDevice, st));
 
+    const bool fastconv = g->fc_ok && bank->fir_mode != OWRX_FIR_DIRECT && (bank->fir_mode == OWRX_FIR_FASTCONV || n_k >= 64);
+    if (fastconv) {
+        if ((rc = g->s1.ensure_new(n_k, st)) != OWRX_OK) return rc;
+        if ((rc = group_fir_fastconv(bank, g, iq, n_avail, n_k, st)) != OWRX_OK) return rc;
+    } else {
     // ---- K3: Shift + FirDecimate
     const int nparts = g->nseg * g->nrs;
     const int ncg = S / K3_CG;
@@ -553,21 +677,9 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     p.side = g->d_partial + (size_t)nparts * n_k * S;
     p.D = g->D; p.nseg = g->nseg; p.nrs = g->nrs; p.RB = g->RB; p.JB = JB; p.n_blocks = (int)n_blocks; p.n_k = (int)n_k; p.slots = S;
     const size_t smem = (size_t)g->RB * K3_PP * sizeof(float) + 2 * (size_t)g->RB * sizeof(float2) + 2 * K3_NW * 128 * sizeof(float);
-    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (bank->profile) {
-        if (bank->prof_used == bank->prof_events.size()) {
-            cudaEvent_t a, b;
-            OWRX_CUDA(cudaEventCreate(&a));
-            OWRX_CUDA(cudaEventCreate(&b));
-            bank->prof_events.emplace_back(a, b);
-        }
-        pe0 = bank->prof_events[bank->prof_used].first;
-        pe1 = bank->prof_events[bank->prof_used].second;
-        bank->prof_used++;
-        OWRX_CUDA(cudaEventRecord(pe0, st));
-    }
+    if ((rc = prof_mark(bank, OWRX_PROF_K3_DIRECT, st, true)) != OWRX_OK) return rc;
     if ((rc = launch_fir_decimate(p, dim3((unsigned)(n_ranges * nparts), (unsigned)ncg), smem, st)) != OWRX_OK) return rc;
-    if (pe1) OWRX_CUDA(cudaEventRecord(pe1, st));
+    if ((rc = prof_mark(bank, OWRX_PROF_K3_DIRECT, st, false)) != OWRX_OK) return rc;
     bank->stats.kernel_launches++;
     {
         const size_t total = n_k * (size_t)S;
@@ -575,6 +687,7 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
                                                                            reinterpret_cast<float2*>(g->s1.append_ptr()));
         OWRX_LAUNCH_CHECK();
         bank->stats.kernel_launches++;
+    }
     }
     if (g->pend_rows == 0) g->pend_first = g->s1.abs_end;
     g->s1.appended(n_k);
@@ -961,6 +1074,7 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     owrx_bank* b = new (std::nothrow) owrx_bank();
     if (!b) return fail(OWRX_E_NOMEM, "out of host memory");
     b->device = device; b->sm_count = sm; b->input_rate = input_rate;
+    if (const char* m = getenv("OWRX_FIR_MODE")) b->fir_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV, atoi(m)));
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking);
@@ -1502,22 +1616,55 @@ int owrx_bank_profile(owrx_bank_t* bank, int enable)
     return OWRX_OK;
 }
 
-int owrx_bank_profile_read(owrx_bank_t* bank, double* k3_ms, uint64_t* k3_launches, int reset)
+static int prof_collect(owrx_bank_t* bank)
 {
-    if (!bank || !k3_ms || !k3_launches) return fail(OWRX_E_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(bank->mu);
-    OWRX_CUDA(cudaSetDevice(bank->device));
     for (size_t i = 0; i < bank->prof_used; i++) {
         OWRX_CUDA(cudaEventSynchronize(bank->prof_events[i].second));
         float ms = 0.f;
         OWRX_CUDA(cudaEventElapsedTime(&ms, bank->prof_events[i].first, bank->prof_events[i].second));
-        bank->prof_k3_ms += ms;
-        bank->prof_k3_launches++;
+        const int tag = bank->prof_tags[i];
+        bank->prof_ms[tag] += ms;
+        bank->prof_launches[tag]++;
     }
     bank->prof_used = 0;
-    *k3_ms = bank->prof_k3_ms;
-    *k3_launches = bank->prof_k3_launches;
-    if (reset) { bank->prof_k3_ms = 0.0; bank->prof_k3_launches = 0; }
+    return OWRX_OK;
+}
+
+int owrx_bank_profile_read(owrx_bank_t* bank, double* k3_ms, uint64_t* k3_launches, int reset)
+{
+    if (!bank || !k3_ms || !k3_launches) return fail(OWRX_E_INVALID, "NULL argument");
+    double ms[OWRX_PROF_KINDS];
+    uint64_t n[OWRX_PROF_KINDS];
+    int rc = owrx_bank_profile_read_ex(bank, ms, n, reset);
+    if (rc != OWRX_OK) return rc;
+    // the dominant kernel of whichever form ran: direct K3, or the fast-convolution contraction
+    const int k = n[OWRX_PROF_FC_CONTRACT] ? OWRX_PROF_FC_CONTRACT : OWRX_PROF_K3_DIRECT;
+    *k3_ms = ms[k];
+    *k3_launches = n[k];
+    return OWRX_OK;
+}
+
+int owrx_bank_profile_read_ex(owrx_bank_t* bank, double* ms, uint64_t* launches, int reset)
+{
+    if (!bank || !ms || !launches) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    int rc = prof_collect(bank);
+    if (rc != OWRX_OK) return rc;
+    for (int k = 0; k < OWRX_PROF_KINDS; k++) {
+        ms[k] = bank->prof_ms[k];
+        launches[k] = bank->prof_launches[k];
+        if (reset) { bank->prof_ms[k] = 0.0; bank->prof_launches[k] = 0; }
+    }
+    return OWRX_OK;
+}
+
+int owrx_bank_set_fir_mode(owrx_bank_t* bank, int mode)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    if (mode < OWRX_FIR_AUTO || mode > OWRX_FIR_FASTCONV) return fail(OWRX_E_INVALID, "unknown FIR mode %d", mode);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    bank->fir_mode = mode;
     return OWRX_OK;
 }
 

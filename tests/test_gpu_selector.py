@@ -9,6 +9,14 @@ from openwebrx_b200.synth import BANDPASS, carrier_plan, make_iq
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["direct", "fastconv"])
+def fir_mode(request, monkeypatch):
+    """every parity case runs through both evaluations of Shift + FirDecimate: the direct-form K3 kernel and the
+    polyphase fast-convolution path K3F (owrx_bank_create reads OWRX_FIR_MODE)"""
+    monkeypatch.setenv("OWRX_FIR_MODE", str(N.FIR_MODES[request.param]))
+    return request.param
+
 AUDIO_TOL = 1e-4       # north_star: demodulated audio within 1e-4 relative RMS (float32), pre-AGC
 KIND = {"nfm": oracle.DEMOD_NFM, "am": oracle.DEMOD_AM, "usb": oracle.DEMOD_SSB, "wfm": oracle.DEMOD_WFM}
 
