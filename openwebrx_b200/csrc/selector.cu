@@ -891,7 +891,7 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
         // ---- Agc -> f3
         if (n_audio) {
             if ((rc = g->f3.ensure_new(n_audio, st)) != OWRX_OK) return rc;
-            agc_kernel<<<(S + 31) / 32, 32, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+            agc_kernel<<<(S + AGC_WARPS - 1) / AGC_WARPS, AGC_WARPS * 32, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
                                                        g->f3.append_ptr());
             OWRX_LAUNCH_CHECK();
             bank->stats.kernel_launches++;

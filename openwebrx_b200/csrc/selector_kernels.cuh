@@ -463,59 +463,102 @@ wfm_deemph_kernel(const float* __restrict__ in, int slots, int n, float alpha, C
     st[s].iir = y;
 }
 
-// Agc (SPEC-DEFINED).  Branch-free (lanes are different channels: a branch would diverge on
-// every sample); all three candidate gains are formed while the envelope comparison resolves, so the
-// sample-to-sample dependency is multiply -> compare -> select.
-struct AgcRun {
+// Agc (SPEC-DEFINED): per non-zero sample, |v|*gain/ref > 1 -> gain *= 1-attack, hang = hang_time;
+// else hang > 0 -> hang--; else gain *= 1+decay; gain clamped to [0, max]; out = clamp(v*gain, +-1).
+//
+// The recurrence is sample-serial, but BETWEEN attack events the state does not depend on the data, only on the
+// count of non-zero samples: the gain is constant during the hang and then follows the iterated product
+// U[k] = fl(U[k-1]*up).  One WARP owns a channel and evaluates 32 consecutive samples at a time (lane = sample):
+//   * ballots give every lane how many hang decrements / rising steps precede it,
+//   * the warp runs the R <= 32 rising steps of the tile as ONE FMUL chain (the only serial work: one instruction per
+//     rising sample; the [0, max] clamp commutes with the monotone chain: min(fl(min(u,M)*up), M) == min(fl(u*up), M)),
+//   * every lane tests its own sample for an attack against the speculative "no attack" gain; the first attack
+//     found (ballot + ffs) is applied and the lanes after it are re-evaluated from the new state.
+// Bit-identical to the sample-by-sample recurrence (tests/test_gpu_selector.py::test_agc_bit_exact_on_own_demod).
+constexpr int AGC_PF = 8;          // tiles prefetched per lane
+constexpr int AGC_WARPS = 4;
+
+struct AgcWarp {
     float gain, dn, up, thr, gmax;
     int hang, hang_time;
-    __device__ __forceinline__ float step(float v)
+    __device__ __forceinline__ float tile(float v, int lane)
     {
-        const bool nz = v != 0.f;                           // zeros are skipped by the algorithm itself
-        const bool att = nz && (fabsf(v) * gain > thr);     // == (fabsf(v) * gain / ref > 1), exactly
-        const bool idle = !nz || (!att && hang > 0);
-        const float g_dn = fmaxf(fminf(gain * dn, gmax), 0.f);
-        const float g_up = fmaxf(fminf(gain * up, gmax), 0.f);
-        const float g_id = fmaxf(fminf(gain, gmax), 0.f);
-        hang = att ? hang_time : ((nz && hang > 0) ? hang - 1 : hang);
-        gain = att ? g_dn : (idle ? g_id : g_up);
-        return fminf(1.f, fmaxf(-1.f, v * gain));
+        const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+        const unsigned nzm = __ballot_sync(full, v != 0.f);
+        unsigned act = full;
+        float o = v;
+        while (true) {
+            const unsigned nza = nzm & act;
+            const bool live = (nza >> lane) & 1u;
+            const bool rise = live && __popc(nza & lt) >= hang;
+            const unsigned rm = __ballot_sync(full, rise);
+            const int rb = __popc(rm & lt), R = __popc(rm);
+            float u = gain, ub = gain;                     // ub = U[rb]: the gain this lane's sample is compared with
+            for (int k = 1; k <= R; k++) {
+                u *= up;
+                ub = k == rb ? u : ub;
+            }
+            const float gb = fminf(ub, gmax);
+            const float ga = fminf(rise ? ub * up : ub, gmax);
+            const bool att = live && fabsf(v) * gb > thr;  // == (|v|*gain/ref > 1), exactly (agc_thr)
+            const unsigned am = __ballot_sync(full, att);
+            const bool mine = (act >> lane) & 1u;
+            if (am == 0u) {
+                if (mine) o = fminf(1.f, fmaxf(-1.f, v * ga));
+                gain = fminf(u, gmax);
+                hang = max(hang - __popc(nza), 0);
+                break;
+            }
+            const int first = __ffs(am) - 1;
+            const float gnew = fmaxf(fminf(__shfl_sync(full, gb, first) * dn, gmax), 0.f);
+            if (mine && lane < first) o = fminf(1.f, fmaxf(-1.f, v * ga));
+            if (lane == first) o = fminf(1.f, fmaxf(-1.f, v * gnew));
+            gain = gnew;
+            hang = hang_time;
+            if (first == 31) break;
+            act = full << (first + 1);
+        }
+        return o;
     }
 };
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(AGC_WARPS * 32)
 agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st,
            float* __restrict__ out)
 {
-    __shared__ float ring[SER_STAGES][SER_TT][32];
-    const int lane = threadIdx.x;
-    const int s = min(blockIdx.x * 32 + lane, slots - 1);
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * AGC_WARPS + (threadIdx.x >> 5);         // one warp per channel slot
+    if (s >= slots || n <= 0) return;
     const ChanCfg c = cfg[s];
-    const bool bypass = c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE;
-    AgcRun a{st[s].agc_gain, 1.f - c.agc_attack, 1.f + c.agc_decay, c.agc_thr, c.agc_max, st[s].agc_hang, c.agc_hang_time};
-    SerialFeed f{ring, in, slots, n, s, lane, (n + SER_TT - 1) / SER_TT};
-    for (int k = 0; k < SER_STAGES - 1; k++) f.issue(k);
-    for (int tile = 0; tile < f.nt; tile++) {
-        f.issue(tile + SER_STAGES - 1);
-        cp_async_wait<SER_STAGES - 1>();
-        const int cnt = min(SER_TT, n - tile * SER_TT);
-        float v[SER_TT];
-#pragma unroll
-        for (int t = 0; t < SER_TT; t++) v[t] = t < cnt ? ring[tile % SER_STAGES][t][lane] : 0.f;
-        if (!bypass) {
-            if (cnt == SER_TT) {
-#pragma unroll
-                for (int t = 0; t < SER_TT; t++) v[t] = a.step(v[t]);
-            } else {
-                for (int t = 0; t < cnt; t++) v[t] = a.step(v[t]);
-            }
-        }
-        float* o = out + (size_t)tile * SER_TT * slots + s;
-#pragma unroll
-        for (int t = 0; t < SER_TT; t++)
-            if (t < cnt) o[(size_t)t * slots] = v[t];
+    const float* x = in + s;
+    float* y = out + s;
+    if (c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE) {       // no Agc in these chains: pass through
+        for (int i = lane; i < n; i += 32) y[(size_t)i * slots] = x[(size_t)i * slots];
+        return;
     }
-    if (!bypass) {
+    AgcWarp a{st[s].agc_gain, 1.f - c.agc_attack, 1.f + c.agc_decay, c.agc_thr, c.agc_max, st[s].agc_hang, c.agc_hang_time};
+    a.gain = fmaxf(fminf(a.gain, a.gmax), 0.f);
+    const int nt = (n + 31) / 32;
+    float pf[AGC_PF];
+#pragma unroll
+    for (int k = 0; k < AGC_PF; k++) {
+        const int i = k * 32 + lane;
+        pf[k] = i < n ? __ldg(x + (size_t)i * slots) : 0.f;
+    }
+    for (int t0 = 0; t0 < nt; t0 += AGC_PF) {
+#pragma unroll
+        for (int k = 0; k < AGC_PF; k++) {
+            const int t = t0 + k;
+            if (t >= nt) break;
+            const float v = pf[k];
+            const int inext = (t + AGC_PF) * 32 + lane;
+            pf[k] = inext < n ? __ldg(x + (size_t)inext * slots) : 0.f;
+            const float o = a.tile(v, lane);               // samples past n are zeros: they change neither state nor outputs
+            const int i = t * 32 + lane;
+            if (i < n) y[(size_t)i * slots] = o;
+        }
+    }
+    if (lane == 0) {
         st[s].agc_gain = a.gain;
         st[s].agc_hang = a.hang;
     }

@@ -204,3 +204,32 @@ def test_squelch_gate_and_power(gpu):
     ref = oracle.fir_f(oracle.limit(oracle.fm_demod(sq)), oracle.nfm_deemphasis_taps(12000))
     assert len(dm) == len(ref) and rel_rms(dm, ref) <= AUDIO_TOL
     assert np.all(dm[-600:] == 0.0) and np.any(dm[:3000] != 0.0)     # closed squelch emits silence (after the hang)
+
+
+def test_agc_bit_exact_on_own_demod(gpu):
+    # the Agc stage is sample-serial; the GPU evaluates it tile-wise (speculative "no attack" trajectory, attacks
+    # applied one at a time).  Given the GPU's OWN pre-AGC samples, the oracle's sample-by-sample recurrence must
+    # reproduce the GPU audio bit for bit — including level steps that force runs of consecutive attacks.
+    fs, out = 2.4e6, 12000
+    cars = carrier_plan(6, fs, seed=31)
+    n = 5333 + 200 * (750 * 6 + 13)
+    iq = make_iq(n, fs, cars, seed=31)
+    iq[n // 3: n // 2] *= np.float32(30.0)            # +29.5 dB step: consecutive attacks
+    iq[n // 2: 2 * n // 3] *= np.float32(0.01)        # deep fade: hang, then the long decay ramp
+    bank, chans = _setup(fs, out, cars, 6, outputs=N.OUT_AUDIO | N.OUT_DEMOD)
+    rng = np.random.default_rng(5)
+    pos = 0
+    while pos < n:
+        step = int(rng.integers(1000, 400000))
+        bank.feed(iq[pos:pos + step])
+        pos += step
+    for ch, car in chans:
+        dm, au = ch.read_demod(), ch.read_audio()
+        assert len(dm) == len(au) >= 4000
+        if car["kind"] == "nfm":
+            ref = oracle.agc(dm, 0, 1.0, 3.0)             # analog.py:37-39
+        elif car["kind"] == "am":
+            ref = oracle.agc(dm, 0, 200.0, 65535.0)       # analog.py:13-15
+        else:
+            ref = oracle.agc(dm, 0, 1.0, 65535.0)         # analog.py:121-122 (bank default profile: slow)
+        assert np.array_equal(au, ref), (car["kind"], int(np.argmax(au != ref)))
