@@ -205,7 +205,9 @@ int owrx_bank_profile_read(owrx_bank_t* bank, double* k3_ms, uint64_t* k3_launch
 #define OWRX_PROF_FC_FORWARD  1   /* fc_forward_kernel: shared per-branch forward FFTs                        */
 #define OWRX_PROF_FC_CONTRACT 2   /* fc_contract_kernel: per-channel spectral contraction over the branches   */
 #define OWRX_PROF_FC_INVERSE  3   /* fc_inverse_kernel: per-channel inverse FFT + post-rotation               */
-#define OWRX_PROF_KINDS       4
+#define OWRX_PROF_TAIL        4   /* every parallel stage between FirDecimate and the Agc (one bracket per block)  */
+#define OWRX_PROF_AGC         5   /* agc_kernel: the sample-serial Agc                                        */
+#define OWRX_PROF_KINDS       6
 int owrx_bank_profile_read_ex(owrx_bank_t* bank, double* ms, uint64_t* launches, int reset);
 
 /* How Shift + FirDecimate (csdr/chain/selector.py:29,95) is evaluated.  Both forms compute the same sums

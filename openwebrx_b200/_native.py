@@ -89,7 +89,7 @@ SIGNATURES = {
     "owrx_bank_profile_read_ex": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
     "owrx_bank_set_fir_mode": (_i, [_vp, _i]),
 }
-PROF_KINDS = ("k3_direct", "fc_forward", "fc_contract", "fc_inverse")
+PROF_KINDS = ("k3_direct", "fc_forward", "fc_contract", "fc_inverse", "tail", "agc")
 FIR_MODES = {"auto": 0, "direct": 1, "fastconv": 2}
 
 for _name, (_res, _args) in SIGNATURES.items():

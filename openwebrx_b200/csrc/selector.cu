@@ -243,9 +243,9 @@ struct owrx_bank {
     float* d_xpose = nullptr; size_t d_xpose_cap = 0;
     owrx_bank_stats_t stats{};
     // H2D copy stream for the chunked host path; side stream + events for the pipelined device path
-    cudaStream_t copy_stream = nullptr, side_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, side_stream = nullptr, serial_stream = nullptr;
     std::vector<cudaEvent_t> chunk_events;
-    cudaEvent_t fir_done = nullptr, tail_done[2] = {nullptr, nullptr}, dev_done = nullptr;
+    cudaEvent_t fir_done = nullptr, ptail_done[2] = {nullptr, nullptr}, tail_done[2] = {nullptr, nullptr}, dev_done = nullptr;
     bool pipelined = false, reserve_sm = false;
     std::vector<cudaEvent_t> fir_events;
     unsigned long long calls = 0;
@@ -254,8 +254,8 @@ struct owrx_bank {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     std::vector<int> prof_tags;
     size_t prof_used = 0;
-    double prof_ms[OWRX_PROF_KINDS] = {0.0, 0.0, 0.0, 0.0};
-    uint64_t prof_launches[OWRX_PROF_KINDS] = {0, 0, 0, 0};
+    double prof_ms[OWRX_PROF_KINDS] = {};
+    uint64_t prof_launches[OWRX_PROF_KINDS] = {};
     int fir_mode = OWRX_FIR_AUTO;
 };
 
@@ -891,9 +891,11 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
         // ---- Agc -> f3
         if (n_audio) {
             if ((rc = g->f3.ensure_new(n_audio, st)) != OWRX_OK) return rc;
-            agc_kernel<<<(S + AGC_WARPS - 1) / AGC_WARPS, AGC_WARPS * 32, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+            if ((rc = prof_mark(bank, OWRX_PROF_AGC, st, true)) != OWRX_OK) return rc;
+            agc_kernel<<<S / AGC_CH, AGC_TL, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
                                                        g->f3.append_ptr());
             OWRX_LAUNCH_CHECK();
+            if ((rc = prof_mark(bank, OWRX_PROF_AGC, st, false)) != OWRX_OK) return rc;
             bank->stats.kernel_launches++;
             g->f3.appended(n_audio);
             if (g->any_tail) {
@@ -1078,6 +1080,9 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->serial_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fir_done, cudaEventDisableTiming);
@@ -1104,6 +1109,9 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     if (bank->tail_done[1]) cudaEventDestroy(bank->tail_done[1]);
     if (bank->copy_stream) cudaStreamDestroy(bank->copy_stream);
     if (bank->side_stream) cudaStreamDestroy(bank->side_stream);
+    if (bank->serial_stream) cudaStreamDestroy(bank->serial_stream);
+    if (bank->ptail_done[0]) cudaEventDestroy(bank->ptail_done[0]);
+    if (bank->ptail_done[1]) cudaEventDestroy(bank->ptail_done[1]);
     if (bank->h_stage) cudaFreeHost(bank->h_stage);
     if (bank->ev0) cudaEventDestroy(bank->ev0);
     if (bank->ev1) cudaEventDestroy(bank->ev1);
@@ -1463,9 +1471,9 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     return OWRX_OK;
 }
 
-// Device-resident path.  With owrx_bank_set_pipelined(bank, 1) the sample-serial stages of block i (Agc,
-// audio tail: one warp per 32 channels) run on the bank's side stream beside the K3 pass of block i+1,
-// which then leaves one SM free for them; owrx_bank_join makes a stream wait for everything issued so far.
+// Device-resident path.  With owrx_bank_set_pipelined(bank, 1) every stage after FirDecimate of block i runs on the
+// bank's side stream beside the Shift + FirDecimate pass of block i+1 on the caller's stream; owrx_bank_join makes a
+// stream wait for everything issued so far.
 int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_samples, void* stream)
 {
     if (!bank || !iq_dev) return fail(OWRX_E_INVALID, "NULL argument");
@@ -1476,8 +1484,10 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
     const int par = (int)(bank->calls & 1);
     int rc = OWRX_OK;
     if (bank->pipelined) {
-        // s1 ping-pong: this block's K3 writes the buffer the tail of two blocks ago was reading
-        OWRX_CUDA(cudaStreamWaitEvent(sa, bank->tail_done[par], 0));
+        // s1 ping-pong: this block's FirDecimate writes the buffer the parallel stages of two blocks ago were reading
+        OWRX_CUDA(cudaStreamWaitEvent(sa, bank->ptail_done[par], 0));
+        // f2 ping-pong: this block's parallel stages write the buffer the Agc of two blocks ago was reading
+        OWRX_CUDA(cudaStreamWaitEvent(sb, bank->tail_done[par], 0));
     }
     bank->reserve_sm = bank->pipelined;
     for (auto& gp : bank->groups) {
@@ -1485,28 +1495,39 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         if (!g) continue;
         size_t consumed = 0;
         // previous block's outputs are dropped; histories stay
-        if ((rc = group_begin_feed(bank, g, n_samples / (size_t)g->D + 1, sa, sa)) != OWRX_OK) return rc;
+        // pipelined: every stage after FirDecimate (rolls of their history buffers included) lives on the side stream
+        if ((rc = group_begin_feed(bank, g, n_samples / (size_t)g->D + 1, sa, sb)) != OWRX_OK) return rc;
         if ((rc = group_fir(bank, g, (const float2*)iq_dev, n_samples, &consumed, sa)) != OWRX_OK) return rc;
         int live = 0;
         for (int cid : g->slot_chan) if (cid >= 0) live++;
         bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
     }
-    for (auto& gp : bank->groups) {
-        Group* g = gp.get();
-        if (!g) continue;
-        if ((rc = group_tail(bank, g, sa)) != OWRX_OK) return rc;
-        g->sq_block_abs += (long long)g->last_blocks;
-    }
     if (bank->pipelined) {
         OWRX_CUDA(cudaEventRecord(bank->fir_done, sa));
         OWRX_CUDA(cudaStreamWaitEvent(sb, bank->fir_done, 0));
     }
+    if ((rc = prof_mark(bank, OWRX_PROF_TAIL, sb, true)) != OWRX_OK) return rc;
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
-        if (g && (rc = group_tail_serial(bank, g, sb)) != OWRX_OK) return rc;
+        if (!g) continue;
+        if ((rc = group_tail(bank, g, sb)) != OWRX_OK) return rc;
+        g->sq_block_abs += (long long)g->last_blocks;
+    }
+    if ((rc = prof_mark(bank, OWRX_PROF_TAIL, sb, false)) != OWRX_OK) return rc;
+    // three-deep pipeline: FirDecimate of block i+2 (sa) | parallel low-rate stages of block i+1 (sb) | the sample-serial
+    // Agc / audio tail of block i (sc).  Ping-pong stage buffers keep consecutive blocks apart; a buffer is reused two
+    // blocks later: s1 after ptail_done[par] (awaited by sa), f2 after tail_done[par] (awaited by sb).
+    cudaStream_t sc = bank->pipelined ? bank->serial_stream : sa;
+    if (bank->pipelined) {
+        OWRX_CUDA(cudaEventRecord(bank->ptail_done[par], sb));
+        OWRX_CUDA(cudaStreamWaitEvent(sc, bank->ptail_done[par], 0));
+    }
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (g && (rc = group_tail_serial(bank, g, sc)) != OWRX_OK) return rc;
     }
     bank->reserve_sm = false;
-    if (bank->pipelined) OWRX_CUDA(cudaEventRecord(bank->tail_done[par], sb));   // awaited by the call after next
+    if (bank->pipelined) OWRX_CUDA(cudaEventRecord(bank->tail_done[par], sc));   // awaited by the call after next
     OWRX_CUDA(cudaEventRecord(bank->dev_done, sa));
     bank->calls++;
     bank->stats.input_samples += n_samples;

@@ -468,97 +468,165 @@ wfm_deemph_kernel(const float* __restrict__ in, int slots, int n, float alpha, C
 //
 // The recurrence is sample-serial, but BETWEEN attack events the state does not depend on the data, only on the
 // count of non-zero samples: the gain is constant during the hang and then follows the iterated product
-// U[k] = fl(U[k-1]*up).  One WARP owns a channel and evaluates 32 consecutive samples at a time (lane = sample):
+// U[k] = fl(U[k-1]*up).  One WARP owns a channel and evaluates 128 consecutive samples at a time (4 per lane):
 //   * ballots give every lane how many hang decrements / rising steps precede it,
-//   * the warp runs the R <= 32 rising steps of the tile as ONE FMUL chain (the only serial work: one instruction per
+//   * the warp runs the R <= 128 rising steps of the tile as ONE FMUL chain (the only serial work: one instruction per
 //     rising sample; the [0, max] clamp commutes with the monotone chain: min(fl(min(u,M)*up), M) == min(fl(u*up), M)),
 //   * every lane tests its own sample for an attack against the speculative "no attack" gain; the first attack
 //     found (ballot + ffs) is applied and the lanes after it are re-evaluated from the new state.
 // Bit-identical to the sample-by-sample recurrence (tests/test_gpu_selector.py::test_agc_bit_exact_on_own_demod).
-constexpr int AGC_PF = 8;          // tiles prefetched per lane
-constexpr int AGC_WARPS = 4;
+constexpr int AGC_CH = 8;          // channels (= warps) per CTA: one 32-byte sector per time row
+constexpr int AGC_TL = 256;        // samples staged per step (= threads per CTA)
+
+constexpr int AGC_E = 4;           // consecutive samples per lane: a warp step covers 128 samples
 
 struct AgcWarp {
     float gain, dn, up, thr, gmax;
     int hang, hang_time;
-    __device__ __forceinline__ float tile(float v, int lane)
+    // v[e] = sample 4*lane + e of the step; returns the outputs in place.  U: per-warp scratch of 132 floats.
+    __device__ __forceinline__ void step(float (&v)[AGC_E], int lane, volatile float* U)
     {
         const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
-        const unsigned nzm = __ballot_sync(full, v != 0.f);
-        unsigned act = full;
-        float o = v;
+        unsigned nzbits = 0;
+#pragma unroll
+        for (int e = 0; e < AGC_E; e++) nzbits |= (v[e] != 0.f ? 1u : 0u) << e;
+        float o[AGC_E];
+#pragma unroll
+        for (int e = 0; e < AGC_E; e++) o[e] = v[e];
+        int j0 = 0;                                        // first sample of the step not yet committed
         while (true) {
-            const unsigned nza = nzm & act;
-            const bool live = (nza >> lane) & 1u;
-            const bool rise = live && __popc(nza & lt) >= hang;
-            const unsigned rm = __ballot_sync(full, rise);
-            const int rb = __popc(rm & lt), R = __popc(rm);
-            float u = gain, ub = gain;                     // ub = U[rb]: the gain this lane's sample is compared with
+            // samples >= j0 still to do: this lane's bits e with 4*lane + e >= j0
+            const int sh = min(max(j0 - AGC_E * lane, 0), AGC_E);
+            const unsigned act = (0xfu << sh) & 0xfu;
+            const unsigned live = nzbits & act;
+            unsigned m[AGC_E];
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) m[e] = __ballot_sync(full, (live >> e) & 1u);
+            int base = 0, n_live = 0;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) { base += __popc(m[e] & lt); n_live += __popc(m[e]); }
+            // rising steps: live samples once the hang counter has run out
+            unsigned rise = 0;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) {
+                const int before = base + __popc(live & ((1u << e) - 1u));
+                rise |= (((live >> e) & 1u) && before >= hang ? 1u : 0u) << e;
+            }
+            int rbase = 0, R = 0;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) {
+                const unsigned r = __ballot_sync(full, (rise >> e) & 1u);
+                rbase += __popc(r & lt);
+                R += __popc(r);
+            }
+            // U[k] = k rising steps applied to the entry gain: the only sample-serial work (FMUL + STS per step)
+            float u = gain;
+            U[0] = u;
+#pragma unroll 8
             for (int k = 1; k <= R; k++) {
                 u *= up;
-                ub = k == rb ? u : ub;
+                U[k] = u;
             }
-            const float gb = fminf(ub, gmax);
-            const float ga = fminf(rise ? ub * up : ub, gmax);
-            const bool att = live && fabsf(v) * gb > thr;  // == (|v|*gain/ref > 1), exactly (agc_thr)
-            const unsigned am = __ballot_sync(full, att);
-            const bool mine = (act >> lane) & 1u;
+            __syncwarp();
+            float gb[AGC_E], ga[AGC_E];
+            unsigned att = 0;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) {
+                const int rb = rbase + __popc(rise & ((1u << e) - 1u));
+                gb[e] = fminf(U[rb], gmax);                                 // gain sample e is compared with
+                ga[e] = fminf(U[rb + ((rise >> e) & 1u)], gmax);            // gain applied to its output (no attack)
+                att |= (((live >> e) & 1u) && fabsf(v[e]) * gb[e] > thr ? 1u : 0u) << e;   // == (|v|*gain/ref > 1), exactly
+            }
+            __syncwarp();
+            const unsigned am = __ballot_sync(full, att != 0u);
             if (am == 0u) {
-                if (mine) o = fminf(1.f, fmaxf(-1.f, v * ga));
+#pragma unroll
+                for (int e = 0; e < AGC_E; e++)
+                    if ((act >> e) & 1u) o[e] = fminf(1.f, fmaxf(-1.f, v[e] * ga[e]));
                 gain = fminf(u, gmax);
-                hang = max(hang - __popc(nza), 0);
+                hang = max(hang - n_live, 0);
                 break;
             }
-            const int first = __ffs(am) - 1;
-            const float gnew = fmaxf(fminf(__shfl_sync(full, gb, first) * dn, gmax), 0.f);
-            if (mine && lane < first) o = fminf(1.f, fmaxf(-1.f, v * ga));
-            if (lane == first) o = fminf(1.f, fmaxf(-1.f, v * gnew));
+            const int L = __ffs(am) - 1;
+            const int ef = __ffs(att) - 1;                                   // this lane's first attacking sample (if any)
+            const float gsel = ef == 0 ? gb[0] : (ef == 1 ? gb[1] : (ef == 2 ? gb[2] : gb[3]));
+            const int e_first = __shfl_sync(full, ef, L);
+            const float gnew = fmaxf(fminf(__shfl_sync(full, gsel, L) * dn, gmax), 0.f);
+            const int jf = AGC_E * L + e_first;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) {
+                const int j = AGC_E * lane + e;
+                if (((act >> e) & 1u) && j < jf) o[e] = fminf(1.f, fmaxf(-1.f, v[e] * ga[e]));
+                if (j == jf) o[e] = fminf(1.f, fmaxf(-1.f, v[e] * gnew));
+            }
             gain = gnew;
             hang = hang_time;
-            if (first == 31) break;
-            act = full << (first + 1);
+            j0 = jf + 1;
+            if (j0 >= 32 * AGC_E) break;
         }
-        return o;
+#pragma unroll
+        for (int e = 0; e < AGC_E; e++) v[e] = o[e];
     }
 };
 
-__global__ void __launch_bounds__(AGC_WARPS * 32)
+// CTA = 8 adjacent channel slots (slots is a multiple of 64).  All 256 threads move [256 samples][8 slots] tiles between
+// global memory (32-byte rows: whole sectors) and shared memory, register-prefetched one tile ahead; warp w then runs
+// channel w's recurrence over the tile, 128 samples at a time.
+__global__ void __launch_bounds__(AGC_TL)
 agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st,
            float* __restrict__ out)
 {
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * AGC_WARPS + (threadIdx.x >> 5);         // one warp per channel slot
-    if (s >= slots || n <= 0) return;
+    __shared__ __align__(16) float xin[2][AGC_CH][AGC_TL];
+    __shared__ __align__(16) float xout[AGC_CH][AGC_TL];
+    __shared__ float U_all[AGC_CH][32 * AGC_E + 4];
+    if (n <= 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int s0 = blockIdx.x * AGC_CH, s = s0 + w;
     const ChanCfg c = cfg[s];
-    const float* x = in + s;
-    float* y = out + s;
-    if (c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE) {       // no Agc in these chains: pass through
-        for (int i = lane; i < n; i += 32) y[(size_t)i * slots] = x[(size_t)i * slots];
-        return;
-    }
+    const bool bypass = c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE;     // no Agc in these chains: pass through
     AgcWarp a{st[s].agc_gain, 1.f - c.agc_attack, 1.f + c.agc_decay, c.agc_thr, c.agc_max, st[s].agc_hang, c.agc_hang_time};
     a.gain = fmaxf(fminf(a.gain, a.gmax), 0.f);
-    const int nt = (n + 31) / 32;
-    float pf[AGC_PF];
-#pragma unroll
-    for (int k = 0; k < AGC_PF; k++) {
-        const int i = k * 32 + lane;
-        pf[k] = i < n ? __ldg(x + (size_t)i * slots) : 0.f;
-    }
-    for (int t0 = 0; t0 < nt; t0 += AGC_PF) {
-#pragma unroll
-        for (int k = 0; k < AGC_PF; k++) {
-            const int t = t0 + k;
-            if (t >= nt) break;
-            const float v = pf[k];
-            const int inext = (t + AGC_PF) * 32 + lane;
-            pf[k] = inext < n ? __ldg(x + (size_t)inext * slots) : 0.f;
-            const float o = a.tile(v, lane);               // samples past n are zeros: they change neither state nor outputs
-            const int i = t * 32 + lane;
-            if (i < n) y[(size_t)i * slots] = o;
+    volatile float* U = U_all[w];
+    const int nt = (n + AGC_TL - 1) / AGC_TL;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int tile, float4& lo, float4& hi) {
+        const int t = tile * AGC_TL + tid;
+        if (t < n) {
+            const float4* p = reinterpret_cast<const float4*>(in + (size_t)t * slots + s0);
+            lo = __ldg(p); hi = __ldg(p + 1);
+        } else {
+            lo = zero4; hi = zero4;                        // zeros change neither state nor outputs
         }
+    };
+    auto stage = [&](int buf, const float4& lo, const float4& hi) {
+        xin[buf][0][tid] = lo.x; xin[buf][1][tid] = lo.y; xin[buf][2][tid] = lo.z; xin[buf][3][tid] = lo.w;
+        xin[buf][4][tid] = hi.x; xin[buf][5][tid] = hi.y; xin[buf][6][tid] = hi.z; xin[buf][7][tid] = hi.w;
+    };
+    float4 lo, hi;
+    fetch(0, lo, hi);
+    stage(0, lo, hi);
+    __syncthreads();
+    for (int tile = 0; tile < nt; tile++) {
+        const int buf = tile & 1;
+        if (tile + 1 < nt) fetch(tile + 1, lo, hi);
+#pragma unroll 1
+        for (int k = 0; k < AGC_TL / (32 * AGC_E); k++) {
+            const float4 x4 = *reinterpret_cast<const float4*>(&xin[buf][w][k * 32 * AGC_E + AGC_E * lane]);
+            float v[AGC_E] = {x4.x, x4.y, x4.z, x4.w};
+            if (!bypass) a.step(v, lane, U);
+            *reinterpret_cast<float4*>(&xout[w][k * 32 * AGC_E + AGC_E * lane]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncthreads();                                   // xout complete, xin[buf] consumed
+        const int t = tile * AGC_TL + tid;
+        if (t < n) {
+            float4* p = reinterpret_cast<float4*>(out + (size_t)t * slots + s0);
+            p[0] = make_float4(xout[0][tid], xout[1][tid], xout[2][tid], xout[3][tid]);
+            p[1] = make_float4(xout[4][tid], xout[5][tid], xout[6][tid], xout[7][tid]);
+        }
+        if (tile + 1 < nt) stage(buf ^ 1, lo, hi);
+        __syncthreads();                                   // next tile staged, xout free
     }
-    if (lane == 0) {
+    if (lane == 0 && !bypass) {
         st[s].agc_gain = a.gain;
         st[s].agc_hang = a.hang;
     }

@@ -14,7 +14,7 @@ from openwebrx_b200 import _native as N                                 # noqa: 
 from openwebrx_b200.synth import BANDPASS, carrier_plan                 # noqa: E402
 
 
-def run(fs, out_rate, n_ch, block, mode, steps=5, wfm=False, **kw):
+def run(fs, out_rate, n_ch, block, mode, steps=20, wfm=False, **kw):
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev); g.manual_seed(1)
     iq = 1e-3 * torch.randn(block, 2, device=dev, generator=g)
@@ -56,8 +56,12 @@ def main():
         "C3/8": dict(fs=61.44e6, out_rate=12000, n_ch=128, block=1 << 24),
         "C5": dict(fs=20e6, out_rate=250000, n_ch=128, block=1 << 23, wfm=True, audio_rate=48000.0, tau=50e-6),
     }
-    pick = sys.argv[1:] or list(shapes)
+    pick = [a for a in sys.argv[1:] if a in shapes] or list(shapes)
+    only = [a for a in sys.argv[1:] if a in ("direct", "fastconv")]
     for name in pick:
+        if only:
+            print(json.dumps({name: run(mode=only[0], **shapes[name])[0]}), flush=True)
+            continue
         a, oa = run(mode="direct", **shapes[name])
         b, ob = run(mode="fastconv", **shapes[name])
         diff = []
