@@ -320,8 +320,11 @@ def run_ours(args):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = N.lib.owrx_launch_count() - launches0
-    k3_ms, k3_n = bank.profile_read(reset=True)
+    prof = bank.profile_read_ex(reset=True)
     bank.profile(False)
+    fastconv = prof["fc_contract"][1] > 0
+    dom = "fc_contract" if fastconv else "k3_direct"
+    k3_ms, k3_n = prof[dom]
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -385,14 +388,32 @@ def run_ours(args):
     # ---- waterfall half of the hot path (config 1 shape), own timed loop on this GPU
     wf_stats = bench_waterfall(torch, dev, hbm_peak)
 
-    # ---- roofline of the dominant kernel (K3)
+    # ---- roofline of the dominant kernel: the fast-convolution contraction (K3F) or, in direct mode, K3
     k3_avg_s = (k3_ms / max(k3_n, 1)) * 1e-3
-    algo_bytes = 8.0 * BLOCK + 8.0 * CH_PER_GPU * n_k            # IQ read once + complex IF written (per launch)
-    achieved = algo_bytes / k3_avg_s / 1e9 if k3_avg_s > 0 else 0.0
-    flops = CH_PER_GPU * float(consumed) * (8.0 + 4.0 * T / D)    # C*Nin*(8 + 4T/D)
     f_obs = (clk or {}).get("sm_mhz") or sm_max
     fp32_peak = 148 * 128 * 2 * f_obs * 1e6 / 1e12
+    if fastconv:
+        M, P = 256, -(-T // D)
+        Kb, Dp = M - P + 1, -(-D // 32) * 32
+        B = -(-n_k // Kb)                                         # overlap-save blocks per launch
+        # operands of the contraction, each moved once: F (16 B, packed-FMA layout), table (8 B), Z (8 B)
+        algo_bytes = 16.0 * M * B * Dp + 8.0 * M * Dp * CH_PER_GPU + 8.0 * M * B * CH_PER_GPU
+        flops = 8.0 * M * B * Dp * CH_PER_GPU                     # complex MAC = 4 FMA per (bin, block, branch, channel)
+        kname = "fc_contract_kernel (K3F: per-channel spectral contraction over the %d polyphase branches, %d blocks x %d ch)" % (D, B, CH_PER_GPU)
+        knote = ("FP32-FMA bound (%.0f FLOP per operand byte): see roofline_fp32; the shared forward FFTs (fc_forward) and the inverse "
+                 "FFT + rotation (fc_inverse) are in stages_ms" % (flops / algo_bytes))
+        tkey = "fc_contract_kernel"
+    else:
+        algo_bytes = 8.0 * BLOCK + 8.0 * CH_PER_GPU * n_k        # IQ read once + complex IF written (per launch)
+        flops = CH_PER_GPU * float(consumed) * (8.0 + 4.0 * T / D)    # C*Nin*(8 + 4T/D)
+        kname = "fir_decimate_kernel (K3: NCO mix + polyphase FIR decimate, 64 ch)"
+        knote = "direct-form DDC is FP32-FMA bound by construction (SURVEY 8d): see roofline_fp32"
+        tkey = "fir_decimate_kernel"
+    achieved = algo_bytes / k3_avg_s / 1e9 if k3_avg_s > 0 else 0.0
     fp32_ach = flops / k3_avg_s / 1e12 if k3_avg_s > 0 else 0.0
+    stages = {k: v[0] / v[1] for k, v in prof.items() if v[1]}
+    # the same work expressed in the reference's own terms (direct form: SURVEY 8d) for comparison across forms
+    direct_equiv = CH_PER_GPU * float(consumed) * (8.0 + 4.0 * T / D) / (ms_step * 1e-3) / 1e12
 
     # ---- CPU baseline beside it (bounded sample, rank 0 only, N = 1 only)
     cpu = None
@@ -413,12 +434,15 @@ def run_ours(args):
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "fir_decimate_kernel (K3: NCO mix + polyphase FIR decimate, 64 ch)", "bound": "hbm", "achieved": achieved,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": load_traffic("fir_decimate_kernel"), "peak_source": peak_src,
+        "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": load_traffic(tkey), "peak_source": peak_src,
                      "kernel_ms": k3_avg_s * 1e3, "kernel_share_of_step": (k3_ms / args.steps) / ms_step if ms_step > 0 else None,
-                     "note": "direct-form DDC is FP32-FMA bound by construction (SURVEY 8d): see roofline_fp32"},
+                     "algorithmic_bytes": algo_bytes, "note": knote},
         "roofline_fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
-                          "peak_def": "148 SM x 128 lanes x 2 x observed SM clock (%.0f MHz)" % f_obs},
+                          "peak_def": "148 SM x 128 lanes x 2 x observed SM clock (%.0f MHz)" % f_obs,
+                          "direct_form_equivalent_tflops": direct_equiv},
+        "fir_form": "fastconv" if fastconv else "direct",
+        "stages_ms": stages,
         "waterfall": wf_stats,
         "cpu_baseline": cpu,
     }

@@ -85,7 +85,7 @@ __device__ __forceinline__ void fc_fft256(float2* v, float2* seq, const float2* 
 }
 
 __global__ void __launch_bounds__(16 * FC_SEQ)
-fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp, int Kb, int B, float2* __restrict__ F)
+fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp, int Kb, int B, float4* __restrict__ F)
 {
     extern __shared__ float2 fc_smem[];
     float2* tw = fc_smem;                       // [256]
@@ -106,62 +106,96 @@ fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp,
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         const int bin = g + 16 * slot<16>(q);
-        F[((size_t)bin * B + b) * Dp + r] = v[q];
+        // operand layout of the contraction's packed FMAs: (re, re) and (-im, im)
+        F[((size_t)bin * B + b) * Dp + r] = make_float4(v[q].x, v[q].x, -v[q].y, v[q].y);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Z[q][b][c] = sum_{r<Dp} F[q][b][r] * Tab[q][r][c]     (complex x complex, FP32 FMA pipe)
-// CTA = (bin q, tile of BT = 8 NW blocks, 64 channel slots).  Warp w owns rows 8w..8w+7, lane l columns 2l, 2l+1:
-// per pair of branches a thread issues 8 broadcast LDS.128 (two F values of each of its rows) + 2 LDS.128 (its two
-// table columns of both branches) for 128 FMAs.  Operand chunks of 32 branches stream through a 3-stage cp.async
-// pipeline.
+// CTA = (bin q, tile of BT = 16 NW blocks, 64 channel slots).  A warp owns 16 rows x 64 columns; its lanes form a
+// 2 x 16 grid: lane (lr, lc) holds rows 16w + 2i + lr (i < 8) and columns {2lc, 2lc+1, 32+2lc, 33+2lc} — an 8 x 4
+// register tile of complex accumulators, so one staged operand feeds 4 (F) or 8 (table) complex MACs and the
+// shared-memory wavefronts per MAC stay well under the FMA pipe's demand.
+// Blackwell packed FP32 (fma.rn.f32x2 -> FFMA2): an accumulator is the (re, im) pair of one output,
+//   acc += (f.re, f.re) * (t.re, t.im);   acc += (-f.im, f.im) * (t.im, t.re)
+// The forward pass stores F already as (re, re, -im, im): one LDS.128 per (row, branch) yields both packed
+// multiplicands; the table pairs (t.re, t.im) of two columns come from one LDS.128 and the swapped pair costs two
+// register moves per column.  Per branch and thread: 10 LDS.128 + 8 MOV + 64 FFMA2.  Operand chunks of 32 branches
+// stream through a 3-stage cp.async pipeline; two warp groups split the branches of a chunk (even / odd) and meet in
+// shared memory at the end, so a 96-row CTA runs 12 warps.
 // ------------------------------------------------------------------------------------------------
 constexpr int FC_ST = 3;
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(f32x2& c, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void lds2x64(f32x2& a, f32x2& b, unsigned addr)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ f32x2 swap2(f32x2 v)
+{
+    float a, b;
+    upk2(v, a, b);
+    return pk2(b, a);
+}
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32)
-fc_contract_kernel(const float2* __restrict__ F, const float2* __restrict__ tab, float2* __restrict__ Z, int B, int Dp, int slots, int nbt)
+__global__ void __launch_bounds__(NW * 64, 1)
+fc_contract_kernel(const float4* __restrict__ F, const float2* __restrict__ tab, float2* __restrict__ Z, int B, int Dp, int slots, int nbt)
 {
-    constexpr int BT = 8 * NW;
+    constexpr int BT = 16 * NW;
+    constexpr int NT = NW * 64;                                       // two warp groups: even / odd branches of a chunk
     extern __shared__ float4 fc_smem4[];
-    float2* Fs = reinterpret_cast<float2*>(fc_smem4);                 // [ST][BT][KC]
-    float2* Ts = Fs + FC_ST * BT * FC_KC;                             // [ST][KC][64]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* Fs = fc_smem4;                                            // [ST][BT][KC]   (re, re, -im, im)
+    float2* Ts = reinterpret_cast<float2*>(Fs + FC_ST * BT * FC_KC);  // [ST][KC][64]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int grp = (tid >> 5) / NW, warp = (tid >> 5) % NW;
+    const int lr = lane >> 4, lc = lane & 15;
     const int q = blockIdx.x / nbt, bt = blockIdx.x % nbt;
     const int cg = blockIdx.y;
     const int b0 = bt * BT;
     const int rows = min(BT, B - b0);
     const int nchunks = Dp / FC_KC;
+    // rows 16w + 2i + lr of this warp that exist: i < ni (the lr = 1 half of a last odd row is clamped at the load)
+    const int ni = min(8, max(0, (rows - warp * 16 + 1) / 2));
 
-    const float2* Fq = F + ((size_t)q * B + b0) * Dp;
+    const float4* Fq = F + ((size_t)q * B + b0) * Dp;
     const float2* Tq = tab + (size_t)q * Dp * slots + (size_t)cg * FC_CG;
 
     auto load_chunk = [&](int chunk, int stage) {
-        float2* fs = Fs + stage * BT * FC_KC;
+        float4* fs = Fs + stage * BT * FC_KC;
         float2* ts = Ts + stage * FC_KC * FC_CG;
-        // F: BT rows x 16 pieces of 16 B
-        for (int i = tid; i < BT * (FC_KC / 2); i += NW * 32) {
-            const int row = i / (FC_KC / 2), pc = i % (FC_KC / 2);
+        for (int i = tid; i < BT * FC_KC; i += NT) {                  // F: BT rows x 32 pieces of 16 B
+            const int row = i / FC_KC, pc = i % FC_KC;
             const int srow = min(row, rows - 1);
-            cp_async16(fs + row * FC_KC + pc * 2, Fq + (size_t)srow * Dp + chunk * FC_KC + pc * 2);
+            cp_async16(fs + row * FC_KC + pc, Fq + (size_t)srow * Dp + chunk * FC_KC + pc);
         }
-        // Tab: KC rows x 32 pieces
-        for (int i = tid; i < FC_KC * (FC_CG / 2); i += NW * 32) {
+        for (int i = tid; i < FC_KC * (FC_CG / 2); i += NT) {         // Tab: KC rows x 32 pieces
             const int kr = i / (FC_CG / 2), pc = i % (FC_CG / 2);
             cp_async16(ts + kr * FC_CG + pc * 2, Tq + (size_t)(chunk * FC_KC + kr) * slots + pc * 2);
         }
     };
 
-    float2 acc[8][2];
+    f32x2 acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[i][c] = 0ull;
 
 #pragma unroll
     for (int s = 0; s < FC_ST - 1; s++) {
         if (s < nchunks) load_chunk(s, s);
         cp_commit();
     }
+    const unsigned fs_base = (unsigned)__cvta_generic_to_shared(Fs) + (unsigned)(((warp * 16 + lr) * FC_KC + grp) * sizeof(float4));
+    const unsigned ts_base = (unsigned)__cvta_generic_to_shared(Ts) + (unsigned)((grp * FC_CG + lc * 2) * sizeof(float2));
     for (int ch = 0; ch < nchunks; ch++) {
         cp_wait<FC_ST - 2>();
         __syncthreads();
@@ -171,31 +205,62 @@ fc_contract_kernel(const float2* __restrict__ F, const float2* __restrict__ tab,
             cp_commit();
         }
         const int stage = ch % FC_ST;
-        const float4* fs = reinterpret_cast<const float4*>(Fs + stage * BT * FC_KC + warp * 8 * FC_KC);
-        const float4* ts = reinterpret_cast<const float4*>(Ts + stage * FC_KC * FC_CG) + lane;
-#pragma unroll 4
-        for (int kk = 0; kk < FC_KC / 2; kk++) {
-            const float4 t0 = ts[(2 * kk) * (FC_CG / 2)];
-            const float4 t1 = ts[(2 * kk + 1) * (FC_CG / 2)];
+        const unsigned fsa = fs_base + (unsigned)(stage * BT * FC_KC * sizeof(float4));
+        const unsigned tsa = ts_base + (unsigned)(stage * FC_KC * FC_CG * sizeof(float2));
+        // this group's branches of the chunk: k = 2 kk + grp
+#define FC_BRANCH_STEP(ROW_GUARD)                                                                       \
+        for (int kk = 0; kk < FC_KC / 2; kk++) {                                                        \
+            f32x2 t[4], s[4];                                                                           \
+            lds2x64(t[0], t[1], tsa + (unsigned)(2 * kk * FC_CG * sizeof(float2)));                     \
+            lds2x64(t[2], t[3], tsa + (unsigned)((2 * kk * FC_CG + 32) * sizeof(float2)));              \
+            _Pragma("unroll") for (int c = 0; c < 4; c++) s[c] = swap2(t[c]);                           \
+            _Pragma("unroll") for (int i = 0; i < 8; i++) {                                             \
+                if (ROW_GUARD) {                                                                        \
+                    f32x2 fa, fb;                                                                       \
+                    lds2x64(fa, fb, fsa + (unsigned)((2 * i * FC_KC + 2 * kk) * sizeof(float4)));       \
+                    _Pragma("unroll") for (int c = 0; c < 4; c++) ffma2(acc[i][c], fa, t[c]);           \
+                    _Pragma("unroll") for (int c = 0; c < 4; c++) ffma2(acc[i][c], fb, s[c]);           \
+                }                                                                                       \
+            }                                                                                           \
+        }
+        if (ni == 8) {
+#pragma unroll 2
+            FC_BRANCH_STEP(true)
+        } else {
+#pragma unroll 1
+            FC_BRANCH_STEP(i < ni)
+        }
+#undef FC_BRANCH_STEP
+    }
+    // the odd-branch group hands its partial sums over through shared memory (the stage buffers are free now)
+    cp_wait<0>();
+    __syncthreads();
+    f32x2* red = reinterpret_cast<f32x2*>(fc_smem4);                  // [NW][32 accumulators][32 lanes]
+    if (grp == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float4 f = fs[i * (FC_KC / 2) + kk];
-                acc[i][0].x = fmaf(f.x, t0.x, acc[i][0].x); acc[i][0].x = fmaf(-f.y, t0.y, acc[i][0].x);
-                acc[i][0].y = fmaf(f.x, t0.y, acc[i][0].y); acc[i][0].y = fmaf(f.y, t0.x, acc[i][0].y);
-                acc[i][1].x = fmaf(f.x, t0.z, acc[i][1].x); acc[i][1].x = fmaf(-f.y, t0.w, acc[i][1].x);
-                acc[i][1].y = fmaf(f.x, t0.w, acc[i][1].y); acc[i][1].y = fmaf(f.y, t0.z, acc[i][1].y);
-                acc[i][0].x = fmaf(f.z, t1.x, acc[i][0].x); acc[i][0].x = fmaf(-f.w, t1.y, acc[i][0].x);
-                acc[i][0].y = fmaf(f.z, t1.y, acc[i][0].y); acc[i][0].y = fmaf(f.w, t1.x, acc[i][0].y);
-                acc[i][1].x = fmaf(f.z, t1.z, acc[i][1].x); acc[i][1].x = fmaf(-f.w, t1.w, acc[i][1].x);
-                acc[i][1].y = fmaf(f.z, t1.w, acc[i][1].y); acc[i][1].y = fmaf(f.w, t1.z, acc[i][1].y);
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) red[(warp * 32 + i * 4 + c) * 32 + lane] = acc[i][c];
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int row = warp * 16 + 2 * i + lr;
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float x0, y0, x1, y1;
+                upk2(acc[i][c], x0, y0);
+                upk2(red[(warp * 32 + i * 4 + c) * 32 + lane], x1, y1);
+                o[2 * c] = x0 + x1; o[2 * c + 1] = y0 + y1;
+            }
+            if (row < rows) {
+                float4* zr = reinterpret_cast<float4*>(Z + ((size_t)q * B + b0 + row) * slots + (size_t)cg * FC_CG) + lc;
+                zr[0] = make_float4(o[0], o[1], o[2], o[3]);
+                zr[16] = make_float4(o[4], o[5], o[6], o[7]);
             }
         }
-    }
-    float4* Zq = reinterpret_cast<float4*>(Z + ((size_t)q * B + b0) * slots + (size_t)cg * FC_CG) + lane;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int row = warp * 8 + i;
-        if (row < rows) Zq[(size_t)row * (slots / 2)] = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
     }
 }
 
@@ -241,13 +306,13 @@ fc_inverse_kernel(const float2* __restrict__ Z, int B, int slots, int D, int Kb,
 constexpr size_t kFftSmem = (256 + FC_SEQ * FC_STR) * sizeof(float2);
 
 template <int NW>
-int launch_contract_nw(const FcShape& sh, const float2* F, const float2* tab, int B, float2* Z, cudaStream_t st)
+int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, int B, float2* Z, cudaStream_t st)
 {
-    constexpr int BT = 8 * NW;
-    const size_t smem = (size_t)FC_ST * (BT * FC_KC + FC_KC * FC_CG) * sizeof(float2);
+    constexpr int BT = 16 * NW;
+    const size_t smem = (size_t)FC_ST * (BT * FC_KC * sizeof(float4) + FC_KC * FC_CG * sizeof(float2));
     OWRX_CUDA(cudaFuncSetAttribute(fc_contract_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nbt = (B + BT - 1) / BT;
-    fc_contract_kernel<NW><<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG)), NW * 32, smem, st>>>(F, tab, Z, B, sh.Dp, sh.slots, nbt);
+    fc_contract_kernel<NW><<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG)), NW * 64, smem, st>>>(F, tab, Z, B, sh.Dp, sh.slots, nbt);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
@@ -265,7 +330,7 @@ int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list,
     return OWRX_OK;
 }
 
-int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float2* d_F, cudaStream_t st)
+int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float4* d_F, cudaStream_t st)
 {
     OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
     fc_forward_kernel<<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
@@ -273,25 +338,20 @@ int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int 
     return OWRX_OK;
 }
 
-int fc_launch_contract(const FcShape& sh, const float2* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, cudaStream_t st)
+int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, cudaStream_t st)
 {
     (void)sm_count;
     static const int force_nw = getenv("OWRX_FC_NW") ? atoi(getenv("OWRX_FC_NW")) : 0;
-    int nw = force_nw;
-    if (!nw) {
-        // smallest tile that covers B in as few tiles as the largest one does
-        const int cands[] = {1, 2, 4, 6, 8, 11};
-        const int best_tiles = (B + 87) / 88;
-        nw = 11;
-        for (int c : cands) if ((B + 8 * c - 1) / (8 * c) == best_tiles) { nw = c; break; }
-    }
+    // as few row tiles as 96-row CTAs allow, then the smallest CTA that still covers them
+    const int nbt = (B + 95) / 96;
+    int nw = force_nw ? force_nw : ((B + nbt - 1) / nbt + 15) / 16;
     switch (nw) {
     case 1: return launch_contract_nw<1>(sh, d_F, d_tab, B, d_Z, st);
     case 2: return launch_contract_nw<2>(sh, d_F, d_tab, B, d_Z, st);
+    case 3: return launch_contract_nw<3>(sh, d_F, d_tab, B, d_Z, st);
     case 4: return launch_contract_nw<4>(sh, d_F, d_tab, B, d_Z, st);
-    case 6: return launch_contract_nw<6>(sh, d_F, d_tab, B, d_Z, st);
-    case 8: return launch_contract_nw<8>(sh, d_F, d_tab, B, d_Z, st);
-    default: return launch_contract_nw<11>(sh, d_F, d_tab, B, d_Z, st);
+    case 5: return launch_contract_nw<5>(sh, d_F, d_tab, B, d_Z, st);
+    default: return launch_contract_nw<6>(sh, d_F, d_tab, B, d_Z, st);
     }
 }
 

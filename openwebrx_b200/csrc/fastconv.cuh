@@ -19,7 +19,8 @@
 namespace owrx {
 
 constexpr int FC_M = 256;        // branch FFT size
-constexpr int FC_KC = 32;        // contraction chunk (branches per pipeline stage); D is padded to a multiple
+constexpr int FC_KC = 32;        // contraction chunk (branches per pipeline stage)
+constexpr int FC_DPAD = 32;      // D is padded to a multiple of this (forward pass: 32 branches per CTA)
 constexpr int FC_CG = 64;        // channel slots per contraction CTA
 
 struct FcShape {
@@ -29,9 +30,9 @@ struct FcShape {
 // rebuild the table columns of `n` slots: slot_list[i], rate_list[i] (device arrays)
 int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, float2* d_tab,
                     cudaStream_t st);
-// F[q][b][r] for blocks b < B of the stream starting at iq (sample 0 = first tap of output 0)
-int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float2* d_F, cudaStream_t st);
-int fc_launch_contract(const FcShape& sh, const float2* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, cudaStream_t st);
+// F[q][b][r] (stored as the packed-FMA operand (re, re, -im, im)) for blocks b < B of the stream starting at iq (sample 0 = first tap of output 0)
+int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float4* d_F, cudaStream_t st);
+int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, cudaStream_t st);
 // out[(k0 + b Kb + m) * slots + c] for k0 + b Kb + m < n_k; phases are relative to iq[-1] of the whole call
 int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
                       float2* out, cudaStream_t st);

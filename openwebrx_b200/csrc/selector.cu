@@ -216,7 +216,7 @@ struct Group {
     // K3F fast-convolution channeliser (fastconv.cuh): tables are built lazily on the first eligible pass
     bool fc_ok = false;
     FcShape fc{};
-    float* d_fc_h = nullptr; float2* d_fc_tab = nullptr; float2* d_fc_F = nullptr; float2* d_fc_Z = nullptr;
+    float* d_fc_h = nullptr; float2* d_fc_tab = nullptr; float4* d_fc_F = nullptr; float2* d_fc_Z = nullptr;
     int* d_fc_slots = nullptr; double* d_fc_rates = nullptr;
     size_t fc_blocks_cap = 0;
     std::vector<double> fc_tab_rate;                 // per slot: Shift rate its table column was built for (NaN = none)
@@ -349,7 +349,7 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     }
     g->fc_taps.resize((size_t)g->T);
     for (int t = 0; t < g->T; t++) g->fc_taps[(size_t)t] = (float)h[t];
-    g->fc = FcShape{g->D, g->T, P, FC_M - P + 1, (g->D + FC_KC - 1) / FC_KC * FC_KC, g->slots};
+    g->fc = FcShape{g->D, g->T, P, FC_M - P + 1, (g->D + FC_DPAD - 1) / FC_DPAD * FC_DPAD, g->slots};
     g->fc_ok = g->D >= 8 && P <= FC_M / 4;
     int rc;
     if ((rc = dev_alloc(&g->d_taps, ht.size())) != OWRX_OK) return rc;
@@ -587,8 +587,8 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
     }
     // ---- scratch for up to Bmax blocks per pass
     const size_t blocks_total = (n_k + (size_t)sh.Kb - 1) / (size_t)sh.Kb;
-    const size_t per_block = (size_t)FC_M * sh.Dp * sizeof(float2);
-    const size_t Bmax = std::max<size_t>(1, std::min<size_t>(4096, ((size_t)256 << 20) / per_block));
+    const size_t per_block = (size_t)FC_M * sh.Dp * sizeof(float4);
+    const size_t Bmax = std::max<size_t>(1, std::min<size_t>(4096, ((size_t)512 << 20) / per_block));
     const size_t need = std::min(blocks_total, Bmax);
     if (need > g->fc_blocks_cap) {
         OWRX_CUDA(cudaStreamSynchronize(st));
