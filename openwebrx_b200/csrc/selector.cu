@@ -773,7 +773,7 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
         g->feed_blocks += nb;
         const float2* sq_in = reinterpret_cast<const float2*>(g->s3.row_abs(g->sq_abs));
         const int hang_blocks = 2;                                       // hangLength = 2*blockLength, selector.py:124
-        squelch_power_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)nb), 128, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, d_power);
+        squelch_power_kernel<<<dim3((unsigned)(S / 32), (unsigned)nb), 256, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, d_power);
         OWRX_LAUNCH_CHECK();
         squelch_gate_kernel<<<(S + 127) / 128, 128, 0, st>>>(d_power, S, (int)nb, hang_blocks, g->d_cfg, g->d_state, d_gate);
         OWRX_LAUNCH_CHECK();
@@ -812,7 +812,7 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
         size_t n_audio = 0;
         if (!g->wfm) {
             // ---- demodulator back: NfmDeemphasis / DcBlock / copy -> f2 (pre-AGC)
-            dc_mean_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)nb), 128, 0, st>>>(g->f1.row_abs(f1_first), S, (int)nb,
+            dc_mean_kernel<<<dim3((unsigned)(S / 32), (unsigned)nb), 256, 0, st>>>(g->f1.row_abs(f1_first), S, (int)nb,
                                                                                         g->sq_len, g->d_cfg, g->d_state,
                                                                                         d_dcmean, g->d_dcprev);
             OWRX_LAUNCH_CHECK();
@@ -820,7 +820,7 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
             const size_t chunk_rows = std::max<size_t>((size_t)g->sq_len, (kRowChunk / (size_t)g->sq_len) * (size_t)g->sq_len);
             for (size_t o = 0; o < n4; o += chunk_rows) {
                 const size_t c = std::min(chunk_rows, n4 - o);
-                demod_back_kernel<<<grid2d(S, c), kBlock2d, 0, st>>>(g->f1.row_abs(f1_first + (long long)o), S, (int)c, g->sq_len,
+                demod_back_kernel<<<grid2d(S, (c + DB_RB - 1) / DB_RB), kBlock2d, 0, st>>>(g->f1.row_abs(f1_first + (long long)o), S, (int)c, g->sq_len,
                                                                      g->d_deemph, g->Td, g->d_cfg,
                                                                      d_dcmean + (o / (size_t)g->sq_len) * S,
                                                                      o == 0 ? g->d_dcprev : d_dcmean + (o / (size_t)g->sq_len - 1) * S,

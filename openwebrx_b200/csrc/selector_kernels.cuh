@@ -198,24 +198,35 @@ struct ChanCfg {
     float agc_thr;      // largest float a with fl(a / agc_ref) <= 1: "err > 1" <=> abs(v)*gain > agc_thr, exactly
 };
 
-// Squelch.  Block power = mean |x|^2 over every `decim`-th sample: one thread per (block, slot),
-// independent loads.  The gate (threshold + hang counter, sequential over blocks) is a second tiny kernel.
-__global__ void __launch_bounds__(128)
+// Squelch.  Block power = mean |x|^2 over every `decim`-th sample.  CTA = (32 slots, one block): eight
+// warps stage |x|^2 of the block's decimated samples in shared memory (row loads of 32 adjacent slots), then warp 0
+// adds them in sample order (the oracle's summation order) from shared memory.  The gate (threshold + hang counter,
+// sequential over blocks) is a second tiny kernel.
+constexpr int SQ_MAXROWS = 256;          // decimated samples staged per pass (32 KB)
+__global__ void __launch_bounds__(256)
 squelch_power_kernel(const float2* __restrict__ in, int slots, int n_blocks, int length, int decim, float* __restrict__ power)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float tile[SQ_MAXROWS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
     const int b = blockIdx.y;
-    if (s >= slots || b >= n_blocks) return;
     const float2* x = in + (size_t)b * length * slots + s;
+    const int cnt = (length + decim - 1) / decim;
     float p = 0.f;
-    int cnt = 0;
+    for (int j0 = 0; j0 < cnt; j0 += SQ_MAXROWS) {
+        const int nj = min(SQ_MAXROWS, cnt - j0);
+        for (int j = w; j < nj; j += 8) {
+            const float2 v = x[(size_t)((j0 + j) * decim) * slots];
+            tile[j][lane] = v.x * v.x + v.y * v.y;
+        }
+        __syncthreads();
+        if (w == 0) {
 #pragma unroll 8
-    for (int i = 0; i < length; i += decim) {
-        const float2 v = x[(size_t)i * slots];
-        p += v.x * v.x + v.y * v.y;
-        cnt++;
+            for (int j = 0; j < nj; j++) p += tile[j][lane];
+        }
+        __syncthreads();
     }
-    power[(size_t)b * slots + s] = p / (float)cnt;
+    if (w == 0) power[(size_t)b * slots + s] = p / (float)cnt;
 }
 
 __global__ void __launch_bounds__(128)
@@ -282,47 +293,94 @@ demod_front_commit_kernel(const float2* __restrict__ in, int slots, int n, int l
 }
 
 // Demodulator back (12 kHz-class groups): NFM -> NfmDeemphasis FIR; AM -> DcBlock (block = squelch
-// block); SSB -> copy.  in points at the row of output 0 and has >= T-1 rows of history before it.
+// block); SSB -> copy.  in points at the row of output 0 and has >= T-1 + 2*DB_RB rows of history before it.
+// A thread owns DB_RB consecutive outputs of one channel; the FIR slides a 2*DB_RB-1 sample window through
+// registers (taps in ascending order, like the oracle): DB_RB loads per DB_RB^2 FMAs.
+constexpr int DB_RB = 8;
 __global__ void __launch_bounds__(128)
 demod_back_kernel(const float* __restrict__ in, int slots, int n, int length, const float* __restrict__ deemph, int T,
                   const ChanCfg* __restrict__ cfg, const float* __restrict__ dc_mean, const float* __restrict__ dc_prev,
                   float* __restrict__ out)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (s >= slots || i >= n) return;
+    const int i0 = (blockIdx.y * blockDim.y + threadIdx.y) * DB_RB;
+    if (s >= slots || i0 >= n) return;
     const int kind = cfg[s].kind;
-    const float* x = in + (size_t)i * slots + s;
-    float y;
+    const float* x = in + s;
+    float y[DB_RB];
     if (kind == OWRX_DEMOD_NFM) {
-        float acc = 0.f;
-        for (int t = 0; t < T; t++) acc += deemph[t] * *(x - (ptrdiff_t)t * slots);
-        y = acc;
+#pragma unroll
+        for (int j = 0; j < DB_RB; j++) y[j] = 0.f;
+        // xw[d + DB_RB - 1] = x[i0 - t0 + d], d in (-DB_RB, DB_RB); rows past the last output are clamped (never weighted
+        // into a stored output)
+        const int last = n - 1;
+        float xw[2 * DB_RB - 1];
+#pragma unroll
+        for (int k = 0; k < 2 * DB_RB - 1; k++) xw[k] = x[(ptrdiff_t)min(i0 - (DB_RB - 1) + k, last) * slots];
+        for (int t0 = 0; t0 < T; t0 += DB_RB) {
+            float h[DB_RB];
+#pragma unroll
+            for (int u = 0; u < DB_RB; u++) h[u] = t0 + u < T ? __ldg(deemph + t0 + u) : 0.f;
+#pragma unroll
+            for (int u = 0; u < DB_RB; u++)
+#pragma unroll
+                for (int j = 0; j < DB_RB; j++) y[j] = fmaf(h[u], xw[DB_RB - 1 + j - u], y[j]);
+#pragma unroll
+            for (int k = 2 * DB_RB - 2; k >= DB_RB; k--) xw[k] = xw[k - DB_RB];
+            const int b = i0 - t0 - DB_RB;
+#pragma unroll
+            for (int k = 0; k < DB_RB; k++) xw[k] = x[(ptrdiff_t)(b - (DB_RB - 1) + k) * slots];
+        }
     } else if (kind == OWRX_DEMOD_AM) {
-        const int b = i / length, ib = i % length;
-        const float last = b == 0 ? dc_prev[s] : dc_mean[(size_t)(b - 1) * slots + s];
-        const float avg = dc_mean[(size_t)b * slots + s];
-        y = *x - (last + (avg - last) * ((float)ib / (float)length));
+#pragma unroll
+        for (int j = 0; j < DB_RB; j++) {
+            const int i = min(i0 + j, n - 1);
+            const int b = i / length, ib = i % length;
+            const float last = b == 0 ? dc_prev[s] : dc_mean[(size_t)(b - 1) * slots + s];
+            const float avg = dc_mean[(size_t)b * slots + s];
+            y[j] = x[(size_t)i * slots] - (last + (avg - last) * ((float)ib / (float)length));
+        }
     } else {
-        y = *x;
+#pragma unroll
+        for (int j = 0; j < DB_RB; j++) y[j] = x[(size_t)min(i0 + j, n - 1) * slots];
     }
-    out[(size_t)i * slots + s] = y;
+#pragma unroll
+    for (int j = 0; j < DB_RB; j++)
+        if (i0 + j < n) out[(size_t)(i0 + j) * slots + s] = y[j];
 }
 
-// DcBlock block means: one thread per (block, slot); sequential float sum like the oracle.
-__global__ void __launch_bounds__(128)
+// DcBlock block means.  CTA = (32 slots, one block): eight warps stage the block's samples in shared memory, warp 0
+// adds them in sample order (sequential float sum like the oracle).
+constexpr int DC_ROWS = 256;
+__global__ void __launch_bounds__(256)
 dc_mean_kernel(const float* __restrict__ in, int slots, int n_blocks, int length, const ChanCfg* __restrict__ cfg,
                ChanState* __restrict__ st, float* __restrict__ dc_mean, float* __restrict__ dc_prev)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float tile[DC_ROWS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
     const int b = blockIdx.y;
-    if (s >= slots || b >= n_blocks) return;
-    if (cfg[s].kind != OWRX_DEMOD_AM) { if (b == 0) dc_prev[s] = 0.f; dc_mean[(size_t)b * slots + s] = 0.f; return; }
+    const bool am = cfg[s].kind == OWRX_DEMOD_AM;
+    if (!__syncthreads_or(am)) {                       // no AM channel among these 32 slots
+        if (w == 0) { if (b == 0) dc_prev[s] = 0.f; dc_mean[(size_t)b * slots + s] = 0.f; }
+        return;
+    }
     const float* x = in + (size_t)b * length * slots + s;
     float acc = 0.f;
-    for (int i = 0; i < length; i++) acc += x[(size_t)i * slots];
-    dc_mean[(size_t)b * slots + s] = acc / (float)length;
-    if (b == 0) dc_prev[s] = st[s].dc_last;
+    for (int i0 = 0; i0 < length; i0 += DC_ROWS) {
+        const int ni = min(DC_ROWS, length - i0);
+        for (int i = w; i < ni; i += 8) tile[i][lane] = x[(size_t)(i0 + i) * slots];
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll 8
+            for (int i = 0; i < ni; i++) acc += tile[i][lane];
+        }
+        __syncthreads();
+    }
+    if (w == 0) {
+        dc_mean[(size_t)b * slots + s] = am ? acc / (float)length : 0.f;
+        if (b == 0) dc_prev[s] = am ? st[s].dc_last : 0.f;
+    }
 }
 
 __global__ void __launch_bounds__(128)
