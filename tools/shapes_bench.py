@@ -78,4 +78,4 @@ if __name__ == "__main__":
     if "c5" in which:
         print(json.dumps({"C5: 20 MS/s, 128 WFM ch (250 kHz IF -> 48 kHz)": time_bank(20e6, 250000, 128, "wfm", 1 << 22, audio_rate=48000.0, tau=50e-6)}))
     if "c4" in which:
-        print(json.dumps({"C4: 61.44 MS/s 65536-pt 30 fps waterfall": time_wf(61.44e6, 65536, 30, 0.3, 32)}))
+        print(json.dumps({"C4: 61.44 MS/s 65536-pt 30 fps waterfall": time_wf(61.44e6, 65536, 30, 0.3, int(os.environ.get("C4_LINES", "128")))}))
