@@ -4,6 +4,8 @@
 #include "fastconv.cuh"
 #include "fft_small.cuh"
 
+#include <algorithm>
+
 namespace owrx {
 
 namespace {
@@ -305,6 +307,112 @@ fc_inverse_kernel(const float2* __restrict__ Z, int B, int slots, int D, int Kb,
 
 constexpr size_t kFftSmem = (256 + FC_SEQ * FC_STR) * sizeof(float2);
 
+// ------------------------------------------------------------------------------------------------
+// K4F band-pass kernels (see fastconv.cuh).  Streams are channel-minor ([row][slot]), so a warp's 32 lanes are 32
+// adjacent channels and every access is a 256-byte row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(16 * FC_SEQ)
+bpf_forward_kernel(const float2* __restrict__ in, int slots, int last_row, int P, float2* __restrict__ X)
+{
+    extern __shared__ float2 fc_smem[];
+    float2* tw = fc_smem;
+    float2* seqs = fc_smem + 256;
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const int ch = blockIdx.x * FC_SEQ + lane;
+    const int jj = (int)blockIdx.y - P;                       // block index relative to output 0
+    fc_fill_twiddles(tw);
+    float2 v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const int row = min(BPF_H * (jj - 1) + 16 * n1 + g, last_row);
+        v[n1] = __ldg(in + (ptrdiff_t)row * slots + ch);
+    }
+    __syncthreads();
+    fc_fft256(v, seqs + lane * FC_STR, tw, g);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int bin = g + 16 * slot<16>(q);
+        X[((size_t)blockIdx.y * FC_M + bin) * slots + ch] = v[q];
+    }
+}
+
+// Y[j][q][c] = sum_{p<P} X[j-p][q][c] * H[p][q][c]: a P-tap complex FIR along the block index for every (bin, channel).
+// A thread owns one (bin, channel) and a segment of blocks; it slides the X window through registers.
+template <int PP>
+__global__ void __launch_bounds__(128)
+bpf_mac_kernel(const float2* __restrict__ X, const float2* __restrict__ H, int slots, int nblk, int seg, float2* __restrict__ Y)
+{
+    const size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x;        // bin * slots + slot
+    const size_t plane = (size_t)FC_M * slots;
+    const int j0 = blockIdx.y * seg, j1 = min(nblk, j0 + seg);
+    if (j0 >= j1) return;
+    float2 h[PP], w[PP];                                              // w[p] = X[j - p]
+#pragma unroll
+    for (int p = 0; p < PP; p++) h[p] = __ldg(H + (size_t)p * plane + idx);
+#pragma unroll
+    for (int p = 1; p < PP; p++) w[p] = __ldg(X + (size_t)(j0 - p + PP) * plane + idx);
+    for (int j = j0; j < j1; j++) {
+        w[0] = __ldg(X + (size_t)(j + PP) * plane + idx);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < PP; p++) {
+            acc.x = fmaf(w[p].x, h[p].x, acc.x); acc.x = fmaf(-w[p].y, h[p].y, acc.x);
+            acc.y = fmaf(w[p].x, h[p].y, acc.y); acc.y = fmaf(w[p].y, h[p].x, acc.y);
+        }
+        Y[(size_t)j * plane + idx] = acc;
+#pragma unroll
+        for (int p = PP - 1; p > 0; p--) w[p] = w[p - 1];
+    }
+}
+
+// generic partition count (window re-read from L2)
+__global__ void __launch_bounds__(128)
+bpf_mac_generic_kernel(const float2* __restrict__ X, const float2* __restrict__ H, int slots, int P, int nblk, float2* __restrict__ Y)
+{
+    const size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x;
+    const size_t plane = (size_t)FC_M * slots;
+    const int j = blockIdx.y;
+    if (j >= nblk) return;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int p = 0; p < P; p++) {
+        const float2 w = __ldg(X + (size_t)(j - p + P) * plane + idx), h = __ldg(H + (size_t)p * plane + idx);
+        acc.x = fmaf(w.x, h.x, acc.x); acc.x = fmaf(-w.y, h.y, acc.x);
+        acc.y = fmaf(w.x, h.y, acc.y); acc.y = fmaf(w.y, h.x, acc.y);
+    }
+    Y[(size_t)j * plane + idx] = acc;
+}
+
+__global__ void __launch_bounds__(16 * FC_SEQ)
+bpf_inverse_kernel(const float2* __restrict__ Y, const float2* __restrict__ in, const int* __restrict__ enabled, int slots, int n_out,
+                   float2* __restrict__ out)
+{
+    extern __shared__ float2 fc_smem[];
+    float2* tw = fc_smem;
+    float2* seqs = fc_smem + 256;
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const int ch = blockIdx.x * FC_SEQ + lane;
+    const int j = blockIdx.y;
+    fc_fill_twiddles(tw);
+    float2 v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        const float2 y = __ldg(Y + ((size_t)j * FC_M + 16 * n1 + g) * slots + ch);
+        v[n1] = make_float2(y.x, -y.y);
+    }
+    __syncthreads();
+    fc_fft256(v, seqs + lane * FC_STR, tw, g);
+    const bool en = enabled[ch] != 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int n = g + 16 * slot<16>(q);
+        const int row = BPF_H * j + n - BPF_H;
+        if (n >= BPF_H && row < n_out) {
+            const size_t o = (size_t)row * slots + ch;
+            out[o] = en ? make_float2(v[q].x * (1.0f / FC_M), -v[q].y * (1.0f / FC_M)) : __ldg(in + o);   // disabled: pass through
+        }
+    }
+}
+
 template <int NW>
 int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, int B, float2* Z, cudaStream_t st)
 {
@@ -353,6 +461,40 @@ int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab
     case 5: return launch_contract_nw<5>(sh, d_F, d_tab, B, d_Z, st);
     default: return launch_contract_nw<6>(sh, d_F, d_tab, B, d_Z, st);
     }
+}
+
+int bpf_launch_forward(const float2* in, int slots, int last_row, int P, int nblk, float2* X, cudaStream_t st)
+{
+    OWRX_CUDA(cudaFuncSetAttribute(bpf_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+    bpf_forward_kernel<<<dim3((unsigned)(slots / FC_SEQ), (unsigned)(nblk + P)), 16 * FC_SEQ, kFftSmem, st>>>(in, slots, last_row, P, X);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+int bpf_launch_mac(const float2* X, const float2* H, int slots, int P, int nblk, float2* Y, cudaStream_t st)
+{
+    const unsigned gx = (unsigned)((size_t)FC_M * slots / 128);
+    // enough block segments to fill the machine; each segment re-reads P-1 warm-up spectra
+    const int nseg = std::max(1, std::min((nblk + 4 * P - 1) / (4 * P), (int)(4 * 148 / std::max(1u, gx)) + 1));
+    const int seg = (nblk + nseg - 1) / nseg;
+    const dim3 grid(gx, (unsigned)((nblk + seg - 1) / seg));
+    switch (P) {
+    case 1: bpf_mac_kernel<1><<<grid, 128, 0, st>>>(X, H, slots, nblk, seg, Y); break;
+    case 2: bpf_mac_kernel<2><<<grid, 128, 0, st>>>(X, H, slots, nblk, seg, Y); break;
+    case 5: bpf_mac_kernel<5><<<grid, 128, 0, st>>>(X, H, slots, nblk, seg, Y); break;
+    case 25: bpf_mac_kernel<25><<<grid, 128, 0, st>>>(X, H, slots, nblk, seg, Y); break;
+    default: bpf_mac_generic_kernel<<<dim3(gx, (unsigned)nblk), 128, 0, st>>>(X, H, slots, P, nblk, Y); break;
+    }
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+int bpf_launch_inverse(const float2* Y, const float2* in, const int* enabled, int slots, int nblk, int n_out, float2* out, cudaStream_t st)
+{
+    OWRX_CUDA(cudaFuncSetAttribute(bpf_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+    bpf_inverse_kernel<<<dim3((unsigned)(slots / FC_SEQ), (unsigned)nblk), 16 * FC_SEQ, kFftSmem, st>>>(Y, in, enabled, slots, n_out, out);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
 }
 
 int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,

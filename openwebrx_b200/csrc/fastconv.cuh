@@ -36,6 +36,20 @@ int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab
 // out[(k0 + b Kb + m) * slots + c] for k0 + b Kb + m < n_k; phases are relative to iq[-1] of the whole call
 int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
                       float2* out, cudaStream_t st);
-int fc_init_tables();
+
+// ------------------------------------------------------------------------------------------------
+// K4F: Bandpass (csdr/chain/selector.py:115-117,159-166; per-channel complex taps at the selector output rate) as a
+// uniformly partitioned overlap-save convolution on 256-point FFTs: the T taps are cut into P = ceil(T/128) partitions
+// of 128, H[p] = FFT_256([h_p | 0]);  X[j] = FFT_256 of input rows [128(j-1), 128(j+1));  Y[j] = sum_p X[j-p] H[p];
+// output rows [128 j, 128(j+1)) = last half of IFFT_256(Y[j]).  4 P complex MACs per output instead of T
+// (T = 3125 at the 250 kHz WFM IF: 100 instead of 3125).  The reference computes the same linear convolution by FFT
+// overlap-add (Bandpass(use_fft=True)).
+// ------------------------------------------------------------------------------------------------
+constexpr int BPF_H = 128;       // hop / partition length
+// X[(j + P) * 256 + q][slot] for j in [-P, nblk): rows are relative to `in` (row 0 = output 0; >= 128 (P+1) history rows before it);
+// rows past last_row are clamped (they only reach outputs that are not stored)
+int bpf_launch_forward(const float2* in, int slots, int last_row, int P, int nblk, float2* X, cudaStream_t st);
+int bpf_launch_mac(const float2* X, const float2* H, int slots, int P, int nblk, float2* Y, cudaStream_t st);
+int bpf_launch_inverse(const float2* Y, const float2* in, const int* enabled, int slots, int nblk, int n_out, float2* out, cudaStream_t st);
 
 }  // namespace owrx

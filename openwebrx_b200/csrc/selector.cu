@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <deque>
 #include <map>
@@ -53,6 +54,28 @@ void design_bandpass(std::vector<float2>& out, int len, double lo, double hi)
     for (int i = 0; i < len; i++) {
         const double ph = 2.0 * M_PI * centre * i;
         out[i] = make_float2((float)(h[i] * cos(ph)), (float)(h[i] * sin(ph)));
+    }
+}
+
+// in-place forward FFT, power-of-two length (host side: band-pass partition spectra)
+void fft_pow2(std::vector<std::complex<double>>& a)
+{
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = -2.0 * M_PI / (double)len;
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; k++) {
+                const std::complex<double> w(cos(ang * (double)k), sin(ang * (double)k));
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
     }
 }
 
@@ -189,6 +212,10 @@ struct Group {
     float* d_taps = nullptr; float* d_deemph = nullptr; float* d_pre = nullptr;
     double* d_rate = nullptr; double* d_phase = nullptr; float2* d_w = nullptr;
     float2* d_bp = nullptr; int* d_bp_en = nullptr;
+    // K4F partitioned-FFT band-pass (fastconv.cuh): H[p][256][slots], scratch spectra
+    int bpP = 1;
+    float2* d_bp_H = nullptr; float2* d_bp_X = nullptr; float2* d_bp_Y = nullptr;
+    size_t bp_blocks_cap = 0;
     ChanCfg* d_cfg = nullptr; ChanState* d_state = nullptr;
     std::vector<double> h_rate, h_phase; std::vector<float2> h_w;
     std::vector<int> h_bp_en; std::vector<ChanCfg> h_cfg;
@@ -256,7 +283,7 @@ struct owrx_bank {
     size_t prof_used = 0;
     double prof_ms[OWRX_PROF_KINDS] = {};
     uint64_t prof_launches[OWRX_PROF_KINDS] = {};
-    int fir_mode = OWRX_FIR_AUTO;
+    int fir_mode = OWRX_FIR_AUTO, bp_mode = OWRX_FIR_AUTO;
 };
 
 namespace {
@@ -274,6 +301,7 @@ void group_release(Group* g)
     cudaFree(g->d_taps); cudaFree(g->d_deemph); cudaFree(g->d_pre);
     cudaFree(g->d_rate); cudaFree(g->d_phase); cudaFree(g->d_w);
     cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state);
+    cudaFree(g->d_bp_H); cudaFree(g->d_bp_X); cudaFree(g->d_bp_Y);
     cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     cudaFree(g->d_tail_mode); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
     cudaFree(g->d_fc_h); cudaFree(g->d_fc_tab); cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates);
@@ -335,6 +363,7 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     g->nrs = (g->D + K3_RBMAX - 1) / K3_RBMAX;
     g->RB = (g->D + g->nrs - 1) / g->nrs;
     g->Tb = filter_len(sp.bp_transition);
+    g->bpP = (g->Tb + BPF_H - 1) / BPF_H;
     g->sq_len = sp.squelch_length;
     g->slots = K3_CG;
     g->slot_chan.assign((size_t)g->slots, -1);
@@ -373,7 +402,7 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     }
     const size_t S = (size_t)g->slots;
     if ((rc = dev_alloc(&g->d_rate, S)) || (rc = dev_alloc(&g->d_phase, S)) || (rc = dev_alloc(&g->d_w, S)) ||
-        (rc = dev_alloc(&g->d_bp, S * g->Tb)) || (rc = dev_alloc(&g->d_bp_en, S)) || (rc = dev_alloc(&g->d_cfg, S)) ||
+        (rc = dev_alloc(&g->d_bp, S * g->Tb)) || (rc = dev_alloc(&g->d_bp_H, S * (size_t)g->bpP * FC_M)) || (rc = dev_alloc(&g->d_bp_en, S)) || (rc = dev_alloc(&g->d_cfg, S)) ||
         (rc = dev_alloc(&g->d_state, S)) || (rc = dev_alloc(&g->d_tail_mode, S)) || (rc = dev_alloc(&g->d_tail, S)) ||
         (rc = dev_alloc(&g->d_tail_count, S)))
         return rc;
@@ -385,8 +414,11 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
 
     const size_t cap = 4096;
     // band-pass input history: Tb-1 taps back, plus the register-blocked kernel's window overshoot (2*BP_RB + padding of T)
-    if ((rc = g->s1.init(2, g->slots, (size_t)(g->Tb + 3 * BP_RB), cap)) != OWRX_OK) return rc;
-    if (g->has_frac && (rc = g->s2.init(2, g->slots, (size_t)(g->Tb + 3 * BP_RB), cap)) != OWRX_OK) return rc;
+    // band-pass input history: Tb-1 taps back plus the register-blocked kernel's window overshoot, or the P+1 hops of the
+    // partitioned-FFT form
+    const size_t bp_hist = std::max<size_t>((size_t)(g->Tb + 3 * BP_RB), (size_t)BPF_H * (size_t)(g->bpP + 1));
+    if ((rc = g->s1.init(2, g->slots, bp_hist, cap)) != OWRX_OK) return rc;
+    if (g->has_frac && (rc = g->s2.init(2, g->slots, bp_hist, cap)) != OWRX_OK) return rc;
     if ((rc = g->s3.init(2, g->slots, (size_t)g->sq_len, cap)) != OWRX_OK) return rc;
     if ((rc = g->f1.init(1, g->slots, 256, cap)) != OWRX_OK) return rc;
     if (wfm && (rc = g->f1p.init(1, g->slots, 32, cap)) != OWRX_OK) return rc;
@@ -462,7 +494,7 @@ int group_grow(owrx_bank* bank, Group* g)
     };
     int rc;
     if ((rc = regrow(&g->d_rate, 1)) || (rc = regrow(&g->d_phase, 1)) || (rc = regrow(&g->d_w, 1)) ||
-        (rc = regrow(&g->d_bp, (size_t)g->Tb)) || (rc = regrow(&g->d_bp_en, 1)) || (rc = regrow(&g->d_cfg, 1)) ||
+        (rc = regrow(&g->d_bp, (size_t)g->Tb)) || (rc = regrow(&g->d_bp_H, (size_t)g->bpP * FC_M)) || (rc = regrow(&g->d_bp_en, 1)) || (rc = regrow(&g->d_cfg, 1)) ||
         (rc = regrow(&g->d_state, 1)) || (rc = regrow(&g->d_tail_mode, 1)) || (rc = regrow(&g->d_tail, 1)) ||
         (rc = regrow(&g->d_tail_count, 1)))
         return rc;
@@ -486,6 +518,8 @@ int group_grow(owrx_bank* bank, Group* g)
         (rc = regrow_buf(g->f1b)) || (rc = regrow_buf(g->f2)) || (rc = regrow_buf(g->f3)))
         return rc;
     cudaFree(g->d_partial); g->d_partial = nullptr; g->partial_cap = 0;
+    cudaFree(g->d_bp_X); cudaFree(g->d_bp_Y);
+    g->d_bp_X = nullptr; g->d_bp_Y = nullptr; g->bp_blocks_cap = 0;
     cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     g->d_gate = nullptr; g->d_power = nullptr; g->d_dcmean = nullptr; g->d_dcprev = nullptr; g->blocks_cap = 0;
     // fast-convolution tables are laid out per slot count: rebuild lazily
@@ -515,6 +549,19 @@ int upload_bandpass(owrx_bank* bank, Chan* ch)
     OWRX_CUDA(cudaStreamSynchronize(bank->stream));
     OWRX_CUDA(cudaMemcpy2D(g->d_bp + ch->slot, (size_t)g->slots * sizeof(float2), taps.data(), sizeof(float2), sizeof(float2),
                            (size_t)g->Tb, cudaMemcpyHostToDevice));
+    // partition spectra H[p] = FFT_256([taps[128p .. 128p+127] | 0]) of the SAME float32 taps (double arithmetic, rounded once)
+    std::vector<float2> H((size_t)g->bpP * FC_M);
+    std::vector<std::complex<double>> buf((size_t)FC_M);
+    for (int p = 0; p < g->bpP; p++) {
+        for (int u = 0; u < FC_M; u++) {
+            const int t = p * BPF_H + u;
+            buf[(size_t)u] = (u < BPF_H && t < g->Tb) ? std::complex<double>(taps[(size_t)t].x, taps[(size_t)t].y) : std::complex<double>(0.0, 0.0);
+        }
+        fft_pow2(buf);
+        for (int q = 0; q < FC_M; q++) H[(size_t)p * FC_M + q] = make_float2((float)buf[(size_t)q].real(), (float)buf[(size_t)q].imag());
+    }
+    OWRX_CUDA(cudaMemcpy2D(g->d_bp_H + ch->slot, (size_t)g->slots * sizeof(float2), H.data(), sizeof(float2), sizeof(float2),
+                           H.size(), cudaMemcpyHostToDevice));
     return OWRX_OK;
 }
 
@@ -746,6 +793,35 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
 
     // ---- Bandpass -> s3 (selector output / IF)
     if ((rc = g->s3.ensure_new(n2, st)) != OWRX_OK) return rc;
+    // long band-pass filters only (the 250 kHz WFM IF: 3125 taps): for the 151-tap filters of the 12 kHz classes the direct
+    // form is cheap and keeps full relative precision on near-zero samples (start-up transients feed a scale-free FmDemod)
+    const bool bp_fft = g->bpP > 4 && bank->bp_mode != OWRX_FIR_DIRECT && (bank->bp_mode == OWRX_FIR_FASTCONV || n2 >= 4 * (size_t)BPF_H);
+    if (bp_fft) {
+        // K4F: partitioned overlap-save on 256-point FFTs, in passes of at most kBpBlocks hops
+        const size_t kBpBlocks = std::max<size_t>(1, ((size_t)96 << 20) / ((size_t)FC_M * S * sizeof(float2)));
+        const size_t blocks_total = (n2 + BPF_H - 1) / BPF_H;
+        const size_t need = std::min(blocks_total, kBpBlocks);
+        if (need > g->bp_blocks_cap) {
+            OWRX_CUDA(cudaStreamSynchronize(st));
+            cudaFree(g->d_bp_X); cudaFree(g->d_bp_Y);
+            g->d_bp_X = nullptr; g->d_bp_Y = nullptr; g->bp_blocks_cap = 0;
+            OWRX_CUDA(cudaMalloc((void**)&g->d_bp_X, (need + (size_t)g->bpP) * FC_M * S * sizeof(float2)));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_bp_Y, need * FC_M * S * sizeof(float2)));
+            g->bp_blocks_cap = need;
+        }
+        for (size_t b0 = 0; b0 < blocks_total; b0 += kBpBlocks) {
+            const int nblk = (int)std::min(kBpBlocks, blocks_total - b0);
+            const size_t o = b0 * BPF_H;
+            const float2* src = reinterpret_cast<const float2*>(bp_in->row_abs(bp_first + (long long)o));
+            const int rows_here = (int)std::min<size_t>((size_t)nblk * BPF_H, n2 - o);
+            if ((rc = bpf_launch_forward(src, S, (int)(n2 - o) - 1, g->bpP, nblk, g->d_bp_X, st)) != OWRX_OK) return rc;
+            if ((rc = bpf_launch_mac(g->d_bp_X, g->d_bp_H, S, g->bpP, nblk, g->d_bp_Y, st)) != OWRX_OK) return rc;
+            if ((rc = bpf_launch_inverse(g->d_bp_Y, src, g->d_bp_en, S, nblk, rows_here,
+                                         reinterpret_cast<float2*>(g->s3.append_ptr()) + o * S, st)) != OWRX_OK)
+                return rc;
+            bank->stats.kernel_launches += 3;
+        }
+    } else
     for (size_t o = 0; o < n2; o += kRowChunk * BP_RB) {
         const size_t c = std::min(kRowChunk * BP_RB, n2 - o);
         bandpass_kernel<<<grid2d(S, (c + BP_RB - 1) / BP_RB), kBlock2d, 0, st>>>(
@@ -1077,6 +1153,8 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (!b) return fail(OWRX_E_NOMEM, "out of host memory");
     b->device = device; b->sm_count = sm; b->input_rate = input_rate;
     if (const char* m = getenv("OWRX_FIR_MODE")) b->fir_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV, atoi(m)));
+    b->bp_mode = b->fir_mode;
+    if (const char* m = getenv("OWRX_BP_MODE")) b->bp_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV, atoi(m)));
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking);
@@ -1686,6 +1764,7 @@ int owrx_bank_set_fir_mode(owrx_bank_t* bank, int mode)
     if (mode < OWRX_FIR_AUTO || mode > OWRX_FIR_FASTCONV) return fail(OWRX_E_INVALID, "unknown FIR mode %d", mode);
     std::lock_guard<std::mutex> lk(bank->mu);
     bank->fir_mode = mode;
+    bank->bp_mode = mode;
     return OWRX_OK;
 }
 
