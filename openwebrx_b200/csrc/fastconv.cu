@@ -342,26 +342,40 @@ template <int PP>
 __global__ void __launch_bounds__(128)
 bpf_mac_kernel(const float2* __restrict__ X, const float2* __restrict__ H, int slots, int nblk, int seg, float2* __restrict__ Y)
 {
+    constexpr int U = 5;                                              // outputs per window shift
     const size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x;        // bin * slots + slot
     const size_t plane = (size_t)FC_M * slots;
     const int j0 = blockIdx.y * seg, j1 = min(nblk, j0 + seg);
     if (j0 >= j1) return;
-    float2 h[PP], w[PP];                                              // w[p] = X[j - p]
+    const float2* Xp = X + idx + (size_t)PP * plane;                  // Xp[j * plane] = X[j], j >= -PP
+    float2 h[PP], w[PP + U - 1];                                      // w[k] = X[j + U - 1 - k] for the group starting at j
 #pragma unroll
     for (int p = 0; p < PP; p++) h[p] = __ldg(H + (size_t)p * plane + idx);
 #pragma unroll
-    for (int p = 1; p < PP; p++) w[p] = __ldg(X + (size_t)(j0 - p + PP) * plane + idx);
-    for (int j = j0; j < j1; j++) {
-        w[0] = __ldg(X + (size_t)(j + PP) * plane + idx);
-        float2 acc = make_float2(0.f, 0.f);
+    for (int k = U; k < PP + U - 1; k++) w[k] = __ldg(Xp + (ptrdiff_t)(j0 + U - 1 - k) * (ptrdiff_t)plane);
+    float2 nx[U];
 #pragma unroll
-        for (int p = 0; p < PP; p++) {
-            acc.x = fmaf(w[p].x, h[p].x, acc.x); acc.x = fmaf(-w[p].y, h[p].y, acc.x);
-            acc.y = fmaf(w[p].x, h[p].y, acc.y); acc.y = fmaf(w[p].y, h[p].x, acc.y);
+    for (int u = 0; u < U; u++) nx[u] = __ldg(Xp + (size_t)min(j0 + u, nblk - 1) * plane);
+    for (int j = j0; j < j1; j += U) {
+#pragma unroll
+        for (int u = 0; u < U; u++) w[U - 1 - u] = nx[u];
+        if (j + U < j1) {                                             // next group's spectra, in flight during the MACs
+#pragma unroll
+            for (int u = 0; u < U; u++) nx[u] = __ldg(Xp + (size_t)min(j + U + u, nblk - 1) * plane);
         }
-        Y[(size_t)j * plane + idx] = acc;
 #pragma unroll
-        for (int p = PP - 1; p > 0; p--) w[p] = w[p - 1];
+        for (int u = 0; u < U; u++) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < PP; p++) {
+                const float2 x = w[U - 1 - u + p];
+                acc.x = fmaf(x.x, h[p].x, acc.x); acc.x = fmaf(-x.y, h[p].y, acc.x);
+                acc.y = fmaf(x.x, h[p].y, acc.y); acc.y = fmaf(x.y, h[p].x, acc.y);
+            }
+            if (j + u < j1) Y[(size_t)(j + u) * plane + idx] = acc;
+        }
+#pragma unroll
+        for (int k = PP + U - 2; k >= U; k--) w[k] = w[k - U];
     }
 }
 

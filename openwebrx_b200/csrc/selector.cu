@@ -940,7 +940,7 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
                 OWRX_LAUNCH_CHECK();
             }
             if (cnt) {
-                wfm_deemph_kernel<<<(S + 31) / 32, 32, 0, st>>>(g->f1b.append_ptr(), S, (int)cnt, g->alpha, g->d_state,
+                wfm_deemph_kernel<<<S / IIR_CH, IIR_TL, 0, st>>>(g->f1b.append_ptr(), S, (int)cnt, g->alpha, g->d_state,
                                                                   g->f2.append_ptr());
                 OWRX_LAUNCH_CHECK();
             }
@@ -968,9 +968,15 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
         if (n_audio) {
             if ((rc = g->f3.ensure_new(n_audio, st)) != OWRX_OK) return rc;
             if ((rc = prof_mark(bank, OWRX_PROF_AGC, st, true)) != OWRX_OK) return rc;
-            agc_kernel<<<S / AGC_CH, AGC_TL, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
-                                                       g->f3.append_ptr());
-            OWRX_LAUNCH_CHECK();
+            if (g->wfm) {
+                // the WFm chain has no Agc (csdr/chain/analog.py:55-67): the audio is the de-emphasised signal
+                OWRX_CUDA(cudaMemcpyAsync(g->f3.append_ptr(), g->f2.rows(g->f2.fill - n_audio), n_audio * (size_t)S * sizeof(float),
+                                          cudaMemcpyDeviceToDevice, st));
+            } else {
+                agc_kernel<<<S / AGC_CH, AGC_TL, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+                                                           g->f3.append_ptr());
+                OWRX_LAUNCH_CHECK();
+            }
             if ((rc = prof_mark(bank, OWRX_PROF_AGC, st, false)) != OWRX_OK) return rc;
             bank->stats.kernel_launches++;
             g->f3.appended(n_audio);

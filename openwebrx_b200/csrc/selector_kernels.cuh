@@ -488,37 +488,108 @@ struct SerialFeed {
     }
 };
 
-// WfmDeemphasis one-pole IIR.
-__global__ void __launch_bounds__(32)
+// WfmDeemphasis one-pole IIR y[n] = alpha x[n] + (1-alpha) y[n-1].  A linear recurrence: one WARP owns a
+// channel and advances 256 samples per step.  Each lane runs its 8 consecutive samples from a zero state, the lane
+// end-states are combined by a warp scan of the affine maps y -> om^8 y + s (5 shuffles), and the lane re-runs its 8
+// samples from its true entry state.  Same recurrence formula per sample; only the entry states are associated
+// differently (float32 rounding at the 1e-7 level against the sequential order).  Tile staging as in agc_kernel below.
+constexpr int IIR_E = 8;           // consecutive samples per lane
+constexpr int IIR_CH = 8;          // channels (= warps) per CTA
+constexpr int IIR_TL = 32 * IIR_E; // samples per warp step (= threads per CTA)
+__global__ void __launch_bounds__(IIR_TL)
 wfm_deemph_kernel(const float* __restrict__ in, int slots, int n, float alpha, ChanState* __restrict__ st,
                   float* __restrict__ out)
 {
-    __shared__ float ring[SER_STAGES][SER_TT][32];
-    const int lane = threadIdx.x;
-    const int s = min(blockIdx.x * 32 + lane, slots - 1);
-    float y = st[s].iir;
+    __shared__ __align__(16) float xin[2][IIR_CH][IIR_TL + 4];
+    __shared__ __align__(16) float xout[IIR_CH][IIR_TL + 4];
+    if (n <= 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int s0 = blockIdx.x * IIR_CH, s = s0 + w;
     const float om = 1.0f - alpha;
-    SerialFeed f{ring, in, slots, n, s, lane, (n + SER_TT - 1) / SER_TT};
-    for (int k = 0; k < SER_STAGES - 1; k++) f.issue(k);
-    for (int tile = 0; tile < f.nt; tile++) {
-        f.issue(tile + SER_STAGES - 1);
-        cp_async_wait<SER_STAGES - 1>();
-        const int cnt = min(SER_TT, n - tile * SER_TT);
-        float v[SER_TT];
+    float om_pow[6];                                   // om^(8 * 2^k)
+    {
+        float p = om;
 #pragma unroll
-        for (int t = 0; t < SER_TT; t++) v[t] = t < cnt ? ring[tile % SER_STAGES][t][lane] : 0.f;
-        if (cnt == SER_TT) {
+        for (int k = 0; k < 3; k++) p *= p;            // om^8
 #pragma unroll
-            for (int t = 0; t < SER_TT; t++) { y = alpha * v[t] + om * y; v[t] = y; }
-        } else {
-            for (int t = 0; t < cnt; t++) { y = alpha * v[t] + om * y; v[t] = y; }
-        }
-        float* o = out + (size_t)tile * SER_TT * slots + s;
-#pragma unroll
-        for (int t = 0; t < SER_TT; t++)
-            if (t < cnt) o[(size_t)t * slots] = v[t];
+        for (int k = 0; k < 6; k++) { om_pow[k] = p; p *= p; }
     }
-    st[s].iir = y;
+    float y = st[s].iir;                               // state entering the current step (warp-uniform)
+    const int nt = (n + IIR_TL - 1) / IIR_TL;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int tile, float4& lo, float4& hi) {
+        const int t = tile * IIR_TL + tid;
+        if (t < n) {
+            const float4* p = reinterpret_cast<const float4*>(in + (size_t)t * slots + s0);
+            lo = __ldg(p); hi = __ldg(p + 1);
+        } else {
+            lo = zero4; hi = zero4;
+        }
+    };
+    auto stage = [&](int buf, const float4& lo, const float4& hi) {
+        xin[buf][0][tid] = lo.x; xin[buf][1][tid] = lo.y; xin[buf][2][tid] = lo.z; xin[buf][3][tid] = lo.w;
+        xin[buf][4][tid] = hi.x; xin[buf][5][tid] = hi.y; xin[buf][6][tid] = hi.z; xin[buf][7][tid] = hi.w;
+    };
+    float4 lo, hi;
+    fetch(0, lo, hi);
+    stage(0, lo, hi);
+    __syncthreads();
+    for (int tile = 0; tile < nt; tile++) {
+        const int buf = tile & 1;
+        if (tile + 1 < nt) fetch(tile + 1, lo, hi);
+        float v[IIR_E];
+        {
+            const float4* xv = reinterpret_cast<const float4*>(&xin[buf][w][IIR_E * lane]);
+            const float4 a = xv[0], b = xv[1];
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        // lane-local response from a zero state
+        float sl = 0.f;
+#pragma unroll
+        for (int e = 0; e < IIR_E; e++) sl = alpha * v[e] + om * sl;
+        // inclusive scan of (A, B): state after lane l = A_l * y_entry + B_l, A = om^(8 (l+1))
+        float B = sl;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float prev = __shfl_up_sync(0xffffffffu, B, 1 << k);
+            if (lane >= (1 << k)) B = om_pow[k] * prev + B;
+        }
+        // A_l = om^(8 (l+1)) by binary powers
+        float A = 1.f;
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+            if ((lane + 1) & (1 << k)) A *= om_pow[k];
+        if (lane == 31) A = om_pow[5];
+        const float endstate = A * y + B;              // state after this lane's 8 samples
+        float yin = __shfl_up_sync(0xffffffffu, endstate, 1);
+        if (lane == 0) yin = y;
+        // true outputs of this lane
+        float yo[IIR_E];
+#pragma unroll
+        for (int e = 0; e < IIR_E; e++) { yin = alpha * v[e] + om * yin; yo[e] = yin; }
+        {
+            float4* ov = reinterpret_cast<float4*>(&xout[w][IIR_E * lane]);
+            ov[0] = make_float4(yo[0], yo[1], yo[2], yo[3]);
+            ov[1] = make_float4(yo[4], yo[5], yo[6], yo[7]);
+        }
+        // the next step's entry state: the state after the last VALID sample of this tile
+        const int valid = min(IIR_TL, n - tile * IIR_TL);
+        const int ll = (valid - 1) / IIR_E, le = (valid - 1) % IIR_E;
+        float cand = yo[IIR_E - 1];
+#pragma unroll
+        for (int e = 0; e < IIR_E - 1; e++) cand = le == e ? yo[e] : cand;
+        y = __shfl_sync(0xffffffffu, cand, ll);
+        __syncthreads();
+        const int t = tile * IIR_TL + tid;
+        if (t < n) {
+            float4* p = reinterpret_cast<float4*>(out + (size_t)t * slots + s0);
+            p[0] = make_float4(xout[0][tid], xout[1][tid], xout[2][tid], xout[3][tid]);
+            p[1] = make_float4(xout[4][tid], xout[5][tid], xout[6][tid], xout[7][tid]);
+        }
+        if (tile + 1 < nt) stage(buf ^ 1, lo, hi);
+        __syncthreads();
+    }
+    if (lane == 0) st[s].iir = y;
 }
 
 // Agc (SPEC-DEFINED): per non-zero sample, |v|*gain/ref > 1 -> gain *= 1-attack, hang = hang_time;
