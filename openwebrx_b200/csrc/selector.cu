@@ -465,6 +465,13 @@ int place_channel(owrx_bank* bank, Chan* ch, int gi)
     if (slot < 0) return fail(OWRX_E_STATE, "group full");     // caller grows before placing
     g->slot_chan[(size_t)slot] = ch->id;
     ch->group = gi; ch->slot = slot;
+    // a new client's modules start with empty histories (the reference builds fresh pycsdr modules): clear whatever the
+    // idle slot computed before
+    OWRX_CUDA(cudaDeviceSynchronize());
+    for (StageBuf* b : {&g->s1, &g->s2, &g->s3, &g->f1, &g->f1p, &g->f1b, &g->f2, &g->f3}) {
+        if (!b->d[b->cur] || !b->fill) continue;
+        OWRX_CUDA(cudaMemset2D(b->d[b->cur] + (size_t)slot * b->width, b->row_floats() * sizeof(float), 0, (size_t)b->width * sizeof(float), b->fill));
+    }
     ChanState st{};
     st.agc_gain = ch->agc_initial;
     OWRX_CUDA(cudaMemcpy(g->d_state + slot, &st, sizeof(st), cudaMemcpyHostToDevice));

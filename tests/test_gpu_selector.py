@@ -233,3 +233,28 @@ def test_agc_bit_exact_on_own_demod(gpu):
         else:
             ref = oracle.agc(dm, 0, 1.0, 65535.0)         # analog.py:121-122 (bank default profile: slow)
         assert np.array_equal(au, ref), (car["kind"], int(np.argmax(au != ref)))
+
+
+def test_retune_and_grow_midstream_direct_equals_fastconv(gpu, monkeypatch):
+    # control-path events between feeds — a retune (Shift.setRate: the fast-convolution table column of that channel is
+    # rebuilt), then 64 more clients (the group's slot layout and every per-slot table grow) — must leave both
+    # evaluations of Shift + FirDecimate in agreement, sample for sample within the audio tolerance
+    fs, out = 2.4e6, 12000
+    cars = carrier_plan(4, fs, seed=33)
+    n = 5333 + 200 * (750 * 3 + 7)
+    iq = make_iq(n, fs, cars, seed=33)
+    a, b = n // 3 + 11, 2 * n // 3 + 5
+    got = {}
+    for mode in ("direct", "fastconv"):
+        monkeypatch.setenv("OWRX_FIR_MODE", str(N.FIR_MODES[mode]))
+        bank, chans = _setup(fs, out, cars, 4, outputs=N.OUT_IF | N.OUT_DEMOD)
+        bank.feed(iq[:a])
+        chans[1][0].setFrequencyOffset(cars[2]["offset"] + 1234)
+        bank.feed(iq[a:b])
+        extra = [bank.add_channel(out, demod="usb", offset=cars[i % 4]["offset"] + 50 * i, bandpass=BANDPASS["usb"]) for i in range(64)]
+        bank.feed(iq[b:])
+        got[mode] = [(ch.read_if(), ch.read_demod()) for ch, _ in chans] + [(extra[0].read_if(), extra[0].read_demod()), (extra[63].read_if(), extra[63].read_demod())]
+    for (if_d, dm_d), (if_f, dm_f) in zip(got["direct"], got["fastconv"]):
+        assert len(if_d) == len(if_f) > 0 and len(dm_d) == len(dm_f)
+        assert rel_rms(if_f, if_d) <= AUDIO_TOL
+        assert rel_rms(dm_f, dm_d) <= AUDIO_TOL
