@@ -230,6 +230,7 @@ struct Group {
     long long sq_block_abs = 0;                      // absolute squelch block counter (for report interval)
     // last run
     size_t last_audio = 0, last_demod = 0, last_if = 0, last_blocks = 0;
+    size_t dr_audio = 0, dr_demod = 0, dr_if = 0, dr_blocks = 0;    // of those, already copied to the host queues
     size_t pass_audio = 0;                           // audio rows produced by the last tail pass
     size_t feed_blocks = 0;                          // squelch blocks processed so far in this feed
     size_t pend_rows = 0;                            // FirDecimate rows appended to s1 since the last tail pass
@@ -274,7 +275,8 @@ struct owrx_bank {
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t fir_done = nullptr, ptail_done[2] = {nullptr, nullptr}, tail_done[2] = {nullptr, nullptr}, dev_done = nullptr;
     bool pipelined = false, reserve_sm = false;
-    std::vector<cudaEvent_t> fir_events;
+    std::vector<cudaEvent_t> fir_events, drain_events;
+    cudaStream_t drain_stream = nullptr;
     unsigned long long calls = 0;
     // optional per-kernel timing of K3 (CUDA events on the launching stream)
     bool profile = false;
@@ -1031,6 +1033,7 @@ int group_begin_feed(owrx_bank* bank, Group* g, size_t rows, cudaStream_t st_fir
     g->f2.roll(0, st_tail);
     g->f3.roll(0, st_tail);
     g->last_audio = g->last_demod = g->last_if = g->last_blocks = 0;
+    g->dr_audio = g->dr_demod = g->dr_if = g->dr_blocks = 0;
     g->pass_audio = 0; g->feed_blocks = 0; g->tail_ran = false;
     const bool grow = g->s1.fill + rows > g->s1.cap_rows || (g->has_frac && g->s2.fill + low > g->s2.cap_rows) ||
                       g->s3.fill + low > g->s3.cap_rows || g->f1.fill + low > g->f1.cap_rows || low > g->f2.cap_rows ||
@@ -1087,7 +1090,7 @@ int ensure_stage(owrx_bank* bank, size_t floats)
 
 // rows [n][slots] of `width`-float elements -> channel-major [slots][n] on the device, one D2H copy, then
 // one contiguous append per channel
-int drain_to_queues(owrx_bank* bank, Group* g, const float* dev_rows, size_t n, int width, int which)
+int drain_to_queues(owrx_bank* bank, Group* g, const float* dev_rows, size_t n, int width, int which, cudaStream_t ds)
 {
     if (!n) return OWRX_OK;
     const size_t floats = n * (size_t)g->slots * width;
@@ -1099,12 +1102,12 @@ int drain_to_queues(owrx_bank* bank, Group* g, const float* dev_rows, size_t n, 
         bank->d_xpose_cap = floats;
     }
     const dim3 grid((unsigned)((g->slots + 31) / 32), (unsigned)((n + 31) / 32));
-    if (width == 1) transpose_kernel<float><<<grid, dim3(32, 8), 0, bank->stream>>>(dev_rows, g->slots, n, bank->d_xpose);
-    else transpose_kernel<float2><<<grid, dim3(32, 8), 0, bank->stream>>>(reinterpret_cast<const float2*>(dev_rows), g->slots, n,
+    if (width == 1) transpose_kernel<float><<<grid, dim3(32, 8), 0, ds>>>(dev_rows, g->slots, n, bank->d_xpose);
+    else transpose_kernel<float2><<<grid, dim3(32, 8), 0, ds>>>(reinterpret_cast<const float2*>(dev_rows), g->slots, n,
                                                                          reinterpret_cast<float2*>(bank->d_xpose));
     OWRX_LAUNCH_CHECK();
-    OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, bank->d_xpose, floats * sizeof(float), cudaMemcpyDeviceToHost, bank->stream));
-    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, bank->d_xpose, floats * sizeof(float), cudaMemcpyDeviceToHost, ds));
+    OWRX_CUDA(cudaStreamSynchronize(ds));
     for (int s = 0; s < g->slots; s++) {
         const int cid = g->slot_chan[(size_t)s];
         if (cid < 0) continue;
@@ -1172,6 +1175,7 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->serial_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->drain_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
@@ -1194,6 +1198,8 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]); cudaFree(bank->d_xpose);
     for (cudaEvent_t e : bank->chunk_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->fir_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : bank->drain_events) cudaEventDestroy(e);
+    if (bank->drain_stream) cudaStreamDestroy(bank->drain_stream);
     if (bank->fir_done) cudaEventDestroy(bank->fir_done);
     if (bank->dev_done) cudaEventDestroy(bank->dev_done);
     if (bank->tail_done[0]) cudaEventDestroy(bank->tail_done[0]);
@@ -1413,30 +1419,43 @@ int owrx_bank_set_outputs(owrx_bank_t* bank, int mask)
     return OWRX_OK;
 }
 
-// host -> queues for one group after its tail pass
-static int group_drain(owrx_bank* bank, Group* g)
+// host <- device for one group: the rows of this feed that are not in the host queues yet, up to the given counts
+// (a snapshot taken when a chunk's kernels were issued; `ds` already waits for that chunk).  `final` also moves the
+// client-audio-tail bytes and closes the feed's S-meter phase.
+struct DrainMark { size_t audio, demod, if_, blocks; };
+static int group_drain(owrx_bank* bank, Group* g, cudaStream_t ds, const DrainMark& upto, bool final)
 {
-    cudaStream_t st = bank->stream;
     int rc;
-    if ((bank->out_mask & OWRX_OUT_AUDIO) && (rc = drain_to_queues(bank, g, g->f3.rows(g->f3.fill - g->last_audio), g->last_audio, 1, 0))) return rc;
-    if (g->any_tail && g->tail_ran && g->last_audio && (rc = drain_tail(bank, g)) != OWRX_OK) return rc;
-    if ((bank->out_mask & OWRX_OUT_DEMOD) && (rc = drain_to_queues(bank, g, g->f2.rows(g->f2.fill - g->last_demod), g->last_demod, 1, 1))) return rc;
-    if ((bank->out_mask & OWRX_OUT_IF) && (rc = drain_to_queues(bank, g, g->s3.rows(g->s3.fill - g->last_if), g->last_if, 2, 2))) return rc;
-    if ((bank->out_mask & OWRX_OUT_POWER) && g->last_blocks) {
+    if ((bank->out_mask & OWRX_OUT_AUDIO) && upto.audio > g->dr_audio &&
+        (rc = drain_to_queues(bank, g, g->f3.rows(g->f3.fill - g->last_audio + g->dr_audio), upto.audio - g->dr_audio, 1, 0, ds)))
+        return rc;
+    g->dr_audio = std::max(g->dr_audio, upto.audio);
+    if (final && g->any_tail && g->tail_ran && g->last_audio && (rc = drain_tail(bank, g)) != OWRX_OK) return rc;
+    if ((bank->out_mask & OWRX_OUT_DEMOD) && upto.demod > g->dr_demod &&
+        (rc = drain_to_queues(bank, g, g->f2.rows(g->f2.fill - g->last_demod + g->dr_demod), upto.demod - g->dr_demod, 1, 1, ds)))
+        return rc;
+    g->dr_demod = std::max(g->dr_demod, upto.demod);
+    if ((bank->out_mask & OWRX_OUT_IF) && upto.if_ > g->dr_if &&
+        (rc = drain_to_queues(bank, g, g->s3.rows(g->s3.fill - g->last_if + g->dr_if), upto.if_ - g->dr_if, 2, 2, ds)))
+        return rc;
+    g->dr_if = std::max(g->dr_if, upto.if_);
+    if ((bank->out_mask & OWRX_OUT_POWER) && upto.blocks > g->dr_blocks) {
         // reportInterval = measurementsPerSec / readingsPerSec = 4 (selector.py:108-109,126)
-        const size_t nb = g->last_blocks;
+        const size_t b0 = g->dr_blocks, nb = upto.blocks - b0;
         if ((rc = ensure_stage(bank, nb * (size_t)g->slots)) != OWRX_OK) return rc;
-        OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, g->d_power, nb * (size_t)g->slots * sizeof(float), cudaMemcpyDeviceToHost, st));
-        OWRX_CUDA(cudaStreamSynchronize(st));
+        OWRX_CUDA(cudaMemcpyAsync(bank->h_stage, g->d_power + b0 * (size_t)g->slots, nb * (size_t)g->slots * sizeof(float),
+                                  cudaMemcpyDeviceToHost, ds));
+        OWRX_CUDA(cudaStreamSynchronize(ds));
         for (size_t b = 0; b < nb; b++) {
-            if (((g->sq_block_abs + (long long)b) % 4) != 0) continue;
+            if (((g->sq_block_abs + (long long)(b0 + b)) % 4) != 0) continue;
             for (int s = 0; s < g->slots; s++) {
                 const int cid = g->slot_chan[(size_t)s];
                 if (cid >= 0) bank->chans[(size_t)cid]->q_power.push_back(bank->h_stage[b * (size_t)g->slots + s]);
             }
         }
     }
-    g->sq_block_abs += (long long)g->last_blocks;
+    g->dr_blocks = std::max(g->dr_blocks, upto.blocks);
+    if (final) g->sq_block_abs += (long long)g->last_blocks;
     return OWRX_OK;
 }
 
@@ -1504,6 +1523,12 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
         const size_t rows = (fill0 + n_samples - g->in_off) / (size_t)g->D + 1;
         if ((rc = group_begin_feed(bank, g, rows, st, tails)) != OWRX_OK) return rc;
     }
+    while (bank->drain_events.size() < n_chunks) {
+        cudaEvent_t e;
+        OWRX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        bank->drain_events.push_back(e);
+    }
+    std::vector<std::vector<DrainMark>> marks(n_chunks);
     while (bank->fir_events.size() < n_chunks) {
         cudaEvent_t e;
         OWRX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1532,6 +1557,21 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
             if ((rc = group_tail(bank, g, tails)) != OWRX_OK) return rc;
             if ((rc = group_tail_serial(bank, g, tails)) != OWRX_OK) return rc;
         }
+        if (overlap) {
+            // outputs of chunk c are complete once `tails` gets here; while the GPU works on chunk c+1 the host copies the
+            // outputs of chunk c-1 into the per-channel queues (drain stream: waits for that chunk only)
+            OWRX_CUDA(cudaEventRecord(bank->drain_events[c], tails));
+            marks[c].clear();
+            for (auto& gp : bank->groups) {
+                Group* g = gp.get();
+                marks[c].push_back(g ? DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks} : DrainMark{0, 0, 0, 0});
+            }
+            if (c >= 1) {
+                OWRX_CUDA(cudaStreamWaitEvent(bank->drain_stream, bank->drain_events[c - 1], 0));
+                for (size_t gi = 0; gi < bank->groups.size(); gi++)
+                    if (bank->groups[gi] && (rc = group_drain(bank, bank->groups[gi].get(), bank->drain_stream, marks[c - 1][gi], false)) != OWRX_OK) return rc;
+            }
+        }
     }
     bank->reserve_sm = false;
     if (overlap) {
@@ -1544,7 +1584,10 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     OWRX_CUDA(cudaEventRecord(bank->ev1, st));
     lap("launched");
     if (trace) { cudaStreamSynchronize(st); lap("gpu done"); }
-    for (auto& gp : bank->groups) if (gp && (rc = group_drain(bank, gp.get())) != OWRX_OK) return rc;
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (g && (rc = group_drain(bank, g, st, DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks}, true)) != OWRX_OK) return rc;
+    }
     lap("drained");
     // drop consumed wideband samples
     if (min_off > 0) {
@@ -1642,7 +1685,7 @@ int owrx_bank_drain(owrx_bank_t* bank)
         if (!g) continue;
         const long long blocks = (long long)g->last_blocks;
         g->sq_block_abs -= blocks;                   // group_drain re-adds it (power report phase)
-        if ((rc = group_drain(bank, g)) != OWRX_OK) return rc;
+        if ((rc = group_drain(bank, g, st, DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks}, true)) != OWRX_OK) return rc;
     }
     OWRX_CUDA(cudaStreamSynchronize(st));
     return OWRX_OK;
