@@ -4,19 +4,13 @@
 #include "fastconv.cuh"
 #include "fft_small.cuh"
 
+#include <cuda.h>
+
 #include <algorithm>
 
 namespace owrx {
 
 namespace {
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ------------------------------------------------------------------------------------------------
 // Tab[q][r][slot] = sum_{s<P} h[D s + r] e^{j 2 pi rate (D s + r)} e^{+j 2 pi q s / M}
@@ -124,8 +118,8 @@ fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp,
 // The forward pass stores F already as (re, re, -im, im): one LDS.128 per (row, branch) yields both packed
 // multiplicands; the table pairs (t.re, t.im) of two columns come from one LDS.128 and the swapped pair costs two
 // register moves per column.  Per branch and thread: 10 LDS.128 + 8 MOV + 64 FFMA2.  Operand chunks of 32 branches
-// stream through a 3-stage cp.async pipeline; two warp groups split the branches of a chunk (even / odd) and meet in
-// shared memory at the end, so a 96-row CTA runs 12 warps.
+// stream through a 3-stage TMA (cp.async.bulk) ring guarded by mbarriers; two warp groups split the branches of a chunk
+// (even / odd) and meet in shared memory at the end, so a 96-row CTA runs 12 consumer warps + 1 producer warp.
 // ------------------------------------------------------------------------------------------------
 constexpr int FC_ST = 3;
 typedef unsigned long long f32x2;
@@ -148,42 +142,76 @@ __device__ __forceinline__ f32x2 swap2(f32x2 v)
     return pk2(b, a);
 }
 
+// ---- TMA (bulk async copy) + mbarrier plumbing for the operand pipeline
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FC_DONE;\n"
+        "bra FC_WAIT;\n"
+        "FC_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// one TMA tile: box (128 floats x rows) of a 2D row-major float tensor -> dense [rows][128] floats in shared memory
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+
+// Warp roles: 2 NW consumer warps (two groups: even / odd branches of a chunk) + 1 producer warp whose elected lane streams
+// the operand chunks with two TMA tile loads each (F: BT blocks x 32 branches; table: 32 branches x 64 slots) into a 3-stage
+// ring guarded by full/empty mbarriers; no CTA-wide barrier inside the branch loop.
 template <int NW>
-__global__ void __launch_bounds__(NW * 64, 1)
-fc_contract_kernel(const float4* __restrict__ F, const float2* __restrict__ tab, float2* __restrict__ Z, int B, int Dp, int slots, int nbt)
+__global__ void __launch_bounds__(NW * 64 + 32, 1)
+fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT, float2* __restrict__ Z, int B, int Dp,
+                   int slots, int nbt)
 {
     constexpr int BT = 16 * NW;
-    constexpr int NT = NW * 64;                                       // two warp groups: even / odd branches of a chunk
-    extern __shared__ float4 fc_smem4[];
+    constexpr unsigned F_STAGE = BT * FC_KC * sizeof(float4), T_STAGE = FC_KC * FC_CG * sizeof(float2);
+    extern __shared__ __align__(128) float4 fc_smem4[];
+    __shared__ unsigned long long bars[2 * FC_ST];                   // full[ST], empty[ST]
     float4* Fs = fc_smem4;                                            // [ST][BT][KC]   (re, re, -im, im)
     float2* Ts = reinterpret_cast<float2*>(Fs + FC_ST * BT * FC_KC);  // [ST][KC][64]
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int grp = (tid >> 5) / NW, warp = (tid >> 5) % NW;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool producer = wid == 2 * NW;
+    const int grp = wid / NW, warp = wid % NW;
     const int lr = lane >> 4, lc = lane & 15;
     const int q = blockIdx.x / nbt, bt = blockIdx.x % nbt;
     const int cg = blockIdx.y;
     const int b0 = bt * BT;
     const int rows = min(BT, B - b0);
     const int nchunks = Dp / FC_KC;
-    // rows 16w + 2i + lr of this warp that exist: i < ni (the lr = 1 half of a last odd row is clamped at the load)
+    // rows 16w + 2i + lr of this warp that exist: i < ni (the lr = 1 half of a last odd row reads a stale row; not stored)
     const int ni = min(8, max(0, (rows - warp * 16 + 1) / 2));
 
-    const float4* Fq = F + ((size_t)q * B + b0) * Dp;
-    const float2* Tq = tab + (size_t)q * Dp * slots + (size_t)cg * FC_CG;
-
-    auto load_chunk = [&](int chunk, int stage) {
-        float4* fs = Fs + stage * BT * FC_KC;
-        float2* ts = Ts + stage * FC_KC * FC_CG;
-        for (int i = tid; i < BT * FC_KC; i += NT) {                  // F: BT rows x 32 pieces of 16 B
-            const int row = i / FC_KC, pc = i % FC_KC;
-            const int srow = min(row, rows - 1);
-            cp_async16(fs + row * FC_KC + pc, Fq + (size_t)srow * Dp + chunk * FC_KC + pc);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned fs0 = (unsigned)__cvta_generic_to_shared(Fs), ts0 = (unsigned)__cvta_generic_to_shared(Ts);
+    if (tid == 0) {
+        for (int s = 0; s < FC_ST; s++) {
+            mbar_init(bar0 + 8 * s, 1);                               // full: the producer's expect_tx arrival
+            mbar_init(bar0 + 8 * (FC_ST + s), 2 * NW);                // empty: one arrival per consumer warp
         }
-        for (int i = tid; i < FC_KC * (FC_CG / 2); i += NT) {         // Tab: KC rows x 32 pieces
-            const int kr = i / (FC_CG / 2), pc = i % (FC_CG / 2);
-            cp_async16(ts + kr * FC_CG + pc * 2, Tq + (size_t)(chunk * FC_KC + kr) * slots + pc * 2);
-        }
-    };
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
 
     f32x2 acc[8][4];
 #pragma unroll
@@ -191,61 +219,66 @@ fc_contract_kernel(const float4* __restrict__ F, const float2* __restrict__ tab,
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[i][c] = 0ull;
 
-#pragma unroll
-    for (int s = 0; s < FC_ST - 1; s++) {
-        if (s < nchunks) load_chunk(s, s);
-        cp_commit();
-    }
-    const unsigned fs_base = (unsigned)__cvta_generic_to_shared(Fs) + (unsigned)(((warp * 16 + lr) * FC_KC + grp) * sizeof(float4));
-    const unsigned ts_base = (unsigned)__cvta_generic_to_shared(Ts) + (unsigned)((grp * FC_CG + lc * 2) * sizeof(float2));
-    for (int ch = 0; ch < nchunks; ch++) {
-        cp_wait<FC_ST - 2>();
-        __syncthreads();
-        {
-            const int nx = ch + FC_ST - 1;
-            if (nx < nchunks) load_chunk(nx, nx % FC_ST);
-            cp_commit();
+    if (producer) {
+        if (lane == 0) {
+            for (int ch = 0; ch < nchunks; ch++) {
+                const int stage = ch % FC_ST, use = ch / FC_ST;
+                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (FC_ST + stage);
+                mbar_wait(empty, (use & 1) ^ 1);                      // every consumer warp has released this slot
+                mbar_expect_tx(full, F_STAGE + T_STAGE);
+                // rows past the last block of a short tile come from the next bin (or are zero-filled past the tensor):
+                // they only feed accumulators that are never stored
+                tma_load_2d(fs0 + stage * F_STAGE, &mapF, ch * FC_KC * 4, q * B + b0, full);
+                tma_load_2d(ts0 + stage * T_STAGE, &mapT, cg * FC_CG * 2, q * Dp + ch * FC_KC, full);
+            }
         }
-        const int stage = ch % FC_ST;
-        const unsigned fsa = fs_base + (unsigned)(stage * BT * FC_KC * sizeof(float4));
-        const unsigned tsa = ts_base + (unsigned)(stage * FC_KC * FC_CG * sizeof(float2));
-        // this group's branches of the chunk: k = 2 kk + grp
+    } else {
+        const unsigned fs_base = fs0 + (unsigned)(((warp * 16 + lr) * FC_KC + grp) * sizeof(float4));
+        const unsigned ts_base = ts0 + (unsigned)((grp * FC_CG + lc * 2) * sizeof(float2));
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int stage = ch % FC_ST, use = ch / FC_ST;
+            mbar_wait(bar0 + 8 * stage, use & 1);                     // the chunk's bytes have landed
+            const unsigned fsa = fs_base + stage * F_STAGE;
+            const unsigned tsa = ts_base + stage * T_STAGE;
+            // this group's branches of the chunk: k = 2 kk + grp
 #define FC_BRANCH_STEP(ROW_GUARD)                                                                       \
-        for (int kk = 0; kk < FC_KC / 2; kk++) {                                                        \
-            f32x2 t[4], s[4];                                                                           \
-            lds2x64(t[0], t[1], tsa + (unsigned)(2 * kk * FC_CG * sizeof(float2)));                     \
-            lds2x64(t[2], t[3], tsa + (unsigned)((2 * kk * FC_CG + 32) * sizeof(float2)));              \
-            _Pragma("unroll") for (int c = 0; c < 4; c++) s[c] = swap2(t[c]);                           \
-            _Pragma("unroll") for (int i = 0; i < 8; i++) {                                             \
-                if (ROW_GUARD) {                                                                        \
-                    f32x2 fa, fb;                                                                       \
-                    lds2x64(fa, fb, fsa + (unsigned)((2 * i * FC_KC + 2 * kk) * sizeof(float4)));       \
-                    _Pragma("unroll") for (int c = 0; c < 4; c++) ffma2(acc[i][c], fa, t[c]);           \
-                    _Pragma("unroll") for (int c = 0; c < 4; c++) ffma2(acc[i][c], fb, s[c]);           \
+            for (int kk = 0; kk < FC_KC / 2; kk++) {                                                    \
+                f32x2 t[4], s[4];                                                                       \
+                lds2x64(t[0], t[1], tsa + (unsigned)(2 * kk * FC_CG * sizeof(float2)));                 \
+                lds2x64(t[2], t[3], tsa + (unsigned)((2 * kk * FC_CG + 32) * sizeof(float2)));          \
+                _Pragma("unroll") for (int c = 0; c < 4; c++) s[c] = swap2(t[c]);                       \
+                _Pragma("unroll") for (int i = 0; i < 8; i++) {                                         \
+                    if (ROW_GUARD) {                                                                    \
+                        f32x2 fa, fb;                                                                   \
+                        lds2x64(fa, fb, fsa + (unsigned)((2 * i * FC_KC + 2 * kk) * sizeof(float4)));   \
+                        _Pragma("unroll") for (int c = 0; c < 4; c++) ffma2(acc[i][c], fa, t[c]);       \
+                        _Pragma("unroll") for (int c = 0; c < 4; c++) ffma2(acc[i][c], fb, s[c]);       \
+                    }                                                                                   \
                 }                                                                                       \
-            }                                                                                           \
-        }
-        if (ni == 8) {
+            }
+            if (ni == 8) {
 #pragma unroll 2
-            FC_BRANCH_STEP(true)
-        } else {
+                FC_BRANCH_STEP(true)
+            } else {
 #pragma unroll 1
-            FC_BRANCH_STEP(i < ni)
-        }
+                FC_BRANCH_STEP(i < ni)
+            }
 #undef FC_BRANCH_STEP
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (FC_ST + stage));   // this warp is done reading the slot
+        }
     }
-    // the odd-branch group hands its partial sums over through shared memory (the stage buffers are free now)
-    cp_wait<0>();
+    // the odd-branch group hands its partial sums over through shared memory (every chunk has been consumed)
     __syncthreads();
     f32x2* red = reinterpret_cast<f32x2*>(fc_smem4);                  // [NW][32 accumulators][32 lanes]
-    if (grp == 1) {
+    if (!producer && grp == 1) {
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
             for (int c = 0; c < 4; c++) red[(warp * 32 + i * 4 + c) * 32 + lane] = acc[i][c];
     }
     __syncthreads();
-    if (grp == 0) {
+    if (!producer && grp == 0) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int row = warp * 16 + 2 * i + lr;
@@ -427,6 +460,31 @@ bpf_inverse_kernel(const float2* __restrict__ Y, const float2* __restrict__ in, 
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2D row-major float32 tensor [rows][cols] with a (box_cols x box_rows) tile
+int make_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_cols, unsigned box_rows)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        OWRX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return OWRX_OK;
+}
+
 template <int NW>
 int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, int B, float2* Z, cudaStream_t st)
 {
@@ -434,7 +492,11 @@ int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, in
     const size_t smem = (size_t)FC_ST * (BT * FC_KC * sizeof(float4) + FC_KC * FC_CG * sizeof(float2));
     OWRX_CUDA(cudaFuncSetAttribute(fc_contract_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nbt = (B + BT - 1) / BT;
-    fc_contract_kernel<NW><<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG)), NW * 64, smem, st>>>(F, tab, Z, B, sh.Dp, sh.slots, nbt);
+    CUtensorMap mapF, mapT;
+    int rc;
+    if ((rc = make_map(&mapF, F, (size_t)sh.Dp * 4, (size_t)FC_M * B, FC_KC * 4, BT)) != OWRX_OK) return rc;
+    if ((rc = make_map(&mapT, tab, (size_t)sh.slots * 2, (size_t)FC_M * sh.Dp, FC_CG * 2, FC_KC)) != OWRX_OK) return rc;
+    fc_contract_kernel<NW><<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG)), NW * 64 + 32, smem, st>>>(mapF, mapT, Z, B, sh.Dp, sh.slots, nbt);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
