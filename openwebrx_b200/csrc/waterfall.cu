@@ -80,6 +80,12 @@ wf_fft_kernel(WfFftParams p)
         if (active) {
             if (FROM_IQ) {
                 const float2* x = p.src + (p.first_frame + frame) * (long long)p.every_n;
+                if (a + 1 < a1) {
+                    // pull the next frame (M * 8 bytes = M/16 lines of 128 B: one per thread) towards the SM while this one is
+                    // transformed: its loads then find L2 instead of HBM
+                    const char* nx = reinterpret_cast<const char*>(x + p.every_n) + (size_t)tid * 128;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                }
 #pragma unroll
                 for (int r = 0; r < 16; r++) {
                     float2 s = __ldg(x + tid + r * T);
