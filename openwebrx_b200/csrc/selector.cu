@@ -1491,8 +1491,9 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     }
     float2* buf = bank->d_iq[bank->iq_cur];
     OWRX_CUDA(cudaEventRecord(bank->ev0, st));
-    // chunks of ~4 M samples keep K3 at a full wave of CTAs; small feeds are a single chunk
-    const size_t chunk = (size_t)1 << 22;
+    // chunks of 2 M samples: the work left after the last H2D chunk (its FIR, low-rate stages and drain) stays short while a
+    // chunk still spans 11+ overlap-save blocks; small feeds are a single chunk
+    static const size_t chunk = (size_t)1 << (getenv("OWRX_FEED_CHUNK_LOG2") ? std::max(16, std::min(26, atoi(getenv("OWRX_FEED_CHUNK_LOG2")))) : 21);
     const size_t n_chunks = std::max<size_t>(1, (n_samples + chunk - 1) / chunk);
     while (bank->chunk_events.size() < n_chunks) {
         cudaEvent_t e;
