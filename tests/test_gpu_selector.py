@@ -258,3 +258,21 @@ def test_retune_and_grow_midstream_direct_equals_fastconv(gpu, monkeypatch):
         assert len(if_d) == len(if_f) > 0 and len(dm_d) == len(dm_f)
         assert rel_rms(if_f, if_d) <= AUDIO_TOL
         assert rel_rms(dm_f, dm_d) <= AUDIO_TOL
+
+
+def test_prime_decimation_and_block_edges(gpu):
+    # D = 211 (prime: nothing to factor for an FFT over the input index — the polyphase form needs no such FFT) and feeds
+    # that end exactly on, one before and one after an overlap-save block boundary (Kb = 230 outputs per block)
+    fs, out = 211 * 12000.0, 12000
+    cars = carrier_plan(3, fs, seed=34)
+    T = 5627                                           # filter_len(0.15 * 12000 / fs)
+    for n_k in (230 * 3, 230 * 3 - 1, 230 * 3 + 1, 64, 65):
+        n = T + 211 * (n_k - 1)
+        iq = make_iq(n, fs, cars, seed=34)
+        bank, chans = _setup(fs, out, cars, 3, outputs=N.OUT_IF)
+        bank.feed(iq)
+        for ch, car in chans:
+            ref = oracle.client_chain_run(iq, fs, out, car["offset"], BANDPASS[car["kind"]], KIND[car["kind"]])
+            got = ch.read_if()
+            assert len(got) == len(ref["if_"]) == n_k
+            assert rel_rms(got, ref["if_"]) <= AUDIO_TOL
