@@ -182,7 +182,7 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
 template <int NW>
 __global__ void __launch_bounds__(NW * 64 + 32, 1)
 fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT, float2* __restrict__ Z, int B, int Dp,
-                   int slots, int nbt)
+                   int slots, int nbt, int nsplit)
 {
     constexpr int BT = 16 * NW;
     constexpr unsigned F_STAGE = BT * FC_KC * sizeof(float4), T_STAGE = FC_KC * FC_CG * sizeof(float2);
@@ -198,7 +198,13 @@ fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_consta
     const int cg = blockIdx.y;
     const int b0 = bt * BT;
     const int rows = min(BT, B - b0);
-    const int nchunks = Dp / FC_KC;
+    // split-K: this CTA contracts branch chunks [ch0, ch0 + nchunks) and writes partial-sum plane blockIdx.z of Z (the
+    // planes are added by fc_inverse_kernel): used when the bin tiles alone leave a poorly filled last wave and a tile is long
+    // enough (many chunks: large D) to amortise the ring fill
+    const int all_chunks = Dp / FC_KC;
+    const int ch0 = (int)(((long long)all_chunks * blockIdx.z) / nsplit);
+    const int nchunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / nsplit) - ch0;
+    Z += (size_t)blockIdx.z * FC_M * B * slots;
     // rows 16w + 2i + lr of this warp that exist: i < ni (the lr = 1 half of a last odd row reads a stale row; not stored)
     const int ni = min(8, max(0, (rows - warp * 16 + 1) / 2));
 
@@ -228,8 +234,8 @@ fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_consta
                 mbar_expect_tx(full, F_STAGE + T_STAGE);
                 // rows past the last block of a short tile come from the next bin (or are zero-filled past the tensor):
                 // they only feed accumulators that are never stored
-                tma_load_2d(fs0 + stage * F_STAGE, &mapF, ch * FC_KC * 4, q * B + b0, full);
-                tma_load_2d(ts0 + stage * T_STAGE, &mapT, cg * FC_CG * 2, q * Dp + ch * FC_KC, full);
+                tma_load_2d(fs0 + stage * F_STAGE, &mapF, (ch0 + ch) * FC_KC * 4, q * B + b0, full);
+                tma_load_2d(ts0 + stage * T_STAGE, &mapT, cg * FC_CG * 2, q * Dp + (ch0 + ch) * FC_KC, full);
             }
         }
     } else {
@@ -304,7 +310,7 @@ fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_consta
 // IFFT(x) = conj(FFT(conj(x))).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(16 * FC_SEQ)
-fc_inverse_kernel(const float2* __restrict__ Z, int B, int slots, int D, int Kb, const double* __restrict__ ch_rate,
+fc_inverse_kernel(const float2* __restrict__ Z, int nsplit, int B, int slots, int D, int Kb, const double* __restrict__ ch_rate,
                   const double* __restrict__ ch_phase, long long k0, long long n_k, float2* __restrict__ out)
 {
     extern __shared__ float2 fc_smem[];
@@ -317,7 +323,12 @@ fc_inverse_kernel(const float2* __restrict__ Z, int B, int slots, int D, int Kb,
     float2 v[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
-        const float2 z = __ldg(Z + ((size_t)(16 * n1 + g) * B + b) * slots + c);
+        const size_t at = ((size_t)(16 * n1 + g) * B + b) * slots + c;
+        float2 z = __ldg(Z + at);
+        for (int sp = 1; sp < nsplit; sp++) {                      // split-K partial sums of the contraction
+            const float2 zz = __ldg(Z + (size_t)sp * FC_M * B * slots + at);
+            z.x += zz.x; z.y += zz.y;
+        }
         v[n1] = make_float2(z.x, -z.y);
     }
     __syncthreads();
@@ -486,7 +497,7 @@ int make_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsig
 }
 
 template <int NW>
-int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, int B, float2* Z, cudaStream_t st)
+int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, int B, float2* Z, int nsplit, cudaStream_t st)
 {
     constexpr int BT = 16 * NW;
     const size_t smem = (size_t)FC_ST * (BT * FC_KC * sizeof(float4) + FC_KC * FC_CG * sizeof(float2));
@@ -496,7 +507,8 @@ int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, in
     int rc;
     if ((rc = make_map(&mapF, F, (size_t)sh.Dp * 4, (size_t)FC_M * B, FC_KC * 4, BT)) != OWRX_OK) return rc;
     if ((rc = make_map(&mapT, tab, (size_t)sh.slots * 2, (size_t)FC_M * sh.Dp, FC_CG * 2, FC_KC)) != OWRX_OK) return rc;
-    fc_contract_kernel<NW><<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG)), NW * 64 + 32, smem, st>>>(mapF, mapT, Z, B, sh.Dp, sh.slots, nbt);
+    fc_contract_kernel<NW><<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG), (unsigned)nsplit), NW * 64 + 32, smem, st>>>(mapF, mapT, Z, B, sh.Dp,
+                                                                                                                                     sh.slots, nbt, nsplit);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
@@ -522,20 +534,43 @@ int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int 
     return OWRX_OK;
 }
 
-int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, cudaStream_t st)
+// CTA shape and split-K factor for B blocks: as few row tiles as 96-row CTAs allow, the smallest CTA that covers them, and
+// the split (<= FC_MAXSPLIT) that wastes the least of the last wave
+void fc_contract_plan(const FcShape& sh, int B, int sm_count, int* nw_out, int* nsplit_out)
 {
-    (void)sm_count;
     static const int force_nw = getenv("OWRX_FC_NW") ? atoi(getenv("OWRX_FC_NW")) : 0;
-    // as few row tiles as 96-row CTAs allow, then the smallest CTA that still covers them
-    const int nbt = (B + 95) / 96;
-    int nw = force_nw ? force_nw : ((B + nbt - 1) / nbt + 15) / 16;
+    static const int force_split = getenv("OWRX_FC_SPLIT") ? atoi(getenv("OWRX_FC_SPLIT")) : 0;
+    const int nbt0 = (B + 95) / 96;
+    const int nw = force_nw ? std::max(1, std::min(6, force_nw)) : std::max(1, std::min(6, ((B + nbt0 - 1) / nbt0 + 15) / 16));
+    const int nbt = (B + 16 * nw - 1) / (16 * nw);
+    const size_t smem = (size_t)FC_ST * (16 * nw * FC_KC * sizeof(float4) + FC_KC * FC_CG * sizeof(float2));
+    const int per_sm = std::max(1, std::min((int)((size_t)(220 << 10) / smem), 2048 / (nw * 64 + 32)));
+    const long long tiles = (long long)FC_M * nbt * (sh.slots / FC_CG), slots = (long long)sm_count * per_sm;
+    const int chunks = sh.Dp / FC_KC;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int sp = 1; sp <= std::min(FC_MAXSPLIT, chunks); sp++) {
+        // waves of CTAs, each 1/sp of a tile plus a fixed prologue/epilogue worth about three chunks (measured: with 27
+        // chunks per tile, C2, splitting only moves the cost into the ring fill and the extra Z planes)
+        const double cost = (double)((tiles * sp + slots - 1) / slots) * (1.0 / sp + 3.0 / chunks);
+        if (cost < best_cost * 0.97) { best_cost = cost; best = sp; }
+    }
+    *nw_out = nw;
+    *nsplit_out = force_split ? std::max(1, std::min(FC_MAXSPLIT, force_split)) : best;
+}
+
+int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, int* nsplit_out, cudaStream_t st)
+{
+    int nw, nsplit;
+    fc_contract_plan(sh, B, sm_count, &nw, &nsplit);
+    *nsplit_out = nsplit;
     switch (nw) {
-    case 1: return launch_contract_nw<1>(sh, d_F, d_tab, B, d_Z, st);
-    case 2: return launch_contract_nw<2>(sh, d_F, d_tab, B, d_Z, st);
-    case 3: return launch_contract_nw<3>(sh, d_F, d_tab, B, d_Z, st);
-    case 4: return launch_contract_nw<4>(sh, d_F, d_tab, B, d_Z, st);
-    case 5: return launch_contract_nw<5>(sh, d_F, d_tab, B, d_Z, st);
-    default: return launch_contract_nw<6>(sh, d_F, d_tab, B, d_Z, st);
+    case 1: return launch_contract_nw<1>(sh, d_F, d_tab, B, d_Z, nsplit, st);
+    case 2: return launch_contract_nw<2>(sh, d_F, d_tab, B, d_Z, nsplit, st);
+    case 3: return launch_contract_nw<3>(sh, d_F, d_tab, B, d_Z, nsplit, st);
+    case 4: return launch_contract_nw<4>(sh, d_F, d_tab, B, d_Z, nsplit, st);
+    case 5: return launch_contract_nw<5>(sh, d_F, d_tab, B, d_Z, nsplit, st);
+    default: return launch_contract_nw<6>(sh, d_F, d_tab, B, d_Z, nsplit, st);
     }
 }
 
@@ -573,11 +608,11 @@ int bpf_launch_inverse(const float2* Y, const float2* in, const int* enabled, in
     return OWRX_OK;
 }
 
-int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
+int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
                       float2* out, cudaStream_t st)
 {
     OWRX_CUDA(cudaFuncSetAttribute(fc_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-    fc_inverse_kernel<<<dim3((unsigned)(sh.slots / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(d_Z, B, sh.slots, sh.D, sh.Kb, d_rate,
+    fc_inverse_kernel<<<dim3((unsigned)(sh.slots / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb, d_rate,
                                                                                                     d_phase, k0, n_k, out);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;

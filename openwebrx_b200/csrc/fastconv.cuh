@@ -22,6 +22,7 @@ constexpr int FC_M = 256;        // branch FFT size
 constexpr int FC_KC = 32;        // contraction chunk (branches per pipeline stage)
 constexpr int FC_DPAD = 32;      // D is padded to a multiple of this (forward pass: 32 branches per CTA)
 constexpr int FC_CG = 64;        // channel slots per contraction CTA
+constexpr int FC_MAXSPLIT = 4;   // split-K planes of Z (scratch is sized for this many)
 
 struct FcShape {
     int D, T, P, Kb, Dp, slots;
@@ -32,10 +33,11 @@ int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list,
                     cudaStream_t st);
 // F[q][b][r] (stored as the packed-FMA operand (re, re, -im, im)) for blocks b < B of the stream starting at iq (sample 0 = first tap of output 0)
 int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float4* d_F, cudaStream_t st);
-int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, cudaStream_t st);
+// d_Z holds FC_MAXSPLIT planes of [M][B][slots]; *nsplit = how many partial-sum planes this launch wrote
+int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, int* nsplit, cudaStream_t st);
 // out[(k0 + b Kb + m) * slots + c] for k0 + b Kb + m < n_k; phases are relative to iq[-1] of the whole call
-int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
-                      float2* out, cudaStream_t st);
+int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, const double* d_rate, const double* d_phase, long long k0,
+                      long long n_k, float2* out, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // K4F: Bandpass (csdr/chain/selector.py:115-117,159-166; per-channel complex taps at the selector output rate) as a

@@ -651,11 +651,11 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z);
         g->d_fc_F = nullptr; g->d_fc_Z = nullptr; g->fc_blocks_cap = 0;
         OWRX_CUDA(cudaMalloc((void**)&g->d_fc_F, need * per_block));
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, need * (size_t)FC_M * S * sizeof(float2)));
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * need * (size_t)FC_M * S * sizeof(float2)));
         g->fc_blocks_cap = need;
     }
     if (!g->d_fc_Z) {
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, g->fc_blocks_cap * (size_t)FC_M * S * sizeof(float2)));
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * g->fc_blocks_cap * (size_t)FC_M * S * sizeof(float2)));
     }
     float2* out = reinterpret_cast<float2*>(g->s1.append_ptr());
     for (size_t b0 = 0; b0 < blocks_total; b0 += Bmax) {
@@ -665,10 +665,11 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         if ((rc = fc_launch_forward(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_F, st)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, false)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, true)) != OWRX_OK) return rc;
-        if ((rc = fc_launch_contract(sh, g->d_fc_F, g->d_fc_tab, B, g->d_fc_Z, bank->sm_count, st)) != OWRX_OK) return rc;
+        int nsplit = 1;
+        if ((rc = fc_launch_contract(sh, g->d_fc_F, g->d_fc_tab, B, g->d_fc_Z, bank->sm_count, &nsplit, st)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, false)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, true)) != OWRX_OK) return rc;
-        if ((rc = fc_launch_inverse(sh, g->d_fc_Z, B, g->d_rate, g->d_phase, (long long)(b0 * (size_t)sh.Kb), (long long)n_k, out, st)) != OWRX_OK)
+        if ((rc = fc_launch_inverse(sh, g->d_fc_Z, nsplit, B, g->d_rate, g->d_phase, (long long)(b0 * (size_t)sh.Kb), (long long)n_k, out, st)) != OWRX_OK)
             return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, false)) != OWRX_OK) return rc;
         bank->stats.kernel_launches += 3;
