@@ -128,6 +128,17 @@ fracdec_cf_kernel(const float2* __restrict__ in, long long in_abs0, int in_slots
 // of one channel (lane <-> channel, so tap and sample loads are coalesced) and slides a 2*BP_RB-1 sample window
 // through registers: per BP_RB taps it loads BP_RB taps + BP_RB samples and issues 4*BP_RB^2 FMAs.
 constexpr int BP_RB = 8;
+// packed FP32 helpers (fma.rn.f32x2 -> FFMA2; a (x, x) pair assembles to the scalar-broadcast operand form)
+typedef unsigned long long bp_f32x2;
+__device__ __forceinline__ bp_f32x2 bp_pk2(float lo, float hi)
+{
+    bp_f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void bp_upk2(bp_f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void bp_ffma2(bp_f32x2& c, bp_f32x2 a, bp_f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b)); }
+
 __global__ void __launch_bounds__(128)
 bandpass_kernel(const float2* __restrict__ in, int in_slots, const int* __restrict__ slot_map,
                 const float2* __restrict__ taps, const int* __restrict__ enabled, int T, int n_out, int slots,
@@ -144,38 +155,50 @@ bandpass_kernel(const float2* __restrict__ in, int in_slots, const int* __restri
             if (i0 + j < n_out) out[(size_t)(i0 + j) * slots + s] = x[(ptrdiff_t)(i0 + j) * in_slots];
         return;
     }
-    float2 acc[BP_RB];
+    // acc = (re, im) of an output: acc += h.re * (v.x, v.y) + h.im * (-v.y, v.x)
+    bp_f32x2 acc[BP_RB];
 #pragma unroll
-    for (int j = 0; j < BP_RB; j++) acc[j] = make_float2(0.f, 0.f);
-    // window xw[k] = x[b - (BP_RB-1) + k], b = i0 - t0; only indices up to i0+BP_RB-1 ever carry weight, and rows past the
-    // last valid output are never read: clamp the row index (their accumulators are discarded)
+    for (int j = 0; j < BP_RB; j++) acc[j] = 0ull;
+    // window xw[k] = x[b - (BP_RB-1) + k], b = i0 - t0 (xn = the same samples as (-y, x)); only indices up to
+    // i0+BP_RB-1 ever carry weight, and rows past the last valid output are never read: clamp the row index (their
+    // accumulators are discarded)
     const int last = n_out - 1;
-    float2 xw[2 * BP_RB - 1];
+    bp_f32x2 xw[2 * BP_RB - 1], xn[2 * BP_RB - 1];
 #pragma unroll
-    for (int k = 0; k < 2 * BP_RB - 1; k++) xw[k] = x[(ptrdiff_t)min(i0 - (BP_RB - 1) + k, last) * in_slots];
+    for (int k = 0; k < 2 * BP_RB - 1; k++) {
+        const float2 v = x[(ptrdiff_t)min(i0 - (BP_RB - 1) + k, last) * in_slots];
+        xw[k] = bp_pk2(v.x, v.y);
+        xn[k] = bp_pk2(-v.y, v.x);
+    }
     for (int t0 = 0; t0 < T; t0 += BP_RB) {
         float2 h[BP_RB];
 #pragma unroll
         for (int u = 0; u < BP_RB; u++) h[u] = t0 + u < T ? taps[(size_t)(t0 + u) * slots + s] : make_float2(0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < BP_RB; u++) {
+            const bp_f32x2 hr = bp_pk2(h[u].x, h[u].x), hi = bp_pk2(h[u].y, h[u].y);
 #pragma unroll
-            for (int j = 0; j < BP_RB; j++) {
-                const float2 v = xw[BP_RB - 1 + j - u];
-                acc[j].x = fmaf(h[u].x, v.x, acc[j].x); acc[j].x = fmaf(-h[u].y, v.y, acc[j].x);
-                acc[j].y = fmaf(h[u].x, v.y, acc[j].y); acc[j].y = fmaf(h[u].y, v.x, acc[j].y);
-            }
+            for (int j = 0; j < BP_RB; j++) bp_ffma2(acc[j], hr, xw[BP_RB - 1 + j - u]);
+#pragma unroll
+            for (int j = 0; j < BP_RB; j++) bp_ffma2(acc[j], hi, xn[BP_RB - 1 + j - u]);
         }
         // slide the window BP_RB samples into the past
 #pragma unroll
-        for (int k = 2 * BP_RB - 2; k >= BP_RB; k--) xw[k] = xw[k - BP_RB];
+        for (int k = 2 * BP_RB - 2; k >= BP_RB; k--) { xw[k] = xw[k - BP_RB]; xn[k] = xn[k - BP_RB]; }
         const int b = i0 - t0 - BP_RB;
 #pragma unroll
-        for (int k = 0; k < BP_RB; k++) xw[k] = x[(ptrdiff_t)(b - (BP_RB - 1) + k) * in_slots];
+        for (int k = 0; k < BP_RB; k++) {
+            const float2 v = x[(ptrdiff_t)(b - (BP_RB - 1) + k) * in_slots];
+            xw[k] = bp_pk2(v.x, v.y);
+            xn[k] = bp_pk2(-v.y, v.x);
+        }
     }
 #pragma unroll
-    for (int j = 0; j < BP_RB; j++)
-        if (i0 + j < n_out) out[(size_t)(i0 + j) * slots + s] = acc[j];
+    for (int j = 0; j < BP_RB; j++) {
+        float re, im;
+        bp_upk2(acc[j], re, im);
+        if (i0 + j < n_out) out[(size_t)(i0 + j) * slots + s] = make_float2(re, im);
+    }
 }
 
 // per-channel serial state
@@ -202,7 +225,7 @@ struct ChanCfg {
 // warps stage |x|^2 of the block's decimated samples in shared memory (row loads of 32 adjacent slots), then warp 0
 // adds them in sample order (the oracle's summation order) from shared memory.  The gate (threshold + hang counter,
 // sequential over blocks) is a second tiny kernel.
-constexpr int SQ_MAXROWS = 256;          // decimated samples staged per pass (32 KB)
+constexpr int SQ_MAXROWS = 96;           // decimated samples staged per pass (12 KB: fits beside a resident contraction CTA)
 __global__ void __launch_bounds__(256)
 squelch_power_kernel(const float2* __restrict__ in, int slots, int n_blocks, int length, int decim, float* __restrict__ power)
 {
@@ -351,7 +374,7 @@ demod_back_kernel(const float* __restrict__ in, int slots, int n, int length, co
 
 // DcBlock block means.  CTA = (32 slots, one block): eight warps stage the block's samples in shared memory, warp 0
 // adds them in sample order (sequential float sum like the oracle).
-constexpr int DC_ROWS = 256;
+constexpr int DC_ROWS = 96;             // 12 KB: fits beside a resident contraction CTA
 __global__ void __launch_bounds__(256)
 dc_mean_kernel(const float* __restrict__ in, int slots, int n_blocks, int length, const ChanCfg* __restrict__ cfg,
                ChanState* __restrict__ st, float* __restrict__ dc_mean, float* __restrict__ dc_prev)
