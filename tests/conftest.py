@@ -8,7 +8,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _ensure_built():
+    """A fresh checkout has no libowrx_b200.so / oracle .so (git-ignored): compile them once (nvcc cross-compiles without a GPU)."""
+    so = os.path.join(ROOT, "openwebrx_b200", "libowrx_b200.so")
+    if not os.path.exists(so):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def pytest_configure(config):
+    _ensure_built()
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
