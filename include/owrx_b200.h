@@ -210,15 +210,18 @@ int owrx_bank_profile_read(owrx_bank_t* bank, double* k3_ms, uint64_t* k3_launch
 #define OWRX_PROF_KINDS       6
 int owrx_bank_profile_read_ex(owrx_bank_t* bank, double* ms, uint64_t* launches, int reset);
 
-/* How Shift + FirDecimate (csdr/chain/selector.py:29,95) is evaluated.  Both forms compute the same sums
+/* How Shift + FirDecimate (csdr/chain/selector.py:29,95) is evaluated.  All forms compute the same sums
  * (float32 rounding differs at the 1e-6 level):
  *   OWRX_FIR_DIRECT    direct-form polyphase FIR, 2T/D FMA per input sample per channel (K3)
  *   OWRX_FIR_FASTCONV  polyphase fast convolution: one shared forward FFT pass + a per-channel spectral contraction,
  *                      ~4.5 FMA per input sample per channel (K3F); needs decimation >= 8
+ *   OWRX_FIR_FASTCONV_TC  the same fast convolution with the spectral contraction on the tensor cores (tcgen05): every
+ *                      float32 operand is carried as three bf16 terms and six partial products are accumulated in FP32
  *   OWRX_FIR_AUTO      (default) fast convolution for feeds that yield >= 64 outputs per channel, direct otherwise */
-#define OWRX_FIR_AUTO     0
-#define OWRX_FIR_DIRECT   1
-#define OWRX_FIR_FASTCONV 2
+#define OWRX_FIR_AUTO        0
+#define OWRX_FIR_DIRECT      1
+#define OWRX_FIR_FASTCONV    2
+#define OWRX_FIR_FASTCONV_TC 3
 int owrx_bank_set_fir_mode(owrx_bank_t* bank, int mode);
 
 #ifdef __cplusplus

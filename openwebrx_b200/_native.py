@@ -90,7 +90,7 @@ SIGNATURES = {
     "owrx_bank_set_fir_mode": (_i, [_vp, _i]),
 }
 PROF_KINDS = ("k3_direct", "fc_forward", "fc_contract", "fc_inverse", "tail", "agc")
-FIR_MODES = {"auto": 0, "direct": 1, "fastconv": 2}
+FIR_MODES = {"auto": 0, "direct": 1, "fastconv": 2, "fastconv_tc": 3}
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here = header/library mismatch: fail loudly

@@ -5,6 +5,7 @@
 #include "fft_small.cuh"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <algorithm>
 
@@ -16,9 +17,20 @@ namespace {
 // Tab[q][r][slot] = sum_{s<P} h[D s + r] e^{j 2 pi rate (D s + r)} e^{+j 2 pi q s / M}
 // Phases in double (two sincospi per entry, then a 27-step double recurrence), rounded once to float.
 // ------------------------------------------------------------------------------------------------
+// x = h + m + l with three bf16 terms (the operand planes of the tensor-core contraction, fastconv_tc.cu)
+__device__ __forceinline__ void split_bf16x3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l)
+{
+    h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    m = __float2bfloat16_rn(r1);
+    l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+
+// TC = false: tab[q][r][slot] complex float32.  TC = true: bf16 planes Tp[2 level + part][q * slots + slot][r].
+template <bool TC>
 __global__ void __launch_bounds__(256)
 fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int slots, const int* __restrict__ slot_list,
-                const double* __restrict__ rate_list, float2* __restrict__ tab)
+                const double* __restrict__ rate_list, void* __restrict__ tab_out)
 {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= (long long)FC_M * D) return;
@@ -44,7 +56,20 @@ fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int sl
         const double nc = c0 * cw - s0 * sw, ns = c0 * sw + s0 * cw;
         c0 = nc; s0 = ns;
     }
-    tab[((size_t)q * Dp + r) * slots + slot] = make_float2((float)ar, (float)ai);
+    if (!TC) {
+        reinterpret_cast<float2*>(tab_out)[((size_t)q * Dp + r) * slots + slot] = make_float2((float)ar, (float)ai);
+    } else {
+        __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(tab_out);
+        const size_t plane = (size_t)FC_M * slots * Dp, at = ((size_t)q * slots + slot) * Dp + r;
+        __nv_bfloat16 a[3], b[3];
+        split_bf16x3((float)ar, a[0], a[1], a[2]);
+        split_bf16x3((float)ai, b[0], b[1], b[2]);
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+            tp[(size_t)(2 * l) * plane + at] = a[l];
+            tp[(size_t)(2 * l + 1) * plane + at] = b[l];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -80,8 +105,10 @@ __device__ __forceinline__ void fc_fft256(float2* v, float2* seq, const float2* 
     dft<16>(v);
 }
 
+// TC = false: F[q][b][r] as (re, re, -im, im).  TC = true: bf16 planes Fp[2 level + part][q * B + b][r].
+template <bool TC>
 __global__ void __launch_bounds__(16 * FC_SEQ)
-fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp, int Kb, int B, float4* __restrict__ F)
+fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp, int Kb, int B, void* __restrict__ F_out)
 {
     extern __shared__ float2 fc_smem[];
     float2* tw = fc_smem;                       // [256]
@@ -102,8 +129,21 @@ fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp,
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         const int bin = g + 16 * slot<16>(q);
-        // operand layout of the contraction's packed FMAs: (re, re) and (-im, im)
-        F[((size_t)bin * B + b) * Dp + r] = make_float4(v[q].x, v[q].x, -v[q].y, v[q].y);
+        if (!TC) {
+            // operand layout of the contraction's packed FMAs: (re, re) and (-im, im)
+            reinterpret_cast<float4*>(F_out)[((size_t)bin * B + b) * Dp + r] = make_float4(v[q].x, v[q].x, -v[q].y, v[q].y);
+        } else {
+            __nv_bfloat16* fp = reinterpret_cast<__nv_bfloat16*>(F_out);
+            const size_t plane = (size_t)FC_M * B * Dp, at = ((size_t)bin * B + b) * Dp + r;
+            __nv_bfloat16 a[3], c[3];
+            split_bf16x3(v[q].x, a[0], a[1], a[2]);
+            split_bf16x3(v[q].y, c[0], c[1], c[2]);
+#pragma unroll
+            for (int l = 0; l < 3; l++) {
+                fp[(size_t)(2 * l) * plane + at] = a[l];
+                fp[(size_t)(2 * l + 1) * plane + at] = c[l];
+            }
+        }
     }
 }
 
@@ -520,16 +560,35 @@ int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list,
 {
     if (n <= 0) return OWRX_OK;
     const long long total = (long long)FC_M * sh.D;
-    fc_table_kernel<<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, d_slot_list,
-                                                                                       d_rate_list, d_tab);
+    fc_table_kernel<false><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, d_slot_list,
+                                                                                              d_rate_list, d_tab);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, void* d_tabp,
+                       cudaStream_t st)
+{
+    if (n <= 0) return OWRX_OK;
+    const long long total = (long long)FC_M * sh.D;
+    fc_table_kernel<true><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, d_slot_list,
+                                                                                             d_rate_list, d_tabp);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
 
 int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float4* d_F, cudaStream_t st)
 {
-    OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-    fc_forward_kernel<<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
+    OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+    fc_forward_kernel<false><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, cudaStream_t st)
+{
+    OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+    fc_forward_kernel<true><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }

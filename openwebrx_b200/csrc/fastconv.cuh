@@ -39,6 +39,18 @@ int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab
 int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, const double* d_rate, const double* d_phase, long long k0,
                       long long n_k, float2* out, cudaStream_t st);
 
+// ---- tensor-core form of the contraction (fastconv_tc.cu): operands as three bf16 terms per float (x = h + m + l),
+// real and imaginary parts in separate K-major planes, plane p = 2 * level + part:
+//   Fp[p][q * B + b][r]  (fc_tc_plane_elems_F bf16 per plane)      Tp[p][q * slots + c][r]  (fc_tc_plane_elems_tab per plane)
+constexpr int FC_TC_PLANES = 6;
+size_t fc_tc_plane_elems_F(const FcShape& sh, int B);
+size_t fc_tc_plane_elems_tab(const FcShape& sh);
+int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, void* d_tabp,
+                       cudaStream_t st);
+int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, cudaStream_t st);
+int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tabp, int B, float2* d_Z, int sm_count, int* nsplit,
+                          cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // K4F: Bandpass (csdr/chain/selector.py:115-117,159-166; per-channel complex taps at the selector output rate) as a
 // uniformly partitioned overlap-save convolution on 256-point FFTs: the T taps are cut into P = ceil(T/128) partitions

@@ -1,0 +1,274 @@
+// fastconv_tc.cu — K3F-b on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Same contraction as fc_contract_kernel (fastconv.cu): Z[q][b][c] = sum_{r<Dp} F[q][b][r] * Tab[q][r][c], complex, the
+// per-channel half of pycsdr Shift + FirDecimate (reference call sites csdr/chain/selector.py:29,57,95,140).  Per bin q it
+// is a dense GEMM [B blocks x Dp branches] . [Dp x 64 slots] — the "true dense contraction" north_star asks for before
+// tensor cores may be used.  FP32 results are required (1e-4 relative RMS on channels up to 50 dB below the wideband
+// power), so every FP32 operand is carried as THREE bf16 terms x = h + m + l (8 + 8 + 8 significand bits; same exponent
+// range as float, no scaling needed) and the product is assembled from the six partial products whose weight is above
+// 2^-24:  hh, hm, mh, hl, lh, mm  (the "bf16x9" scheme minus its three smallest terms), accumulated in FP32 in TMEM.
+//
+// Complex arithmetic without duplicating an operand in HBM: real and imaginary parts are separate planes,
+//   D1 = F_re . [T_re | T_im]   (TMEM columns   0..127)         D2 = F_im . [T_re | T_im]   (TMEM columns 128..255)
+//   Z_re = D1[:, c] - D2[:, 64 + c]        Z_im = D1[:, 64 + c] + D2[:, c]        (combined by the epilogue warps)
+// so both MMAs of a product share one B descriptor and every instruction is M128 x N128 x K16.
+//
+// Operand planes (bf16, K-major, written by fc_forward_tc_kernel / fc_table_tc_kernel), plane p = 2 * level + part:
+//   Fp[p][q * B + b][r]        Tp[p][q * slots + c][r]            r < Dp contiguous
+// CTA = (bin q, row tile of <= 128 blocks, 64 channel slots, split-K plane).  Warp 0: TMA producer (one 3D box per operand
+// and stage: 32 branches x rows x 6 planes, SWIZZLE_64B).  Warp 1: TMEM allocation + MMA issue (one thread; 24
+// tcgen05.mma per stage; tcgen05.commit releases the stage).  Warps 2-5: epilogue (tcgen05.ld -> combine -> Z).
+#include "fastconv.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+namespace owrx {
+
+namespace {
+
+constexpr int TC_KC = 32;                                   // branches per stage = one 64-byte swizzle row of bf16
+constexpr int TC_ST = 3;                                    // pipeline stages
+constexpr int TC_NPL = 6;                                   // planes: 3 levels x (re, im)
+constexpr unsigned TC_ROWB = TC_KC * 2;                     // bytes per tile row
+constexpr unsigned TC_B_PLANE = FC_CG * TC_ROWB;            // 4096
+constexpr unsigned TC_B_STAGE = TC_NPL * TC_B_PLANE;        // 24576
+constexpr unsigned TC_COLS = 256;                           // TMEM columns: D1 | D2
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in [0,14), LBO unused (one
+// swizzle atom along K), SBO = 8 rows x 64 B = 512 >> 4 in [32,46), version 1 in [46,48), layout type 4 (SWIZZLE_64B) in [61,64)
+__device__ __forceinline__ unsigned long long smem_desc(unsigned addr)
+{
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major,
+// N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr unsigned TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float* v)
+{
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// the six partial products (A level, B level), smallest first
+__constant__ int kTcProd[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
+
+__global__ void __launch_bounds__(192, 1)
+fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float2* __restrict__ Z, int B, int Dp,
+                      int slots, int nbt, int mrows, int nsplit)
+{
+    extern __shared__ unsigned char tc_smem_raw[];
+    __shared__ unsigned long long bars[2 * TC_ST + 1];               // full[ST], empty[ST], accumulators ready
+    __shared__ unsigned tmem_slot;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int q = blockIdx.x / nbt, bt = blockIdx.x % nbt;
+    const int cg = blockIdx.y;
+    const int b0 = bt * mrows;
+    const int rows = min(mrows, B - b0);
+    const int all_chunks = Dp / TC_KC;
+    const int ch0 = (int)(((long long)all_chunks * blockIdx.z) / nsplit);
+    const int nchunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / nsplit) - ch0;
+    Z += (size_t)blockIdx.z * FC_M * B * slots;
+
+    const unsigned a_plane = (unsigned)mrows * TC_ROWB;              // mrows is a multiple of 8: every plane starts 512-aligned
+    const unsigned a_stage = TC_NPL * a_plane;
+    const unsigned stage_bytes = a_stage + TC_B_STAGE;
+    const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned bar_acc = bar0 + 8 * (2 * TC_ST);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_ST; s++) {
+            mbar_init(bar0 + 8 * s, 1);                               // full: the producer's expect_tx arrival
+            mbar_init(bar0 + 8 * (TC_ST + s), 1);                     // empty: one tcgen05.commit arrival
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (wid == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_slot)),
+                     "r"(TC_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem = tmem_slot;
+
+    if (wid == 0) {
+        if (lane == 0) {
+            for (int ch = 0; ch < nchunks; ch++) {
+                const int stage = ch % TC_ST, use = ch / TC_ST;
+                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (TC_ST + stage);
+                mbar_wait(empty, (use & 1) ^ 1);                      // the MMAs that read this slot have completed
+                mbar_expect_tx(full, stage_bytes);
+                const unsigned sa = smem0 + stage * stage_bytes;
+                // rows past the tile's last block come from the next bin (or are zero-filled past the tensor): they only
+                // feed accumulator rows that are never stored
+                tma_load_3d(sa, &mapA, (ch0 + ch) * TC_KC, q * B + b0, 0, full);
+                tma_load_3d(sa + a_stage, &mapB, (ch0 + ch) * TC_KC, q * slots + cg * FC_CG, 0, full);
+            }
+        }
+        __syncwarp();
+    } else if (wid == 1) {
+        if (lane == 0) {
+            for (int ch = 0; ch < nchunks; ch++) {
+                const int stage = ch % TC_ST, use = ch / TC_ST;
+                mbar_wait(bar0 + 8 * stage, use & 1);                 // the stage's bytes have landed
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const unsigned sa = smem0 + stage * stage_bytes, sb = sa + a_stage;
+#pragma unroll
+                for (int kk = 0; kk < TC_KC / 16; kk++) {
+#pragma unroll
+                    for (int p = 0; p < 6; p++) {
+                        const int la = kTcProd[p][0], lb = kTcProd[p][1];
+                        const unsigned long long d_re = smem_desc(sa + (unsigned)(2 * la) * a_plane + kk * 32);
+                        const unsigned long long d_im = smem_desc(sa + (unsigned)(2 * la + 1) * a_plane + kk * 32);
+                        const unsigned long long d_b = smem_desc(sb + (unsigned)(2 * lb) * TC_B_PLANE + kk * 32);
+                        const unsigned acc = (ch | kk | p) != 0;
+                        umma(tmem, d_re, d_b, acc);                   // D1 += F_re . [T_re | T_im]
+                        umma(tmem + 128, d_im, d_b, acc);             // D2 += F_im . [T_re | T_im]
+                    }
+                }
+                umma_commit(bar0 + 8 * (TC_ST + stage));              // slot free once these MMAs have read it
+            }
+            umma_commit(bar_acc);                                     // accumulators complete
+        }
+        __syncwarp();
+    } else {
+        // epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; thread <-> row (block) of the tile
+        const int quarter = wid & 3;
+        const int row = quarter * 32 + lane;
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const unsigned trow = tmem + ((unsigned)(quarter * 32) << 16);
+        float4* zr = reinterpret_cast<float4*>(Z + ((size_t)q * B + b0 + row) * slots + (size_t)cg * FC_CG);
+#pragma unroll 1
+        for (int c0 = 0; c0 < FC_CG; c0 += 16) {
+            float d1r[16], d1i[16], d2r[16], d2i[16];
+            tmem_ld16(trow + c0, d1r);                                // F_re . T_re
+            tmem_ld16(trow + 64 + c0, d1i);                           // F_re . T_im
+            tmem_ld16(trow + 128 + c0, d2r);                          // F_im . T_re
+            tmem_ld16(trow + 192 + c0, d2i);                          // F_im . T_im
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (row < rows) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2)
+                    zr[(c0 + i) >> 1] = make_float4(d1r[i] - d2i[i], d1i[i] + d2r[i], d1r[i + 1] - d2i[i + 1], d1i[i + 1] + d2r[i + 1]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (wid == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TC_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// bf16 tensor [6 planes][rows][cols] (cols contiguous) with a (32 cols x box_rows x 6 planes) box, SWIZZLE_64B
+int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_rows)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        OWRX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)TC_NPL};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * rows * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)TC_KC, box_rows, (cuuint32_t)TC_NPL};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled (bf16 planes) failed (%d)", (int)r);
+    return OWRX_OK;
+}
+
+}  // namespace
+
+size_t fc_tc_plane_elems_F(const FcShape& sh, int B) { return (size_t)FC_M * B * sh.Dp; }
+size_t fc_tc_plane_elems_tab(const FcShape& sh) { return (size_t)FC_M * sh.slots * sh.Dp; }
+
+int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tabp, int B, float2* d_Z, int sm_count, int* nsplit_out,
+                          cudaStream_t st)
+{
+    static const int force_split = getenv("OWRX_FC_SPLIT") ? atoi(getenv("OWRX_FC_SPLIT")) : 0;
+    // row tiles of <= 128 blocks, balanced, a multiple of 8 rows (the swizzle atom)
+    const int nbt = (B + 127) / 128;
+    const int mrows = std::min(128, (((B + nbt - 1) / nbt) + 7) / 8 * 8);
+    const unsigned stage_bytes = TC_NPL * (unsigned)mrows * TC_ROWB + TC_B_STAGE;
+    const size_t smem = (size_t)TC_ST * stage_bytes + 1024;
+    // split-K only when the tiles alone cannot occupy the machine (HBM-bound: a partly filled last wave still streams at full rate)
+    const long long tiles = (long long)FC_M * nbt * (sh.slots / FC_CG);
+    int nsplit = tiles >= sm_count ? 1 : (int)std::min<long long>(FC_MAXSPLIT, (sm_count + tiles - 1) / tiles);
+    nsplit = std::max(1, std::min(nsplit, sh.Dp / TC_KC));
+    if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, sh.Dp / TC_KC}));
+    *nsplit_out = nsplit;
+    OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUtensorMap mapA, mapB;
+    int rc;
+    if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)FC_M * B, (unsigned)mrows)) != OWRX_OK) return rc;
+    if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)FC_M * sh.slots, (unsigned)FC_CG)) != OWRX_OK) return rc;
+    fc_contract_tc_kernel<<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG), (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp,
+                                                                                                                          sh.slots, nbt, mrows, nsplit);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+}  // namespace owrx

@@ -248,6 +248,9 @@ struct Group {
     int* d_fc_slots = nullptr; double* d_fc_rates = nullptr;
     size_t fc_blocks_cap = 0;
     std::vector<double> fc_tab_rate;                 // per slot: Shift rate its table column was built for (NaN = none)
+    // tensor-core form (fastconv_tc.cu): bf16 operand planes of the table and of the branch spectra
+    void* d_fc_tabp = nullptr; void* d_fc_Fp = nullptr; size_t fc_blocks_cap_tc = 0;
+    std::vector<double> fc_tabp_rate;
     std::vector<float> fc_taps;                      // h[t] rounded to float (same values K3 uses)
 };
 
@@ -307,6 +310,7 @@ void group_release(Group* g)
     cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     cudaFree(g->d_tail_mode); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
     cudaFree(g->d_fc_h); cudaFree(g->d_fc_tab); cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates);
+    cudaFree(g->d_fc_tabp); cudaFree(g->d_fc_Fp);
     g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1p.release(); g->f1b.release(); g->f2.release(); g->f3.release();
 }
 
@@ -532,8 +536,9 @@ int group_grow(owrx_bank* bank, Group* g)
     cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     g->d_gate = nullptr; g->d_power = nullptr; g->d_dcmean = nullptr; g->d_dcprev = nullptr; g->blocks_cap = 0;
     // fast-convolution tables are laid out per slot count: rebuild lazily
-    cudaFree(g->d_fc_tab); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates);
-    g->d_fc_tab = nullptr; g->d_fc_Z = nullptr; g->d_fc_slots = nullptr; g->d_fc_rates = nullptr;
+    cudaFree(g->d_fc_tab); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates); cudaFree(g->d_fc_tabp);
+    g->d_fc_tab = nullptr; g->d_fc_Z = nullptr; g->d_fc_slots = nullptr; g->d_fc_rates = nullptr; g->d_fc_tabp = nullptr;
+    g->fc_tabp_rate.clear();
     g->fc.slots = ns;
     g->fc_tab_rate.clear();
     g->slots = ns;
@@ -601,7 +606,7 @@ int prof_mark(owrx_bank* bank, int tag, cudaStream_t st, bool begin)
 
 // K3F: Shift + FirDecimate of one group by polyphase fast convolution (fastconv.cuh); same outputs as the direct
 // K3 pass.  `iq`, `n_avail`, the d_rate/d_phase tables and s1 capacity are already set up by group_fir.
-int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_t n_k, cudaStream_t st)
+int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_t n_k, cudaStream_t st, bool tc)
 {
     const int S = g->slots;
     int rc;
@@ -610,25 +615,34 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         OWRX_CUDA(cudaMalloc((void**)&g->d_fc_h, g->fc_taps.size() * sizeof(float)));
         OWRX_CUDA(cudaMemcpyAsync(g->d_fc_h, g->fc_taps.data(), g->fc_taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     }
-    if (!g->d_fc_tab) {
-        // zero-fill on `st` (a non-blocking stream: a legacy-stream cudaMemset would not be ordered before the table kernel)
+    if (!g->d_fc_slots) {
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_slots, (size_t)S * sizeof(int)));
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_rates, (size_t)S * sizeof(double)));
+    }
+    // zero-fill on `st` (a non-blocking stream: a legacy-stream cudaMemset would not be ordered before the table kernel)
+    if (!tc && !g->d_fc_tab) {
         const size_t tab_bytes = (size_t)FC_M * sh.Dp * S * sizeof(float2);
         OWRX_CUDA(cudaMalloc((void**)&g->d_fc_tab, tab_bytes));
         OWRX_CUDA(cudaMemsetAsync(g->d_fc_tab, 0, tab_bytes, st));
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_slots, (size_t)S * sizeof(int)));
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_rates, (size_t)S * sizeof(double)));
         g->fc_tab_rate.assign((size_t)S, NAN);
+    }
+    if (tc && !g->d_fc_tabp) {
+        const size_t tab_bytes = (size_t)FC_TC_PLANES * fc_tc_plane_elems_tab(sh) * 2;
+        OWRX_CUDA(cudaMalloc(&g->d_fc_tabp, tab_bytes));
+        OWRX_CUDA(cudaMemsetAsync(g->d_fc_tabp, 0, tab_bytes, st));
+        g->fc_tabp_rate.assign((size_t)S, NAN);
     }
     // ---- (re)build the table columns of retuned / new channels
     {
+        std::vector<double>& built = tc ? g->fc_tabp_rate : g->fc_tab_rate;
         std::vector<int> sl;
         std::vector<double> rt;
         for (int s = 0; s < S; s++) {
             const int cid = g->slot_chan[(size_t)s];
             if (cid < 0) continue;
             const double r = bank->chans[(size_t)cid]->rate;
-            if (g->fc_tab_rate[(size_t)s] == r) continue;
-            g->fc_tab_rate[(size_t)s] = r;
+            if (built[(size_t)s] == r) continue;
+            built[(size_t)s] = r;
             sl.push_back(s);
             rt.push_back(r);
         }
@@ -637,36 +651,49 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
             OWRX_CUDA(cudaMemcpyAsync(g->d_fc_slots, sl.data(), sl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
             OWRX_CUDA(cudaMemcpyAsync(g->d_fc_rates, rt.data(), rt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
             OWRX_CUDA(cudaStreamSynchronize(st));                     // pageable sources: safe to drop the vectors
-            if ((rc = fc_launch_table(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tab, st)) != OWRX_OK) return rc;
+            rc = tc ? fc_launch_table_tc(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tabp, st)
+                    : fc_launch_table(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tab, st);
+            if (rc != OWRX_OK) return rc;
             bank->stats.kernel_launches++;
         }
     }
-    // ---- scratch for up to Bmax blocks per pass
+    // ---- scratch for up to Bmax blocks per pass (branch spectra: 16 B per complex as packed-FMA operands, 12 B as bf16 planes)
     const size_t blocks_total = (n_k + (size_t)sh.Kb - 1) / (size_t)sh.Kb;
-    const size_t per_block = (size_t)FC_M * sh.Dp * sizeof(float4);
+    const size_t per_block = (size_t)FC_M * sh.Dp * (tc ? (size_t)FC_TC_PLANES * 2 : sizeof(float4));
     const size_t Bmax = std::max<size_t>(1, std::min<size_t>(4096, ((size_t)512 << 20) / per_block));
     const size_t need = std::min(blocks_total, Bmax);
-    if (need > g->fc_blocks_cap) {
+    const size_t z_cap = std::max(g->fc_blocks_cap, g->fc_blocks_cap_tc);
+    if (need > z_cap || (!tc && need > g->fc_blocks_cap) || (tc && need > g->fc_blocks_cap_tc)) {
         OWRX_CUDA(cudaStreamSynchronize(st));
-        cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z);
-        g->d_fc_F = nullptr; g->d_fc_Z = nullptr; g->fc_blocks_cap = 0;
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_F, need * per_block));
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * need * (size_t)FC_M * S * sizeof(float2)));
-        g->fc_blocks_cap = need;
+        if (need > z_cap) { cudaFree(g->d_fc_Z); g->d_fc_Z = nullptr; }
+        if (!tc) {
+            cudaFree(g->d_fc_F); g->d_fc_F = nullptr; g->fc_blocks_cap = 0;
+            OWRX_CUDA(cudaMalloc((void**)&g->d_fc_F, need * per_block));
+            g->fc_blocks_cap = need;
+        } else {
+            cudaFree(g->d_fc_Fp); g->d_fc_Fp = nullptr; g->fc_blocks_cap_tc = 0;
+            OWRX_CUDA(cudaMalloc(&g->d_fc_Fp, need * per_block));
+            g->fc_blocks_cap_tc = need;
+        }
     }
     if (!g->d_fc_Z) {
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * g->fc_blocks_cap * (size_t)FC_M * S * sizeof(float2)));
+        const size_t cap = std::max(g->fc_blocks_cap, g->fc_blocks_cap_tc);
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * cap * (size_t)FC_M * S * sizeof(float2)));
     }
     float2* out = reinterpret_cast<float2*>(g->s1.append_ptr());
     for (size_t b0 = 0; b0 < blocks_total; b0 += Bmax) {
         const int B = (int)std::min(Bmax, blocks_total - b0);
         const size_t s_off = b0 * (size_t)sh.Kb * (size_t)sh.D;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, true)) != OWRX_OK) return rc;
-        if ((rc = fc_launch_forward(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_F, st)) != OWRX_OK) return rc;
+        rc = tc ? fc_launch_forward_tc(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_Fp, st)
+                : fc_launch_forward(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_F, st);
+        if (rc != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, false)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, true)) != OWRX_OK) return rc;
         int nsplit = 1;
-        if ((rc = fc_launch_contract(sh, g->d_fc_F, g->d_fc_tab, B, g->d_fc_Z, bank->sm_count, &nsplit, st)) != OWRX_OK) return rc;
+        rc = tc ? fc_launch_contract_tc(sh, g->d_fc_Fp, g->d_fc_tabp, B, g->d_fc_Z, bank->sm_count, &nsplit, st)
+                : fc_launch_contract(sh, g->d_fc_F, g->d_fc_tab, B, g->d_fc_Z, bank->sm_count, &nsplit, st);
+        if (rc != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, false)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, true)) != OWRX_OK) return rc;
         if ((rc = fc_launch_inverse(sh, g->d_fc_Z, nsplit, B, g->d_rate, g->d_phase, (long long)(b0 * (size_t)sh.Kb), (long long)n_k, out, st)) != OWRX_OK)
@@ -704,10 +731,10 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
     OWRX_CUDA(cudaMemcpyAsync(g->d_phase, g->h_phase.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
     OWRX_CUDA(cudaMemcpyAsync(g->d_w, g->h_w.data(), (size_t)S * sizeof(float2), cudaMemcpyHostToDevice, st));
 
-    const bool fastconv = g->fc_ok && bank->fir_mode != OWRX_FIR_DIRECT && (bank->fir_mode == OWRX_FIR_FASTCONV || n_k >= 64);
+    const bool fastconv = g->fc_ok && bank->fir_mode != OWRX_FIR_DIRECT && (bank->fir_mode >= OWRX_FIR_FASTCONV || n_k >= 64);
     if (fastconv) {
         if ((rc = g->s1.ensure_new(n_k, st)) != OWRX_OK) return rc;
-        if ((rc = group_fir_fastconv(bank, g, iq, n_avail, n_k, st)) != OWRX_OK) return rc;
+        if ((rc = group_fir_fastconv(bank, g, iq, n_avail, n_k, st, bank->fir_mode == OWRX_FIR_FASTCONV_TC)) != OWRX_OK) return rc;
     } else {
     // ---- K3: Shift + FirDecimate
     const int nparts = g->nseg * g->nrs;
@@ -1169,8 +1196,8 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     owrx_bank* b = new (std::nothrow) owrx_bank();
     if (!b) return fail(OWRX_E_NOMEM, "out of host memory");
     b->device = device; b->sm_count = sm; b->input_rate = input_rate;
-    if (const char* m = getenv("OWRX_FIR_MODE")) b->fir_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV, atoi(m)));
-    b->bp_mode = b->fir_mode;
+    if (const char* m = getenv("OWRX_FIR_MODE")) b->fir_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV_TC, atoi(m)));
+    b->bp_mode = std::min(b->fir_mode, OWRX_FIR_FASTCONV);
     if (const char* m = getenv("OWRX_BP_MODE")) b->bp_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV, atoi(m)));
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
@@ -1819,7 +1846,7 @@ int owrx_bank_profile_read_ex(owrx_bank_t* bank, double* ms, uint64_t* launches,
 int owrx_bank_set_fir_mode(owrx_bank_t* bank, int mode)
 {
     if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
-    if (mode < OWRX_FIR_AUTO || mode > OWRX_FIR_FASTCONV) return fail(OWRX_E_INVALID, "unknown FIR mode %d", mode);
+    if (mode < OWRX_FIR_AUTO || mode > OWRX_FIR_FASTCONV_TC) return fail(OWRX_E_INVALID, "unknown FIR mode %d", mode);
     std::lock_guard<std::mutex> lk(bank->mu);
     bank->fir_mode = mode;
     bank->bp_mode = mode;

@@ -10,10 +10,11 @@ from openwebrx_b200.synth import BANDPASS, carrier_plan, make_iq
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["direct", "fastconv"])
+@pytest.fixture(autouse=True, params=["direct", "fastconv", "fastconv_tc"])
 def fir_mode(request, monkeypatch):
-    """every parity case runs through both evaluations of Shift + FirDecimate: the direct-form K3 kernel and the
-    polyphase fast-convolution path K3F (owrx_bank_create reads OWRX_FIR_MODE)"""
+    """every parity case runs through all evaluations of Shift + FirDecimate: the direct-form K3 kernel, the polyphase
+    fast-convolution path K3F with its contraction on the FP32 pipe, and K3F with the contraction on the tensor cores
+    (tcgen05, bf16x3 operands) (owrx_bank_create reads OWRX_FIR_MODE)"""
     monkeypatch.setenv("OWRX_FIR_MODE", str(N.FIR_MODES[request.param]))
     return request.param
 
@@ -245,7 +246,7 @@ def test_retune_and_grow_midstream_direct_equals_fastconv(gpu, monkeypatch):
     iq = make_iq(n, fs, cars, seed=33)
     a, b = n // 3 + 11, 2 * n // 3 + 5
     got = {}
-    for mode in ("direct", "fastconv"):
+    for mode in ("direct", "fastconv", "fastconv_tc"):
         monkeypatch.setenv("OWRX_FIR_MODE", str(N.FIR_MODES[mode]))
         bank, chans = _setup(fs, out, cars, 4, outputs=N.OUT_IF | N.OUT_DEMOD)
         bank.feed(iq[:a])
@@ -254,10 +255,11 @@ def test_retune_and_grow_midstream_direct_equals_fastconv(gpu, monkeypatch):
         extra = [bank.add_channel(out, demod="usb", offset=cars[i % 4]["offset"] + 50 * i, bandpass=BANDPASS["usb"]) for i in range(64)]
         bank.feed(iq[b:])
         got[mode] = [(ch.read_if(), ch.read_demod()) for ch, _ in chans] + [(extra[0].read_if(), extra[0].read_demod()), (extra[63].read_if(), extra[63].read_demod())]
-    for (if_d, dm_d), (if_f, dm_f) in zip(got["direct"], got["fastconv"]):
-        assert len(if_d) == len(if_f) > 0 and len(dm_d) == len(dm_f)
-        assert rel_rms(if_f, if_d) <= AUDIO_TOL
-        assert rel_rms(dm_f, dm_d) <= AUDIO_TOL
+    for other in ("fastconv", "fastconv_tc"):
+        for (if_d, dm_d), (if_f, dm_f) in zip(got["direct"], got[other]):
+            assert len(if_d) == len(if_f) > 0 and len(dm_d) == len(dm_f)
+            assert rel_rms(if_f, if_d) <= AUDIO_TOL, other
+            assert rel_rms(dm_f, dm_d) <= AUDIO_TOL, other
 
 
 def test_prime_decimation_and_block_edges(gpu):
@@ -313,7 +315,7 @@ def test_full_size_block_properties(gpu, fir_mode):
         assert rel_rms(two[c][0], one[c][0]) <= 1e-5, c
         assert rel_rms(two[c][1], one[c][1]) <= AUDIO_TOL, c
         assert np.array_equal(half[c][0], one[c][0] * np.complex64(0.5)), c
-    if fir_mode == "fastconv":
+    if fir_mode != "direct":
         direct = run(iq, [], n_channels=3, mode="direct")
         for c in range(3):
             assert rel_rms(one[c][0], direct[c][0]) <= AUDIO_TOL, c

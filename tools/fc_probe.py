@@ -57,19 +57,24 @@ def main():
         "C5": dict(fs=20e6, out_rate=250000, n_ch=128, block=1 << 23, wfm=True, audio_rate=48000.0, tau=50e-6),
     }
     pick = [a for a in sys.argv[1:] if a in shapes] or list(shapes)
-    only = [a for a in sys.argv[1:] if a in ("direct", "fastconv")]
+    only = [a for a in sys.argv[1:] if a in ("direct", "fastconv", "fastconv_tc")]
     for name in pick:
         if only:
             print(json.dumps({name: run(mode=only[0], **shapes[name])[0]}), flush=True)
             continue
+        def rel(oa, ob):
+            diff = []
+            for x, y in zip(oa, ob):
+                n = min(len(x), len(y))
+                den = float(np.sqrt(np.mean(np.abs(x[:n]) ** 2)))
+                diff.append(float(np.sqrt(np.mean(np.abs(x[:n] - y[:n]) ** 2))) / den if den else 0.0)
+            return diff
+
         a, oa = run(mode="direct", **shapes[name])
         b, ob = run(mode="fastconv", **shapes[name])
-        diff = []
-        for x, y in zip(oa, ob):
-            n = min(len(x), len(y))
-            den = float(np.sqrt(np.mean(np.abs(x[:n]) ** 2)))
-            diff.append(float(np.sqrt(np.mean(np.abs(x[:n] - y[:n]) ** 2))) / den if den else 0.0)
-        print(json.dumps({name: dict(direct=a, fastconv=b, if_rel_rms_direct_vs_fastconv=diff)}), flush=True)
+        c, oc = run(mode="fastconv_tc", **shapes[name])
+        print(json.dumps({name: dict(direct=a, fastconv=b, fastconv_tc=c, if_rel_rms_direct_vs_fastconv=rel(oa, ob),
+                                     if_rel_rms_direct_vs_tc=rel(oa, oc), if_rel_rms_fastconv_vs_tc=rel(ob, oc))}), flush=True)
 
 
 if __name__ == "__main__":
