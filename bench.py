@@ -323,6 +323,8 @@ def run_ours(args):
     prof = bank.profile_read_ex(reset=True)
     bank.profile(False)
     fastconv = prof["fc_contract"][1] > 0
+    fir_form = bank.fir_form()
+    tc = fir_form == "fastconv_tc"
     dom = "fc_contract" if fastconv else "k3_direct"
     k3_ms, k3_n = prof[dom]
     clk = clocks.stop() if rank == 0 else None
@@ -396,13 +398,24 @@ def run_ours(args):
         M, P = 256, -(-T // D)
         Kb, Dp = M - P + 1, -(-D // 32) * 32
         B = -(-n_k // Kb)                                         # overlap-save blocks per launch
-        # operands of the contraction, each moved once: F (16 B, packed-FMA layout), table (8 B), Z (8 B)
-        algo_bytes = 16.0 * M * B * Dp + 8.0 * M * Dp * CH_PER_GPU + 8.0 * M * B * CH_PER_GPU
         flops = 8.0 * M * B * Dp * CH_PER_GPU                     # complex MAC = 4 FMA per (bin, block, branch, channel)
-        kname = "fc_contract_kernel (K3F: per-channel spectral contraction over the %d polyphase branches, %d blocks x %d ch)" % (D, B, CH_PER_GPU)
-        knote = ("FP32-FMA bound (%.0f FLOP per operand byte): see roofline_fp32; the shared forward FFTs (fc_forward) and the inverse "
-                 "FFT + rotation (fc_inverse) are in stages_ms" % (flops / algo_bytes))
-        tkey = "fc_contract_kernel"
+        if tc:
+            # operands of the tensor-core contraction, each moved once: branch spectra and table as 3 bf16 terms per float
+            # (12 B per complex entry), Z as complex float32 (8 B)
+            algo_bytes = 12.0 * M * B * Dp + 12.0 * M * Dp * CH_PER_GPU + 8.0 * M * B * CH_PER_GPU
+            kname = ("fc_contract_tc_kernel (K3F: per-channel spectral contraction over the %d polyphase branches, %d blocks x %d ch, "
+                     "tcgen05 bf16x3 -> FP32 in TMEM)" % (D, B, CH_PER_GPU))
+            knote = ("HBM bound: 6 bf16 MMAs per FP32 product keep the tensor pipe under 15 %% busy; timed inside the three-stream pipeline "
+                     "(standalone ncu capture: profiles/r1_fc_contract_tc.md); the shared forward FFTs (fc_forward) and the inverse FFT + "
+                     "rotation (fc_inverse) are in stages_ms")
+            tkey = "fc_contract_tc_kernel"
+        else:
+            # operands of the contraction, each moved once: F (16 B, packed-FMA layout), table (8 B), Z (8 B)
+            algo_bytes = 16.0 * M * B * Dp + 8.0 * M * Dp * CH_PER_GPU + 8.0 * M * B * CH_PER_GPU
+            kname = "fc_contract_kernel (K3F: per-channel spectral contraction over the %d polyphase branches, %d blocks x %d ch)" % (D, B, CH_PER_GPU)
+            knote = ("FP32-FMA bound (%.0f FLOP per operand byte): see roofline_fp32; the shared forward FFTs (fc_forward) and the inverse "
+                     "FFT + rotation (fc_inverse) are in stages_ms" % (flops / algo_bytes))
+            tkey = "fc_contract_kernel"
     else:
         algo_bytes = 8.0 * BLOCK + 8.0 * CH_PER_GPU * n_k        # IQ read once + complex IF written (per launch)
         flops = CH_PER_GPU * float(consumed) * (8.0 + 4.0 * T / D)    # C*Nin*(8 + 4T/D)
@@ -412,6 +425,18 @@ def run_ours(args):
     achieved = algo_bytes / k3_avg_s / 1e9 if k3_avg_s > 0 else 0.0
     fp32_ach = flops / k3_avg_s / 1e12 if k3_avg_s > 0 else 0.0
     stages = {k: v[0] / v[1] for k, v in prof.items() if v[1]}
+    tensor = None
+    if fastconv and tc:
+        # issued bf16 MMA work of the same launch: 6 partial products x 2 accumulator halves per (128-row tile, 128 columns, 16 branches)
+        mma_flops = 6.0 * 2.0 * (2.0 * 128 * 128 * 16) * (Dp // 16) * M * (-(-B // 128)) * (CH_PER_GPU // 64)
+        try:
+            bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            bf16_peak = 1646.0
+        t_ach = mma_flops / k3_avg_s / 1e12 if k3_avg_s > 0 else 0.0
+        tensor = {"achieved": t_ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": t_ach / bf16_peak,
+                  "note": "issued bf16 MMA FLOPs incl. the padded rows of the 128-row tile; the kernel is HBM bound (roofline), not tensor bound; "
+                          "roofline_fp32.achieved is the same launch in FP32-equivalent FLOPs"}
     # the same work expressed in the reference's own terms (direct form: SURVEY 8d) for comparison across forms
     direct_equiv = CH_PER_GPU * float(consumed) * (8.0 + 4.0 * T / D) / (ms_step * 1e-3) / 1e12
 
@@ -441,7 +466,8 @@ def run_ours(args):
         "roofline_fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak if fp32_peak else None,
                           "peak_def": "148 SM x 128 lanes x 2 x observed SM clock (%.0f MHz)" % f_obs,
                           "direct_form_equivalent_tflops": direct_equiv},
-        "fir_form": "fastconv" if fastconv else "direct",
+        "roofline_tensor": tensor,
+        "fir_form": fir_form,
         "stages_ms": stages,
         "waterfall": wf_stats,
         "cpu_baseline": cpu,

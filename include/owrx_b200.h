@@ -217,12 +217,15 @@ int owrx_bank_profile_read_ex(owrx_bank_t* bank, double* ms, uint64_t* launches,
  *                      ~4.5 FMA per input sample per channel (K3F); needs decimation >= 8
  *   OWRX_FIR_FASTCONV_TC  the same fast convolution with the spectral contraction on the tensor cores (tcgen05): every
  *                      float32 operand is carried as three bf16 terms and six partial products are accumulated in FP32
- *   OWRX_FIR_AUTO      (default) fast convolution for feeds that yield >= 64 outputs per channel, direct otherwise */
+ *   OWRX_FIR_AUTO      (default) direct for feeds that yield < 64 outputs per channel, else fast convolution — on the
+ *                      tensor cores when a pass holds >= 16 overlap-save blocks, on the FP32 pipe below that */
 #define OWRX_FIR_AUTO        0
 #define OWRX_FIR_DIRECT      1
 #define OWRX_FIR_FASTCONV    2
 #define OWRX_FIR_FASTCONV_TC 3
 int owrx_bank_set_fir_mode(owrx_bank_t* bank, int mode);
+/* the form the latest Shift + FirDecimate pass used (OWRX_FIR_DIRECT / _FASTCONV / _FASTCONV_TC; 0 before any pass) */
+int owrx_bank_fir_form(const owrx_bank_t* bank);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 """ctypes binding of libowrx_b200.so (include/owrx_b200.h).
 
-There is no CPU fallback: if the library has not been built (`python -m openwebrx_b200._build` or
+There is no CPU fallback: if the library has not been built (`python openwebrx_b200/_build.py` or
 `__graft_entry__.build()`), importing this module raises ImportError; if no sm_100 device is usable
 every create call raises RuntimeError.
 """
@@ -31,7 +31,7 @@ class BankStats(C.Structure):
 
 if not os.path.exists(SO_PATH):
     raise ImportError(
-        "libowrx_b200.so is not built (%s). Run `python -m openwebrx_b200._build`; this package has no CPU fallback."
+        "libowrx_b200.so is not built (%s). Run `python openwebrx_b200/_build.py`; this package has no CPU fallback."
         % SO_PATH)
 
 lib = C.CDLL(SO_PATH)
@@ -88,6 +88,7 @@ SIGNATURES = {
     "owrx_bank_profile_read": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
     "owrx_bank_profile_read_ex": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
     "owrx_bank_set_fir_mode": (_i, [_vp, _i]),
+    "owrx_bank_fir_form": (_i, [_vp]),
 }
 PROF_KINDS = ("k3_direct", "fc_forward", "fc_contract", "fc_inverse", "tail", "agc")
 FIR_MODES = {"auto": 0, "direct": 1, "fastconv": 2, "fastconv_tc": 3}

@@ -180,8 +180,13 @@ class ChannelBank:
         return {name: (ms[i], n[i]) for i, name in enumerate(N.PROF_KINDS)}
 
     def set_fir_mode(self, mode="auto"):
-        """how Shift + FirDecimate is evaluated: "auto" | "direct" (K3) | "fastconv" (K3F)"""
+        """how Shift + FirDecimate is evaluated: "auto" | "direct" (K3) | "fastconv" (K3F, FP32 pipe) | "fastconv_tc" (K3F, tcgen05)"""
         N.check(N.lib.owrx_bank_set_fir_mode(self._h, N.FIR_MODES[mode] if isinstance(mode, str) else int(mode)))
+
+    def fir_form(self):
+        """the form the latest Shift + FirDecimate pass used: "direct" | "fastconv" | "fastconv_tc" (None before any pass)"""
+        v = N.lib.owrx_bank_fir_form(self._h)
+        return {1: "direct", 2: "fastconv", 3: "fastconv_tc"}.get(v)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -289,6 +289,7 @@ struct owrx_bank {
     double prof_ms[OWRX_PROF_KINDS] = {};
     uint64_t prof_launches[OWRX_PROF_KINDS] = {};
     int fir_mode = OWRX_FIR_AUTO, bp_mode = OWRX_FIR_AUTO;
+    int fir_form_used = 0;                           // form of the latest Shift + FirDecimate pass (owrx_bank_fir_form)
 };
 
 namespace {
@@ -733,9 +734,15 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
 
     const bool fastconv = g->fc_ok && bank->fir_mode != OWRX_FIR_DIRECT && (bank->fir_mode >= OWRX_FIR_FASTCONV || n_k >= 64);
     if (fastconv) {
+        // contraction on the tensor cores once a pass holds enough overlap-save blocks: below ~16 rows the FP32-pipe kernel,
+        // whose table is 8 instead of 12 bytes per entry, is bound by the same table read and moves fewer bytes
+        const size_t fc_blocks = (n_k + (size_t)g->fc.Kb - 1) / (size_t)g->fc.Kb;
+        const bool tc = bank->fir_mode == OWRX_FIR_FASTCONV_TC || (bank->fir_mode == OWRX_FIR_AUTO && fc_blocks >= 16);
+        bank->fir_form_used = tc ? OWRX_FIR_FASTCONV_TC : OWRX_FIR_FASTCONV;
         if ((rc = g->s1.ensure_new(n_k, st)) != OWRX_OK) return rc;
-        if ((rc = group_fir_fastconv(bank, g, iq, n_avail, n_k, st, bank->fir_mode == OWRX_FIR_FASTCONV_TC)) != OWRX_OK) return rc;
+        if ((rc = group_fir_fastconv(bank, g, iq, n_avail, n_k, st, tc)) != OWRX_OK) return rc;
     } else {
+    bank->fir_form_used = OWRX_FIR_DIRECT;
     // ---- K3: Shift + FirDecimate
     const int nparts = g->nseg * g->nrs;
     const int ncg = S / K3_CG;
@@ -1851,6 +1858,12 @@ int owrx_bank_set_fir_mode(owrx_bank_t* bank, int mode)
     bank->fir_mode = mode;
     bank->bp_mode = mode;
     return OWRX_OK;
+}
+
+int owrx_bank_fir_form(const owrx_bank_t* bank)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    return bank->fir_form_used;
 }
 
 int owrx_bank_get_stats(const owrx_bank_t* bank, owrx_bank_stats_t* st)

@@ -9,9 +9,12 @@ if ROOT not in sys.path:
 
 
 def _ensure_built():
-    """A fresh checkout has no libowrx_b200.so / oracle .so (git-ignored): compile them once (nvcc cross-compiles without a GPU)."""
+    """A fresh checkout has no libowrx_b200.so / oracle .so (git-ignored) and an edited source leaves a stale one: (re)compile
+    (nvcc cross-compiles without a GPU)."""
     so = os.path.join(ROOT, "openwebrx_b200", "libowrx_b200.so")
-    if not os.path.exists(so):
+    # on the GPU box the prebuilt library travels with the snapshot: build only if it is missing; in the development
+    # container (where /root/reference exists) also refresh a stale one (incremental, mtime-based)
+    if not os.path.exists(so) or os.path.isdir("/root/reference"):
         import __graft_entry__
         __graft_entry__.build()
 

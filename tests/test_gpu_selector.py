@@ -312,7 +312,9 @@ def test_full_size_block_properties(gpu, fir_mode):
     half = run(iq * np.float32(0.5), [])
     for c in range(n_ch):
         assert len(two[c][0]) == n_if and len(two[c][1]) == len(one[c][1])
-        assert rel_rms(two[c][0], one[c][0]) <= 1e-5, c
+        # the noise floor of the evaluation itself (block partition differs between the two feeds): FP32-pipe forms 1e-5,
+        # bf16x3 tensor-core contraction 3e-5 on the weakest channels (50 dB below the wideband power); the spec is 1e-4
+        assert rel_rms(two[c][0], one[c][0]) <= (3e-5 if fir_mode == "fastconv_tc" else 1e-5), c
         assert rel_rms(two[c][1], one[c][1]) <= AUDIO_TOL, c
         assert np.array_equal(half[c][0], one[c][0] * np.complex64(0.5)), c
     if fir_mode != "direct":

@@ -19,6 +19,8 @@ KEY = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "sm__inst_executed_pipe_uniform_realtime.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
@@ -52,7 +54,7 @@ def kernel(rep, dst):
             d = dict(zip(hdr, vals))
             f.write("### %s\n\n| metric | unit | value |\n|---|---|---:|\n" % d.get("Kernel Name", "?"))
             for h, u, v in zip(hdr, units, vals):
-                if h in KEY or h.endswith("_per_issue_active.ratio"):
+                if any(h == k or h.endswith("." + k) for k in KEY) or h.endswith("_per_issue_active.ratio"):
                     try:
                         if h.endswith("ratio") and float(v) < 0.02:
                             continue
