@@ -74,8 +74,7 @@ class ClockSampler:
 
     def _nvml_loop(self):
         import pynvml
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        h, mx = self.handle, self.max_mhz
         while not self.stop_flag:
             try:
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
@@ -83,15 +82,18 @@ class ClockSampler:
                     mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((float(sm), float(mx), int(mask)))
+                self.samples.append((float(sm), float(mx), int(mask), time.perf_counter()))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def start(self):
         try:
             import pynvml
-            pynvml.nvmlInit()
+            pynvml.nvmlInit()                 # the slow part, done before any timed work
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
             self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
             self.thread.start()
             return
@@ -110,17 +112,29 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """start of the timed region: the sampler has been running since before the warm-up (NVML start-up is slow), samples
+        from here on are the ones reported"""
+        self.t_mark = time.perf_counter()
+
     def stop(self):
         reasons = set()
+        window = "timed region"
         if self.thread is not None:
+            t_end = time.perf_counter()
             self.stop_flag = True
             self.thread.join(1.0)
-            for _, _, mask in self.samples:
+            t0 = getattr(self, "t_mark", 0.0)
+            inside = [x for x in self.samples if t0 <= x[3] <= t_end]
+            if len(inside) < 3:
+                # a timed region of a few ms holds too few polls: use every sample since the start of the warm-up (same load)
+                inside, window = list(self.samples), "warm-up + timed region"
+            for _, _, mask, _ in inside:
                 for name, bit in self.REASONS:
                     if mask & bit:
                         reasons.add(name)
-            sm = [x[0] for x in self.samples]
-            mx = [x[1] for x in self.samples]
+            sm = [x[0] for x in inside]
+            mx = [x[1] for x in inside]
         elif self.proc is not None:
             time.sleep(0.05)
             self.proc.terminate()
@@ -140,7 +154,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source"], "samples": 0}
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def channel_plan(rank, n_ch):
@@ -300,18 +314,19 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     bank.set_pipelined(True)       # low-rate stages of block i overlap the K3 pass of block i+1 (side stream)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()             # NVML start-up takes longer than a short timed region: poll from the warm-up on
     for i in range(args.warmup):
         step(i)
     bank.join(sp)
     barrier()
     bank.profile(True)
     bank.profile_read(reset=True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = N.lib.owrx_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     ev0.record(stream)
     for i in range(args.steps):
         step(i)

@@ -53,6 +53,11 @@ void owrx_wf_destroy(owrx_wf_t* wf);
 int owrx_wf_set_every_n_samples(owrx_wf_t* wf, int every_n_samples);   /* Fft.setEveryNSamples, csdr/chain/fft.py:55 */
 int owrx_wf_set_avg_number(owrx_wf_t* wf, int avg_number);             /* FftAverager.setFftAverages, csdr/chain/fft.py:12-16 */
 int owrx_wf_set_compression(owrx_wf_t* wf, int compression);           /* FftChain.setCompression, csdr/chain/fft.py:87-96 */
+/* Spectral-subtraction noise filter on the averaged line power (BASELINE config 4).  NOT a reference module: OpenWebRX+
+ * has no waterfall noise filter (its NoiseFilter is audio-only, csdr/chain/clientaudio.py:13-14) — spec-defined stage after
+ * power averaging, off by default.  Per bin, across lines:
+ *   N = first line ? P : min(P, N * (1 + growth));   P' = max(P - alpha * N, beta * P);   dB = 10 log10(P') + corrections */
+int owrx_wf_set_noise_filter(owrx_wf_t* wf, int enable, float alpha, float beta, float growth);
 size_t owrx_wf_line_bytes(const owrx_wf_t* wf);
 
 /* Streaming host path (what the pycsdr shim calls): append n_samples of interleaved IQ from HOST

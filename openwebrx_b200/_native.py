@@ -50,6 +50,7 @@ SIGNATURES = {
     "owrx_wf_set_every_n_samples": (_i, [_vp, _i]),
     "owrx_wf_set_avg_number": (_i, [_vp, _i]),
     "owrx_wf_set_compression": (_i, [_vp, _i]),
+    "owrx_wf_set_noise_filter": (_i, [_vp, _i, _f, _f, _f]),
     "owrx_wf_line_bytes": (_sz, [_vp]),
     "owrx_wf_feed": (_i, [_vp, _vp, _sz]),
     "owrx_wf_read": (_i, [_vp, _vp, _sz, _psz]),

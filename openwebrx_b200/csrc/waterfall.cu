@@ -189,6 +189,28 @@ __global__ void __launch_bounds__(256) wf_colpass_kernel(WfColParams p)
     }
 }
 
+// Spectral-subtraction noise filter (BASELINE config 4: "65536-pt high-zoom waterfall ... with spectral-subtraction noise
+// filter").  SPEC-DEFINED — the reference has no waterfall noise filter; same arithmetic as the oracle's
+// oc_wf_noise_filter.  One thread per bin walks the lines of the batch in order (the floor estimate is a recurrence across
+// lines): sums the frame-subset partials, updates N = first ? P : min(P, N (1 + growth)), and leaves
+// P' = max(P - alpha N, beta P) in subset 0 (the other subsets are zeroed) for wf_finalize_kernel.
+__global__ void __launch_bounds__(256)
+wf_noise_kernel(float* __restrict__ partial, int subsets, int n, size_t n_lines, float* __restrict__ noise, int first, float alpha,
+                float beta, float growth)
+{
+    const int bin = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bin >= n) return;
+    float nf = first ? 0.0f : noise[bin];
+    for (size_t line = 0; line < n_lines; line++) {
+        float* ps = partial + line * (size_t)subsets * (size_t)n + bin;
+        float s = 0.0f;
+        for (int k = 0; k < subsets; k++) { s += ps[(size_t)k * n]; if (k) ps[(size_t)k * n] = 0.0f; }
+        nf = (first && line == 0) ? s : fminf(s, nf * (1.0f + growth));
+        ps[0] = fmaxf(s - alpha * nf, beta * s);
+    }
+    noise[bin] = nf;
+}
+
 // sums partials, log, swap, optional quantise.  One thread per output position.
 __global__ void __launch_bounds__(256)
 wf_finalize_kernel(const float* __restrict__ partial, int subsets, int n, float corr, size_t n_lines,
@@ -362,6 +384,10 @@ struct owrx_wf {
     uint8_t* h_out = nullptr;   size_t h_out_cap = 0;
     std::deque<std::vector<uint8_t>> queue;
     std::mutex mu;
+    // spec-defined noise filter (owrx_wf_set_noise_filter): per-bin floor estimate carried across lines
+    bool nf_on = false, nf_primed = false;
+    float nf_alpha = 0.f, nf_beta = 0.f, nf_growth = 0.f;
+    float* d_noise = nullptr;
 };
 
 static size_t wf_line_bytes(const owrx_wf* wf)
@@ -453,6 +479,13 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
     if (!adpcm && out_dev) db = (float*)out_dev;   // compression "none": the line IS the float32 dB row
     const float corr = wf->avg > 0 ? wf->add_db - 10.0f * log10f((float)wf->avg) : wf->add_db;
     const size_t total = lines * (size_t)n;
+    if (wf->nf_on && lines) {
+        if (!wf->d_noise) OWRX_CUDA(cudaMalloc((void**)&wf->d_noise, (size_t)n * sizeof(float)));
+        wf_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wf->d_partial, subsets, n, lines, wf->d_noise, wf->nf_primed ? 0 : 1,
+                                                                    wf->nf_alpha, wf->nf_beta, wf->nf_growth);
+        OWRX_LAUNCH_CHECK();
+        wf->nf_primed = true;
+    }
     wf_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(wf->d_partial, subsets, n, corr, lines, db,
                                                                        adpcm ? s16_dev : nullptr);
     OWRX_LAUNCH_CHECK();
@@ -602,7 +635,7 @@ void owrx_wf_destroy(owrx_wf_t* wf)
     if (wf->adpcm_done[0]) cudaEventDestroy(wf->adpcm_done[0]);
     if (wf->adpcm_done[1]) cudaEventDestroy(wf->adpcm_done[1]);
     if (wf->side) cudaStreamDestroy(wf->side);
-    cudaFree(wf->d_in); cudaFree(wf->d_in_alt); cudaFree(wf->d_out);
+    cudaFree(wf->d_in); cudaFree(wf->d_in_alt); cudaFree(wf->d_out); cudaFree(wf->d_noise);
     if (wf->h_out) cudaFreeHost(wf->h_out);
     if (wf->stream) cudaStreamDestroy(wf->stream);
     delete wf;
@@ -620,7 +653,20 @@ int owrx_wf_set_avg_number(owrx_wf_t* wf, int avg_number)
 {
     if (!wf || avg_number < 0) return fail(OWRX_E_INVALID, "bad avg_number");
     std::lock_guard<std::mutex> g(wf->mu);
+    if (wf->avg != avg_number) wf->nf_primed = false;           // the power scale (sum over avg frames) changes: re-seed the floor
     wf->avg = avg_number;
+    return OWRX_OK;
+}
+
+int owrx_wf_set_noise_filter(owrx_wf_t* wf, int enable, float alpha, float beta, float growth)
+{
+    if (!wf) return fail(OWRX_E_INVALID, "NULL waterfall");
+    if (enable && !(alpha >= 0.f && alpha <= 4.f && beta >= 0.f && beta <= 1.f && growth >= 0.f && growth <= 1.f))
+        return fail(OWRX_E_INVALID, "noise filter parameters out of range (alpha 0..4, beta 0..1, growth 0..1)");
+    std::lock_guard<std::mutex> g(wf->mu);
+    wf->nf_on = enable != 0;
+    wf->nf_alpha = alpha; wf->nf_beta = beta; wf->nf_growth = growth;
+    wf->nf_primed = false;
     return OWRX_OK;
 }
 

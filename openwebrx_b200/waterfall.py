@@ -70,6 +70,11 @@ class Waterfall:
         N.check(N.lib.owrx_wf_set_compression(self._h, self._comp(compression)))
         self.compression = compression
 
+    def set_noise_filter(self, enable=True, alpha=0.9, beta=0.05, growth=0.02):
+        """Spectral-subtraction noise filter on the averaged line power (BASELINE config 4).  An extension: the reference's
+        FftChain has no such stage; spec in include/owrx_b200.h, oracle in oracle.fftchain_run(noise_filter=)."""
+        N.check(N.lib.owrx_wf_set_noise_filter(self._h, 1 if enable else 0, float(alpha), float(beta), float(growth)))
+
     # --- data path
     @property
     def line_bytes(self):

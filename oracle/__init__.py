@@ -67,6 +67,8 @@ def lib():
         L.oc_fft_adpcm.argtypes = [vp, vp, i32]
         L.oc_fftchain_run.restype = sz
         L.oc_fftchain_run.argtypes = [vp, sz, i32, i32, i32, f32, i32, vp, sz, vp, vp]
+        L.oc_fftchain_run_nf.restype = sz
+        L.oc_fftchain_run_nf.argtypes = [vp, sz, i32, i32, i32, f32, i32, vp, sz, vp, vp, f32, f32, f32]
         L.oc_fftchain_params.argtypes = [f64, i32, f64, f64, vp, vp]
         L.oc_decimator_params.argtypes = [f64, f64, vp, vp, vp, vp]
         L.oc_shift.argtypes = [vp, vp, sz, f64, f64, C.c_uint64, i32]
@@ -180,8 +182,9 @@ def fft_adpcm(db):
     return out
 
 
-def fftchain_run(iq, n, every_n, avg, add_db=-70.0, compression="adpcm"):
-    """Returns dict(lines=bytes array [L, line_bytes], s16=[L, n+10] or None, db=[L, n])."""
+def fftchain_run(iq, n, every_n, avg, add_db=-70.0, compression="adpcm", noise_filter=None):
+    """Returns dict(lines=bytes array [L, line_bytes], s16=[L, n+10] or None, db=[L, n]).
+    noise_filter = (alpha, beta, growth): the spec-defined spectral-subtraction stage of BASELINE config 4."""
     iq = _cf(iq)
     comp = 1 if compression == "adpcm" else 0
     fpl = avg if avg > 0 else 1
@@ -191,7 +194,11 @@ def fftchain_run(iq, n, every_n, avg, add_db=-70.0, compression="adpcm"):
     out = np.empty((max(L, 1), line_bytes), np.uint8)
     s16 = np.empty((max(L, 1), n + 10), np.int16)
     db = np.empty((max(L, 1), n), np.float32)
-    got = lib().oc_fftchain_run(_p(iq), len(iq), n, every_n, avg, add_db, comp, _p(out), out.size, _p(s16), _p(db))
+    if noise_filter is not None:
+        a, b, g = noise_filter
+        got = lib().oc_fftchain_run_nf(_p(iq), len(iq), n, every_n, avg, add_db, comp, _p(out), out.size, _p(s16), _p(db), a, b, g)
+    else:
+        got = lib().oc_fftchain_run(_p(iq), len(iq), n, every_n, avg, add_db, comp, _p(out), out.size, _p(s16), _p(db))
     assert got == L, (got, L)
     return dict(lines=out[:L], s16=s16[:L] if comp else None, db=db[:L])
 

@@ -295,9 +295,44 @@ void oc_fftchain_params(double samp_rate, int fft_size, double voverlap, double 
 }
 
 /* Whole FftChain: Fft -> LogPower|LogAveragePower -> FftSwap -> [FftAdpcm]; csdr/chain/fft.py:25-49 */
+/* Spectral-subtraction noise filter on the averaged power of one waterfall line (BASELINE config 4).  SPEC-DEFINED: the
+ * reference has no waterfall noise filter (its NoiseFilter is audio-only, csdr/chain/clientaudio.py:13-14, algorithm
+ * not in the tree) — this is the stage the survey prescribes, excluded from reference-parity claims.
+ * Per bin, across lines: noise floor by minimum tracking with upward drift, subtracted in the linear domain with a
+ * spectral floor:   N = first ? P : min(P, N * (1 + growth));   P' = max(P - alpha * N, beta * P). */
+void oc_wf_noise_filter(float* pw, float* noise, int n, int first, float alpha, float beta, float growth)
+{
+    for (int i = 0; i < n; i++) {
+        const float p = pw[i];
+        const float nf = first ? p : fminf(p, noise[i] * (1.0f + growth));
+        noise[i] = nf;
+        pw[i] = fmaxf(p - alpha * nf, beta * p);
+    }
+}
+
+static size_t fftchain_core(const oc_cf32* iq, size_t n_samples, int n, int every_n, int avg, float add_db,
+                            int compression, uint8_t* out, size_t out_cap, int16_t* s16_out, float* db_out,
+                            int nf_on, float nf_alpha, float nf_beta, float nf_growth);
+
 size_t oc_fftchain_run(const oc_cf32* iq, size_t n_samples, int n, int every_n, int avg, float add_db,
                        int compression, uint8_t* out, size_t out_cap, int16_t* s16_out, float* db_out)
 {
+    return fftchain_core(iq, n_samples, n, every_n, avg, add_db, compression, out, out_cap, s16_out, db_out, 0, 0.f, 0.f, 0.f);
+}
+
+size_t oc_fftchain_run_nf(const oc_cf32* iq, size_t n_samples, int n, int every_n, int avg, float add_db,
+                          int compression, uint8_t* out, size_t out_cap, int16_t* s16_out, float* db_out,
+                          float nf_alpha, float nf_beta, float nf_growth)
+{
+    return fftchain_core(iq, n_samples, n, every_n, avg, add_db, compression, out, out_cap, s16_out, db_out, 1, nf_alpha, nf_beta,
+                         nf_growth);
+}
+
+static size_t fftchain_core(const oc_cf32* iq, size_t n_samples, int n, int every_n, int avg, float add_db,
+                            int compression, uint8_t* out, size_t out_cap, int16_t* s16_out, float* db_out,
+                            int nf_on, float nf_alpha, float nf_beta, float nf_growth)
+{
+    float* noise = (float*)malloc(sizeof(float) * (size_t)n);
     size_t line_bytes = compression ? (size_t)(n + 10) / 2 : (size_t)n * 4;
     size_t frames_per_line = avg > 0 ? (size_t)avg : 1;
     size_t nframes = 0, nlines = 0;
@@ -320,10 +355,17 @@ size_t oc_fftchain_run(const oc_cf32* iq, size_t n_samples, int n, int every_n, 
                 oc_fft_frame(iq + f * (size_t)every_n, window, X, n);
                 for (int i = 0; i < n; i++) pw[i] += X[i].re * X[i].re + X[i].im * X[i].im;
             }
+            if (nf_on) oc_wf_noise_filter(pw, noise, n, l == 0, nf_alpha, nf_beta, nf_growth);
             for (int i = 0; i < n; i++) line[i] = 10.0f * log10f(pw[i]) + corr;
         } else {
             oc_fft_frame(iq + l * (size_t)every_n, window, X, n);
-            oc_log_power(X, line, n, add_db);
+            if (nf_on) {
+                for (int i = 0; i < n; i++) pw[i] = X[i].re * X[i].re + X[i].im * X[i].im;
+                oc_wf_noise_filter(pw, noise, n, l == 0, nf_alpha, nf_beta, nf_growth);
+                for (int i = 0; i < n; i++) line[i] = 10.0f * log10f(pw[i]) + add_db;
+            } else {
+                oc_log_power(X, line, n, add_db);
+            }
         }
         oc_fft_swap(line, swapped, n);
         if (db_out) memcpy(db_out + l * (size_t)n, swapped, sizeof(float) * (size_t)n);
@@ -337,7 +379,7 @@ size_t oc_fftchain_run(const oc_cf32* iq, size_t n_samples, int n, int every_n, 
         }
         nlines++;
     }
-    free(window); free(X); free(pw); free(line); free(swapped); free(s);
+    free(window); free(X); free(pw); free(line); free(swapped); free(s); free(noise);
     return nlines;
 }
 

@@ -56,6 +56,13 @@ void oc_fft_adpcm(const float* db, uint8_t* out, int n);                /* FftAd
 size_t oc_fftchain_run(const oc_cf32* iq, size_t n_samples, int n, int every_n, int avg, float add_db,
                        int compression, uint8_t* out, size_t out_cap, int16_t* s16_out, float* db_out);
 
+/* spec-defined waterfall noise filter (BASELINE config 4; no reference counterpart, see csdr_oracle.c): in-place on the
+   averaged linear power of one line, `noise` = per-bin floor estimate carried across lines */
+void oc_wf_noise_filter(float* pw, float* noise, int n, int first, float alpha, float beta, float growth);
+size_t oc_fftchain_run_nf(const oc_cf32* iq, size_t n_samples, int n, int every_n, int avg, float add_db,
+                          int compression, uint8_t* out, size_t out_cap, int16_t* s16_out, float* db_out,
+                          float nf_alpha, float nf_beta, float nf_growth);
+
 /* ---------- Selector stages: csdr/chain/selector.py:29,33,95,115-130 ---------- */
 /* Shift: y[i] = x[i] * exp(j 2 pi frac(phase0 + rate*(n0+i+1))); returns nothing, pure function of
    the absolute sample index.  fast != 0 uses a float32 rotation recurrence re-seeded every 256

@@ -137,6 +137,58 @@ def test_c4_shape_65536(gpu):
     assert np.abs(s16.astype(np.int32) - ref["s16"].astype(np.int32)).max() <= 1
 
 
+def test_c4_noise_filter_spectral_subtraction(gpu):
+    # BASELINE config 4: 65536-pt / 30 fps at 61.44 MS/s "with spectral-subtraction noise filter".  The reference has no
+    # waterfall noise filter: spec-defined stage (include/owrx_b200.h), checked against the oracle's
+    # restatement of the same spec — three lines, so the per-bin floor recurrence runs across lines
+    fs, n, fps, ov = 61.44e6, 65536, 30, 0.3
+    avg, every_n = fftchain_params(fs, n, ov, fps)
+    nf = (0.9, 0.05, 0.02)
+    iq = _iq(every_n * avg * 3 + n, fs, k=20)
+    ref = oracle.fftchain_run(iq, n, every_n, avg, noise_filter=nf)
+    plain = oracle.fftchain_run(iq, n, every_n, avg)
+    wf = Waterfall(fs, n, ov, fps, "adpcm")
+    wf.set_noise_filter(True, *nf)
+    lines, db, s16 = _run_gpu_batch(wf, iq)
+    assert lines.shape == (3, 32773)
+    assert np.abs(db - ref["db"]).max() <= DB_TOL
+    assert np.abs(s16.astype(np.int32) - ref["s16"].astype(np.int32)).max() <= 1
+    # the filter does something: first line = P (1 - alpha) -> 10 dB down everywhere; later lines stay >= the 13 dB floor
+    assert np.allclose(plain["db"][0] - db[0], -10 * np.log10(1 - nf[0]), atol=0.02)
+    assert (plain["db"][1:] - db[1:]).max() <= -10 * np.log10(nf[1]) + 0.02
+    # GPU bytes == oracle encode of the GPU's own int16 (bit-exact codec)
+    for l in range(3):
+        assert np.array_equal(lines[l], oracle.ima_adpcm_encode(s16[l]))
+
+
+def test_noise_filter_streaming_state_and_off_switch(gpu):
+    fs, n, fps, ov = 2.4e6, 1024, 60, 0.3
+    avg, every_n = fftchain_params(fs, n, ov, fps)
+    nf = (1.0, 0.1, 0.05)
+    iq = _iq(every_n * avg * 6 + n + 99, fs, seed=5)
+    ref = oracle.fftchain_run(iq, n, every_n, avg, compression="none", noise_filter=nf)
+    wf = Waterfall(fs, n, ov, fps, "none")
+    wf.set_noise_filter(True, *nf)
+    rng = np.random.default_rng(1)
+    got, pos = [], 0
+    while pos < len(iq):                                   # ragged feeds: the floor estimate is carried from line to line
+        step = int(rng.integers(1, 3 * every_n * avg))
+        got += wf.feed(iq[pos:pos + step])
+        pos += step
+    got = np.stack([np.frombuffer(l, np.float32) for l in got])
+    assert got.shape == ref["db"].shape == (6, n)
+    assert np.abs(got - ref["db"]).max() <= DB_TOL
+    # alpha = 0, beta = 0: the stage is the identity
+    wf2 = Waterfall(fs, n, ov, fps, "none")
+    wf2.set_noise_filter(True, 0.0, 0.0, 0.02)
+    wf3 = Waterfall(fs, n, ov, fps, "none")
+    a = np.stack([np.frombuffer(l, np.float32) for l in wf2.feed(iq)])
+    b = np.stack([np.frombuffer(l, np.float32) for l in wf3.feed(iq)])
+    assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        wf3.set_noise_filter(True, -1.0, 0.0, 0.0)
+
+
 def test_streaming_feed_ragged_equals_batch(gpu):
     fs, n, fps, ov = 2.4e6, 4096, 9, 0.3
     avg, every_n = fftchain_params(fs, n, ov, fps)

@@ -270,3 +270,26 @@ def test_empty_and_short_inputs():
     assert len(oracle.fractional_decimator_cf(np.zeros(5, np.complex64), 1.5)) == 0
     o = oracle.client_chain_run(np.zeros(100, np.complex64), 240000.0, 12000, 0, None, oracle.DEMOD_NFM)
     assert len(o["if_"]) == 0 and len(o["audio"]) == 0
+
+
+def test_wf_noise_filter_matches_float64_restatement():
+    # the spec-defined spectral-subtraction stage of BASELINE config 4 (no reference counterpart: SURVEY 8d C4)
+    n, every_n, avg = 256, 180, 4
+    rng = np.random.default_rng(3)
+    iq = (rng.standard_normal(every_n * avg * 5 + n) + 1j * rng.standard_normal(every_n * avg * 5 + n)).astype(np.complex64) * 0.1
+    iq += 0.5 * np.exp(2j * np.pi * 0.123 * np.arange(len(iq))).astype(np.complex64)
+    a, b, g = 0.9, 0.05, 0.02
+    got = oracle.fftchain_run(iq, n, every_n, avg, compression="none", noise_filter=(a, b, g))["db"]
+    w = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(n) / (n - 1))
+    noise = None
+    for l in range(5):
+        p = np.zeros(n)
+        for j in range(avg):
+            s0 = (l * avg + j) * every_n
+            p += np.abs(np.fft.fft(iq[s0:s0 + n].astype(np.complex128) * w)) ** 2
+        noise = p.copy() if noise is None else np.minimum(p, noise * (1 + g))
+        q = np.maximum(p - a * noise, b * p)
+        want = np.fft.fftshift(10 * np.log10(q) - 70 - 10 * np.log10(avg))
+        assert np.abs(got[l] - want).max() < 5e-3
+    off = oracle.fftchain_run(iq, n, every_n, avg, compression="none")["db"]
+    assert np.allclose(off[0] - got[0], -10 * np.log10(1 - a), atol=1e-3)
