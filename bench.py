@@ -357,11 +357,11 @@ def run_ours(args):
     ch2 = [bank2.add_channel(OUT_RATE, demod=c["kind"], offset=c["offset"], bandpass=BANDPASS[c["kind"]]) for c in my_plan]
     hp = h_iq.data_ptr()
 
-    audio_buf = np.empty(1 << 17, np.float32)
+    audio_buf = np.empty((len(ch2), 1 << 15), np.float32)      # ~20 160 samples per channel and block
 
     def e2e_step():
         """one block through the public host API: H2D of the block from pinned memory, the whole chain, audio D2H and
-        the per-channel read a consumer does (owrx_chan_read_audio into a caller buffer)"""
+        the read of every channel's audio into a caller buffer (owrx_bank_read_audio_all)"""
         if world > 1:
             # rank 0 uploads, NCCL carries the block to the other GPUs, every rank returns its audio to the host
             if rank == 0:
@@ -369,15 +369,9 @@ def run_ours(args):
             broadcast_block(iq, 0)
             bank2.process_device(iq, BLOCK, stream=sp)
             bank2.drain()
-            got = 0
-            for c in ch2:
-                got += c.read_audio_into(audio_buf)
-            return got
+            return sum(bank2.read_audio_all(ch2, audio_buf))
         bank2.feed_ptr(hp, BLOCK)
-        got = 0
-        for c in ch2:
-            got += c.read_audio_into(audio_buf)
-        return got
+        return sum(bank2.read_audio_all(ch2, audio_buf))
 
     for i in range(max(1, min(args.warmup, 3))):
         e2e_step()

@@ -155,6 +155,9 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
 int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples);
 /* Pop queued outputs of one channel (float32 audio after AGC / pre-AGC demod / complex IF). */
 int owrx_chan_read_audio(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n);
+/* the same pop for many channels in one call (what a fan-out thread serving every websocket of a source does,
+ * owrx/dsp.py:863-870 per client): channel chans[i] -> out[i * cap_samples ...], counts[i] samples */
+int owrx_bank_read_audio_all(owrx_bank_t* bank, const int* chans, int n_chans, float* out, size_t cap_samples, size_t* counts);
 int owrx_chan_read_demod(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n);
 int owrx_chan_read_if(owrx_bank_t* bank, int chan, float* out_iq, size_t cap_samples, size_t* n);
 int owrx_chan_read_power(owrx_bank_t* bank, int chan, float* out, size_t cap, size_t* n);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "owrx_bank_profile": (_i, [_vp, _i]),
     "owrx_bank_profile_read": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
     "owrx_bank_profile_read_ex": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_uint64), _i]),
+    "owrx_bank_read_audio_all": (_i, [_vp, C.POINTER(_i), _i, _vp, _sz, _psz]),
     "owrx_bank_set_fir_mode": (_i, [_vp, _i]),
     "owrx_bank_fir_form": (_i, [_vp]),
 }

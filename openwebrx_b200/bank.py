@@ -179,6 +179,15 @@ class ChannelBank:
         N.check(N.lib.owrx_bank_profile_read_ex(self._h, ms, n, 1 if reset else 0))
         return {name: (ms[i], n[i]) for i, name in enumerate(N.PROF_KINDS)}
 
+    def read_audio_all(self, channels, buf):
+        """pop the queued float32 audio of every channel in `channels` with ONE library call: channel i -> buf[i, :counts[i]]
+        (buf: C-contiguous float32 [len(channels), cap]); returns the per-channel sample counts"""
+        ids = (C.c_int * len(channels))(*[c.id for c in channels])
+        counts = (C.c_size_t * len(channels))()
+        assert buf.dtype == np.float32 and buf.flags.c_contiguous and buf.shape[0] >= len(channels)
+        N.check(N.lib.owrx_bank_read_audio_all(self._h, ids, len(channels), buf.ctypes.data_as(C.c_void_p), buf.shape[1], counts))
+        return list(counts)
+
     def set_fir_mode(self, mode="auto"):
         """how Shift + FirDecimate is evaluated: "auto" | "direct" (K3) | "fastconv" (K3F, FP32 pipe) | "fastconv_tc" (K3F, tcgen05)"""
         N.check(N.lib.owrx_bank_set_fir_mode(self._h, N.FIR_MODES[mode] if isinstance(mode, str) else int(mode)))

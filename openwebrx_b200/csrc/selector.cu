@@ -1775,6 +1775,20 @@ int owrx_chan_read_audio(owrx_bank_t* bank, int chan, float* out, size_t cap_sam
     return pop_queue(ch->q_audio, out, cap_samples, n, 1);
 }
 
+int owrx_bank_read_audio_all(owrx_bank_t* bank, const int* chans, int n_chans, float* out, size_t cap_samples, size_t* counts)
+{
+    if (!bank || !chans || n_chans < 0 || !out || !counts) return fail(OWRX_E_INVALID, "bad argument");
+    for (int i = 0; i < n_chans; i++)
+        if (!get_chan(bank, chans[i])) return fail(OWRX_E_INVALID, "unknown channel %d", chans[i]);
+    std::lock_guard<std::mutex> lk(bank->mu);
+    for (int i = 0; i < n_chans; i++) {
+        Chan* ch = get_chan(bank, chans[i]);
+        int rc = pop_queue(ch->q_audio, out + (size_t)i * cap_samples, cap_samples, &counts[i], 1);
+        if (rc != OWRX_OK) return rc;
+    }
+    return OWRX_OK;
+}
+
 int owrx_chan_read_demod(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n)
 {
     Chan* ch = get_chan(bank, chan);

@@ -321,3 +321,23 @@ def test_full_size_block_properties(gpu, fir_mode):
         direct = run(iq, [], n_channels=3, mode="direct")
         for c in range(3):
             assert rel_rms(one[c][0], direct[c][0]) <= AUDIO_TOL, c
+
+
+def test_read_audio_all_equals_per_channel_reads(gpu):
+    fs, out = 2.4e6, 12000
+    cars = carrier_plan(5, fs, seed=41)
+    iq = make_iq(5333 + 200 * 1500, fs, cars, seed=41)
+    per_chan, batched = [], None
+    for use_all in (False, True):
+        bank, chans = _setup(fs, out, cars, 5, outputs=N.OUT_AUDIO)
+        bank.feed(iq)
+        if use_all:
+            buf = np.zeros((5, 4096), np.float32)
+            counts = bank.read_audio_all([ch for ch, _ in chans], buf)
+            batched = [buf[i, :counts[i]].copy() for i in range(5)]
+            assert bank.read_audio_all([ch for ch, _ in chans], buf) == [0] * 5          # queues are empty now
+        else:
+            per_chan = [ch.read_audio() for ch, _ in chans]
+        bank.close()
+    for a, b in zip(per_chan, batched):
+        assert len(a) == len(b) > 1000 and np.array_equal(a, b)

@@ -13,10 +13,10 @@ print("H2D 134MB pinned: %.2f ms (%.1f GB/s)"%(t*1e3, BLOCK*8/t/1e9))
 bank=ChannelBank(FS)
 ch=[bank.add_channel(12000,demod=c["kind"],offset=c["offset"],bandpass=BANDPASS[c["kind"]]) for c in cars]
 hp=h.data_ptr()
-buf=np.empty(1<<17,np.float32)
+buf=np.empty((len(ch),1<<15),np.float32)
 def step():
     bank.feed_ptr(hp,BLOCK)
-    return sum(c.read_audio_into(buf) for c in ch)
+    return sum(bank.read_audio_all(ch,buf))
 for i in range(3): step()
 s0=bank.stats()
 t0=time.perf_counter()
