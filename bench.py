@@ -16,6 +16,8 @@ dominant kernel (K3: NCO mix + polyphase FIR decimation); `waterfall` reports th
 hot path (BASELINE config 1 shape) from its own timed loop; `cpu_baseline` the oracle on host cores.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -252,7 +254,7 @@ def run_ours(args):
     import torch.distributed as dist
     from openwebrx_b200 import ChannelBank, Waterfall, _native as N, fftchain_params
     from openwebrx_b200.synth import BANDPASS
-    from openwebrx_b200.sharding import broadcast_block
+    from openwebrx_b200.sharding import MulticastHop, broadcast_block
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -280,7 +282,27 @@ def run_ours(args):
     if world > 1:
         dist.broadcast(iq, 0)
     iq_src = iq
-    bcast_buf = [torch.empty_like(iq), torch.empty_like(iq)] if world > 1 else [iq]
+    # the hop: NVSwitch multicast (one multimem.st pass on the ingest GPU, see openwebrx_b200/sharding.py) when the GPUs
+    # support it, else an NCCL broadcast; OWRX_HOP=nccl forces the latter
+    hop, hop_kind = None, "none"
+    if world > 1:
+        hop_kind = "nccl-broadcast"
+        # measured on 2 and 8 B200 (tools/hop_sweep.sh): both hops hide behind the DSP pass; NCCL's is the faster end to end
+        # (0.49 vs 0.61 ms per step at 8 GPUs: the multicast protocol's two cross-GPU barriers per block cost more than
+        # NCCL's copy kernels), so it is the default and OWRX_HOP=multicast selects the NVLS form
+        if os.environ.get("OWRX_HOP", "nccl") == "multicast":
+            try:
+                hop = MulticastHop(2 * BLOCK, dev)
+                hop_kind = "nvls-multicast"
+            except Exception as e:                       # no NVLS on this box / torch build: keep NCCL
+                print("[bench] multicast hop unavailable (%s: %s); using NCCL broadcast" % (type(e).__name__, e), file=sys.stderr)
+                hop = None
+        flag = torch.tensor([1 if hop is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks or none
+        if int(flag.item()) == 0:
+            hop, hop_kind = None, "nccl-broadcast"
+    bcast_buf = [torch.empty_like(iq), torch.empty_like(iq)] if (world > 1 and hop is None) else [iq]
+    iq_alt = [iq, iq.clone()] if world == 1 else None
     # a created (non-default) stream: the C ABI treats a NULL handle as "use the object's own stream"
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.synchronize()
@@ -298,15 +320,26 @@ def run_ours(args):
             buf.copy_(iq_src, non_blocking=True)        # "fresh" samples from the ingest side
         pending[0] = broadcast_block(buf, 0, async_op=True)
 
+    sent = [0]
+
     def step(i):
-        if world > 1:
+        if hop is not None:
+            # block i+1 crosses the switch on the hop stream while block i is processed; buffers alternate
+            while sent[0] <= i + 1:
+                hop.send(sent[0], iq_src if rank == 0 else None)
+                sent[0] += 1
+            buf = hop.recv(i, stream)
+            bank.process_device(buf, BLOCK, stream=sp)
+            hop.release(i, stream)
+        elif world > 1:
             if pending[0] is None:
                 issue_broadcast(i)
             pending[0].wait()                            # current stream waits for block i
             issue_broadcast(i + 1)
             bank.process_device(bcast_buf[i & 1], BLOCK, stream=sp)
         else:
-            bank.process_device(iq, BLOCK, stream=sp)
+            # two resident blocks, alternated: 268 MB of input between two reads of the same bytes (L2 is 126 MB)
+            bank.process_device(iq_alt[i & 1], BLOCK, stream=sp)
 
     def barrier():
         if world > 1:
@@ -321,6 +354,12 @@ def run_ours(args):
         step(i)
     bank.join(sp)
     barrier()
+    if hop is not None:
+        # the hop delivers the ingest rank's block bit for bit: compare a checksum of the last received buffer
+        chk = hop.bufs[(args.warmup - 1) & 1].double().sum().reshape(1)
+        ref = iq_src.double().sum().reshape(1) if rank == 0 else torch.zeros(1, device=dev, dtype=torch.float64)
+        dist.broadcast(ref, 0)
+        assert torch.equal(chk, ref), "multicast hop delivered a different block"
     bank.profile(True)
     bank.profile_read(reset=True)
     launches0 = N.lib.owrx_launch_count()
@@ -328,8 +367,10 @@ def run_ours(args):
     barrier()
     clocks.mark()
     ev0.record(stream)
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
-        step(i)
+        step(args.warmup + i)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps     # CPU time to enqueue one step (diagnostic)
     bank.join(sp)                  # the timed region ends when the last block's audio is complete
     ev1.record(stream)
     barrier()
@@ -366,8 +407,17 @@ def run_ours(args):
             # rank 0 uploads, NCCL carries the block to the other GPUs, every rank returns its audio to the host
             if rank == 0:
                 iq.copy_(h_iq, non_blocking=True)
-            broadcast_block(iq, 0)
-            bank2.process_device(iq, BLOCK, stream=sp)
+            if hop is not None:
+                j = sent[0]
+                sent[0] += 1
+                hop.stream.wait_stream(stream)           # the upload is on the bench stream
+                hop.send(j, iq if rank == 0 else None)
+                buf = hop.recv(j, stream)
+                bank2.process_device(buf, BLOCK, stream=sp)
+                hop.release(j, stream)
+            else:
+                broadcast_block(iq, 0)
+                bank2.process_device(iq, BLOCK, stream=sp)
             bank2.drain()
             return sum(bank2.read_audio_all(ch2, audio_buf))
         bank2.feed_ptr(hp, BLOCK)
@@ -414,9 +464,9 @@ def run_ours(args):
             algo_bytes = 12.0 * M * B * Dp + 12.0 * M * Dp * CH_PER_GPU + 8.0 * M * B * CH_PER_GPU
             kname = ("fc_contract_tc_kernel (K3F: per-channel spectral contraction over the %d polyphase branches, %d blocks x %d ch, "
                      "tcgen05 bf16x3 -> FP32 in TMEM)" % (D, B, CH_PER_GPU))
-            knote = ("HBM bound: 6 bf16 MMAs per FP32 product keep the tensor pipe under 15 %% busy; timed inside the three-stream pipeline "
-                     "(standalone ncu capture: profiles/r1_fc_contract_tc.md); the shared forward FFTs (fc_forward) and the inverse FFT + "
-                     "rotation (fc_inverse) are in stages_ms")
+            knote = ("HBM bound (ncu: DRAM 63 % of its peak, tensor pipe active 14 % of cycles; issued MMA FLOPs in roofline_tensor); timed "
+                     "inside the three-stream pipeline (standalone ncu capture: profiles/r1_fc_contract_tc.md, 83.5 us); the shared forward "
+                     "FFTs (fc_forward) and the inverse FFT + rotation (fc_inverse) are in stages_ms")
             tkey = "fc_contract_tc_kernel"
         else:
             # operands of the contraction, each moved once: F (16 B, packed-FMA layout), table (8 B), Z (8 B)
@@ -462,11 +512,12 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: Selector DDC + NFM/AM/USB demod, 10 MS/s wideband, %d x 12 kHz channels per GPU" % CH_PER_GPU,
                    "channels_total": world * CH_PER_GPU, "block_samples": BLOCK, "decimation": D, "fir_taps": T,
-                   "l2": "input block 134 MB > 126 MB L2; no flush needed", "parallelism": "channels sharded x%d, IQ block NCCL-broadcast" % world if world > 1 else "1 GPU",
+                   "l2": "two resident 134 MB input blocks alternate (268 MB between re-reads > 126 MB L2); no flush needed", "parallelism": "channels sharded x%d, IQ block hop: %s" % (world, hop_kind) if world > 1 else "1 GPU",
                    "realtime_factor": value / (FS / 1e6 * CH_PER_GPU * world)},
         "e2e": {"value": e2e_value, "unit": "channel-MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clk,
         "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": load_traffic(tkey), "peak_source": peak_src,
@@ -530,10 +581,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, ...) is sent to stderr, and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    sys.stdout.write(out.getvalue())
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -36,6 +36,13 @@ const char* owrx_version(void);
 uint64_t owrx_launch_count(void);
 int owrx_device_count(int* n);
 
+/* Multi-GPU IQ hop (the cross-GPU form of every client reading the one source ring, owrx/dsp.py:835-837,
+ * owrx/source/__init__.py:307-330): copies n_bytes from src_dev (this GPU) to multicast_dst, an NVSwitch multicast (NVLS)
+ * address that maps the same offset of a buffer on every GPU of the group — one pass of multimem.st stores replicates the
+ * block into all of them.  The multicast mapping is created by the host (e.g. torch.distributed symmetric memory); the
+ * caller orders a cross-GPU barrier after this call on `stream` before the block is read.  16-byte aligned pointers and size. */
+int owrx_iq_multicast_store(const void* src_dev, void* multicast_dst, size_t n_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Waterfall — replaces the pycsdr chain  Fft -> LogPower|LogAveragePower -> FftSwap -> [FftAdpcm]
  * built by FftChain (csdr/chain/fft.py:25-49) and driven by SpectrumThread (owrx/fft.py:40-73).

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 SO = os.path.join(HERE, "libowrx_b200.so")
-SOURCES = ["core.cu", "waterfall.cu", "selector.cu", "k3_fir.cu", "fastconv.cu", "fastconv_tc.cu"]
+SOURCES = ["core.cu", "waterfall.cu", "selector.cu", "k3_fir.cu", "fastconv.cu", "fastconv_tc.cu", "iq_hop.cu"]
 # per-file extra flags: K3's FFMA2 loop is scheduled better by ptxas -O1 (see k3_fir.cu)
 EXTRA_FLAGS = {"k3_fir.cu": ["-Xptxas", "-O1"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -45,6 +45,7 @@ SIGNATURES = {
     "owrx_version": (C.c_char_p, []),
     "owrx_launch_count": (C.c_uint64, []),
     "owrx_device_count": (_i, [C.POINTER(_i)]),
+    "owrx_iq_multicast_store": (_i, [_vp, _vp, _sz, _vp]),
     "owrx_wf_create": (_i, [_i, _i, _i, _i, _f, _i, _pp]),
     "owrx_wf_destroy": (None, [_vp]),
     "owrx_wf_set_every_n_samples": (_i, [_vp, _i]),
