@@ -441,6 +441,30 @@ def run_ours(args):
     e2e_value = world * CH_PER_GPU * e2e_consumed / (e2e_ms * 1e-3) / 1e6
     d2h = (n_audio // e2e_steps) * 4
 
+    # ---- the same end-to-end step for a source that delivers complex int16 (the reference converts such
+    # sources on the CPU, owrx/source/fifi_sdr.py:27-28): half the PCIe bytes, Convert on the GPU.  Reported beside e2e.
+    e2e_cs16 = None
+    if world == 1:
+        h16 = torch.empty(BLOCK, 2, dtype=torch.int16).pin_memory()
+        h16.copy_((iq.clamp(-1, 1) * 32767.0).to(torch.int16))
+        bank3 = ChannelBank(FS, device=local)
+        ch3 = [bank3.add_channel(OUT_RATE, demod=c["kind"], offset=c["offset"], bandpass=BANDPASS[c["kind"]]) for c in my_plan]
+        hp16 = h16.data_ptr()
+        for i in range(3):
+            bank3.feed_ptr(hp16, BLOCK, fmt="cs16")
+            bank3.read_audio_all(ch3, audio_buf)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            bank3.feed_ptr(hp16, BLOCK, fmt="cs16")
+            bank3.read_audio_all(ch3, audio_buf)
+        torch.cuda.synchronize()
+        ms16 = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        e2e_cs16 = {"value": CH_PER_GPU * e2e_consumed / (ms16 * 1e-3) / 1e6, "unit": "channel-MS/s", "h2d_bytes_per_step": BLOCK * 4,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms16,
+                    "note": "same step fed with complex int16 host samples (owrx_bank_feed_fmt): Convert runs on the GPU"}
+        bank3.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -516,6 +540,7 @@ def run_ours(args):
                    "realtime_factor": value / (FS / 1e6 * CH_PER_GPU * world)},
         "e2e": {"value": e2e_value, "unit": "channel-MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms},
+        "e2e_cs16": e2e_cs16,
         "gpu_launches": int(launches),
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clk,

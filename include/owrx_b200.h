@@ -36,6 +36,14 @@ const char* owrx_version(void);
 uint64_t owrx_launch_count(void);
 int owrx_device_count(int* n);
 
+/* Wideband IQ ingress formats.  Sources that do not deliver complex float32 are converted by the reference on
+ * the CPU — Chain([Convert(Format.COMPLEX_SHORT, Format.COMPLEX_FLOAT), Gain(Format.COMPLEX_FLOAT, 5.0)]),
+ * owrx/source/fifi_sdr.py:27-28 via owrx/source/direct.py:59-71; owrx_*_feed_fmt takes the raw samples (interleaved I, Q)
+ * and does that Convert (+ Gain) on the GPU:  CS16: x / 32767;  CU8: x / 127.5 - 1;  then * gain. */
+#define OWRX_IQ_CF32 0   /* complex float32, 8 bytes per sample (what owrx_wf_feed / owrx_bank_feed take) */
+#define OWRX_IQ_CS16 1   /* complex int16 little-endian, 4 bytes per sample */
+#define OWRX_IQ_CU8  2   /* complex uint8 offset binary (rtl_sdr raw), 2 bytes per sample */
+
 /* Multi-GPU IQ hop (the cross-GPU form of every client reading the one source ring, owrx/dsp.py:835-837,
  * owrx/source/__init__.py:307-330): copies n_bytes from src_dev (this GPU) to multicast_dst, an NVSwitch multicast (NVLS)
  * address that maps the same offset of a buffer on every GPU of the group — one pass of multimem.st stores replicates the
@@ -57,6 +65,7 @@ typedef struct owrx_wf owrx_wf_t;
 int owrx_wf_create(int device, int fft_size, int every_n_samples, int avg_number, float add_db,
                    int compression, owrx_wf_t** out);
 void owrx_wf_destroy(owrx_wf_t* wf);
+int owrx_wf_feed_fmt(owrx_wf_t* wf, const void* iq, size_t n_samples, int format, float gain);   /* owrx_wf_feed for OWRX_IQ_* input */
 int owrx_wf_set_every_n_samples(owrx_wf_t* wf, int every_n_samples);   /* Fft.setEveryNSamples, csdr/chain/fft.py:55 */
 int owrx_wf_set_avg_number(owrx_wf_t* wf, int avg_number);             /* FftAverager.setFftAverages, csdr/chain/fft.py:12-16 */
 int owrx_wf_set_compression(owrx_wf_t* wf, int compression);           /* FftChain.setCompression, csdr/chain/fft.py:87-96 */
@@ -160,6 +169,8 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
 
 /* Streaming host path: one wideband block from HOST memory, shared by every channel. */
 int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples);
+/* the same for raw OWRX_IQ_CS16 / OWRX_IQ_CU8 samples (Convert + Gain on the GPU, half / a quarter of the PCIe bytes) */
+int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq, size_t n_samples, int format, float gain);
 /* Pop queued outputs of one channel (float32 audio after AGC / pre-AGC demod / complex IF). */
 int owrx_chan_read_audio(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n);
 /* the same pop for many channels in one call (what a fan-out thread serving every websocket of a source does,

@@ -15,6 +15,8 @@ COMPRESSION_NONE, COMPRESSION_ADPCM = 0, 1
 DEMOD_NFM, DEMOD_AM, DEMOD_SSB, DEMOD_WFM, DEMOD_NONE = 0, 1, 2, 3, 4
 AGC_SLOW, AGC_FAST = 0, 1
 OUT_AUDIO, OUT_DEMOD, OUT_IF, OUT_POWER = 1, 2, 4, 8
+IQ_CF32, IQ_CS16, IQ_CU8 = 0, 1, 2
+IQ_FORMATS = {"cf32": IQ_CF32, "cs16": IQ_CS16, "cu8": IQ_CU8}
 AUDIO_F32, AUDIO_S16, AUDIO_ADPCM = 0, 1, 2
 
 
@@ -54,6 +56,7 @@ SIGNATURES = {
     "owrx_wf_set_noise_filter": (_i, [_vp, _i, _f, _f, _f]),
     "owrx_wf_line_bytes": (_sz, [_vp]),
     "owrx_wf_feed": (_i, [_vp, _vp, _sz]),
+    "owrx_wf_feed_fmt": (_i, [_vp, _vp, _sz, _i, _f]),
     "owrx_wf_read": (_i, [_vp, _vp, _sz, _psz]),
     "owrx_wf_process_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _psz, _vp]),
     "owrx_wf_lines_for": (_sz, [_vp, _sz]),
@@ -72,6 +75,7 @@ SIGNATURES = {
     "owrx_chan_set_squelch_level": (_i, [_vp, _i, _f]),
     "owrx_chan_set_demod": (_i, [_vp, _i, _i, _d, _d, _i]),
     "owrx_bank_feed": (_i, [_vp, _vp, _sz]),
+    "owrx_bank_feed_fmt": (_i, [_vp, _vp, _sz, _i, _f]),
     "owrx_chan_read_audio": (_i, [_vp, _i, _vp, _sz, _psz]),
     "owrx_chan_read_demod": (_i, [_vp, _i, _vp, _sz, _psz]),
     "owrx_chan_read_if": (_i, [_vp, _i, _vp, _sz, _psz]),

@@ -142,8 +142,18 @@ class ChannelBank:
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
         N.check(N.lib.owrx_bank_feed(self._h, iq.ctypes.data_as(C.c_void_p), iq.size))
 
-    def feed_ptr(self, host_ptr, n_samples):
-        N.check(N.lib.owrx_bank_feed(self._h, host_ptr, n_samples))
+    def feed_ptr(self, host_ptr, n_samples, fmt="cf32", gain=1.0):
+        if fmt == "cf32" and gain == 1.0:
+            N.check(N.lib.owrx_bank_feed(self._h, host_ptr, n_samples))
+        else:
+            N.check(N.lib.owrx_bank_feed_fmt(self._h, host_ptr, n_samples, N.IQ_FORMATS[fmt], float(gain)))
+
+    def feed_raw(self, raw, fmt, gain=1.0):
+        """One wideband block of RAW source samples from host memory: fmt "cs16" (int16 array, interleaved I, Q) or "cu8"
+        (uint8, offset binary).  The reference's CPU-side Convert (+ Gain) (owrx/source/fifi_sdr.py:27-28) runs on the GPU."""
+        raw = np.ascontiguousarray(raw, dtype=np.int16 if fmt == "cs16" else np.uint8)
+        assert raw.size % 2 == 0
+        N.check(N.lib.owrx_bank_feed_fmt(self._h, raw.ctypes.data_as(C.c_void_p), raw.size // 2, N.IQ_FORMATS[fmt], float(gain)))
 
     def process_device(self, iq_dev, n_samples, stream=None):
         N.check(N.lib.owrx_bank_process_device(self._h, _ptr(iq_dev), n_samples, _ptr(stream)))

@@ -5,6 +5,7 @@
 // Filter design follows SURVEY.md Appendix A.1 (double precision, rounded once to float32).
 #include "selector_kernels.cuh"
 #include "fastconv.cuh"
+#include "ingress.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -289,6 +290,7 @@ struct owrx_bank {
     double prof_ms[OWRX_PROF_KINDS] = {};
     uint64_t prof_launches[OWRX_PROF_KINDS] = {};
     int fir_mode = OWRX_FIR_AUTO, bp_mode = OWRX_FIR_AUTO;
+    unsigned char* d_raw = nullptr; size_t raw_cap = 0;   // staging for raw (non-float) ingress chunks (owrx_bank_feed_fmt)
     int fir_form_used = 0;                           // form of the latest Shift + FirDecimate pass (owrx_bank_fir_form)
 };
 
@@ -1230,7 +1232,7 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     cudaSetDevice(bank->device);
     cudaDeviceSynchronize();
     for (auto& g : bank->groups) if (g) group_release(g.get());
-    cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]); cudaFree(bank->d_xpose);
+    cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]); cudaFree(bank->d_xpose); cudaFree(bank->d_raw);
     for (cudaEvent_t e : bank->chunk_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->fir_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->drain_events) cudaEventDestroy(e);
@@ -1498,7 +1500,15 @@ static int group_drain(owrx_bank* bank, Group* g, cudaStream_t ds, const DrainMa
 // c+1 is still crossing PCIe.  The low-rate stages run once over everything the chunks produced.
 int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
 {
-    if (!bank || (!iq && n_samples)) return fail(OWRX_E_INVALID, "NULL argument");
+    return owrx_bank_feed_fmt(bank, iq, n_samples, OWRX_IQ_CF32, 1.0f);
+}
+
+int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, int format, float gain)
+{
+    if (!bank || (!iq_raw && n_samples)) return fail(OWRX_E_INVALID, "NULL argument");
+    const size_t in_bytes = iq_format_bytes(format);
+    if (!in_bytes) return fail(OWRX_E_INVALID, "unknown IQ format %d", format);
+    const float* iq = static_cast<const float*>(iq_raw);             // OWRX_IQ_CF32 view
     std::lock_guard<std::mutex> lk(bank->mu);
     OWRX_CUDA(cudaSetDevice(bank->device));
     cudaStream_t st = bank->stream;
@@ -1525,6 +1535,12 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
         bank->iq_cap = cap;
     }
     float2* buf = bank->d_iq[bank->iq_cur];
+    if (format != OWRX_IQ_CF32 && n_samples * in_bytes > bank->raw_cap) {
+        OWRX_CUDA(cudaStreamSynchronize(bank->copy_stream));
+        cudaFree(bank->d_raw); bank->d_raw = nullptr; bank->raw_cap = 0;
+        OWRX_CUDA(cudaMalloc((void**)&bank->d_raw, n_samples * in_bytes));
+        bank->raw_cap = n_samples * in_bytes;
+    }
     OWRX_CUDA(cudaEventRecord(bank->ev0, st));
     // chunks of 2 M samples: the work left after the last H2D chunk (its FIR, low-rate stages and drain) stays short while a
     // chunk still spans 11+ overlap-save blocks; small feeds are a single chunk
@@ -1540,7 +1556,17 @@ int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
     OWRX_CUDA(cudaStreamWaitEvent(bank->copy_stream, bank->fir_done, 0));
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t o = c * chunk, len = std::min(chunk, n_samples - o);
-        if (len) OWRX_CUDA(cudaMemcpyAsync(buf + bank->iq_fill + o, iq + 2 * o, len * sizeof(float2), cudaMemcpyHostToDevice, bank->copy_stream));
+        if (len && format == OWRX_IQ_CF32) {
+            OWRX_CUDA(cudaMemcpyAsync(buf + bank->iq_fill + o, iq + 2 * o, len * sizeof(float2), cudaMemcpyHostToDevice, bank->copy_stream));
+        } else if (len) {
+            // raw samples cross PCIe as they are; Convert (+ Gain) runs on the copy stream behind each chunk's upload
+            unsigned char* d_raw = bank->d_raw + o * in_bytes;
+            OWRX_CUDA(cudaMemcpyAsync(d_raw, static_cast<const unsigned char*>(iq_raw) + o * in_bytes, len * in_bytes, cudaMemcpyHostToDevice,
+                                      bank->copy_stream));
+            int rcc = iq_convert_launch(format, d_raw, buf + bank->iq_fill + o, len, gain, bank->copy_stream);
+            if (rcc != OWRX_OK) return rcc;
+            bank->stats.kernel_launches++;
+        }
         OWRX_CUDA(cudaEventRecord(bank->chunk_events[c], bank->copy_stream));
     }
     int rc;

@@ -16,6 +16,7 @@
 //   wf_adpcm_kernel         IMA-ADPCM, state reset per line, low nibble first.
 #include "common.cuh"
 #include "fft_small.cuh"
+#include "ingress.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -388,6 +389,7 @@ struct owrx_wf {
     bool nf_on = false, nf_primed = false;
     float nf_alpha = 0.f, nf_beta = 0.f, nf_growth = 0.f;
     float* d_noise = nullptr;
+    unsigned char* d_raw = nullptr; size_t raw_cap = 0;      // staging for raw (non-float) ingress (owrx_wf_feed_fmt)
 };
 
 static size_t wf_line_bytes(const owrx_wf* wf)
@@ -635,7 +637,7 @@ void owrx_wf_destroy(owrx_wf_t* wf)
     if (wf->adpcm_done[0]) cudaEventDestroy(wf->adpcm_done[0]);
     if (wf->adpcm_done[1]) cudaEventDestroy(wf->adpcm_done[1]);
     if (wf->side) cudaStreamDestroy(wf->side);
-    cudaFree(wf->d_in); cudaFree(wf->d_in_alt); cudaFree(wf->d_out); cudaFree(wf->d_noise);
+    cudaFree(wf->d_in); cudaFree(wf->d_in_alt); cudaFree(wf->d_out); cudaFree(wf->d_noise); cudaFree(wf->d_raw);
     if (wf->h_out) cudaFreeHost(wf->h_out);
     if (wf->stream) cudaStreamDestroy(wf->stream);
     delete wf;
@@ -697,13 +699,20 @@ int owrx_wf_process_device(owrx_wf_t* wf, const void* iq_dev, size_t n_samples, 
 
 int owrx_wf_feed(owrx_wf_t* wf, const float* iq, size_t n_samples)
 {
-    if (!wf || (!iq && n_samples)) return fail(OWRX_E_INVALID, "NULL argument");
+    return owrx_wf_feed_fmt(wf, iq, n_samples, OWRX_IQ_CF32, 1.0f);
+}
+
+int owrx_wf_feed_fmt(owrx_wf_t* wf, const void* iq_raw, size_t n_samples, int format, float gain)
+{
+    if (!wf || (!iq_raw && n_samples)) return fail(OWRX_E_INVALID, "NULL argument");
+    const size_t in_bytes = iq_format_bytes(format);
+    if (!in_bytes) return fail(OWRX_E_INVALID, "unknown IQ format %d", format);
     std::lock_guard<std::mutex> g(wf->mu);
     OWRX_CUDA(cudaSetDevice(wf->device));
     // honour a pending skip (every_n > fft_size leaves a gap after the last consumed frame)
     if (wf->skip) {
         const size_t d = std::min(wf->skip, n_samples);
-        iq += 2 * d; n_samples -= d; wf->skip -= d;
+        iq_raw = static_cast<const unsigned char*>(iq_raw) + d * in_bytes; n_samples -= d; wf->skip -= d;
     }
     if (!n_samples) return OWRX_OK;
     const size_t need = wf->in_fill + n_samples;
@@ -717,7 +726,20 @@ int owrx_wf_feed(owrx_wf_t* wf, const float* iq, size_t n_samples)
         wf->d_in = nb; wf->d_in_alt = nullptr; wf->in_cap = cap;
         OWRX_CUDA(cudaMalloc((void**)&wf->d_in_alt, cap * sizeof(float2)));
     }
-    OWRX_CUDA(cudaMemcpyAsync(wf->d_in + wf->in_fill, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, wf->stream));
+    if (format == OWRX_IQ_CF32) {
+        OWRX_CUDA(cudaMemcpyAsync(wf->d_in + wf->in_fill, iq_raw, n_samples * sizeof(float2), cudaMemcpyHostToDevice, wf->stream));
+    } else {
+        // raw samples cross PCIe as they are; Convert (+ Gain) on the GPU (owrx/source/fifi_sdr.py:27-28)
+        if (n_samples * in_bytes > wf->raw_cap) {
+            OWRX_CUDA(cudaStreamSynchronize(wf->stream));
+            cudaFree(wf->d_raw); wf->d_raw = nullptr; wf->raw_cap = 0;
+            OWRX_CUDA(cudaMalloc((void**)&wf->d_raw, n_samples * in_bytes));
+            wf->raw_cap = n_samples * in_bytes;
+        }
+        OWRX_CUDA(cudaMemcpyAsync(wf->d_raw, iq_raw, n_samples * in_bytes, cudaMemcpyHostToDevice, wf->stream));
+        int rcc = iq_convert_launch(format, wf->d_raw, wf->d_in + wf->in_fill, n_samples, gain, wf->stream);
+        if (rcc != OWRX_OK) return rcc;
+    }
     wf->in_fill += n_samples;
     const size_t lines = wf_lines_for(wf, wf->in_fill);
     if (!lines) { OWRX_CUDA(cudaStreamSynchronize(wf->stream)); return OWRX_OK; }

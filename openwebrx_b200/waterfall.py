@@ -89,6 +89,14 @@ class Waterfall:
         N.check(N.lib.owrx_wf_feed(self._h, iq.ctypes.data_as(C.c_void_p), iq.size))
         return self.read()
 
+    def feed_raw(self, raw, fmt, gain=1.0):
+        """RAW source samples from host memory: fmt "cs16" (int16, interleaved I, Q) or "cu8" (uint8, offset binary); the
+        reference's CPU-side Convert (+ Gain) (owrx/source/fifi_sdr.py:27-28) runs on the GPU.  Returns completed lines."""
+        raw = np.ascontiguousarray(raw, dtype=np.int16 if fmt == "cs16" else np.uint8)
+        assert raw.size % 2 == 0
+        N.check(N.lib.owrx_wf_feed_fmt(self._h, raw.ctypes.data_as(C.c_void_p), raw.size // 2, N.IQ_FORMATS[fmt], float(gain)))
+        return self.read()
+
     def read(self):
         lb = self.line_bytes
         out = []

@@ -87,6 +87,8 @@ def lib():
         L.oc_agc_init.argtypes = [vp, i32, f32, f32]
         L.oc_agc_process.argtypes = [vp, vp, sz, vp]
         L.oc_convert_f_s16.argtypes = [vp, sz, vp]
+        L.oc_convert_s16_f.argtypes = [vp, sz, f32, vp]
+        L.oc_convert_u8_f.argtypes = [vp, sz, f32, vp]
         L.oc_adpcm_sync_encode.restype = sz; L.oc_adpcm_sync_encode.argtypes = [vp, sz, vp, sz]
         L.oc_client_chain_run.restype = i32
         L.oc_client_chain_run.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp]
@@ -309,6 +311,14 @@ def agc(x, profile=0, initial_gain=1.0, max_gain=65535.0):
     lib().oc_agc_init(C.byref(a), profile, initial_gain, max_gain)
     lib().oc_agc_process(C.byref(a), _p(x), len(x), _p(y))
     return y
+
+
+def convert_raw_iq(raw, fmt, gain=1.0):
+    """source-side Convert (+ Gain): raw int16 ("cs16") / uint8 ("cu8") interleaved I, Q -> complex64"""
+    raw = np.ascontiguousarray(raw, np.int16 if fmt == "cs16" else np.uint8)
+    out = np.empty(raw.size, np.float32)
+    (lib().oc_convert_s16_f if fmt == "cs16" else lib().oc_convert_u8_f)(_p(raw), raw.size, gain, _p(out))
+    return out.view(np.complex64)
 
 
 def convert_f_s16(x):

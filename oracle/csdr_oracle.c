@@ -658,6 +658,25 @@ void oc_agc_process(oc_agc* a, const float* x, size_t n, float* y)
     a->gain = gain; a->hang_counter = hang;
 }
 
+/* Convert(Format.COMPLEX_SHORT, Format.COMPLEX_FLOAT) [+ Gain(Format.COMPLEX_FLOAT, g)] — the source-side format conversion,
+ * owrx/source/fifi_sdr.py:27-28 wired by owrx/source/direct.py:59-71.  csdr: y = (float)x / SHRT_MAX.  n = number of REAL values. */
+void oc_convert_s16_f(const int16_t* x, size_t n, float gain, float* y)
+{
+    for (size_t i = 0; i < n; i++) {
+        float v = (float)x[i] / 32767.0f;
+        y[i] = gain != 1.0f ? v * gain : v;
+    }
+}
+
+/* Convert(Format.COMPLEX_CHAR / uint8 offset binary, ...): csdr  y = (float)x / (UCHAR_MAX / 2.0) - 1.0 */
+void oc_convert_u8_f(const uint8_t* x, size_t n, float gain, float* y)
+{
+    for (size_t i = 0; i < n; i++) {
+        float v = (float)x[i] / 127.5f - 1.0f;
+        y[i] = gain != 1.0f ? v * gain : v;
+    }
+}
+
 /* Convert(Format.FLOAT, Format.SHORT) — csdr/chain/clientaudio.py:12; SURVEY A.12 */
 void oc_convert_f_s16(const float* x, size_t n, int16_t* y)
 {

@@ -90,6 +90,8 @@ void oc_wfm_deemphasis(const float* x, size_t n, int sample_rate, double tau, fl
 typedef struct { float reference, attack, decay, max_gain, gain; int hang_time, hang_counter; } oc_agc;
 void oc_agc_init(oc_agc* a, int profile /*0 slow,1 fast*/, float initial_gain, float max_gain);
 void oc_agc_process(oc_agc* a, const float* x, size_t n, float* y);
+void oc_convert_s16_f(const int16_t* x, size_t n, float gain, float* y);   /* Convert(COMPLEX_SHORT -> COMPLEX_FLOAT) + Gain */
+void oc_convert_u8_f(const uint8_t* x, size_t n, float gain, float* y);     /* Convert(uint8 offset binary -> float) + Gain */
 void oc_convert_f_s16(const float* x, size_t n, int16_t* y);
 /* AdpcmEncoder(sync=True): csdr/chain/clientaudio.py:34; framing htdocs/lib/AudioEngine.js:449-491 */
 size_t oc_adpcm_sync_encode(const int16_t* s, size_t n, uint8_t* out, size_t cap);

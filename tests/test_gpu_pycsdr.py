@@ -170,3 +170,36 @@ def test_unmodified_reference_fftchain_on_gpu(gpu):
         sys.path.remove(REF)
         for k in [k for k in sys.modules if k == "csdr" or k.startswith("csdr.") or k == "owrx" or k.startswith("owrx.")]:
             sys.modules.pop(k)
+
+
+def test_raw_ingress_formats_equal_cpu_side_convert(gpu):
+    """int16 / uint8 source samples converted on the GPU (owrx_*_feed_fmt) give exactly what the reference's
+    CPU-side Convert (+ Gain) followed by the float path gives (owrx/source/fifi_sdr.py:27-28, owrx/source/direct.py:59-71)"""
+    import oracle
+    from openwebrx_b200 import ChannelBank, Waterfall, _native as N
+    from openwebrx_b200.synth import BANDPASS, carrier_plan, make_iq
+    fs = 2.4e6
+    cars = carrier_plan(3, fs, seed=51)
+    iq = make_iq(5333 + 200 * 1500 + 4099, fs, cars, seed=51)
+    for fmt, gain in (("cs16", 5.0), ("cu8", 1.0)):
+        f = iq.view(np.float32)
+        raw = (np.clip(f, -1, 1) * 30000).astype(np.int16) if fmt == "cs16" else (np.clip(f, -1, 1) * 120 + 127.5).astype(np.uint8)
+        as_float = oracle.convert_raw_iq(raw, fmt, gain)
+        outs = []
+        for use_raw in (True, False):
+            bank = ChannelBank(fs, outputs=N.OUT_IF | N.OUT_DEMOD)
+            chans = [bank.add_channel(12000, demod=c["kind"], offset=c["offset"], bandpass=BANDPASS[c["kind"]]) for c in cars]
+            cut = 2 * 123457                                   # ragged two-part feed (chunk boundaries inside the raw stream)
+            if use_raw:
+                bank.feed_raw(raw[:cut], fmt, gain); bank.feed_raw(raw[cut:], fmt, gain)
+            else:
+                bank.feed(as_float[:cut // 2]); bank.feed(as_float[cut // 2:])
+            outs.append([(c.read_if(), c.read_demod()) for c in chans])
+            bank.close()
+        for (a_if, a_dm), (b_if, b_dm) in zip(*outs):
+            assert len(a_if) == len(b_if) > 1000 and np.array_equal(a_if, b_if) and np.array_equal(a_dm, b_dm)
+        wf_a, wf_b = Waterfall(fs, 1024, 0.3, 60, "adpcm"), Waterfall(fs, 1024, 0.3, 60, "adpcm")
+        la, lb = wf_a.feed_raw(raw, fmt, gain), wf_b.feed(as_float)
+        assert len(la) == len(lb) >= 4 and all(x == y for x, y in zip(la, lb))
+    with pytest.raises(ValueError):
+        N.check(N.lib.owrx_bank_feed_fmt(ChannelBank(fs)._h, raw.ctypes.data, 10, 7, 1.0))

@@ -293,3 +293,15 @@ def test_wf_noise_filter_matches_float64_restatement():
         assert np.abs(got[l] - want).max() < 5e-3
     off = oracle.fftchain_run(iq, n, every_n, avg, compression="none")["db"]
     assert np.allclose(off[0] - got[0], -10 * np.log10(1 - a), atol=1e-3)
+
+
+def test_source_format_conversion_matches_csdr_convert():
+    # Convert(COMPLEX_SHORT -> COMPLEX_FLOAT) + Gain(5.0): owrx/source/fifi_sdr.py:27-28; csdr divides by SHRT_MAX / (UCHAR_MAX / 2)
+    rng = np.random.default_rng(4)
+    s16 = rng.integers(-32768, 32768, 2000, dtype=np.int16)
+    got = oracle.convert_raw_iq(s16, "cs16", 5.0).view(np.float32)
+    assert np.array_equal(got, (s16.astype(np.float32) / np.float32(32767.0)) * np.float32(5.0))
+    u8 = rng.integers(0, 256, 2000, dtype=np.uint8)
+    got = oracle.convert_raw_iq(u8, "cu8").view(np.float32)
+    assert np.array_equal(got, u8.astype(np.float32) / np.float32(127.5) - np.float32(1.0))
+    assert got.min() == -1.0 and got.max() == 1.0 and oracle.convert_raw_iq(np.array([32767, -32767], np.int16), "cs16")[0] == 1 - 1j
