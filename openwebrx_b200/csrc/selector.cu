@@ -1544,7 +1544,9 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
     OWRX_CUDA(cudaEventRecord(bank->ev0, st));
     // chunks of 2 M samples: the work left after the last H2D chunk (its FIR, low-rate stages and drain) stays short while a
     // chunk still spans 11+ overlap-save blocks; small feeds are a single chunk
-    static const size_t chunk = (size_t)1 << (getenv("OWRX_FEED_CHUNK_LOG2") ? std::max(16, std::min(26, atoi(getenv("OWRX_FEED_CHUNK_LOG2")))) : 21);
+    // (raw formats: the same 16 MB of PCIe traffic per chunk, i.e. 4 M int16 / 8 M uint8 samples)
+    static const size_t chunk_f32 = (size_t)1 << (getenv("OWRX_FEED_CHUNK_LOG2") ? std::max(16, std::min(26, atoi(getenv("OWRX_FEED_CHUNK_LOG2")))) : 21);
+    const size_t chunk = chunk_f32 * (sizeof(float2) / in_bytes);
     const size_t n_chunks = std::max<size_t>(1, (n_samples + chunk - 1) / chunk);
     while (bank->chunk_events.size() < n_chunks) {
         cudaEvent_t e;
