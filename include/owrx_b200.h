@@ -169,6 +169,15 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
 
 /* Streaming host path: one wideband block from HOST memory, shared by every channel. */
 int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples);
+/* Streaming mode.  By default owrx_bank_feed returns when the block's outputs are in the host queues.  With deferred drain
+ * enabled a feed only enqueues its work (uploads, kernels) and returns; the block's outputs reach the queues at the start of
+ * the NEXT feed — after that feed's uploads have been queued behind this one's, so PCIe never idles and the kernel tail,
+ * D2H and queue hand-over of block i run under the upload of block i+1 — or when owrx_bank_flush is called.  Outputs,
+ * state and order are identical to the synchronous mode (tests/test_gpu_selector.py::test_deferred_drain_...).
+ * The host buffer passed to a feed must stay valid until the next feed / flush returns.  Calls that reconfigure the bank
+ * (add / remove channel, owrx_chan_set_*) complete a pending feed first. */
+int owrx_bank_set_deferred_drain(owrx_bank_t* bank, int enable);
+int owrx_bank_flush(owrx_bank_t* bank);
 /* the same for raw OWRX_IQ_CS16 / OWRX_IQ_CU8 samples (Convert + Gain on the GPU, half / a quarter of the PCIe bytes) */
 int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq, size_t n_samples, int format, float gain);
 /* Pop queued outputs of one channel (float32 audio after AGC / pre-AGC demod / complex IF). */

@@ -76,6 +76,8 @@ SIGNATURES = {
     "owrx_chan_set_demod": (_i, [_vp, _i, _i, _d, _d, _i]),
     "owrx_bank_feed": (_i, [_vp, _vp, _sz]),
     "owrx_bank_feed_fmt": (_i, [_vp, _vp, _sz, _i, _f]),
+    "owrx_bank_set_deferred_drain": (_i, [_vp, _i]),
+    "owrx_bank_flush": (_i, [_vp]),
     "owrx_chan_read_audio": (_i, [_vp, _i, _vp, _sz, _psz]),
     "owrx_chan_read_demod": (_i, [_vp, _i, _vp, _sz, _psz]),
     "owrx_chan_read_if": (_i, [_vp, _i, _vp, _sz, _psz]),

@@ -155,6 +155,14 @@ class ChannelBank:
         assert raw.size % 2 == 0
         N.check(N.lib.owrx_bank_feed_fmt(self._h, raw.ctypes.data_as(C.c_void_p), raw.size // 2, N.IQ_FORMATS[fmt], float(gain)))
 
+    def set_deferred_drain(self, enable=True):
+        """streaming mode: feed() only enqueues (uploads + kernels) and returns; the block's outputs reach the queues at the start
+        of the next feed (behind its uploads) or at flush().  The fed host buffer must stay valid until then."""
+        N.check(N.lib.owrx_bank_set_deferred_drain(self._h, 1 if enable else 0))
+
+    def flush(self):
+        N.check(N.lib.owrx_bank_flush(self._h))
+
     def process_device(self, iq_dev, n_samples, stream=None):
         N.check(N.lib.owrx_bank_process_device(self._h, _ptr(iq_dev), n_samples, _ptr(stream)))
 

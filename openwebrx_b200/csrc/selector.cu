@@ -291,6 +291,10 @@ struct owrx_bank {
     uint64_t prof_launches[OWRX_PROF_KINDS] = {};
     int fir_mode = OWRX_FIR_AUTO, bp_mode = OWRX_FIR_AUTO;
     unsigned char* d_raw = nullptr; size_t raw_cap = 0;   // staging for raw (non-float) ingress chunks (owrx_bank_feed_fmt)
+    // deferred drain (owrx_bank_set_deferred_drain): a feed returns once its work is enqueued; its last outputs reach the
+    // host queues at the start of the next feed — after that feed's uploads are under way — or in owrx_bank_flush
+    bool deferred = false, pending_final = false;
+    cudaEvent_t carry_done = nullptr;
     int fir_form_used = 0;                           // form of the latest Shift + FirDecimate pass (owrx_bank_fir_form)
 };
 
@@ -1195,6 +1199,9 @@ int pop_queue(FQ& q, float* out, size_t cap, size_t* n, size_t unit)
 
 extern "C" {
 
+// deferred-drain mode (owrx_bank_set_deferred_drain): every call that reconfigures the bank first completes the pending feed
+static int finish_pending(owrx_bank* bank);
+
 int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
 {
     if (!out) return fail(OWRX_E_INVALID, "out is NULL");
@@ -1218,6 +1225,7 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fir_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->carry_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->dev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->tail_done[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->tail_done[1], cudaEventDisableTiming);
@@ -1233,6 +1241,7 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     cudaDeviceSynchronize();
     for (auto& g : bank->groups) if (g) group_release(g.get());
     cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]); cudaFree(bank->d_xpose); cudaFree(bank->d_raw);
+    if (bank->carry_done) cudaEventDestroy(bank->carry_done);
     for (cudaEvent_t e : bank->chunk_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->fir_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->drain_events) cudaEventDestroy(e);
@@ -1258,6 +1267,7 @@ static int add_channel_spec(owrx_bank_t* bank, const owrx_chan_spec_t& sp, int* 
 {
     std::lock_guard<std::mutex> lk(bank->mu);
     OWRX_CUDA(cudaSetDevice(bank->device));
+    if (bank->pending_final) { int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     int gi = find_group(bank, sp), rc;
     if (gi < 0 && (rc = group_create(bank, sp, &gi)) != OWRX_OK) return rc;
     Group* g = bank->groups[(size_t)gi].get();
@@ -1291,6 +1301,7 @@ int owrx_bank_remove_channel(owrx_bank_t* bank, int chan)
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     if (ch->group >= 0) {
         Group* g = bank->groups[(size_t)ch->group].get();
         g->slot_chan[(size_t)ch->slot] = -1;
@@ -1317,6 +1328,7 @@ int owrx_chan_set_shift_rate(owrx_bank_t* bank, int chan, double rate)
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     ch->rate = rate;
     return OWRX_OK;
 }
@@ -1326,6 +1338,7 @@ int owrx_chan_set_bandpass(owrx_bank_t* bank, int chan, double lo_rate, double h
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     ch->bp_enabled = enabled != 0; ch->bp_lo = lo_rate; ch->bp_hi = hi_rate;
     return upload_bandpass(bank, ch);
@@ -1336,6 +1349,7 @@ int owrx_chan_set_squelch_level(owrx_bank_t* bank, int chan, float level)
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     ch->cfg.sq_level = level;
     Group* g = bank->groups[(size_t)ch->group].get();
     g->h_cfg[(size_t)ch->slot] = ch->cfg;
@@ -1349,6 +1363,7 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     if (kind < OWRX_DEMOD_NFM || kind > OWRX_DEMOD_NONE) return fail(OWRX_E_INVALID, "unknown demodulator %d", kind);
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     Group* g = bank->groups[(size_t)ch->group].get();
     const float level = ch->cfg.sq_level;
@@ -1397,6 +1412,7 @@ int owrx_chan_set_agc(owrx_bank_t* bank, int chan, int profile, float initial_ga
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     Group* g = bank->groups[(size_t)ch->group].get();
     ch->cfg.agc_decay = profile == OWRX_AGC_FAST ? 0.001f : 0.0001f;
@@ -1421,6 +1437,7 @@ int owrx_chan_set_audio_format(owrx_bank_t* bank, int chan, int format)
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     if (format != OWRX_AUDIO_F32 && format != OWRX_AUDIO_S16 && format != OWRX_AUDIO_ADPCM) return fail(OWRX_E_INVALID, "unknown audio format %d", format);
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     Group* g = bank->groups[(size_t)ch->group].get();
     if (format != ch->audio_fmt) {
@@ -1452,6 +1469,7 @@ int owrx_bank_set_outputs(owrx_bank_t* bank, int mask)
 {
     if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     bank->out_mask = mask;
     return OWRX_OK;
 }
@@ -1496,6 +1514,21 @@ static int group_drain(owrx_bank* bank, Group* g, cudaStream_t ds, const DrainMa
     return OWRX_OK;
 }
 
+// deferred-drain mode: move the last outputs of the previous feed into the host queues (waits for that feed's kernels)
+static int finish_pending(owrx_bank* bank)
+{
+    if (!bank->pending_final) return OWRX_OK;
+    int rc;
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (g && (rc = group_drain(bank, g, bank->stream, DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks}, true)) != OWRX_OK)
+            return rc;
+    }
+    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    bank->pending_final = false;
+    return OWRX_OK;
+}
+
 // Host path.  The block is uploaded in chunks on a copy stream; the K3 pass of chunk c runs while chunk
 // c+1 is still crossing PCIe.  The low-rate stages run once over everything the chunks produced.
 int owrx_bank_feed(owrx_bank_t* bank, const float* iq, size_t n_samples)
@@ -1521,6 +1554,10 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
     for (auto& g : bank->groups) if (g) any = true;
     if (!any) return OWRX_OK;                         // nobody listening: samples are dropped like an unread ring
     const size_t need = bank->iq_fill + n_samples;
+    int rc;
+    if (need > bank->iq_cap || (format != OWRX_IQ_CF32 && n_samples * in_bytes > bank->raw_cap)) {
+        if ((rc = finish_pending(bank)) != OWRX_OK) return rc;       // reallocation below synchronises: nothing to overlap with
+    }
     if (need > bank->iq_cap) {
         const size_t cap = std::max(need, bank->iq_cap * 2);
         for (int b = 0; b < 2; b++) {
@@ -1553,9 +1590,9 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
         OWRX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         bank->chunk_events.push_back(e);
     }
-    // the copy stream must not overwrite the buffer before earlier work on `st` (carry copy) is done
-    OWRX_CUDA(cudaEventRecord(bank->fir_done, st));
-    OWRX_CUDA(cudaStreamWaitEvent(bank->copy_stream, bank->fir_done, 0));
+    // the copy stream must not write the buffer before the previous feed's carry copy into it is done (that copy follows the
+    // previous feed's last FirDecimate pass on `st`; the low-rate stages of that feed do not touch the wideband buffers)
+    OWRX_CUDA(cudaStreamWaitEvent(bank->copy_stream, bank->carry_done, 0));
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t o = c * chunk, len = std::min(chunk, n_samples - o);
         if (len && format == OWRX_IQ_CF32) {
@@ -1571,7 +1608,8 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
         }
         OWRX_CUDA(cudaEventRecord(bank->chunk_events[c], bank->copy_stream));
     }
-    int rc;
+    // deferred drain: the previous feed's last outputs go to the host queues now, while this feed's chunks cross PCIe
+    if ((rc = finish_pending(bank)) != OWRX_OK) return rc;
     const size_t fill0 = bank->iq_fill;
     // with several chunks the low-rate stages of chunk c run on the side stream beside the K3 pass of chunk c+1
     const bool overlap = n_chunks > 1;
@@ -1630,7 +1668,9 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
                 Group* g = gp.get();
                 marks[c].push_back(g ? DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks} : DrainMark{0, 0, 0, 0});
             }
-            if (c >= 1) {
+            // (deferred drain: the host does not wait inside a feed at all — every output of the block moves at the start of
+            // the next feed, so that feed's uploads queue right behind this one's and PCIe never idles)
+            if (c >= 1 && !bank->deferred) {
                 OWRX_CUDA(cudaStreamWaitEvent(bank->drain_stream, bank->drain_events[c - 1], 0));
                 for (size_t gi = 0; gi < bank->groups.size(); gi++)
                     if (bank->groups[gi] && (rc = group_drain(bank, bank->groups[gi].get(), bank->drain_stream, marks[c - 1][gi], false)) != OWRX_OK) return rc;
@@ -1638,22 +1678,10 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
         }
     }
     bank->reserve_sm = false;
-    if (overlap) {
-        OWRX_CUDA(cudaEventRecord(bank->fir_done, tails));
-        OWRX_CUDA(cudaStreamWaitEvent(st, bank->fir_done, 0));
-    }
+    // drop consumed wideband samples: the carry moves to the other buffer right behind the last FirDecimate pass on `st`
     bank->iq_fill += n_samples;
     size_t min_off = bank->iq_fill;
     for (auto& gp : bank->groups) if (gp) min_off = std::min(min_off, gp->in_off);
-    OWRX_CUDA(cudaEventRecord(bank->ev1, st));
-    lap("launched");
-    if (trace) { cudaStreamSynchronize(st); lap("gpu done"); }
-    for (auto& gp : bank->groups) {
-        Group* g = gp.get();
-        if (g && (rc = group_drain(bank, g, st, DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks}, true)) != OWRX_OK) return rc;
-    }
-    lap("drained");
-    // drop consumed wideband samples
     if (min_off > 0) {
         const size_t tail = bank->iq_fill - min_off;
         if (tail) OWRX_CUDA(cudaMemcpyAsync(bank->d_iq[bank->iq_cur ^ 1], buf + min_off, tail * sizeof(float2), cudaMemcpyDeviceToDevice, st));
@@ -1661,12 +1689,47 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
         bank->iq_fill = tail;
         for (auto& gp : bank->groups) if (gp) gp->in_off -= min_off;
     }
+    OWRX_CUDA(cudaEventRecord(bank->carry_done, st));
+    if (overlap) {
+        OWRX_CUDA(cudaEventRecord(bank->fir_done, tails));
+        OWRX_CUDA(cudaStreamWaitEvent(st, bank->fir_done, 0));
+    }
+    OWRX_CUDA(cudaEventRecord(bank->ev1, st));
+    lap("launched");
+    bank->stats.input_samples += n_samples;
+    if (bank->deferred) {
+        bank->pending_final = true;                   // drained by the next feed (behind its uploads) or owrx_bank_flush
+        return OWRX_OK;
+    }
+    if (trace) { cudaStreamSynchronize(st); lap("gpu done"); }
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (g && (rc = group_drain(bank, g, st, DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks}, true)) != OWRX_OK) return rc;
+    }
+    lap("drained");
     OWRX_CUDA(cudaStreamSynchronize(st));
     lap("end");
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, bank->ev0, bank->ev1) == cudaSuccess) bank->stats.device_ms += ms;
-    bank->stats.input_samples += n_samples;
     return OWRX_OK;
+}
+
+int owrx_bank_set_deferred_drain(owrx_bank_t* bank, int enable)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    int rc = finish_pending(bank);
+    bank->deferred = enable != 0;
+    return rc;
+}
+
+int owrx_bank_flush(owrx_bank_t* bank)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    return finish_pending(bank);
 }
 
 // Device-resident path.  With owrx_bank_set_pipelined(bank, 1) every stage after FirDecimate of block i runs on the
@@ -1676,6 +1739,7 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
 {
     if (!bank || !iq_dev) return fail(OWRX_E_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     cudaStream_t sa = stream ? (cudaStream_t)stream : bank->stream;
     cudaStream_t sb = bank->pipelined ? bank->side_stream : sa;
@@ -1738,6 +1802,7 @@ int owrx_bank_drain(owrx_bank_t* bank)
 {
     if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
     std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     cudaStream_t st = bank->stream;
     OWRX_CUDA(cudaStreamWaitEvent(st, bank->dev_done, 0));

@@ -341,3 +341,44 @@ def test_read_audio_all_equals_per_channel_reads(gpu):
         bank.close()
     for a, b in zip(per_chan, batched):
         assert len(a) == len(b) > 1000 and np.array_equal(a, b)
+
+
+def test_deferred_drain_streams_the_same_outputs(gpu):
+    # streaming mode (owrx_bank_set_deferred_drain): a feed returns before its last outputs are drained; they arrive with the
+    # next feed or flush().  Everything popped in total must equal the synchronous mode bit for bit, including a retune and
+    # a new client between feeds (reconfiguration completes the pending feed first) and ADPCM client audio bytes.
+    fs, out = 2.4e6, 12000
+    cars = carrier_plan(4, fs, seed=61)
+    n = 5333 + 200 * 6000
+    iq = make_iq(n, fs, cars, seed=61)
+    cuts = [0, 400_003, 400_003 + 2_200_000 // 3, 900_001, n]
+    got = {}
+    for deferred in (False, True):
+        bank, chans = _setup(fs, out, cars, 4, outputs=N.OUT_AUDIO | N.OUT_IF)
+        chans[3][0].setAudioFormat("adpcm")
+        bank.set_deferred_drain(deferred)
+        audio = [[] for _ in range(5)]
+        if_ = [[] for _ in range(5)]
+        raw = []
+        extra = None
+        for k in range(len(cuts) - 1):
+            bank.feed(iq[cuts[k]:cuts[k + 1]])
+            if k == 1:
+                chans[1][0].setFrequencyOffset(cars[2]["offset"] + 777)
+                extra = bank.add_channel(out, demod="usb", offset=cars[0]["offset"] + 300, bandpass=BANDPASS["usb"])
+            allch = [c for c, _ in chans] + ([extra] if extra is not None else [])
+            for i, c in enumerate(allch):
+                audio[i].append(c.read_audio()); if_[i].append(c.read_if())
+            raw.append(chans[3][0].read_bytes())
+        bank.flush()
+        allch = [c for c, _ in chans] + [extra]
+        for i, c in enumerate(allch):
+            audio[i].append(c.read_audio()); if_[i].append(c.read_if())
+        raw.append(chans[3][0].read_bytes())
+        got[deferred] = ([np.concatenate(a) for a in audio], [np.concatenate(a) for a in if_], b"".join(bytes(r) for r in raw))
+        bank.close()
+    for i in range(5):
+        assert len(got[True][0][i]) == len(got[False][0][i]) and len(got[True][1][i]) == len(got[False][1][i]) > 0
+        assert np.array_equal(got[True][0][i], got[False][0][i]), i
+        assert np.array_equal(got[True][1][i], got[False][1][i]), i
+    assert got[True][2] == got[False][2] and len(got[True][2]) > 1000
