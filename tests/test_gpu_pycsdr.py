@@ -203,3 +203,44 @@ def test_raw_ingress_formats_equal_cpu_side_convert(gpu):
         assert len(la) == len(lb) >= 4 and all(x == y for x, y in zip(la, lb))
     with pytest.raises(ValueError):
         N.check(N.lib.owrx_bank_feed_fmt(ChannelBank(fs)._h, raw.ctypes.data, 10, 7, 1.0))
+
+
+def test_f3_resampler_and_secondary_fft_shapes(gpu):
+    """the same kernels at the reference's secondary shapes.
+    (a) Resampler for background services (owrx/source/resampler.py:11-24): Chain([Shift(shift), FirDecimate(decimation,
+        0.15 * if_rate / samp_rate)]) producing COMPLEX_FLOAT at the service rate — here 2.4 MS/s -> 48 kHz (D = 50), checked
+        stage by stage against the oracle's Shift and FirDecimate;
+    (b) secondary FFT on the selector output (owrx/dsp.py:220-225): 2048 points at 12 kHz, 9 fps -> LogAveragePower with avg 1."""
+    import oracle
+    from openwebrx_b200 import ChannelBank, Waterfall, _native as N, fftchain_params
+    from openwebrx_b200.synth import carrier_plan, make_iq
+    fs, rate = 2.4e6, 48000.0
+    cars = carrier_plan(3, fs, seed=71)
+    D = int(fs / rate)
+    tr = 0.15 * (fs / D) / fs
+    taps = oracle.firdes_lowpass(oracle.filter_len(tr), 0.5 / D)
+    iq = make_iq(len(taps) + D * 3000, fs, cars, seed=71)
+    bank = ChannelBank(fs, outputs=N.OUT_IF)
+    chans = [bank.add_channel(rate, demod="none", offset=c["offset"]) for c in cars]      # no Bandpass, Squelch open
+    bank.feed(iq)
+    for ch, c in zip(chans, cars):
+        want = oracle.fir_decimate(oracle.shift(iq, -c["offset"] / fs), taps, D)
+        got = ch.read_if()
+        assert len(got) == len(want) == 3001
+        err = np.sqrt(np.mean(np.abs(got - want) ** 2)) / np.sqrt(np.mean(np.abs(want) ** 2))
+        assert err <= 1e-4, err
+    bank.close()
+    # (b) the selector output of a 12 kHz client feeds a 2048-point FftChain
+    avg, every_n = fftchain_params(12000, 2048, 0.3, 9)
+    assert (avg, every_n) == (1, 1333)
+    rng = np.random.default_rng(72)
+    x = (rng.standard_normal(every_n * 6 + 2048) + 1j * rng.standard_normal(every_n * 6 + 2048)).astype(np.complex64) * 0.05
+    x += (0.3 * np.exp(2j * np.pi * 0.11 * np.arange(len(x)))).astype(np.complex64)
+    ref = oracle.fftchain_run(x, 2048, every_n, avg)
+    wf = Waterfall(12000, 2048, 0.3, 9, "adpcm")
+    lines = wf.feed(x)
+    assert len(lines) == len(ref["lines"]) == 7
+    for l, want in zip(lines, ref["lines"]):
+        got_db = oracle.ima_adpcm_decode(np.frombuffer(l, np.uint8))[10:].astype(np.int32)
+        want_db = oracle.ima_adpcm_decode(np.ascontiguousarray(want))[10:].astype(np.int32)
+        assert np.abs(got_db - want_db).max() <= 300        # 1/100 dB units through the lossy codec: a few quantiser steps
