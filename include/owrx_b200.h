@@ -66,6 +66,12 @@ int owrx_wf_create(int device, int fft_size, int every_n_samples, int avg_number
                    int compression, owrx_wf_t** out);
 void owrx_wf_destroy(owrx_wf_t* wf);
 int owrx_wf_feed_fmt(owrx_wf_t* wf, const void* iq, size_t n_samples, int format, float gain);   /* owrx_wf_feed for OWRX_IQ_* input */
+/* Websocket framing of the outputs (owrx/connection.py:473-481): one message = a 1-byte type prefix + payload.
+ * owrx_wf_read_message pops ONE waterfall line as 0x01 + line (write_spectrum_data); owrx_chan_read_message pops the
+ * queued client-audio bytes (owrx_chan_set_audio_format S16 / ADPCM) as type_byte + data with type_byte 0x02
+ * (write_dsp_data) or 0x04 (write_hd_audio).  *n = 0 when nothing is queued.  The S-meter message is JSON built by the
+ * host from owrx_chan_read_power (write_s_meter_level, :483-489). */
+int owrx_wf_read_message(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes);
 int owrx_wf_set_every_n_samples(owrx_wf_t* wf, int every_n_samples);   /* Fft.setEveryNSamples, csdr/chain/fft.py:55 */
 int owrx_wf_set_avg_number(owrx_wf_t* wf, int avg_number);             /* FftAverager.setFftAverages, csdr/chain/fft.py:12-16 */
 int owrx_wf_set_compression(owrx_wf_t* wf, int compression);           /* FftChain.setCompression, csdr/chain/fft.py:87-96 */
@@ -199,6 +205,8 @@ int owrx_chan_read_power(owrx_bank_t* bank, int chan, float* out, size_t cap, si
 #define OWRX_AUDIO_ADPCM 2
 int owrx_chan_set_audio_format(owrx_bank_t* bank, int chan, int format);
 int owrx_chan_read_bytes(owrx_bank_t* bank, int chan, void* out, size_t cap_bytes, size_t* n);
+/* the same bytes as one websocket message: type_byte (0x02 audio / 0x04 HD audio) + data; see owrx_wf_read_message */
+int owrx_chan_read_message(owrx_bank_t* bank, int chan, int type_byte, void* out, size_t cap_bytes, size_t* n);
 /* which optional outputs are materialised for the host (bitmask of OWRX_OUT_*; default AUDIO) */
 #define OWRX_OUT_AUDIO 1
 #define OWRX_OUT_DEMOD 2

@@ -57,6 +57,8 @@ SIGNATURES = {
     "owrx_wf_line_bytes": (_sz, [_vp]),
     "owrx_wf_feed": (_i, [_vp, _vp, _sz]),
     "owrx_wf_feed_fmt": (_i, [_vp, _vp, _sz, _i, _f]),
+    "owrx_wf_read_message": (_i, [_vp, _vp, _sz, _psz]),
+    "owrx_chan_read_message": (_i, [_vp, _i, _i, _vp, _sz, _psz]),
     "owrx_wf_read": (_i, [_vp, _vp, _sz, _psz]),
     "owrx_wf_process_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _psz, _vp]),
     "owrx_wf_lines_for": (_sz, [_vp, _sz]),

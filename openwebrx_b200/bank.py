@@ -69,6 +69,14 @@ class Channel:
         code = {"f32": N.AUDIO_F32, "s16": N.AUDIO_S16, "adpcm": N.AUDIO_ADPCM}[fmt]
         N.check(N.lib.owrx_chan_set_audio_format(self.bank._h, self.id, code))
 
+    def read_message(self, hd=False, cap=1 << 16):
+        """queued client-audio bytes as one websocket message: b"\x02" + data (write_dsp_data) or b"\x04" + data
+        (write_hd_audio), owrx/connection.py:477-481; None when nothing is queued"""
+        buf = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        N.check(N.lib.owrx_chan_read_message(self.bank._h, self.id, 0x04 if hd else 0x02, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n)))
+        return buf[:n.value].tobytes() if n.value else None
+
     def read_bytes(self):
         chunks = []
         buf = np.empty(1 << 16, np.uint8)

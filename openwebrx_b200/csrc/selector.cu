@@ -1465,6 +1465,23 @@ int owrx_chan_read_bytes(owrx_bank_t* bank, int chan, void* out, size_t cap_byte
     return OWRX_OK;
 }
 
+int owrx_chan_read_message(owrx_bank_t* bank, int chan, int type_byte, void* out, size_t cap_bytes, size_t* n)
+{
+    Chan* ch = get_chan(bank, chan);
+    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (type_byte != 0x02 && type_byte != 0x04) return fail(OWRX_E_INVALID, "message type must be 0x02 (audio) or 0x04 (HD audio)");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    *n = 0;
+    if (ch->q_bytes.empty() || cap_bytes < 2) return OWRX_OK;
+    const size_t take = std::min(cap_bytes - 1, ch->q_bytes.size());
+    uint8_t* o = (uint8_t*)out;
+    o[0] = (uint8_t)type_byte;                                 // write_dsp_data / write_hd_audio (owrx/connection.py:477-481)
+    memcpy(o + 1, ch->q_bytes.data(), take);
+    ch->q_bytes.erase(ch->q_bytes.begin(), ch->q_bytes.begin() + (ptrdiff_t)take);
+    *n = take + 1;
+    return OWRX_OK;
+}
+
 int owrx_bank_set_outputs(owrx_bank_t* bank, int mask)
 {
     if (!bank) return fail(OWRX_E_INVALID, "NULL bank");

@@ -791,6 +791,22 @@ int owrx_wf_read(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes)
     return OWRX_OK;
 }
 
+int owrx_wf_read_message(owrx_wf_t* wf, void* out, size_t cap_bytes, size_t* n_bytes)
+{
+    if (!wf || !out || !n_bytes) return fail(OWRX_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(wf->mu);
+    *n_bytes = 0;
+    if (wf->queue.empty()) return OWRX_OK;
+    const size_t len = wf->queue.front().size();
+    if (len + 1 > cap_bytes) return fail(OWRX_E_OVERFLOW, "buffer smaller than one framed line (%zu bytes)", len + 1);
+    uint8_t* o = (uint8_t*)out;
+    o[0] = 0x01;                                               // write_spectrum_data: bytes([0x01]) + data (owrx/connection.py:473-475)
+    memcpy(o + 1, wf->queue.front().data(), len);
+    wf->queue.pop_front();
+    *n_bytes = len + 1;
+    return OWRX_OK;
+}
+
 int owrx_wf_set_pipelined(owrx_wf_t* wf, int enable)
 {
     if (!wf) return fail(OWRX_E_INVALID, "NULL waterfall");

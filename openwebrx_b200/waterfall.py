@@ -97,6 +97,17 @@ class Waterfall:
         N.check(N.lib.owrx_wf_feed_fmt(self._h, raw.ctypes.data_as(C.c_void_p), raw.size // 2, N.IQ_FORMATS[fmt], float(gain)))
         return self.read()
 
+    def read_messages(self):
+        """completed lines as websocket messages: b"\x01" + line each (write_spectrum_data, owrx/connection.py:473-475)"""
+        out = []
+        buf = np.empty(self.line_bytes + 1, np.uint8)
+        while True:
+            n = C.c_size_t()
+            N.check(N.lib.owrx_wf_read_message(self._h, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n)))
+            if n.value == 0:
+                return out
+            out.append(buf[:n.value].tobytes())
+
     def read(self):
         lb = self.line_bytes
         out = []

@@ -244,3 +244,33 @@ def test_f3_resampler_and_secondary_fft_shapes(gpu):
         got_db = oracle.ima_adpcm_decode(np.frombuffer(l, np.uint8))[10:].astype(np.int32)
         want_db = oracle.ima_adpcm_decode(np.ascontiguousarray(want))[10:].astype(np.int32)
         assert np.abs(got_db - want_db).max() <= 300        # 1/100 dB units through the lossy codec: a few quantiser steps
+
+
+def test_f2_websocket_message_framing(gpu):
+    """outputs leave as websocket messages — a 1-byte type prefix + payload (owrx/connection.py:473-481)"""
+    from openwebrx_b200 import ChannelBank, Waterfall
+    from openwebrx_b200.synth import BANDPASS, carrier_plan, make_iq
+    fs = 2.4e6
+    cars = carrier_plan(2, fs, seed=81)
+    iq = make_iq(5333 + 200 * 3000 + 5000, fs, cars, seed=81)
+    wf_a, wf_b = Waterfall(fs, 1024, 0.3, 60, "adpcm"), Waterfall(fs, 1024, 0.3, 60, "adpcm")
+    plain = wf_a.feed(iq)
+    N.check(N.lib.owrx_wf_feed(wf_b._h, iq.ctypes.data, iq.size))
+    msgs = wf_b.read_messages()
+    assert len(msgs) == len(plain) >= 4 and all(m == b"\x01" + l for m, l in zip(msgs, plain))
+    out = {}
+    for framed in (False, True):
+        bank = ChannelBank(fs)
+        ch = bank.add_channel(12000, demod="nfm", offset=cars[0]["offset"], bandpass=BANDPASS["nfm"])
+        ch.setAudioFormat("adpcm")
+        bank.feed(iq)
+        if framed:
+            m = ch.read_message(cap=1 << 20)
+            assert m[:1] == b"\x02" and ch.read_message() is None
+            out[framed] = m[1:]
+        else:
+            out[framed] = bytes(ch.read_bytes())
+        bank.close()
+    assert out[True] == out[False] and out[True][:4] == b"SYNC"
+    with pytest.raises(ValueError):
+        N.check(N.lib.owrx_chan_read_message(ChannelBank(fs)._h, 0, 3, iq.ctypes.data, 10, None))
