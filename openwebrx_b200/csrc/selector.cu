@@ -740,10 +740,11 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
 
     const bool fastconv = g->fc_ok && bank->fir_mode != OWRX_FIR_DIRECT && (bank->fir_mode >= OWRX_FIR_FASTCONV || n_k >= 64);
     if (fastconv) {
-        // contraction on the tensor cores once a pass holds enough overlap-save blocks: below ~16 rows the FP32-pipe kernel,
-        // whose table is 8 instead of 12 bytes per entry, is bound by the same table read and moves fewer bytes
+        // contraction on the tensor cores once a pass holds enough overlap-save blocks: below ~12 rows the FP32-pipe kernel,
+        // whose table is 8 instead of 12 bytes per entry, is bound by the same table read and moves fewer bytes; from there
+        // on its FMA time (8 M B Dp S FLOP at ~35 TFLOP/s) exceeds the tensor-core form's byte time (12 M Dp (B + S) at ~5 TB/s)
         const size_t fc_blocks = (n_k + (size_t)g->fc.Kb - 1) / (size_t)g->fc.Kb;
-        const bool tc = bank->fir_mode == OWRX_FIR_FASTCONV_TC || (bank->fir_mode == OWRX_FIR_AUTO && fc_blocks >= 16);
+        const bool tc = bank->fir_mode == OWRX_FIR_FASTCONV_TC || (bank->fir_mode == OWRX_FIR_AUTO && fc_blocks >= 12);
         bank->fir_form_used = tc ? OWRX_FIR_FASTCONV_TC : OWRX_FIR_FASTCONV;
         if ((rc = g->s1.ensure_new(n_k, st)) != OWRX_OK) return rc;
         if ((rc = group_fir_fastconv(bank, g, iq, n_avail, n_k, st, tc)) != OWRX_OK) return rc;
