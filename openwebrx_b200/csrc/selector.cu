@@ -1024,7 +1024,13 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
                 OWRX_CUDA(cudaMemcpyAsync(g->f3.append_ptr(), g->f2.rows(g->f2.fill - n_audio), n_audio * (size_t)S * sizeof(float),
                                           cudaMemcpyDeviceToDevice, st));
             } else {
-                agc_kernel<<<S / AGC_CH, AGC_TL, 0, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+                // The Agc is a latency-bound dependent chain (one warp per channel): every cycle another kernel's warps take
+                // on its scheduler stretches it.  Its CTAs therefore claim 100 KB of dynamic shared memory they do not use, so
+                // that no 177 KB contraction CTA and at most one 68 KB FFT CTA can share their SM (measured inside the
+                // three-stream pipeline, C2: Agc stage 0.32 -> 0.26 ms, step 0.34 -> 0.32 ms).  OWRX_AGC_PAD_KB overrides.
+                static const int agc_pad = (getenv("OWRX_AGC_PAD_KB") ? atoi(getenv("OWRX_AGC_PAD_KB")) : 100) << 10;
+                if (agc_pad) OWRX_CUDA(cudaFuncSetAttribute(agc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, agc_pad));
+                agc_kernel<<<S / AGC_CH, AGC_TL, agc_pad, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
                                                            g->f3.append_ptr());
                 OWRX_LAUNCH_CHECK();
             }

@@ -636,12 +636,86 @@ struct AgcWarp {
     float gain, dn, up, thr, gmax;
     int hang, hang_time;
     // v[e] = sample 4*lane + e of the step; returns the outputs in place.  U: per-warp scratch of 132 floats.
+    // The same step when every one of the 128 samples is non-zero (the usual case: audio is exactly 0 only behind a closed
+    // squelch).  The "how many live / rising samples precede me" counts of the general path are then plain index
+    // arithmetic — sample j of the step (pending from j0) has j - j0 live samples before it, is a rising step iff
+    // j - j0 >= hang, and has max(j - j0 - hang, 0) rising steps before it — so the eight ballots per pass go away, and the
+    // chain values are stored four at a time.  Ud[k + 3] = U[k] (so that k = 1, 5, 9, ... are 16-byte aligned).
+    __device__ __forceinline__ void step_dense(float (&v)[AGC_E], int lane, float* Ud)
+    {
+        const unsigned full = 0xffffffffu;
+        float o[AGC_E];
+        int j0 = 0;
+        while (true) {
+            const int R = max(32 * AGC_E - j0 - hang, 0);                   // rising steps among the pending samples
+            float u = gain;
+            Ud[3] = u;
+            int k = 1;
+            for (; k + 3 <= R; k += 4) {
+                const float a = u * up, b = a * up, c = b * up, d = c * up;
+                *reinterpret_cast<float4*>(&Ud[k + 3]) = make_float4(a, b, c, d);
+                u = d;
+            }
+            for (; k <= R; k++) {
+                u *= up;
+                Ud[k + 3] = u;
+            }
+            __syncwarp();
+            float gb[AGC_E], ga[AGC_E];
+            unsigned att = 0, pend = 0;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) {
+                const int d = AGC_E * lane + e - j0;                        // live samples before this one (if pending)
+                const int rb = max(d - hang, 0);
+                const int is_rise = d >= hang ? 1 : 0;
+                const int idx = max(rb, 0);
+                gb[e] = fminf(Ud[idx + 3], gmax);
+                ga[e] = fminf(Ud[idx + is_rise + 3], gmax);
+                const bool p = d >= 0;
+                pend |= (p ? 1u : 0u) << e;
+                att |= (p && fabsf(v[e]) * gb[e] > thr ? 1u : 0u) << e;
+            }
+            __syncwarp();
+            const unsigned am = __ballot_sync(full, att != 0u);
+            if (am == 0u) {
+#pragma unroll
+                for (int e = 0; e < AGC_E; e++)
+                    if ((pend >> e) & 1u) o[e] = fminf(1.f, fmaxf(-1.f, v[e] * ga[e]));
+                gain = fminf(u, gmax);
+                hang = max(hang - (32 * AGC_E - j0), 0);
+                break;
+            }
+            const int L = __ffs(am) - 1;
+            const int ef = __ffs(att) - 1;
+            const float gsel = ef == 0 ? gb[0] : (ef == 1 ? gb[1] : (ef == 2 ? gb[2] : gb[3]));
+            const int e_first = __shfl_sync(full, ef, L);
+            const float gnew = fmaxf(fminf(__shfl_sync(full, gsel, L) * dn, gmax), 0.f);
+            const int jf = AGC_E * L + e_first;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) {
+                const int j = AGC_E * lane + e;
+                if (((pend >> e) & 1u) && j < jf) o[e] = fminf(1.f, fmaxf(-1.f, v[e] * ga[e]));
+                if (j == jf) o[e] = fminf(1.f, fmaxf(-1.f, v[e] * gnew));
+            }
+            gain = gnew;
+            hang = hang_time;
+            j0 = jf + 1;
+            if (j0 >= 32 * AGC_E) break;
+        }
+#pragma unroll
+        for (int e = 0; e < AGC_E; e++) v[e] = o[e];
+    }
+
     __device__ __forceinline__ void step(float (&v)[AGC_E], int lane, volatile float* U)
     {
         const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
         unsigned nzbits = 0;
 #pragma unroll
         for (int e = 0; e < AGC_E; e++) nzbits |= (v[e] != 0.f ? 1u : 0u) << e;
+        if (__all_sync(full, nzbits == 0xfu)) {
+            step_dense(v, lane, const_cast<float*>(U));
+            return;
+        }
         float o[AGC_E];
 #pragma unroll
         for (int e = 0; e < AGC_E; e++) o[e] = v[e];
@@ -730,7 +804,7 @@ agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __rest
 {
     __shared__ __align__(16) float xin[2][AGC_CH][AGC_TL];
     __shared__ __align__(16) float xout[AGC_CH][AGC_TL];
-    __shared__ float U_all[AGC_CH][32 * AGC_E + 4];
+    __shared__ __align__(16) float U_all[AGC_CH][32 * AGC_E + 8];
     if (n <= 0) return;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int s0 = blockIdx.x * AGC_CH, s = s0 + w;
