@@ -374,12 +374,12 @@ demod_back_kernel(const float* __restrict__ in, int slots, int n, int length, co
 
 // DcBlock block means.  CTA = (32 slots, one block): eight warps stage the block's samples in shared memory, warp 0
 // adds them in sample order (sequential float sum like the oracle).
-constexpr int DC_ROWS = 96;             // 12 KB: fits beside a resident contraction CTA
+constexpr int DC_ROWS = 96;             // 2 x 12 KB: fits beside a resident contraction CTA
 __global__ void __launch_bounds__(256)
 dc_mean_kernel(const float* __restrict__ in, int slots, int n_blocks, int length, const ChanCfg* __restrict__ cfg,
                ChanState* __restrict__ st, float* __restrict__ dc_mean, float* __restrict__ dc_prev)
 {
-    __shared__ float tile[DC_ROWS][32];
+    __shared__ float tile[2][DC_ROWS][32];             // double-buffered: warps 1-7 fetch tile t+1 while warp 0 adds tile t
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int s = blockIdx.x * 32 + lane;
     const int b = blockIdx.y;
@@ -390,13 +390,17 @@ dc_mean_kernel(const float* __restrict__ in, int slots, int n_blocks, int length
     }
     const float* x = in + (size_t)b * length * slots + s;
     float acc = 0.f;
-    for (int i0 = 0; i0 < length; i0 += DC_ROWS) {
-        const int ni = min(DC_ROWS, length - i0);
-        for (int i = w; i < ni; i += 8) tile[i][lane] = x[(size_t)(i0 + i) * slots];
-        __syncthreads();
+    const int nt = (length + DC_ROWS - 1) / DC_ROWS;
+    for (int i = w; i < min(DC_ROWS, length); i += 8) tile[0][i][lane] = x[(size_t)i * slots];
+    __syncthreads();
+    for (int t = 0; t < nt; t++) {
+        const int i0 = t * DC_ROWS, ni = min(DC_ROWS, length - i0);
         if (w == 0) {
 #pragma unroll 8
-            for (int i = 0; i < ni; i++) acc += tile[i][lane];
+            for (int i = 0; i < ni; i++) acc += tile[t & 1][i][lane];
+        } else if (t + 1 < nt) {
+            const int n1 = min(DC_ROWS, length - i0 - DC_ROWS);
+            for (int i = w - 1; i < n1; i += 7) tile[(t + 1) & 1][i][lane] = x[(size_t)(i0 + DC_ROWS + i) * slots];
         }
         __syncthreads();
     }
