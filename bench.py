@@ -262,6 +262,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the hop runs beside the DSP kernels: NCCL's copy CTAs take SMs from the latency-bound low-rate stages.  16 channels
+        # carry the 134 MB block in ~0.26 ms (hidden behind the 0.33 ms DSP pass) with half the CTAs of the default; measured
+        # on 2 B200 (tools/nccl_channels_sweep.sh): 4 -> 0.95, 8 -> 0.52, 16 -> 0.39, default -> 0.45 ms per step
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "16")
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, sm_max, peak_src = load_peaks()
 
@@ -286,7 +290,7 @@ def run_ours(args):
     # support it, else an NCCL broadcast; OWRX_HOP=nccl forces the latter
     hop, hop_kind = None, "none"
     if world > 1:
-        hop_kind = "nccl-broadcast"
+        hop_kind = "nccl-broadcast" if os.environ.get("OWRX_HOP") != "none" else "NONE (diagnostic run: not a valid multi-GPU number)"
         # measured on 2 and 8 B200 (tools/hop_sweep.sh): both hops hide behind the DSP pass; NCCL's is the faster end to end
         # (0.49 vs 0.61 ms per step at 8 GPUs: the multicast protocol's two cross-GPU barriers per block cost more than
         # NCCL's copy kernels), so it is the default and OWRX_HOP=multicast selects the NVLS form
@@ -315,9 +319,9 @@ def run_ours(args):
     def issue_broadcast(i):
         # the hop: rank 0's block reaches every GPU over NVLink (NCCL broadcast).  Issued one block ahead on NCCL's own
         # stream, so the transfer of block i+1 overlaps the K3 pass of block i (double-buffered).
-        buf = bcast_buf[i & 1]
-        if rank == 0:
-            buf.copy_(iq_src, non_blocking=True)        # "fresh" samples from the ingest side
+        # rank 0 sends its resident block as it is (inputs are resident in HBM when the timed region starts); the others
+        # receive into alternating buffers
+        buf = iq_src if rank == 0 else bcast_buf[i & 1]
         pending[0] = broadcast_block(buf, 0, async_op=True)
 
     sent = [0]
@@ -331,12 +335,14 @@ def run_ours(args):
             buf = hop.recv(i, stream)
             bank.process_device(buf, BLOCK, stream=sp)
             hop.release(i, stream)
+        elif world > 1 and os.environ.get("OWRX_HOP") == "none":
+            bank.process_device(iq_src, BLOCK, stream=sp)    # diagnostic only: no hop, every rank reads its resident copy
         elif world > 1:
             if pending[0] is None:
                 issue_broadcast(i)
             pending[0].wait()                            # current stream waits for block i
             issue_broadcast(i + 1)
-            bank.process_device(bcast_buf[i & 1], BLOCK, stream=sp)
+            bank.process_device(iq_src if rank == 0 else bcast_buf[i & 1], BLOCK, stream=sp)
         else:
             # two resident blocks, alternated: 268 MB of input between two reads of the same bytes (L2 is 126 MB)
             bank.process_device(iq_alt[i & 1], BLOCK, stream=sp)
