@@ -1614,9 +1614,12 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
         OWRX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         bank->chunk_events.push_back(e);
     }
-    // the copy stream must not write the buffer before the previous feed's carry copy into it is done (that copy follows the
-    // previous feed's last FirDecimate pass on `st`; the low-rate stages of that feed do not touch the wideband buffers)
-    OWRX_CUDA(cudaStreamWaitEvent(bank->copy_stream, bank->carry_done, 0));
+    // The uploads need no ordering against earlier device work: they fill [iq_fill, iq_fill + n) of the current buffer, the
+    // previous feed's carry copy (on `st`) fills [0, iq_fill) of the same buffer, and the last kernels that READ this buffer
+    // belong to the feed before the previous one, which has been synchronised (finish_pending / the synchronous return) before
+    // this call.  So this feed's chunks queue right behind the previous feed's on the copy stream: PCIe never idles.
+    static const bool wait_carry = getenv("OWRX_FEED_WAIT_CARRY") != nullptr;    // the conservative ordering, for A/B runs
+    if (wait_carry) OWRX_CUDA(cudaStreamWaitEvent(bank->copy_stream, bank->carry_done, 0));
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t o = c * chunk, len = std::min(chunk, n_samples - o);
         if (len && format == OWRX_IQ_CF32) {
