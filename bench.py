@@ -406,14 +406,20 @@ def run_ours(args):
 
     audio_buf = np.empty((len(ch2), 1 << 15), np.float32)      # ~20 160 samples per channel and block
 
+    up_count = [0]
+    if world > 1 and hop is None:
+        up_stream = torch.cuda.Stream(device=dev)
+        up_buf = [torch.empty_like(iq), torch.empty_like(iq)]
+        up_done = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_step():
         """one block through the public host API: H2D of the block from pinned memory, the whole chain, audio D2H and
         the read of every channel's audio into a caller buffer (owrx_bank_read_audio_all)"""
         if world > 1:
             # rank 0 uploads, NCCL carries the block to the other GPUs, every rank returns its audio to the host
-            if rank == 0:
-                iq.copy_(h_iq, non_blocking=True)
             if hop is not None:
+                if rank == 0:
+                    iq.copy_(h_iq, non_blocking=True)
                 j = sent[0]
                 sent[0] += 1
                 hop.stream.wait_stream(stream)           # the upload is on the bench stream
@@ -422,8 +428,22 @@ def run_ours(args):
                 bank2.process_device(buf, BLOCK, stream=sp)
                 hop.release(j, stream)
             else:
-                broadcast_block(iq, 0)
-                bank2.process_device(iq, BLOCK, stream=sp)
+                # streaming: rank 0 uploads block j+1 (copy stream) while block j crosses NVLink and is processed
+                j = up_count[0]
+                up_count[0] += 1
+                if rank == 0:
+                    if j == 0:
+                        with torch.cuda.stream(up_stream):
+                            up_buf[0].copy_(h_iq, non_blocking=True)
+                            up_done[0].record(up_stream)
+                    stream.wait_event(up_done[j & 1])
+                    up_stream.wait_stream(stream)                # buffer (j+1)&1 was read by the hop of block j-1
+                    with torch.cuda.stream(up_stream):
+                        up_buf[(j + 1) & 1].copy_(h_iq, non_blocking=True)
+                        up_done[(j + 1) & 1].record(up_stream)
+                buf = up_buf[j & 1]
+                broadcast_block(buf, 0)
+                bank2.process_device(buf, BLOCK, stream=sp)
             bank2.drain()
             return sum(bank2.read_audio_all(ch2, audio_buf))
         bank2.feed_ptr(hp, BLOCK)
@@ -575,7 +595,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "channel-MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms,
                 "mode": "streaming (owrx_bank_set_deferred_drain): block i's outputs are drained under block i+1's upload; all "
-                        "blocks' audio read inside the timed region (last block after owrx_bank_flush)" if world == 1 else "H2D on rank 0 + IQ hop + owrx_bank_process_device + drain"},
+                        "blocks' audio read inside the timed region (last block after owrx_bank_flush)" if world == 1 else "streaming: H2D of block j+1 on rank 0 under the hop + owrx_bank_process_device + drain + reads of block j"},
         "e2e_sync": e2e_sync,
         "e2e_cs16": e2e_cs16,
         "gpu_launches": int(launches),
