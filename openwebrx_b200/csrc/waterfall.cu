@@ -543,7 +543,13 @@ static int wf_process(owrx_wf* wf, const float2* iq_dev, size_t n_samples, uint8
             OWRX_CUDA(cudaStreamWaitEvent(wf->side, wf->fin_done, 0));
             sa = wf->side;
         }
-        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, 0, sa>>>(s16, out_dev, n + 10, lines);
+        // the encoder is a latency-bound serial chain per line (one warp per 32 lines): beside the FFT pass of the next batch
+        // its warps lose issue slots to 16 FFT warps per SM.  Claiming shared memory it does not use keeps a second FFT CTA
+        // (86 KB) off its SM: 150 KB leaves its 19 CTAs alone on their SMs (C1, 592 lines per batch: 0.87 -> 0.78 ms per batch;
+        // OWRX_WF_ADPCM_PAD_KB overrides)
+        static const int adpcm_pad = (getenv("OWRX_WF_ADPCM_PAD_KB") ? atoi(getenv("OWRX_WF_ADPCM_PAD_KB")) : 150) << 10;
+        if (adpcm_pad) OWRX_CUDA(cudaFuncSetAttribute(wf_adpcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, adpcm_pad));
+        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, side_adpcm ? adpcm_pad : 0, sa>>>(s16, out_dev, n + 10, lines);
         OWRX_LAUNCH_CHECK();
         if (side_adpcm) {
             OWRX_CUDA(cudaEventRecord(wf->adpcm_done[wf->s16_cur], sa));
