@@ -140,9 +140,16 @@ class Buffer(Writer):
         self._bytes = 0
         self._readers = weakref.WeakSet()
         self._runner = None
+        # set by the source-side Convert (+ Gain) pump: this COMPLEX_FLOAT buffer physically carries the source's raw
+        # samples ("cs16" / "cu8") and the gain to apply; the GPU does the conversion (owrx_*_feed_fmt)
+        self._raw = None
 
     def getFormat(self):
         return self._format
+
+    def _write_raw(self, data, fmt, gain):
+        self._raw = (fmt, float(gain))
+        self.write(data)
 
     def getReader(self):
         r = Reader(self)
@@ -494,15 +501,58 @@ class _Unfused(_Stage):
 
 
 class Convert(_Unfused):
+    """Convert(inFormat, outFormat).  Two uses in the reference: the client-audio Convert(FLOAT, SHORT)
+    (csdr/chain/clientaudio.py:12, fused into the audio tail) and the SOURCE-side conversion
+    Chain([Convert(COMPLEX_SHORT, COMPLEX_FLOAT), Gain(COMPLEX_FLOAT, 5.0)]) of sources that do not deliver floats
+    (owrx/source/fifi_sdr.py:27-28, wired by owrx/source/direct.py:59-71).  The latter never converts on the host: a pump
+    thread hands the raw samples on, tagged with their format and the accumulated gain, and the runner of the
+    COMPLEX_FLOAT buffer feeds them through owrx_wf_feed_fmt / owrx_bank_feed_fmt."""
+
+    _RAW = {Format.COMPLEX_SHORT: "cs16", Format.COMPLEX_CHAR: "cu8"}
+
     def __init__(self, inFormat, outFormat):
         super().__init__(inFormat, outFormat)
         self.IN, self.OUT = inFormat, outFormat
+        self._pump = None
+
+    def _ingress(self):
+        return self.OUT is Format.COMPLEX_FLOAT and self.IN in self._RAW
+
+    def setReader(self, reader):
+        super().setReader(reader)
+        if self._ingress() and reader is not None and (self._pump is None or not self._pump.is_alive()):
+            self._pump = threading.Thread(target=self._run, args=(reader,), daemon=True, name="pycsdr-b200-ingress")
+            self._pump.start()
+
+    def _sink(self):
+        """the COMPLEX_FLOAT buffer at the end of Convert [-> Gain ...] and the product of the gains on the way"""
+        gain, buf = 1.0, self._writer
+        for _ in range(8):
+            if not isinstance(buf, Buffer):
+                return None, gain
+            nxt = _GRAPH.consumer_of(buf)
+            if isinstance(nxt, Gain) and nxt.IN is Format.COMPLEX_FLOAT and nxt._writer is not None:
+                gain *= nxt.gain
+                buf = nxt._writer
+                continue
+            return buf, gain
+        return None, gain
+
+    def _run(self, reader):
+        while not self._stopped and self._reader is reader:
+            data = reader.read()
+            if data is None:
+                break
+            sink, gain = self._sink()
+            if sink is not None:
+                sink._write_raw(data, self._RAW[self.IN], gain)
 
 
 class Gain(_Unfused):
     def __init__(self, format, gain):
         super().__init__(format, gain)
         self.IN = self.OUT = format
+        self.gain = float(gain)
 
 
 class AdpcmEncoder(_Unfused):
@@ -653,10 +703,16 @@ class _WaterfallPlan:
         self.line_bytes = N.lib.owrx_wf_line_bytes(self.handle)
         self.buf = np.empty(self.line_bytes * 64, np.uint8)
 
-    def feed(self, data):
+    def feed(self, data, raw=None):
         N = _native()
-        arr = np.frombuffer(data, dtype=np.float32)
-        N.check(N.lib.owrx_wf_feed(self.handle, arr.ctypes.data_as(C.c_void_p), arr.size // 2))
+        if raw is None:
+            arr = np.frombuffer(data, dtype=np.float32)
+            N.check(N.lib.owrx_wf_feed(self.handle, arr.ctypes.data_as(C.c_void_p), arr.size // 2))
+        else:
+            arr = np.frombuffer(data, dtype=np.uint8)
+            fmt, gain = raw
+            N.check(N.lib.owrx_wf_feed_fmt(self.handle, arr.ctypes.data_as(C.c_void_p), arr.size // (4 if fmt == "cs16" else 2),
+                                           N.IQ_FORMATS[fmt], gain))
         lb = self.line_bytes
         while True:
             n = C.c_size_t()
@@ -912,10 +968,11 @@ class _SourceRunner(threading.Thread):
                         break
                     continue
                 idle = 0
+                raw = self.buffer._raw          # source-side Convert (+ Gain): the buffer carries raw samples
                 for plan in list(self.wf_plans.values()):
-                    plan.feed(data)
+                    plan.feed(data, raw)
                 if self.channels:
-                    self._feed_bank(N, data)
+                    self._feed_bank(N, data, raw)
             except Exception:
                 logger.exception("pycsdr-b200 runner failed")
                 break
@@ -947,9 +1004,15 @@ class _SourceRunner(threading.Thread):
             out.append(buf[:n.value].tobytes())
         return b"".join(out)
 
-    def _feed_bank(self, N, data):
-        arr = np.frombuffer(data, dtype=np.float32)
-        N.check(N.lib.owrx_bank_feed(self.bank, arr.ctypes.data_as(C.c_void_p), arr.size // 2))
+    def _feed_bank(self, N, data, raw=None):
+        if raw is None:
+            arr = np.frombuffer(data, dtype=np.float32)
+            N.check(N.lib.owrx_bank_feed(self.bank, arr.ctypes.data_as(C.c_void_p), arr.size // 2))
+        else:
+            arr = np.frombuffer(data, dtype=np.uint8)
+            fmt, gain = raw
+            N.check(N.lib.owrx_bank_feed_fmt(self.bank, arr.ctypes.data_as(C.c_void_p), arr.size // (4 if fmt == "cs16" else 2),
+                                             N.IQ_FORMATS[fmt], gain))
         for st in list(self.channels.values()):
             cid = st["cid"]
             if st["demod"] == "none":

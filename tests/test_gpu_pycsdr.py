@@ -274,3 +274,47 @@ def test_f2_websocket_message_framing(gpu):
     assert out[True] == out[False] and out[True][:4] == b"SYNC"
     with pytest.raises(ValueError):
         N.check(N.lib.owrx_chan_read_message(ChannelBank(fs)._h, 0, 3, iq.ctypes.data, 10, None))
+
+
+def test_f4_source_side_convert_chain_through_the_shim(gpu):
+    """the reference's source-side conversion chain (owrx/source/fifi_sdr.py:27-28) in front of a waterfall chain and a
+    client chain, all through the pycsdr shim: raw int16 samples go to the GPU as they are; results equal the library fed
+    with the oracle's Convert + Gain output"""
+    from openwebrx_b200 import ChannelBank, Waterfall
+    fs = 2.4e6
+    cars = carrier_plan(2, fs, seed=91)
+    iq = make_iq(5333 + 200 * 2250 + 4099, fs, cars, seed=91)
+    raw = (np.clip(iq.view(np.float32), -1, 1) * 6000).astype(np.int16)         # x 5.0 stays within +-1
+    as_float = oracle.convert_raw_iq(raw, "cs16", 5.0)
+    # ---- the shim topology: Buffer(CS16) -> Convert -> Gain(5) -> Buffer(CF32) -> {FftChain modules, Selector-like chain}
+    src = M.Buffer(Format.COMPLEX_SHORT)
+    conv, gain = M.Convert(Format.COMPLEX_SHORT, Format.COMPLEX_FLOAT), M.Gain(Format.COMPLEX_FLOAT, 5.0)
+    mid, fbuf = M.Buffer(Format.COMPLEX_FLOAT), M.Buffer(Format.COMPLEX_FLOAT)
+    conv.setWriter(mid); gain.setReader(mid.getReader()); conv.setReader(src.getReader()); gain.setWriter(fbuf)
+    avg, every_n = 4, 700
+    fft, lap, swap, ad = M.Fft(size=1024, every_n_samples=every_n), M.LogAveragePower(add_db=-70.0, fft_size=1024, avg_number=avg), \
+        M.FftSwap(fft_size=1024), M.FftAdpcm(fft_size=1024)
+    b1, b2, b3, out = M.Buffer(Format.COMPLEX_FLOAT), M.Buffer(Format.FLOAT), M.Buffer(Format.FLOAT), M.Buffer(Format.CHAR)
+    fft.setWriter(b1); lap.setReader(b1.getReader()); lap.setWriter(b2); swap.setReader(b2.getReader()); swap.setWriter(b3)
+    ad.setReader(b3.getReader()); ad.setWriter(out)
+    rd = out.getReader()
+    fft.setReader(fbuf.getReader())
+    time.sleep(0.3)
+    n_lines = ((len(iq) - 1024) // every_n + 1) // avg
+    src.write(raw.tobytes())
+    lines = []
+    deadline = time.time() + 20
+    while len(lines) < n_lines and time.time() < deadline:
+        d = rd.read()
+        if d is None:
+            break
+        lines.append(bytes(d))
+    want = oracle.fftchain_run(as_float, 1024, every_n, avg)
+    assert len(lines) == n_lines == len(want["lines"])
+    wf = Waterfall(fs, 1024, 0.0, 1, "adpcm")
+    N.check(N.lib.owrx_wf_set_every_n_samples(wf._h, every_n)); N.check(N.lib.owrx_wf_set_avg_number(wf._h, avg))
+    direct = wf.feed(as_float)
+    assert lines == direct                                                    # same bytes as the library fed with floats
+    for m in (fft, lap, swap, ad, conv, gain):
+        m.stop()
+    rd.stop()

@@ -7,6 +7,7 @@ import threading
 import time
 from abc import ABCMeta
 
+import numpy as np
 import pytest
 
 import pycsdr.modules as M
@@ -172,3 +173,49 @@ def test_reference_classes_run_unmodified_on_the_shim():
         sys.path.remove(REF)
         for k in [k for k in sys.modules if k == "csdr" or k.startswith("csdr.") or k == "owrx" or k.startswith("owrx.")]:
             sys.modules.pop(k)
+
+
+def test_source_side_convert_gain_forwards_raw_samples_tagged():
+    """owrx/source/fifi_sdr.py:27-28 + owrx/source/direct.py:59-71: Buffer(COMPLEX_SHORT) -> Chain([Convert(COMPLEX_SHORT,
+    COMPLEX_FLOAT), Gain(COMPLEX_FLOAT, 5.0)]) -> Buffer(COMPLEX_FLOAT).  The shim never converts on the host: the raw
+    samples arrive in the float buffer tagged ("cs16", 5.0) for owrx_*_feed_fmt."""
+    import time
+    raw_buf = M.Buffer(Format.COMPLEX_SHORT)
+    conv, gain = M.Convert(Format.COMPLEX_SHORT, Format.COMPLEX_FLOAT), M.Gain(Format.COMPLEX_FLOAT, 5.0)
+    mid, out = M.Buffer(Format.COMPLEX_FLOAT), M.Buffer(Format.COMPLEX_FLOAT)
+    # the order csdr.chain.Chain wires its workers in: internal buffers first, then reader and writer
+    conv.setWriter(mid); gain.setReader(mid.getReader())
+    conv.setReader(raw_buf.getReader()); gain.setWriter(out)
+    rd = out.getReader()
+    payload = np.arange(-8, 8, dtype=np.int16).tobytes()
+    raw_buf.write(payload)
+    got = rd.read()
+    assert bytes(got) == payload and out._raw == ("cs16", 5.0)
+    with pytest.raises(ValueError):
+        conv.setReader(M.Buffer(Format.COMPLEX_FLOAT).getReader())        # wrong input format
+    # the client-audio Convert(FLOAT, SHORT) is no ingress stage: no pump
+    c2 = M.Convert(Format.FLOAT, Format.SHORT)
+    c2.setReader(M.Buffer(Format.FLOAT).getReader())
+    assert c2._pump is None
+    raw_buf.getReader  # keep alive
+    conv.stop(); gain.stop()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs the reference tree (build container only)")
+def test_reference_fifi_sdr_format_conversion_runs_on_the_shim():
+    """the reference's UNMODIFIED FifiSdrSource.getFormatConversion() (owrx/source/fifi_sdr.py:27-28), wired the way
+    DirectSource.getBuffer does (owrx/source/direct.py:59-71), hands raw int16 samples on with gain 5.0"""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from owrx.source.fifi_sdr import FifiSdrSource
+    conversion = FifiSdrSource.getFormatConversion(None)
+    assert conversion.getInputFormat() is Format.COMPLEX_SHORT and conversion.getOutputFormat() is Format.COMPLEX_FLOAT
+    src = M.Buffer(Format.COMPLEX_SHORT)
+    conversion.setReader(src.getReader())
+    out = M.Buffer(Format.COMPLEX_FLOAT)
+    conversion.setWriter(out)
+    rd = out.getReader()
+    payload = np.arange(100, dtype=np.int16).tobytes()
+    src.write(payload)
+    assert bytes(rd.read()) == payload and out._raw == ("cs16", 5.0)
+    conversion.stop()
