@@ -154,6 +154,15 @@ def make_vectors():
     rng = np.random.default_rng(103)
     s16 = (8000 * np.sin(np.arange(5000) * 0.05) + 300 * rng.standard_normal(5000)).astype(np.int16)
     v["au_s16"] = s16; v["au_adpcm"] = oracle.adpcm_sync_encode(s16)
+    # spec-defined waterfall noise filter (BASELINE config 4) on the same IQ: three lines so that the floor recurrence runs
+    iq3 = make_iq(700 * 12 + 1024, fs, cars, seed=104)
+    v["wfnf_iq"] = iq3
+    v["wfnf_db"] = oracle.fftchain_run(iq3, 1024, 700, 4, compression="none", noise_filter=(0.9, 0.05, 0.02))["db"]
+    # source-side Convert(COMPLEX_SHORT, COMPLEX_FLOAT) + Gain(5.0) (owrx/source/fifi_sdr.py:27-28) and the uint8 form
+    raw16 = rng.integers(-32768, 32768, 512, dtype=np.int16)
+    raw8 = rng.integers(0, 256, 512, dtype=np.uint8)
+    v["raw_cs16"] = raw16; v["raw_cs16_cf"] = oracle.convert_raw_iq(raw16, "cs16", 5.0)
+    v["raw_cu8"] = raw8; v["raw_cu8_cf"] = oracle.convert_raw_iq(raw8, "cu8", 1.0)
     np.savez_compressed(os.path.join(HERE, "oracle_vectors.npz"), **v)
 
 

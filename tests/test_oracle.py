@@ -305,3 +305,11 @@ def test_source_format_conversion_matches_csdr_convert():
     got = oracle.convert_raw_iq(u8, "cu8").view(np.float32)
     assert np.array_equal(got, u8.astype(np.float32) / np.float32(127.5) - np.float32(1.0))
     assert got.min() == -1.0 and got.max() == 1.0 and oracle.convert_raw_iq(np.array([32767, -32767], np.int16), "cs16")[0] == 1 - 1j
+
+
+def test_golden_noise_filter_and_source_conversions():
+    # regression pins for the spec-defined noise filter and the source-side Convert (+ Gain) restatements
+    r = oracle.fftchain_run(GOLD["wfnf_iq"], 1024, 700, 4, compression="none", noise_filter=(0.9, 0.05, 0.02))
+    assert np.abs(r["db"] - GOLD["wfnf_db"]).max() < 1e-4
+    assert np.array_equal(oracle.convert_raw_iq(GOLD["raw_cs16"], "cs16", 5.0), GOLD["raw_cs16_cf"])
+    assert np.array_equal(oracle.convert_raw_iq(GOLD["raw_cu8"], "cu8", 1.0), GOLD["raw_cu8_cf"])
