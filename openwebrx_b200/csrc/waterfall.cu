@@ -75,6 +75,13 @@ wf_fft_kernel(WfFftParams p)
         for (int q = 0; q < 16; q++) accS[q * T + tid] = 0.0f;
     }
 
+    // the Hamming window values of this thread's 16 points are the same for every frame of the line: keep them in registers
+    float wreg[16];
+    if (FROM_IQ && active) {
+#pragma unroll
+        for (int r = 0; r < 16; r++) wreg[r] = __ldg(p.window + tid + r * T);
+    }
+
     for (int a = a0; a < a1; a++) {
         float2 v[16];
         const long long frame = (long long)line * p.frames_per_line + a;
@@ -90,8 +97,7 @@ wf_fft_kernel(WfFftParams p)
 #pragma unroll
                 for (int r = 0; r < 16; r++) {
                     float2 s = __ldg(x + tid + r * T);
-                    float w = __ldg(p.window + tid + r * T);
-                    v[r] = make_float2(s.x * w, s.y * w);
+                    v[r] = make_float2(s.x * wreg[r], s.y * wreg[r]);
                 }
             } else {
                 const float2* x = p.src + (frame * p.r0 + k1) * (long long)M;
