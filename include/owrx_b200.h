@@ -261,7 +261,7 @@ int owrx_bank_profile_read_ex(owrx_bank_t* bank, double* ms, uint64_t* launches,
  *   OWRX_FIR_FASTCONV_TC  the same fast convolution with the spectral contraction on the tensor cores (tcgen05): every
  *                      float32 operand is carried as three bf16 terms and six partial products are accumulated in FP32
  *   OWRX_FIR_AUTO      (default) direct for feeds that yield < 64 outputs per channel, else fast convolution — on the
- *                      tensor cores when a pass holds >= 12 overlap-save blocks, on the FP32 pipe below that */
+ *                      tensor cores when a pass holds enough overlap-save blocks (> ~21 at 64 slots, > ~18 at 128), on the FP32 pipe below that */
 #define OWRX_FIR_AUTO        0
 #define OWRX_FIR_DIRECT      1
 #define OWRX_FIR_FASTCONV    2

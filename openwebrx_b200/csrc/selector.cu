@@ -740,11 +740,14 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
 
     const bool fastconv = g->fc_ok && bank->fir_mode != OWRX_FIR_DIRECT && (bank->fir_mode >= OWRX_FIR_FASTCONV || n_k >= 64);
     if (fastconv) {
-        // contraction on the tensor cores once a pass holds enough overlap-save blocks: below ~12 rows the FP32-pipe kernel,
-        // whose table is 8 instead of 12 bytes per entry, is bound by the same table read and moves fewer bytes; from there
-        // on its FMA time (8 M B Dp S FLOP at ~35 TFLOP/s) exceeds the tensor-core form's byte time (12 M Dp (B + S) at ~5 TB/s)
+        // contraction on the tensor cores once a pass holds enough overlap-save blocks B for the S slots of the group.  Per
+        // (bin, branch) the FP32-pipe form costs 8 B S FLOP at ~35 TFLOP/s (it is FMA-bound; its table is 8 bytes per entry),
+        // the tensor-core form moves 12 (B + S) bytes at ~3.3 TB/s for short passes (table 12 bytes per entry, read once per
+        // pass): tensor cores win for B > ~21 at 64 slots and B > ~18 at 128.  Measured: C3 (128 slots, B = 15) 0.57 ms on
+        // the FP32 pipe vs 0.69 ms on the tensor cores; C2 (64 slots, B = 88) 0.29 vs 0.10 ms.
         const size_t fc_blocks = (n_k + (size_t)g->fc.Kb - 1) / (size_t)g->fc.Kb;
-        const bool tc = bank->fir_mode == OWRX_FIR_FASTCONV_TC || (bank->fir_mode == OWRX_FIR_AUTO && fc_blocks >= 12);
+        const double fp32_cost = 8.0 * (double)fc_blocks * S / 35e12, tc_cost = 12.0 * ((double)fc_blocks + S) / 3.3e12;
+        const bool tc = bank->fir_mode == OWRX_FIR_FASTCONV_TC || (bank->fir_mode == OWRX_FIR_AUTO && fp32_cost > tc_cost);
         bank->fir_form_used = tc ? OWRX_FIR_FASTCONV_TC : OWRX_FIR_FASTCONV;
         if ((rc = g->s1.ensure_new(n_k, st)) != OWRX_OK) return rc;
         if ((rc = group_fir_fastconv(bank, g, iq, n_avail, n_k, st, tc)) != OWRX_OK) return rc;
