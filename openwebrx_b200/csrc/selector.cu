@@ -1227,8 +1227,16 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (const char* m = getenv("OWRX_BP_MODE")) b->bp_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV, atoi(m)));
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->serial_stream, cudaStreamNonBlocking);
+    // The parallel low-rate stages are a chain of a dozen small dependent launches: on a high-priority stream their CTAs go
+    // ahead of the bulk FIR passes of later blocks whenever an SM frees resources (C2 inside the three-stream pipeline: step
+    // 0.33 -> 0.30 ms; the forward FFT pass stretches from 0.08 to 0.15 ms but is not the longest stage).  Bit 1 of
+    // OWRX_TAIL_PRIORITY does the same for the serial Agc stream (no measurable effect: its CTAs already sit alone on
+    // their SMs); 0 restores equal priorities.
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    static const int tail_prio = getenv("OWRX_TAIL_PRIORITY") ? atoi(getenv("OWRX_TAIL_PRIORITY")) : 1;
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->side_stream, cudaStreamNonBlocking, (tail_prio & 1) ? prio_hi : prio_lo);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->serial_stream, cudaStreamNonBlocking, (tail_prio & 2) ? prio_hi : prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->drain_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[1], cudaEventDisableTiming);
