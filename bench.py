@@ -36,6 +36,7 @@ CH_PER_GPU = 64
 BLOCK = 1 << 24           # samples per step: 134 MB of complex64 > the 126 MB L2
 WF_FS, WF_N, WF_FPS, WF_OV = 2_400_000, 4096, 9, 0.3     # config 1 (waterfall)
 METRIC = "channel-MS/s (input MS/s x clients) + waterfall FFT frames/s"
+WORKLOAD = "C2: Selector DDC + NFM/AM/USB demod, 10 MS/s wideband, %d x 12 kHz channels per GPU" % CH_PER_GPU
 
 
 def load_peaks():
@@ -243,7 +244,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "channel-MS/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(ms)) if ms else None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: Selector DDC + NFM/AM/USB demod, 10 MS/s wideband, 64 x 12 kHz channels", "cpu": True},
+            "config": {"workload": WORKLOAD, "cpu": True},
             "cpu_baseline": {"value": value, "unit": "channel-MS/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "channel-MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -588,7 +589,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "channel-MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: Selector DDC + NFM/AM/USB demod, 10 MS/s wideband, %d x 12 kHz channels per GPU" % CH_PER_GPU,
+        "config": {"workload": WORKLOAD,
                    "channels_total": world * CH_PER_GPU, "block_samples": BLOCK, "decimation": D, "fir_taps": T,
                    "l2": "two resident 134 MB input blocks alternate (268 MB between re-reads > 126 MB L2); no flush needed", "parallelism": "channels sharded x%d, IQ block hop: %s" % (world, hop_kind) if world > 1 else "1 GPU",
                    "realtime_factor": value / (FS / 1e6 * CH_PER_GPU * world)},

@@ -215,8 +215,16 @@ int owrx_chan_read_message(owrx_bank_t* bank, int chan, int type_byte, void* out
 int owrx_bank_set_outputs(owrx_bank_t* bank, int mask);
 
 /* Device-resident batch path (bench / embedding): process one wideband block that already lives
- * in device memory; outputs stay on the device and are NOT queued for the host. */
+ * in device memory; outputs stay on the device and are NOT queued for the host.
+ * Stream contract — [carry | new]: FirDecimate consumes whole decimation steps, so a call uses only the first
+ * ((n - T) / D + 1) * D samples of the block (T taps, D decimation; nothing if n < T) and keeps NO copy of the rest.  A caller
+ * that streams consecutive blocks presents the next block starting at sample owrx_bank_last_consumed() of this one (the
+ * unconsumed tail followed by the new samples); the NCO phase and every stage history carry over exactly as in
+ * owrx_bank_feed, which does this carry internally.  With several decimation classes in one bank the reported count is the
+ * slowest group's; groups that got further skip their lead in the next block. */
 int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_samples, void* stream);
+/* samples of the last owrx_bank_process_device block that every channel is done with (see the stream contract above) */
+int owrx_bank_last_consumed(const owrx_bank_t* bank, size_t* n_samples);
 /* Pipelined device path: the low-rate stages of block i run on the bank's side stream while the K3 pass of
  * block i+1 runs on the caller's stream.  owrx_bank_join makes `stream` wait for everything issued so far. */
 int owrx_bank_set_pipelined(owrx_bank_t* bank, int enable);

@@ -58,7 +58,10 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed:\n" + "\n".join(failed))
     if force or procs or _stale(SO, objs):
-        cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # the CUDA runtime is linked dynamically (libcudart.so.12: the process shares ONE runtime with torch when both are
+        # loaded, and the artefact carries only the runtime symbols it calls); rpath covers processes that load no torch
+        cmd = [nvcc, "-shared", "-cudart", "shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                                      "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout)

@@ -174,6 +174,13 @@ class ChannelBank:
     def process_device(self, iq_dev, n_samples, stream=None):
         N.check(N.lib.owrx_bank_process_device(self._h, _ptr(iq_dev), n_samples, _ptr(stream)))
 
+    def last_consumed(self):
+        """samples of the last process_device block every channel is done with: the next block of a continuous stream starts
+        there ([carry | new], include/owrx_b200.h)"""
+        n = C.c_size_t()
+        N.check(N.lib.owrx_bank_last_consumed(self._h, C.byref(n)))
+        return n.value
+
     def stats(self):
         st = N.BankStats()
         N.check(N.lib.owrx_bank_get_stats(self._h, C.byref(st)))

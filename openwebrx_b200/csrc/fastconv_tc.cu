@@ -215,165 +215,6 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Persistent stream-K schedule of the same contraction.  The one-tile-per-CTA grid above runs 256 tiles (C2) on 148 SMs:
-// a full wave and a 73 %-full one.  Here the work is cut in UNITS = (tile, 32-branch chunk) — W = tiles x chunks — and CTA g
-// of a one-per-SM grid owns the contiguous range [W g / G, W (g+1) / G): every SM streams the same number of bytes.  A
-// range crosses tile boundaries, so a CTA works through SEGMENTS (tile, chunk range); a tile cut by a range boundary is
-// accumulated in pieces by neighbouring CTAs, piece k going to partial-sum plane k of Z (planes >= 1 are zeroed by the
-// launcher; fc_inverse_kernel adds the planes).  The operand ring runs on across segments, and two TMEM accumulator stages
-// (2 x 256 columns) let the epilogue of one segment drain while the MMAs of the next one run.
-// Opt-in (OWRX_FC_STREAMK=1): measured slower than the plain grid on this workload, see fc_launch_contract_tc.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sk_owner(long long u, long long W, int G)      // CTA whose range holds unit u
-{
-    return (int)(((u + 1) * G - 1) / W);
-}
-
-__global__ void __launch_bounds__(192, 1)
-fc_contract_tc_sk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float2* __restrict__ Z, int B, int Dp,
-                         int slots, int nbt, int mrows, long long W)
-{
-    extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ unsigned long long bars[2 * TC_ST + 4];               // full[ST], empty[ST], acc_full[2], acc_empty[2]
-    __shared__ unsigned tmem_slot;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int G = gridDim.x, g = blockIdx.x;
-    const int C = Dp / TC_KC;                                         // chunks per tile
-    const int ncg = slots / FC_CG;
-    const long long u0 = W * g / G, u1 = W * (g + 1) / G;
-    const size_t plane = (size_t)FC_M * B * slots;
-
-    const unsigned a_plane = (unsigned)mrows * TC_ROWB;
-    const unsigned a_stage = TC_NPL * a_plane;
-    const unsigned stage_bytes = a_stage + TC_B_STAGE;
-    const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
-    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
-    const unsigned bar_accf = bar0 + 8 * (2 * TC_ST), bar_acce = bar_accf + 16;
-
-    if (tid == 0) {
-        for (int s = 0; s < TC_ST; s++) {
-            mbar_init(bar0 + 8 * s, 1);
-            mbar_init(bar0 + 8 * (TC_ST + s), 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(bar_accf + 8 * s, 1);                           // one tcgen05.commit
-            mbar_init(bar_acce + 8 * s, 4);                           // one arrival per epilogue warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (wid == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_slot)),
-                     "r"(2 * TC_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const unsigned tmem = tmem_slot;
-
-    if (wid == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (long long u = u0; u < u1; u++, it++) {
-                const int t = (int)(u / C), c = (int)(u % C);
-                const int cg = t % ncg, qb = t / ncg, q = qb / nbt, bt = qb % nbt;
-                const int stage = it % TC_ST, use = it / TC_ST;
-                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (TC_ST + stage);
-                mbar_wait(empty, (use & 1) ^ 1);
-                mbar_expect_tx(full, stage_bytes);
-                const unsigned sa = smem0 + stage * stage_bytes;
-                tma_load_3d(sa, &mapA, c * TC_KC, q * B + bt * mrows, 0, full);
-                tma_load_3d(sa + a_stage, &mapB, c * TC_KC, q * slots + cg * FC_CG, 0, full);
-            }
-        }
-        __syncwarp();
-    } else if (wid == 1) {
-        if (lane == 0) {
-            int it = 0, seg = 0;
-            bool open = false;                                        // a segment's accumulation is in progress
-            for (long long u = u0; u < u1; u++, it++) {
-                const int c = (int)(u % C);
-                const int as = seg & 1;
-                if (!open) {
-                    mbar_wait(bar_acce + 8 * as, ((seg >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator stage
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                }
-                const int stage = it % TC_ST, use = it / TC_ST;
-                mbar_wait(bar0 + 8 * stage, use & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const unsigned sa = smem0 + stage * stage_bytes, sb = sa + a_stage;
-                const unsigned td = tmem + (unsigned)as * TC_COLS;
-#pragma unroll
-                for (int kk = 0; kk < TC_KC / 16; kk++) {
-#pragma unroll
-                    for (int p = 0; p < 6; p++) {
-                        const int la = kTcProd[p][0], lb = kTcProd[p][1];
-                        const unsigned long long d_re = smem_desc(sa + (unsigned)(2 * la) * a_plane + kk * 32);
-                        const unsigned long long d_im = smem_desc(sa + (unsigned)(2 * la + 1) * a_plane + kk * 32);
-                        const unsigned long long d_b = smem_desc(sb + (unsigned)(2 * lb) * TC_B_PLANE + kk * 32);
-                        const unsigned acc = (open || kk || p) ? 1u : 0u;
-                        umma(td, d_re, d_b, acc);
-                        umma(td + 128, d_im, d_b, acc);
-                    }
-                }
-                open = true;
-                umma_commit(bar0 + 8 * (TC_ST + stage));
-                if (c == C - 1 || u == u1 - 1) {                      // the segment ends with this chunk
-                    umma_commit(bar_accf + 8 * as);
-                    open = false;
-                    seg++;
-                }
-            }
-        }
-        __syncwarp();
-    } else {
-        const int quarter = wid & 3;
-        const int row = quarter * 32 + lane;
-        int seg = 0;
-        long long u = u0;
-        while (u < u1) {
-            const int t = (int)(u / C), c_begin = (int)(u % C);
-            const long long seg_end = min(u1, (long long)(t + 1) * C);
-            const int cg = t % ncg, qb = t / ncg, q = qb / nbt, bt = qb % nbt;
-            const int b0 = bt * mrows;
-            const int rows = min(mrows, B - b0);
-            // piece index of this segment within its tile = CTAs between the tile's first owner and this one
-            const int piece = c_begin == 0 ? 0 : g - sk_owner((long long)t * C, W, G);
-            const int as = seg & 1;
-            mbar_wait(bar_accf + 8 * as, (seg >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const unsigned trow = tmem + (unsigned)as * TC_COLS + ((unsigned)(quarter * 32) << 16);
-            float4* zr = reinterpret_cast<float4*>(Z + (size_t)piece * plane + ((size_t)q * B + b0 + row) * slots + (size_t)cg * FC_CG);
-#pragma unroll 1
-            for (int c0 = 0; c0 < FC_CG; c0 += 16) {
-                float d1r[16], d1i[16], d2r[16], d2i[16];
-                tmem_ld16(trow + c0, d1r);
-                tmem_ld16(trow + 64 + c0, d1i);
-                tmem_ld16(trow + 128 + c0, d2r);
-                tmem_ld16(trow + 192 + c0, d2i);
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                if (row < rows) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2)
-                        zr[(c0 + i) >> 1] = make_float4(d1r[i] - d2i[i], d1i[i] + d2r[i], d1r[i + 1] - d2i[i + 1], d1i[i + 1] + d2r[i + 1]);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_acce + 8 * as) : "memory");
-            seg++;
-            u = seg_end;
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (wid == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * TC_COLS) : "memory");
-    }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -408,11 +249,6 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
                           cudaStream_t st)
 {
     static const int force_split = getenv("OWRX_FC_SPLIT") ? atoi(getenv("OWRX_FC_SPLIT")) : 0;
-    // stream-K is opt-in (OWRX_FC_STREAMK=1).  Measured on C2 (88 blocks x 64 slots): 0.105 ms alone against 0.093 ms for the
-    // one-tile-per-CTA grid — each SM streams ~30 GB/s either way (HBM latency under load against three 58 KB stages in
-    // flight), so levelling the second wave buys nothing and the extra Z plane costs a memset and a second read — and
-    // 0.18 ms inside the three-stream pipeline, where a one-CTA-per-SM grid waits for SMs other kernels hold
-    static const bool no_streamk = getenv("OWRX_FC_STREAMK") == nullptr || atoi(getenv("OWRX_FC_STREAMK")) == 0;
     // row tiles of <= 128 blocks, balanced, a multiple of 8 rows (the swizzle atom)
     const int nbt = (B + 127) / 128;
     const int mrows = std::min(128, (((B + nbt - 1) / nbt) + 7) / 8 * 8);
@@ -424,26 +260,6 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
     int rc;
     if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)FC_M * B, (unsigned)mrows)) != OWRX_OK) return rc;
     if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)FC_M * sh.slots, (unsigned)FC_CG)) != OWRX_OK) return rc;
-
-    // ---- persistent stream-K: one CTA per SM, equal unit ranges; pieces of a cut tile go to separate Z planes
-    if (!no_streamk && !force_split) {
-        const long long W = tiles * chunks;
-        const int G = (int)std::min<long long>(sm_count, W);
-        int pieces = 1;
-        for (long long t = 0; t < tiles; t++) {
-            const int g_first = (int)(((t * chunks + 1) * G - 1) / W), g_last = (int)((((t + 1) * chunks) * G - 1) / W);
-            pieces = std::max(pieces, g_last - g_first + 1);
-        }
-        if (pieces <= FC_MAXSPLIT) {
-            *nsplit_out = pieces;
-            const size_t plane = (size_t)FC_M * B * sh.slots;
-            if (pieces > 1) OWRX_CUDA(cudaMemsetAsync(d_Z + plane, 0, (size_t)(pieces - 1) * plane * sizeof(float2), st));
-            OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tc_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            fc_contract_tc_sk_kernel<<<(unsigned)G, 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt, mrows, W);
-            OWRX_LAUNCH_CHECK();
-            return OWRX_OK;
-        }
-    }
 
     // ---- one tile per CTA (split-K only when the tiles alone cannot occupy the machine)
     int nsplit = tiles >= sm_count ? 1 : (int)std::min<long long>(FC_MAXSPLIT, (sm_count + tiles - 1) / tiles);

@@ -223,6 +223,7 @@ struct Group {
     bool cfg_dirty = true;
     // stream position
     size_t in_off = 0;                               // streaming: offset of the next block in the bank's IQ buffer
+    size_t dev_lead = 0;                             // device path: samples at the head of the next block this group has consumed already
     long long frac_m = 0, wfm_m = 0, sq_abs = 0;
     StageBuf s1, s2, s3, f1, f1p, f1b, f2, f3;
     float2* d_partial = nullptr; size_t partial_cap = 0;
@@ -296,6 +297,7 @@ struct owrx_bank {
     bool deferred = false, pending_final = false;
     cudaEvent_t carry_done = nullptr;
     int fir_form_used = 0;                           // form of the latest Shift + FirDecimate pass (owrx_bank_fir_form)
+    size_t last_consumed = 0;                        // device path: samples of the last block every group is done with
 };
 
 namespace {
@@ -909,11 +911,6 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
         OWRX_LAUNCH_CHECK();
         // ---- demodulator front -> f1
         if ((rc = g->f1.ensure_new(n4, st)) != OWRX_OK) return rc;
-        for (size_t o = 0; o < n4; o += kRowChunk) {
-            // chunks are multiples of 4 rows but gate lookup uses absolute row / sq_len: pass whole range per chunk
-            const size_t c = std::min(kRowChunk, n4 - o);
-            (void)c;
-        }
         {
             // single logical launch split in row chunks that are multiples of sq_len
             const size_t chunk_rows = std::max<size_t>((size_t)g->sq_len, (kRowChunk / (size_t)g->sq_len) * (size_t)g->sq_len);
@@ -1316,9 +1313,10 @@ int owrx_bank_add_channel_ex(owrx_bank_t* bank, const owrx_chan_spec_t* spec, in
 
 int owrx_bank_remove_channel(owrx_bank_t* bank, int chan)
 {
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
-    std::lock_guard<std::mutex> lk(bank->mu);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     if (ch->group >= 0) {
         Group* g = bank->groups[(size_t)ch->group].get();
@@ -1343,9 +1341,10 @@ int owrx_bank_channel_count(const owrx_bank_t* bank)
 
 int owrx_chan_set_shift_rate(owrx_bank_t* bank, int chan, double rate)
 {
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
-    std::lock_guard<std::mutex> lk(bank->mu);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     ch->rate = rate;
     return OWRX_OK;
@@ -1353,9 +1352,10 @@ int owrx_chan_set_shift_rate(owrx_bank_t* bank, int chan, double rate)
 
 int owrx_chan_set_bandpass(owrx_bank_t* bank, int chan, double lo_rate, double hi_rate, int enabled)
 {
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
-    std::lock_guard<std::mutex> lk(bank->mu);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     ch->bp_enabled = enabled != 0; ch->bp_lo = lo_rate; ch->bp_hi = hi_rate;
@@ -1364,9 +1364,10 @@ int owrx_chan_set_bandpass(owrx_bank_t* bank, int chan, double lo_rate, double h
 
 int owrx_chan_set_squelch_level(owrx_bank_t* bank, int chan, float level)
 {
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
-    std::lock_guard<std::mutex> lk(bank->mu);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     ch->cfg.sq_level = level;
     Group* g = bank->groups[(size_t)ch->group].get();
@@ -1377,10 +1378,11 @@ int owrx_chan_set_squelch_level(owrx_bank_t* bank, int chan, float level)
 
 int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate, double tau, int agc_profile)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
     if (kind < OWRX_DEMOD_NFM || kind > OWRX_DEMOD_NONE) return fail(OWRX_E_INVALID, "unknown demodulator %d", kind);
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     Group* g = bank->groups[(size_t)ch->group].get();
@@ -1427,9 +1429,10 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
 
 int owrx_chan_set_agc(owrx_bank_t* bank, int chan, int profile, float initial_gain, float max_gain)
 {
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
-    std::lock_guard<std::mutex> lk(bank->mu);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     Group* g = bank->groups[(size_t)ch->group].get();
@@ -1451,10 +1454,11 @@ int owrx_chan_set_agc(owrx_bank_t* bank, int chan, int profile, float initial_ga
 
 int owrx_chan_set_audio_format(owrx_bank_t* bank, int chan, int format)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
     if (format != OWRX_AUDIO_F32 && format != OWRX_AUDIO_S16 && format != OWRX_AUDIO_ADPCM) return fail(OWRX_E_INVALID, "unknown audio format %d", format);
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     Group* g = bank->groups[(size_t)ch->group].get();
@@ -1473,9 +1477,10 @@ int owrx_chan_set_audio_format(owrx_bank_t* bank, int chan, int format)
 
 int owrx_chan_read_bytes(owrx_bank_t* bank, int chan, void* out, size_t cap_bytes, size_t* n)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (!bank || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     const size_t take = std::min(cap_bytes, ch->q_bytes.size());
     memcpy(out, ch->q_bytes.data(), take);
     ch->q_bytes.erase(ch->q_bytes.begin(), ch->q_bytes.begin() + (ptrdiff_t)take);
@@ -1485,10 +1490,11 @@ int owrx_chan_read_bytes(owrx_bank_t* bank, int chan, void* out, size_t cap_byte
 
 int owrx_chan_read_message(owrx_bank_t* bank, int chan, int type_byte, void* out, size_t cap_bytes, size_t* n)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (!bank || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
     if (type_byte != 0x02 && type_byte != 0x04) return fail(OWRX_E_INVALID, "message type must be 0x02 (audio) or 0x04 (HD audio)");
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     *n = 0;
     if (ch->q_bytes.empty() || cap_bytes < 2) return OWRX_OK;
     const size_t take = std::min(cap_bytes - 1, ch->q_bytes.size());
@@ -1797,10 +1803,20 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         // previous block's outputs are dropped; histories stay
         // pipelined: every stage after FirDecimate (rolls of their history buffers included) lives on the side stream
         if ((rc = group_begin_feed(bank, g, n_samples / (size_t)g->D + 1, sa, sb)) != OWRX_OK) return rc;
-        if ((rc = group_fir(bank, g, (const float2*)iq_dev, n_samples, &consumed, sa)) != OWRX_OK) return rc;
+        // groups consume whole decimation steps: a group that got further than the slowest one in the previous block starts
+        // `dev_lead` samples into this one (the caller presents [carry | new] from owrx_bank_last_consumed on)
+        const size_t lead = std::min(g->dev_lead, n_samples);
+        if ((rc = group_fir(bank, g, (const float2*)iq_dev + lead, n_samples - lead, &consumed, sa)) != OWRX_OK) return rc;
+        g->dev_lead = lead + consumed;               // rebased on the slowest group below
         int live = 0;
         for (int cid : g->slot_chan) if (cid >= 0) live++;
         bank->stats.channel_samples += (uint64_t)consumed * (uint64_t)live;
+    }
+    {
+        size_t cmin = n_samples;
+        for (auto& gp : bank->groups) if (gp) cmin = std::min(cmin, gp->dev_lead);
+        for (auto& gp : bank->groups) if (gp) gp->dev_lead -= cmin;
+        bank->last_consumed = cmin;
     }
     if (bank->pipelined) {
         OWRX_CUDA(cudaEventRecord(bank->fir_done, sa));
@@ -1879,18 +1895,30 @@ int owrx_bank_join(owrx_bank_t* bank, void* stream)
     return OWRX_OK;
 }
 
+int owrx_bank_last_consumed(const owrx_bank_t* bank, size_t* n_samples)
+{
+    if (!bank || !n_samples) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(const_cast<owrx_bank_t*>(bank)->mu);
+    *n_samples = bank->last_consumed;
+    return OWRX_OK;
+}
+
 int owrx_bank_last_audio_count(const owrx_bank_t* bank, int chan, size_t* n)
 {
+    if (!bank || !n) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(const_cast<owrx_bank_t*>(bank)->mu);
     Chan* ch = get_chan(const_cast<owrx_bank_t*>(bank), chan);
-    if (!ch || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     *n = bank->groups[(size_t)ch->group]->last_audio;
     return OWRX_OK;
 }
 
 int owrx_bank_last_audio_device(const owrx_bank_t* bank, int chan, const float** base, size_t* stride, size_t* slot)
 {
+    if (!bank || !base || !stride || !slot) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(const_cast<owrx_bank_t*>(bank)->mu);
     Chan* ch = get_chan(const_cast<owrx_bank_t*>(bank), chan);
-    if (!ch || !base || !stride || !slot) return fail(OWRX_E_INVALID, "bad argument");
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     const Group* g = bank->groups[(size_t)ch->group].get();
     *base = g->f3.rows(g->f3.fill - g->last_audio);
     *stride = (size_t)g->slots;
@@ -1900,18 +1928,19 @@ int owrx_bank_last_audio_device(const owrx_bank_t* bank, int chan, const float**
 
 int owrx_chan_read_audio(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (!bank || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     return pop_queue(ch->q_audio, out, cap_samples, n, 1);
 }
 
 int owrx_bank_read_audio_all(owrx_bank_t* bank, const int* chans, int n_chans, float* out, size_t cap_samples, size_t* counts)
 {
     if (!bank || !chans || n_chans < 0 || !out || !counts) return fail(OWRX_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(bank->mu);
     for (int i = 0; i < n_chans; i++)
         if (!get_chan(bank, chans[i])) return fail(OWRX_E_INVALID, "unknown channel %d", chans[i]);
-    std::lock_guard<std::mutex> lk(bank->mu);
     for (int i = 0; i < n_chans; i++) {
         Chan* ch = get_chan(bank, chans[i]);
         int rc = pop_queue(ch->q_audio, out + (size_t)i * cap_samples, cap_samples, &counts[i], 1);
@@ -1922,25 +1951,28 @@ int owrx_bank_read_audio_all(owrx_bank_t* bank, const int* chans, int n_chans, f
 
 int owrx_chan_read_demod(owrx_bank_t* bank, int chan, float* out, size_t cap_samples, size_t* n)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (!bank || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     return pop_queue(ch->q_demod, out, cap_samples, n, 1);
 }
 
 int owrx_chan_read_if(owrx_bank_t* bank, int chan, float* out_iq, size_t cap_samples, size_t* n)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch || !out_iq || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (!bank || !out_iq || !n) return fail(OWRX_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     return pop_queue(ch->q_if, out_iq, cap_samples, n, 2);
 }
 
 int owrx_chan_read_power(owrx_bank_t* bank, int chan, float* out, size_t cap, size_t* n)
 {
-    Chan* ch = get_chan(bank, chan);
-    if (!ch || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
+    if (!bank || !out || !n) return fail(OWRX_E_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(bank->mu);
+    Chan* ch = get_chan(bank, chan);
+    if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     return pop_queue(ch->q_power, out, cap, n, 1);
 }
 

@@ -34,6 +34,9 @@ def make_iq(n, fs, carriers, seed=SEED, noise=1e-3, t0=0):
                 sig = a * np.exp(1j * (2 * np.pi * f * t + 2.5 * np.sin(2 * np.pi * 1000.0 * t)))
             elif kind == "wfm":
                 sig = a * np.exp(1j * (2 * np.pi * f * t + 75.0 * np.sin(2 * np.pi * 1000.0 * t)))
+            elif kind == "amfm":
+                # one carrier that carries audio for an envelope detector (1 kHz, m = 0.5) AND a discriminator (700 Hz, +-2.5 kHz)
+                sig = a * (1.0 + 0.5 * np.cos(2 * np.pi * 1000.0 * t)) / 1.5 * np.exp(1j * (2 * np.pi * f * t + (2500.0 / 700.0) * np.sin(2 * np.pi * 700.0 * t)))
             elif kind == "usb":
                 sig = a * 0.5 * (np.exp(2j * np.pi * (f + 700.0) * t) + np.exp(2j * np.pi * (f + 1900.0) * t))
             else:

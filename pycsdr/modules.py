@@ -33,7 +33,9 @@ logger = logging.getLogger(__name__)
 version = "0.18.36"
 csdr_version = "0.18.36"
 
-_BUFFER_CAP_BYTES = 1 << 30
+# ring capacity of a Buffer: a reader that falls further behind than this loses the oldest data (a few seconds of the
+# fastest source: 61.44 MS/s complex float32 = 491 MB/s)
+_BUFFER_CAP_BYTES = 1 << 28
 
 
 def _native():
@@ -82,6 +84,9 @@ class Reader:
         self._buffer = buffer
         self._pos = buffer._end
         self._stopped = False
+        # True while the reader is only a wiring token of a fused (descriptor) stage: the source runner reads the Buffer
+        # through its own cursor, nobody ever calls read() on this one, so it must not pin chunks in Buffer._trim
+        self._virtual = False
 
     def getFormat(self):
         return self._buffer._format
@@ -95,6 +100,9 @@ class Reader:
     def _read(self, everything):
         b = self._buffer
         with b._cond:
+            if self._virtual:                 # somebody reads this cursor after all: it counts again, from "now"
+                self._virtual = False
+                self._pos = max(self._pos, b._end)
             while not self._stopped and self._pos >= b._end:
                 b._cond.wait()
             if self._stopped:
@@ -155,6 +163,7 @@ class Buffer(Writer):
         r = Reader(self)
         with self._cond:
             self._readers.add(r)
+        _GRAPH.touch()            # a new cursor on a Buffer between fused stages makes that Buffer's content needed
         return r
 
     def write(self, data):
@@ -169,7 +178,7 @@ class Buffer(Writer):
             self._cond.notify_all()
 
     def _trim(self):
-        live = [r._pos for r in self._readers if not r._stopped]
+        live = [r._pos for r in self._readers if not r._stopped and not r._virtual]
         low = min(live) if live else self._end
         while self._chunks and (self._start < low or self._bytes > _BUFFER_CAP_BYTES):
             self._bytes -= len(self._chunks.popleft())
@@ -177,7 +186,9 @@ class Buffer(Writer):
 
     def _extra_readers(self, used):
         with self._cond:
-            return [r for r in self._readers if r is not used and not r._stopped]
+            # virtual readers are wiring tokens of fused stages: only cursors somebody really reads count (a Python pump, or the
+            # own reader of a runner that serves heads attached to this Buffer)
+            return [r for r in self._readers if r is not used and not r._stopped and not r._virtual]
 
 
 # ================================================================================================
@@ -229,9 +240,15 @@ class _Stage(Module):
             raise ValueError("invalid reader format: %s, expected %s" % (reader.getFormat().name, self.getInputFormat().name))
         self._reader = reader
         self._stopped = False
+        if isinstance(reader, Reader):
+            reader._virtual = self._consumes_through_runner()
         _GRAPH.touch()
         if self.HEAD and reader is not None:
             _SourceRunner.attach(reader._buffer)
+
+    def _consumes_through_runner(self):
+        """descriptor stages never call reader.read(): their data arrives through the source Buffer's runner"""
+        return True
 
     def setWriter(self, writer):
         if isinstance(writer, Buffer) and writer.getFormat() is not self.getOutputFormat():
@@ -518,6 +535,9 @@ class Convert(_Unfused):
     def _ingress(self):
         return self.OUT is Format.COMPLEX_FLOAT and self.IN in self._RAW
 
+    def _consumes_through_runner(self):
+        return not self._ingress()            # the source-side pump below really reads its reader
+
     def setReader(self, reader):
         super().setReader(reader)
         if self._ingress() and reader is not None and (self._pump is None or not self._pump.is_alive()):
@@ -646,10 +666,12 @@ def _walk(head):
         w = cur._writer
         if not isinstance(w, Buffer):
             break
+        # the stage that continues THIS chain: a Buffer can have further readers that start chains of their own (the secondary
+        # FFT and the SecondarySelector on ClientDemodulatorChain.selectorBuffer, owrx/dsp.py:49,188-225) — those are heads
         nxt = None
         for m in list(_GRAPH.modules):
             r = m._reader
-            if r is not None and r._buffer is w and not m._stopped and not r._stopped:
+            if r is not None and r._buffer is w and not m._stopped and not r._stopped and not m.HEAD:
                 nxt = m
                 break
         if nxt is None:
@@ -820,6 +842,7 @@ class _SourceRunner(threading.Thread):
         self.bank = None
         self.channels = {}        # id(Shift stage) -> dict(plan state)
         self.unsupported = set()
+        self.processed = 0        # sequence number of the source Buffer up to which every plan has been fed and drained
 
     @classmethod
     def attach(cls, buffer):
@@ -864,7 +887,18 @@ class _SourceRunner(threading.Thread):
                         logger.error("pycsdr-b200: client chain %s is not a fusable hot-path chain; it will not run",
                                      [type(m).__name__ for m in chain])
                     continue
-                self._update_channel(N, head, d, links)
+                try:
+                    self._update_channel(N, head, d, links)
+                except (ValueError, BufferError) as e:
+                    # one client's spec was rejected by the library (e.g. a band-pass transition out of range): that chain
+                    # does not run; every other client of this source keeps running
+                    if id(head) not in self.unsupported:
+                        self.unsupported.add(id(head))
+                        logger.error("pycsdr-b200: client chain %s rejected: %s", [type(m).__name__ for m in chain], e)
+                    st = self.channels.pop(id(head), None)
+                    if st is not None:
+                        N.lib.owrx_bank_remove_channel(self.bank, st["cid"])
+                    continue
                 live_ch.add(id(head))
         for k in [k for k in self.wf_plans if k not in live_wf]:
             self.wf_plans.pop(k).close()
@@ -950,6 +984,7 @@ class _SourceRunner(threading.Thread):
         N = None
         idle = 0
         while True:
+            self.processed = self.reader._pos
             data = self.reader._read(True)      # the runner batches everything that has arrived into one GPU pass
             if data is None:
                 break
@@ -973,9 +1008,17 @@ class _SourceRunner(threading.Thread):
                     plan.feed(data, raw)
                 if self.channels:
                     self._feed_bank(N, data, raw)
+            except (ValueError, BufferError):
+                # a bad argument on one plan: logged, the source keeps feeding (only CUDA / memory failures are fatal)
+                logger.exception("pycsdr-b200 runner: block dropped")
+                continue
             except Exception:
                 logger.exception("pycsdr-b200 runner failed")
                 break
+        with self._lock:
+            if self.buffer._runner is self:
+                self.buffer._runner = None
+        self.reader.stop()                      # a dead runner must not pin chunks of the source Buffer
         for p in self.wf_plans.values():
             p.close()
         if self.bank is not None and N is not None:

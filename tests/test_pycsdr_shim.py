@@ -219,3 +219,28 @@ def test_reference_fifi_sdr_format_conversion_runs_on_the_shim():
     src.write(payload)
     assert bytes(rd.read()) == payload and out._raw == ("cs16", 5.0)
     conversion.stop()
+
+
+def test_fused_stage_readers_do_not_pin_the_source_buffer():
+    """head stages get a Reader through Chain.setReader that nobody ever reads (the runner reads the Buffer through
+    its own cursor): such wiring tokens must not make Buffer._trim keep every chunk"""
+    src = M.Buffer(Format.COMPLEX_FLOAT)
+    fft = M.Fft(size=1024, every_n_samples=700)
+    fft.setReader(src.getReader())                      # attaches a runner with its own reader; this one is only a token
+    assert fft._reader._virtual
+    runner = src._runner
+    assert runner is not None
+    chunk = bytes(8 * 1000)
+    for _ in range(200):
+        src.write(chunk)
+    deadline = time.time() + 10
+    while time.time() < deadline and runner.processed < src._end:
+        time.sleep(0.01)
+    src.write(chunk)                                    # a write trims what every live cursor has passed
+    time.sleep(0.2)
+    assert len(src._chunks) <= 4, len(src._chunks)
+    # a cursor somebody really reads counts again, from the moment it is read
+    r = src.getReader()
+    src.write(b"\x01" * 8)
+    assert bytes(r.read()) == b"\x01" * 8
+    fft.stop()
