@@ -183,8 +183,8 @@ def synth_iq_torch(n, fs, carriers, device, seed=20260101):
                 env = a * (1.0 + 0.5 * torch.cos(2 * np.pi * 1000.0 * t)) / 1.5
                 ph = 2 * np.pi * ((f * t) % 1.0)
                 re += (env * torch.cos(ph)).float(); im += (env * torch.sin(ph)).float()
-            elif kind == "nfm":
-                ph = 2 * np.pi * ((f * t) % 1.0) + 2.5 * torch.sin(2 * np.pi * 1000.0 * t)
+            elif kind in ("nfm", "wfm"):
+                ph = 2 * np.pi * ((f * t) % 1.0) + (2.5 if kind == "nfm" else 75.0) * torch.sin(2 * np.pi * 1000.0 * t)
                 re += (a * torch.cos(ph)).float(); im += (a * torch.sin(ph)).float()
             else:
                 for df in (700.0, 1900.0):

@@ -162,6 +162,168 @@ wf_fft_kernel(WfFftParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wf_fft2_kernel — the same Stockham FFT on PACKED FP32 (Blackwell FADD2 / FMUL2 / FFMA2), two frames of a line per pass.
+// A thread's 16 points carry BOTH frames: re = (re of frame a, re of frame a + 1), im likewise, so every butterfly add,
+// twiddle multiply, window multiply and |X|^2 is one packed instruction for two frames, the twiddles and window values
+// are fetched once per pair, and one CTA barrier serves two frames.  Shared memory holds one float4 (re0, re1, im0, im1)
+// per point: 128-bit LDS / STS, a quarter-warp per wavefront, conflict-free with the pad-every-16 layout.
+// Against wf_fft_kernel (one frame per pass, scalar FP32) the issued instructions per frame roughly halve; what remains is
+// the L1 / shared-memory datapath: 2 exchanges x (write + read) x 8 bytes per point per frame, plus the frame itself.
+// ------------------------------------------------------------------------------------------------
+struct C2 {
+    float2 re, im;
+};
+#define OWRX_P2(x) make_float2((x), (x))
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }          // folds into operand modifiers
+__device__ __forceinline__ C2 c2add(C2 a, C2 b) { return C2{__fadd2_rn(a.re, b.re), __fadd2_rn(a.im, b.im)}; }
+__device__ __forceinline__ C2 c2sub(C2 a, C2 b) { return C2{__fadd2_rn(a.re, neg2(b.re)), __fadd2_rn(a.im, neg2(b.im))}; }
+__device__ __forceinline__ C2 c2mul(C2 a, float c, float s)                                   // a * (c + i s), both frames
+{
+    C2 r;
+    r.re = __ffma2_rn(a.re, OWRX_P2(c), __fmul2_rn(a.im, OWRX_P2(-s)));
+    r.im = __ffma2_rn(a.re, OWRX_P2(s), __fmul2_rn(a.im, OWRX_P2(c)));
+    return r;
+}
+__device__ __forceinline__ void c2dft2(C2& a, C2& b)
+{
+    const C2 t = a;
+    a = c2add(t, b);
+    b = c2sub(t, b);
+}
+__device__ __forceinline__ void c2dft4(C2& a, C2& b, C2& c, C2& d)
+{
+    const C2 t0 = c2add(a, c), t1 = c2sub(a, c), t2 = c2add(b, d), bd = c2sub(b, d);
+    // t3 = -i (b - d) = (bd.im, -bd.re)
+    a = c2add(t0, t2);
+    c = c2sub(t0, t2);
+    b = C2{__fadd2_rn(t1.re, bd.im), __fadd2_rn(t1.im, neg2(bd.re))};
+    d = C2{__fadd2_rn(t1.re, neg2(bd.im)), __fadd2_rn(t1.im, bd.re)};
+}
+// v * W8^1 = ((re + im), (im - re)) / sqrt 2;   v * W8^3 = ((im - re), -(re + im)) / sqrt 2;   v * W4^1 = (im, -re)
+__device__ __forceinline__ C2 c2w8_1(C2 v) { return C2{__fmul2_rn(__fadd2_rn(v.re, v.im), OWRX_P2(OWRX_SQRT1_2)), __fmul2_rn(__fadd2_rn(v.im, neg2(v.re)), OWRX_P2(OWRX_SQRT1_2))}; }
+__device__ __forceinline__ C2 c2w8_3(C2 v) { return C2{__fmul2_rn(__fadd2_rn(v.im, neg2(v.re)), OWRX_P2(OWRX_SQRT1_2)), __fmul2_rn(__fadd2_rn(v.re, v.im), OWRX_P2(-OWRX_SQRT1_2))}; }
+__device__ __forceinline__ C2 c2mi(C2 v) { return C2{v.im, neg2(v.re)}; }
+__device__ __forceinline__ void c2dft16(C2* v)
+{
+    // same index algebra as dft<16> (fft_small.cuh): n = 4 n1 + n2, m = m1 + 4 m2
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) c2dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    v[5] = c2mul(v[5], OWRX_COS_PI_8, -OWRX_SIN_PI_8);
+    v[6] = c2w8_1(v[6]);
+    v[7] = c2mul(v[7], OWRX_SIN_PI_8, -OWRX_COS_PI_8);
+    v[9] = c2w8_1(v[9]);
+    v[10] = c2mi(v[10]);
+    v[11] = c2w8_3(v[11]);
+    v[13] = c2mul(v[13], OWRX_SIN_PI_8, -OWRX_COS_PI_8);
+    v[14] = c2w8_3(v[14]);
+    v[15] = c2mul(v[15], -OWRX_COS_PI_8, OWRX_SIN_PI_8);
+#pragma unroll
+    for (int m1 = 0; m1 < 4; m1++) c2dft4(v[4 * m1], v[4 * m1 + 1], v[4 * m1 + 2], v[4 * m1 + 3]);
+}
+
+// M = 4096 points: 256 threads x 16 points, radix 16 x 16 x 16; one CTA per (line, four-step row, frame subset).
+template <bool FROM_IQ>
+__global__ void __launch_bounds__(256, 2)
+wf_fft2_kernel(WfFftParams p)
+{
+    constexpr int M = 4096, T = 256;
+    extern __shared__ float4 smem4[];                       // [M + M / 16]
+    const int tid = threadIdx.x;
+    int unit = blockIdx.x;
+    const int subset = unit % p.subsets;
+    unit /= p.subsets;
+    const int k1 = unit % p.r0;
+    const int line = unit / p.r0;
+    const int per = (p.frames_per_line + p.subsets - 1) / p.subsets;
+    const int a0 = subset * per;
+    const int a1 = min(p.frames_per_line, a0 + per);
+
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) acc[q] = 0.0f;
+    const int k = tid & 15;
+    const int base2 = (tid >> 4) * 256 + k;
+
+    for (int a = a0; a < a1; a += 2) {
+        const bool two = a + 1 < a1;
+        C2 v[16];
+        const long long frame = (long long)line * p.frames_per_line + a;
+        if (FROM_IQ) {
+            const float2* x0 = p.src + (p.first_frame + frame) * (long long)p.every_n;
+            const float2* x1 = x0 + p.every_n;
+            if (a + 2 < a1) {
+                // pull the next pair of frames towards L2 while this one is transformed (one 128-byte line per thread and frame)
+                const char* nx = reinterpret_cast<const char*>(x1 + p.every_n) + (size_t)tid * 128;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                if (a + 3 < a1) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)p.every_n * 8));
+            }
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const float2 s0 = __ldg(x0 + tid + r * T);
+                const float2 s1 = two ? __ldg(x1 + tid + r * T) : make_float2(0.f, 0.f);
+                const float w = __ldg(p.window + tid + r * T);
+                v[r].re = __fmul2_rn(make_float2(s0.x, s1.x), OWRX_P2(w));
+                v[r].im = __fmul2_rn(make_float2(s0.y, s1.y), OWRX_P2(w));
+            }
+        } else {
+            const float2* x0 = p.src + (frame * p.r0 + k1) * (long long)M;
+            const float2* x1 = x0 + (long long)p.r0 * M;
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const float2 s0 = __ldg(x0 + tid + r * T);
+                const float2 s1 = two ? __ldg(x1 + tid + r * T) : make_float2(0.f, 0.f);
+                v[r].re = make_float2(s0.x, s1.x);
+                v[r].im = make_float2(s0.y, s1.y);
+            }
+        }
+        // pass 1: radix 16, Ns = 1
+        c2dft16(v);
+        __syncthreads();                                    // the previous pair's pass-3 reads are done
+#pragma unroll
+        for (int q = 0; q < 16; q++) smem4[pad16(tid * 16 + slot<16>(q))] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
+        __syncthreads();
+        // pass 2: radix 16, Ns = 16
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const float4 t = smem4[pad16(tid + r * T)];
+            v[r].re = make_float2(t.x, t.y);
+            v[r].im = make_float2(t.z, t.w);
+        }
+#pragma unroll
+        for (int r = 1; r < 16; r++) {
+            const float2 w = __ldg(p.tw2 + r * 16 + k);
+            v[r] = c2mul(v[r], w.x, w.y);
+        }
+        c2dft16(v);
+        __syncthreads();                                    // every pass-2 read is done: the buffer is reused in place
+#pragma unroll
+        for (int q = 0; q < 16; q++) smem4[pad16(base2 + slot<16>(q) * 16)] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
+        __syncthreads();
+        // pass 3: radix 16, Ns = 256
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const float4 t = smem4[pad16(tid + r * 256)];
+            v[r].re = make_float2(t.x, t.y);
+            v[r].im = make_float2(t.z, t.w);
+        }
+#pragma unroll
+        for (int r = 1; r < 16; r++) {
+            const float2 w = __ldg(p.tw3 + r * 256 + tid);
+            v[r] = c2mul(v[r], w.x, w.y);
+        }
+        c2dft16(v);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float2 pw = __ffma2_rn(v[q].im, v[q].im, __fmul2_rn(v[q].re, v[q].re));
+            acc[q] += pw.x + pw.y;
+        }
+    }
+    float* out = p.partial + ((size_t)line * p.subsets + subset) * (size_t)p.n;
+#pragma unroll
+    for (int q = 0; q < 16; q++) out[(size_t)k1 + (size_t)p.r0 * (tid + slot<16>(q) * 256)] = acc[q];
+}
+
 struct WfColParams {
     const float2* iq;
     const float* window;
@@ -432,6 +594,22 @@ template <int LOG2M, bool FROM_IQ> static int launch_fft(const WfFftParams& p, s
     return OWRX_OK;
 }
 
+template <bool FROM_IQ> static int launch_fft2(const WfFftParams& p, size_t units, cudaStream_t st)
+{
+    const size_t smem = (size_t)(4096 + 4096 / 16) * sizeof(float4);
+    OWRX_CUDA(cudaFuncSetAttribute(wf_fft2_kernel<FROM_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wf_fft2_kernel<FROM_IQ><<<(unsigned)units, 256, smem, st>>>(p);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+// OWRX_WF_SCALAR=1 keeps the one-frame-per-pass scalar kernel for the 4096-point rows (A/B runs)
+static bool wf_use_packed()
+{
+    static const bool scalar = getenv("OWRX_WF_SCALAR") && atoi(getenv("OWRX_WF_SCALAR")) != 0;
+    return !scalar;
+}
+
 static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame, size_t lines, uint8_t* out_dev,
                         float* db_dev, int16_t* s16_dev, cudaStream_t st)
 {
@@ -457,7 +635,7 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
         case 9:  rc = launch_fft<9, true>(p, units, st); break;
         case 10: rc = launch_fft<10, true>(p, units, st); break;
         case 11: rc = launch_fft<11, true>(p, units, st); break;
-        case 12: rc = launch_fft<12, true>(p, units, st); break;
+        case 12: rc = wf_use_packed() ? launch_fft2<true>(p, units, st) : launch_fft<12, true>(p, units, st); break;
         default: return fail(OWRX_E_INVALID, "unsupported fft size");
         }
         if (rc != OWRX_OK) return rc;
@@ -477,7 +655,7 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
         }
         OWRX_LAUNCH_CHECK();
         p.src = wf->d_y; p.first_frame = 0;
-        if ((rc = launch_fft<12, false>(p, units, st)) != OWRX_OK) return rc;
+        if ((rc = wf_use_packed() ? launch_fft2<false>(p, units, st) : launch_fft<12, false>(p, units, st)) != OWRX_OK) return rc;
     }
 
     // finalize: log / swap / quantise.  The ADPCM encoder runs once per batch (wf_process), not per chunk:

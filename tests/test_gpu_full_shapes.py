@@ -61,10 +61,18 @@ def _oracle_many(iq, fs, out, cars, **kw):
 
 
 def _run_bank(iq, fs, out, cars, mode, **kw):
+    """the block through the DEVICE path in one call, as bench.py runs it (the host path would cut it into 2 M-sample upload
+    chunks and OWRX_FIR_AUTO would choose the form per chunk)"""
+    import torch
     bank = ChannelBank(fs, outputs=N.OUT_IF | N.OUT_DEMOD)
     bank.set_fir_mode(mode)
     chans = [bank.add_channel(out, demod=c["kind"], offset=c["offset"], bandpass=BANDPASS[c["kind"]], **kw) for c in cars]
-    bank.feed(iq)
+    d_iq = torch.from_numpy(iq.view(np.float32)).cuda()
+    st = torch.cuda.Stream()
+    bank.process_device(d_iq, len(iq), stream=st.cuda_stream)
+    bank.join(st.cuda_stream)
+    st.synchronize()
+    bank.drain()
     form = bank.fir_form()
     res = [(ch.read_if(), ch.read_demod()) for ch in chans]
     bank.close()
@@ -123,7 +131,7 @@ def test_c5_shape_wfm_from_20msps(gpu):
     fs, out = 20e6, 250000
     cars = carrier_plan(8, fs, seed=35, wfm=True, span=0.4)
     n = 2133 + 80 * (15625 * 3 + 50)
-    iq = _gpu_iq(n, fs, [dict(c, kind="nfm") for c in cars], seed=35)     # narrow FM carriers at the WFM channels' centres
+    iq = _gpu_iq(n, fs, cars, seed=35)                                    # +-75 kHz deviation, 1 kHz tone
     refs = _oracle_many(iq, fs, out, cars, audio_rate=48000.0, wfm_tau=50e-6)
     for mode in ("auto", "direct"):
         form, res = _run_bank(iq, fs, out, cars, mode, audio_rate=48000.0, tau=50e-6)

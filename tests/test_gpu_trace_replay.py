@@ -84,24 +84,25 @@ def test_spectrum_thread_trace_with_data(gpu):
         rp.close()
 
 
-def _best_lag(a, b, span=400):
-    """lag d maximising sum a[i + d] b[i] (|d| <= span)"""
+SPAN = 3400        # the streams may be offset by up to one squelch block of audio (750 samples; 3000 for the WFM chain) + FIR lead
+
+
+def _best_lag(a, b, span=SPAN):
+    """lag d maximising sum a[i + d] b[i] (|d| <= span), by FFT cross-correlation"""
     n = min(len(a), len(b)) - 2 * span
     ref = b[span:span + n].astype(np.float64)
-    best, arg = -1e300, 0
-    for d in range(-span, span + 1):
-        v = float(np.dot(a[span + d:span + d + n].astype(np.float64), ref))
-        if v > best:
-            best, arg = v, d
-    return arg
+    seg = a[:span + n + span].astype(np.float64)
+    m = 1 << int(np.ceil(np.log2(len(seg) + n)))
+    xc = np.fft.irfft(np.fft.rfft(seg, m) * np.conj(np.fft.rfft(ref, m)), m)[:2 * span + 1]
+    return int(np.argmax(xc)) - span
 
 
 def _compare_audio(got, want):
     """normalised correlation and gain ratio over the second half, after aligning the streams"""
     d = _best_lag(got, want)
-    n = min(len(got), len(want)) - 800
-    a = got[400 + d:400 + d + n].astype(np.float64)[n // 2:]
-    b = want[400:400 + n].astype(np.float64)[n // 2:]
+    n = min(len(got), len(want)) - 2 * SPAN
+    a = got[SPAN + d:SPAN + d + n].astype(np.float64)[n // 2:]
+    b = want[SPAN:SPAN + n].astype(np.float64)[n // 2:]
     corr = float(np.dot(a, b) / np.sqrt(np.dot(a, a) * np.dot(b, b)))
     gain = float(np.sqrt(np.dot(a, a) / np.dot(b, b)))
     resid = float(np.sqrt(np.mean((a / gain - b) ** 2)) / np.sqrt(np.mean(b ** 2)))
