@@ -40,6 +40,8 @@ struct WfFftParams {
     int r0;                  // four-step rows (1 when FROM_IQ)
     int n;                   // full FFT size N = r0 * M
     long long first_frame;   // FROM_IQ: global frame index of line 0 of this launch
+    int units;               // wf_fft2_kernel: (line, row, subset) units of this launch, handed out through `counter`
+    int* counter;            // wf_fft2_kernel: zeroed before the launch
 };
 
 // One CTA per (line, row k1, frame subset).  M = 2^LOG2M points, T = M/16 threads.
@@ -229,21 +231,26 @@ wf_fft2_kernel(WfFftParams p)
 {
     constexpr int M = 4096, T = 256;
     extern __shared__ float4 smem4[];                       // [M + M / 16]
+    __shared__ int s_next;
     const int tid = threadIdx.x;
-    int unit = blockIdx.x;
+    const int k = tid & 15;
+    const int base2 = (tid >> 4) * 256 + k;
+    const int per = (p.frames_per_line + p.subsets - 1) / p.subsets;
+    // Persistent CTAs take (line, row, subset) units from a global counter: the grid is one resident wave, and an SM that is
+    // late (or held by the side-stream ADPCM encoder) simply takes fewer units — no wave quantisation.
+    for (int cur = blockIdx.x; cur < p.units;) {
+    int unit = cur;
     const int subset = unit % p.subsets;
     unit /= p.subsets;
     const int k1 = unit % p.r0;
     const int line = unit / p.r0;
-    const int per = (p.frames_per_line + p.subsets - 1) / p.subsets;
     const int a0 = subset * per;
     const int a1 = min(p.frames_per_line, a0 + per);
+    if (tid == 0) s_next = atomicAdd(p.counter, 1) + (int)gridDim.x;
 
     float acc[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) acc[q] = 0.0f;
-    const int k = tid & 15;
-    const int base2 = (tid >> 4) * 256 + k;
 
     for (int a = a0; a < a1; a += 2) {
         const bool two = a + 1 < a1;
@@ -322,6 +329,9 @@ wf_fft2_kernel(WfFftParams p)
     float* out = p.partial + ((size_t)line * p.subsets + subset) * (size_t)p.n;
 #pragma unroll
     for (int q = 0; q < 16; q++) out[(size_t)k1 + (size_t)p.r0 * (tid + slot<16>(q) * 256)] = acc[q];
+    __syncthreads();                                        // s_next is visible; every read of the shared buffer is done
+    cur = s_next;
+    }
 }
 
 struct WfColParams {
@@ -537,6 +547,7 @@ struct owrx_wf {
     float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_twn = nullptr;
     // scratch
     float* d_partial = nullptr; size_t partial_cap = 0;
+    int* d_counter = nullptr;                                  // work counter of the persistent FFT kernel
     float2* d_y = nullptr;      size_t y_cap = 0;
     int16_t* d_s16 = nullptr;   size_t s16_cap = 0;
     // pipelined mode: the (latency-bound, one warp per 32 lines) ADPCM pass of batch i runs on a high-priority side
@@ -594,11 +605,13 @@ template <int LOG2M, bool FROM_IQ> static int launch_fft(const WfFftParams& p, s
     return OWRX_OK;
 }
 
-template <bool FROM_IQ> static int launch_fft2(const WfFftParams& p, size_t units, cudaStream_t st)
+template <bool FROM_IQ> static int launch_fft2(const WfFftParams& p, size_t units, int sm_count, cudaStream_t st)
 {
     const size_t smem = (size_t)(4096 + 4096 / 16) * sizeof(float4);
     OWRX_CUDA(cudaFuncSetAttribute(wf_fft2_kernel<FROM_IQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wf_fft2_kernel<FROM_IQ><<<(unsigned)units, 256, smem, st>>>(p);
+    OWRX_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(int), st));
+    const unsigned grid = (unsigned)std::min<size_t>(units, (size_t)2 * sm_count);       // 2 CTAs per SM (128 registers, 70 KB)
+    wf_fft2_kernel<FROM_IQ><<<grid, 256, smem, st>>>(p);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
@@ -620,6 +633,11 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
     const size_t base_units = lines * (size_t)wf->r0;
     if (base_units < (size_t)2 * wf->sm_count)
         subsets = (int)std::min<size_t>((size_t)std::min(fpl, 8), ((size_t)2 * wf->sm_count + base_units - 1) / base_units);
+    // the persistent packed kernel balances through its work counter: aim at ~8 units per resident CTA, each of at least
+    // 8 frame pairs (a subset costs one more partial-sum row for wf_finalize_kernel to add)
+    if (wf->m == 4096 && wf_use_packed() && base_units < (size_t)16 * wf->sm_count)
+        subsets = (int)std::max<size_t>(subsets, std::min<size_t>((size_t)std::max(1, std::min(fpl / 16, 8)),
+                                                                  ((size_t)16 * wf->sm_count + base_units - 1) / base_units));
     int rc;
     if ((rc = grow(&wf->d_partial, &wf->partial_cap, lines * (size_t)subsets * (size_t)n)) != OWRX_OK) return rc;
 
@@ -627,6 +645,8 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
     p.window = wf->d_window; p.tw2 = wf->d_tw2; p.tw3 = wf->d_tw3; p.partial = wf->d_partial;
     p.every_n = wf->every_n; p.frames_per_line = fpl; p.subsets = subsets; p.r0 = wf->r0; p.n = n;
     const size_t units = lines * (size_t)wf->r0 * (size_t)subsets;
+    if (units > (size_t)0x7fffffff) return fail(OWRX_E_INVALID, "batch too large");
+    p.units = (int)units; p.counter = wf->d_counter;
 
     if (wf->r0 == 1) {
         p.src = iq_dev; p.first_frame = first_frame;
@@ -635,7 +655,7 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
         case 9:  rc = launch_fft<9, true>(p, units, st); break;
         case 10: rc = launch_fft<10, true>(p, units, st); break;
         case 11: rc = launch_fft<11, true>(p, units, st); break;
-        case 12: rc = wf_use_packed() ? launch_fft2<true>(p, units, st) : launch_fft<12, true>(p, units, st); break;
+        case 12: rc = wf_use_packed() ? launch_fft2<true>(p, units, wf->sm_count, st) : launch_fft<12, true>(p, units, st); break;
         default: return fail(OWRX_E_INVALID, "unsupported fft size");
         }
         if (rc != OWRX_OK) return rc;
@@ -655,7 +675,7 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
         }
         OWRX_LAUNCH_CHECK();
         p.src = wf->d_y; p.first_frame = 0;
-        if ((rc = wf_use_packed() ? launch_fft2<false>(p, units, st) : launch_fft<12, false>(p, units, st)) != OWRX_OK) return rc;
+        if ((rc = wf_use_packed() ? launch_fft2<false>(p, units, wf->sm_count, st) : launch_fft<12, false>(p, units, st)) != OWRX_OK) return rc;
     }
 
     // finalize: log / swap / quantise.  The ADPCM encoder runs once per batch (wf_process), not per chunk:
@@ -760,6 +780,7 @@ static int wf_build_tables(owrx_wf* wf)
             double a = -2.0 * M_PI * (double)r * k / (double)m;
             tw3[(size_t)r * 256 + k] = make_float2((float)cos(a), (float)sin(a));
         }
+    OWRX_CUDA(cudaMalloc((void**)&wf->d_counter, sizeof(int)));
     OWRX_CUDA(cudaMalloc((void**)&wf->d_window, win.size() * sizeof(float)));
     OWRX_CUDA(cudaMalloc((void**)&wf->d_tw2, tw2.size() * sizeof(float2)));
     OWRX_CUDA(cudaMalloc((void**)&wf->d_tw3, tw3.size() * sizeof(float2)));
@@ -820,7 +841,7 @@ void owrx_wf_destroy(owrx_wf_t* wf)
     if (!wf) return;
     cudaSetDevice(wf->device);
     if (wf->stream) cudaStreamSynchronize(wf->stream);
-    cudaFree(wf->d_window); cudaFree(wf->d_tw2); cudaFree(wf->d_tw3); cudaFree(wf->d_twn);
+    cudaFree(wf->d_window); cudaFree(wf->d_tw2); cudaFree(wf->d_tw3); cudaFree(wf->d_twn); cudaFree(wf->d_counter);
     cudaDeviceSynchronize();
     cudaFree(wf->d_partial); cudaFree(wf->d_y); cudaFree(wf->d_s16); cudaFree(wf->d_s16_alt);
     if (wf->fin_done) cudaEventDestroy(wf->fin_done);

@@ -79,3 +79,142 @@ class MulticastHop:
 
     def release(self, j, stream):
         self.free[j & 1].record(stream)
+
+
+def gather_block(out, my_slice, group=None):
+    """One hop of the SHARDED ingest: every rank holds 1/N of the wideband block (what it uploaded over its own PCIe link);
+    afterwards every rank holds the whole block.  `out`: flat tensor of N x len(my_slice) elements.  NCCL over NVLink on GPUs,
+    gloo in CPU tests."""
+    import torch.distributed as dist
+    return dist.all_gather_into_tensor(out, my_slice, group=group)
+
+
+class _HopBase:
+    """double-buffered per-block hop: gather(j, my_slice) on the hop's own stream, one block ahead of the consumer;
+    recv(j, stream) makes the consumer wait for the landing and returns the whole block; release(j, stream) marks its last read"""
+
+    def _init_common(self, block_samples, world, rank, device):
+        import torch
+        self._torch = torch
+        self.world, self.rank = world, rank
+        self.block_floats = 2 * int(block_samples)
+        if self.block_floats % world:
+            raise ValueError("the block must divide evenly among the ranks")
+        self.shard_floats = self.block_floats // world
+        self.stream = torch.cuda.Stream(device=device)
+        self.landed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self._timing = []
+
+    def recv(self, j, stream):
+        stream.wait_event(self.landed[j & 1])
+        return self.bufs[j & 1]
+
+    def release(self, j, stream):
+        self.free[j & 1].record(stream)
+
+    def _timed(self):
+        torch = self._torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if len(self._timing) < 256:
+            self._timing.append((e0, e1))
+        return e0, e1
+
+    def mean_ms(self):
+        """mean device time of a gather on the hop's stream (waits for the peers included), first calls excluded"""
+        self.stream.synchronize()
+        t = [a.elapsed_time(b) for a, b in self._timing[3:]]
+        self._timing = []
+        return sum(t) / len(t) if t else None
+
+
+class NcclGatherHop(_HopBase):
+    """the slices are all-gathered by NCCL (copy kernels on every rank's SMs, NCCL_MAX_NCHANNELS bounds how many)"""
+
+    def __init__(self, block_samples, world, rank, device, group=None):
+        import torch
+        self._init_common(block_samples, world, rank, device)
+        self.group = group
+        self.bufs = [torch.empty(self.block_floats // 2, 2, device=device), torch.empty(self.block_floats // 2, 2, device=device)]
+        import os
+        self.kind = "ncclAllGather (NCCL_MAX_NCHANNELS=%s)" % os.environ.get("NCCL_MAX_NCHANNELS", "default")
+
+    def gather(self, j, my_slice):
+        b = j & 1
+        torch = self._torch
+        self.stream.wait_event(self.free[b])                     # this rank's consumer is done with buffer b
+        with torch.cuda.stream(self.stream):
+            e0, e1 = self._timed()
+            e0.record(self.stream)
+            gather_block(self.bufs[b].view(-1), my_slice.reshape(-1), self.group)
+            e1.record(self.stream)
+            self.landed[b].record(self.stream)
+
+
+class PullGatherHop(_HopBase):
+    """SM-free all-gather over NVSwitch: both block buffers live in ONE symmetric allocation (torch.distributed symmetric memory:
+    every rank's buffer is mapped into every other rank's address space), a rank copies its own slice in and PULLS the other
+    N - 1 slices with peer-to-peer cudaMemcpyAsync — copy engines, no copy kernel beside the DSP kernels — each rank reading
+    from N - 1 different peers at once, so no single NVLink port carries more than one block per hop.  Ordering across GPUs
+    is by the symmetric memory's stream-ordered signals: "my slice of block j is in place" (channel b) before a peer pulls it,
+    "I have pulled your slice" (channel 2 + b) before its owner overwrites it two blocks later.  Every wait carries a time-out
+    (a lost peer traps the waiting stream instead of hanging the GPU)."""
+
+    TIMEOUT_MS = 20000
+
+    def __init__(self, block_samples, world, rank, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self._init_common(block_samples, world, rank, device)
+        self.mem = symm.empty(2 * self.block_floats, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.mem, group if group is not None else dist.group.WORLD)
+        self.peer = [self.handle.get_buffer(r, (2 * self.block_floats,), torch.float32, 0) for r in range(world)]
+        self.bufs = [self.mem[:self.block_floats].view(-1, 2), self.mem[self.block_floats:].view(-1, 2)]
+        self.kind = "copy-engine pull all-gather over symmetric memory (peer cudaMemcpyAsync, signal-ordered)"
+        self.calls = [0, 0]
+
+    def gather(self, j, my_slice):
+        b = j & 1
+        torch, h, S = self._torch, self.handle, self.shard_floats
+        base = b * self.block_floats
+        self.stream.wait_event(self.free[b])                     # this rank's consumer is done with buffer b
+        with torch.cuda.stream(self.stream):
+            e0, e1 = self._timed()
+            e0.record(self.stream)
+            if self.calls[b]:
+                for k in range(1, self.world):                   # every peer has pulled the slice this one replaces
+                    h.wait_signal((self.rank + k) % self.world, channel=2 + b, timeout_ms=self.TIMEOUT_MS)
+            self.calls[b] += 1
+            self.mem[base + self.rank * S: base + (self.rank + 1) * S].copy_(my_slice.reshape(-1), non_blocking=True)
+            for k in range(1, self.world):
+                h.put_signal((self.rank + k) % self.world, channel=b, timeout_ms=self.TIMEOUT_MS)
+            for k in range(1, self.world):                       # staggered: rank r starts with r + 1, so the sources differ at any moment
+                p = (self.rank + k) % self.world
+                h.wait_signal(p, channel=b, timeout_ms=self.TIMEOUT_MS)
+                self.mem[base + p * S: base + (p + 1) * S].copy_(self.peer[p][base + p * S: base + (p + 1) * S], non_blocking=True)
+            for k in range(1, self.world):
+                h.put_signal((self.rank + k) % self.world, channel=2 + b, timeout_ms=self.TIMEOUT_MS)
+            e1.record(self.stream)
+            self.landed[b].record(self.stream)
+
+
+def make_hop(kind, block_samples, world, rank, device, group=None):
+    """kind: "nccl" | "pull" | "auto" (pull when the GPUs offer symmetric memory, else nccl; every rank takes the same branch)"""
+    import sys
+    import torch
+    import torch.distributed as dist
+    if kind in ("pull", "auto"):
+        hop, ok = None, 1
+        try:
+            hop = PullGatherHop(block_samples, world, rank, device, group)
+        except Exception as e:                               # no symmetric memory on this box / torch build
+            print("[hop] pull all-gather unavailable (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 1:
+            return hop
+        if kind == "pull":
+            raise RuntimeError("OWRX_HOP=pull but symmetric memory is not available on every rank")
+    return NcclGatherHop(block_samples, world, rank, device, group)

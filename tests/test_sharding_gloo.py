@@ -38,6 +38,12 @@ def _worker(rank, world, port, n_channels, q):
             if rank == 0:
                 block.mul_(1.0)                    # ingest rank owns the data
             broadcast_block(block, 0)
+        # the sharded-ingest hop: every rank holds 1/N of the block, afterwards every rank holds all of it
+        from openwebrx_b200.sharding import gather_block
+        shard = block.numel() // world
+        out = torch.zeros_like(block)
+        gather_block(out, block[rank * shard:(rank + 1) * shard].clone())
+        assert torch.equal(out, block)
         mine = list(shard_channels(n_channels, world, rank))
         gathered = [None] * world
         dist.all_gather_object(gathered, (mine, float(block.double().sum()), int(block.numel())))
