@@ -654,13 +654,18 @@ struct AgcWarp {
             const int R = max(32 * AGC_E - j0 - hang, 0);                   // rising steps among the pending samples
             float u = gain;
             Ud[3] = u;
-            int k = 1;
-            for (; k + 3 <= R; k += 4) {
-                const float a = u * up, b = a * up, c = b * up, d = c * up;
-                *reinterpret_cast<float4*>(&Ud[k + 3]) = make_float4(a, b, c, d);
-                u = d;
+            // the chain of R <= 128 dependent FMULs is the only sample-serial work of the step: straight-line groups of four
+            // (4 FMUL + one 16-byte store, each group under one warp-uniform predicate computed up front), no loop-carried
+            // counter or branch between the multiplies
+#pragma unroll
+            for (int c = 0; c < 32 * AGC_E / 4; c++) {
+                if (4 * c + 4 <= R) {
+                    const float a = u * up, b = a * up, cc = b * up, d = cc * up;
+                    *reinterpret_cast<float4*>(&Ud[4 * c + 4]) = make_float4(a, b, cc, d);
+                    u = d;
+                }
             }
-            for (; k <= R; k++) {
+            for (int k = (R & ~3) + 1; k <= R; k++) {
                 u *= up;
                 Ud[k + 3] = u;
             }

@@ -334,6 +334,174 @@ wf_fft2_kernel(WfFftParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wf_big_kernel<R0> — the whole four-step FFT of N = R0 x 4096 points (8192 ... 65536) in ONE persistent kernel.
+// A thread-block CLUSTER of R0 / 2 CTAs (8 for 65536 points) owns a frame pair at a time:
+//   stage A  every CTA takes 4096 / (R0 / 2) columns: windowed loads of both frames, packed radix-R0 column DFT, W_N twiddle,
+//            and writes the R0 rows it produced into the cluster's PRIVATE scratch Y[row][4096] (float4 = both frames);
+//   cluster barrier (release / acquire);
+//   stage B  every CTA transforms two rows (one per 256-thread team, each with its own shared-memory buffer and named
+//            barrier): the packed radix 16 x 16 x 16 passes of wf_fft2_kernel, |X|^2 accumulated in registers.
+// The scratch is double-buffered, so one cluster barrier per frame pair orders everything, and it is only 2 x R0 x 64 KB
+// per cluster (36 MB for all 18 clusters of a 65536-point run): it is rewritten every frame pair and stays in L2.  The
+// separate column-pass kernel it replaces wrote every transformed frame to HBM and read it back: 3 x the input bytes.
+// ------------------------------------------------------------------------------------------------
+template <int R> __device__ __forceinline__ void c2dft(C2* v);
+template <> __device__ __forceinline__ void c2dft<2>(C2* v) { c2dft2(v[0], v[1]); }
+template <> __device__ __forceinline__ void c2dft<4>(C2* v) { c2dft4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void c2dft<8>(C2* v)
+{
+    c2dft4(v[0], v[2], v[4], v[6]);
+    c2dft4(v[1], v[3], v[5], v[7]);
+    v[3] = c2w8_1(v[3]);
+    v[5] = c2mi(v[5]);
+    v[7] = c2w8_3(v[7]);
+    c2dft2(v[0], v[1]);
+    c2dft2(v[2], v[3]);
+    c2dft2(v[4], v[5]);
+    c2dft2(v[6], v[7]);
+}
+template <> __device__ __forceinline__ void c2dft<16>(C2* v) { c2dft16(v); }
+
+struct WfBigParams {
+    const float2* iq;        // wideband IQ
+    const float* window;     // N floats
+    const float2* twn;       // [R0][4096] exp(-2 pi i k1 n2 / N)
+    const float2* tw2;       // [16][16]
+    const float2* tw3;       // [16][256]
+    float4* y;               // [cluster][2][R0][4096] scratch
+    float* partial;          // [line][subset][N]
+    int every_n, frames_per_line, subsets, n, units;
+    long long first_frame;
+};
+
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, 256;" ::"r"(team + 1) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ float4 ldcg4(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <int R0>
+__global__ void __launch_bounds__(512, 1)
+wf_big_kernel(WfBigParams p)
+{
+    constexpr int M = 4096;
+    constexpr int CS = R0 / 2;                              // CTAs per cluster
+    constexpr int COLS = M / CS / 512;                      // columns per thread in stage A
+    constexpr int BUF = M + M / 16;
+    extern __shared__ float4 smem4[];                       // [2 teams][BUF]
+    const int tid = threadIdx.x, team = tid >> 8, tt = tid & 255;
+    unsigned crank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+    float4* const buf = smem4 + team * BUF;
+    float4* const ybase = p.y + (size_t)cid * 2 * R0 * M;
+    const int k = tt & 15;
+    const int base2 = (tt >> 4) * 256 + k;
+    const int k1 = 2 * (int)crank + team;                   // the row this team transforms
+    const int per = (p.frames_per_line + p.subsets - 1) / p.subsets;
+    unsigned pc = 0;                                        // frame pairs done by this cluster: scratch parity
+
+    for (int unit = cid; unit < p.units; unit += n_clusters) {
+        const int subset = unit % p.subsets, line = unit / p.subsets;
+        const int a0 = subset * per, a1 = min(p.frames_per_line, a0 + per);
+        float acc[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) acc[q] = 0.0f;
+        for (int a = a0; a < a1; a += 2, pc++) {
+            const bool two = a + 1 < a1;
+            float4* const y = ybase + (size_t)(pc & 1) * R0 * M;
+            const long long frame = (long long)line * p.frames_per_line + a;
+            const float2* x0 = p.iq + (p.first_frame + frame) * (long long)p.every_n;
+            const float2* x1 = x0 + p.every_n;
+            // ---- stage A: column pass over this CTA's columns
+#pragma unroll 1
+            for (int c = 0; c < COLS; c++) {
+                const int n2 = (int)crank * (M / CS) + c * 512 + tid;
+                C2 u[R0];
+#pragma unroll
+                for (int n1 = 0; n1 < R0; n1++) {
+                    const float2 s0 = __ldg(x0 + n2 + M * n1);
+                    const float2 s1 = two ? __ldg(x1 + n2 + M * n1) : make_float2(0.f, 0.f);
+                    const float w = __ldg(p.window + n2 + M * n1);
+                    u[n1].re = __fmul2_rn(make_float2(s0.x, s1.x), OWRX_P2(w));
+                    u[n1].im = __fmul2_rn(make_float2(s0.y, s1.y), OWRX_P2(w));
+                }
+                c2dft<R0>(u);
+#pragma unroll
+                for (int q = 0; q < R0; q++) {
+                    const int row = slot<R0>(q);
+                    C2 o = u[q];
+                    if (row > 0) {
+                        const float2 w = __ldg(p.twn + row * M + n2);
+                        o = c2mul(o, w.x, w.y);
+                    }
+                    y[(size_t)row * M + n2] = make_float4(o.re.x, o.re.y, o.im.x, o.im.y);
+                }
+            }
+            cluster_sync_all();                             // every row of this frame pair is in the scratch
+            // ---- stage B: this team's row, packed radix 16 x 16 x 16
+            C2 v[16];
+            const float4* yr = y + (size_t)k1 * M;
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const float4 t = ldcg4(yr + tt + r * 256);
+                v[r].re = make_float2(t.x, t.y);
+                v[r].im = make_float2(t.z, t.w);
+            }
+            c2dft16(v);
+            team_sync(team);                                // the previous pair's pass-3 reads of this team are done
+#pragma unroll
+            for (int q = 0; q < 16; q++) buf[pad16(tt * 16 + slot<16>(q))] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
+            team_sync(team);
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const float4 t = buf[pad16(tt + r * 256)];
+                v[r].re = make_float2(t.x, t.y);
+                v[r].im = make_float2(t.z, t.w);
+            }
+#pragma unroll
+            for (int r = 1; r < 16; r++) {
+                const float2 w = __ldg(p.tw2 + r * 16 + k);
+                v[r] = c2mul(v[r], w.x, w.y);
+            }
+            c2dft16(v);
+            team_sync(team);
+#pragma unroll
+            for (int q = 0; q < 16; q++) buf[pad16(base2 + slot<16>(q) * 16)] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
+            team_sync(team);
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const float4 t = buf[pad16(tt + r * 256)];
+                v[r].re = make_float2(t.x, t.y);
+                v[r].im = make_float2(t.z, t.w);
+            }
+#pragma unroll
+            for (int r = 1; r < 16; r++) {
+                const float2 w = __ldg(p.tw3 + r * 256 + tt);
+                v[r] = c2mul(v[r], w.x, w.y);
+            }
+            c2dft16(v);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const float2 pw = __ffma2_rn(v[q].im, v[q].im, __fmul2_rn(v[q].re, v[q].re));
+                acc[q] += pw.x + pw.y;
+            }
+        }
+        float* out = p.partial + ((size_t)line * p.subsets + subset) * (size_t)p.n;
+#pragma unroll
+        for (int q = 0; q < 16; q++) out[(size_t)k1 + (size_t)R0 * (tt + slot<16>(q) * 256)] = acc[q];
+    }
+    cluster_sync_all();                                     // no CTA of the cluster exits while another may still arrive
+}
+
 struct WfColParams {
     const float2* iq;
     const float* window;
@@ -548,6 +716,8 @@ struct owrx_wf {
     // scratch
     float* d_partial = nullptr; size_t partial_cap = 0;
     int* d_counter = nullptr;                                  // work counter of the persistent FFT kernel
+    float4* d_ybig = nullptr; size_t ybig_cap = 0;            // wf_big_kernel: per-cluster row scratch (L2-resident)
+    int big_clusters = 0;                                      // clusters of the fused kernel the device keeps resident
     float2* d_y = nullptr;      size_t y_cap = 0;
     int16_t* d_s16 = nullptr;   size_t s16_cap = 0;
     // pipelined mode: the (latency-bound, one warp per 32 lines) ADPCM pass of batch i runs on a high-priority side
@@ -623,6 +793,46 @@ static bool wf_use_packed()
     return !scalar;
 }
 
+// the fused four-step kernel: clusters of R0 / 2 CTAs, as many clusters as the device keeps resident at once
+template <int R0> static int launch_big(owrx_wf* wf, WfBigParams& p, cudaStream_t st)
+{
+    constexpr int CS = R0 / 2;
+    const size_t smem = 2 * (size_t)(4096 + 4096 / 16) * sizeof(float4);
+    OWRX_CUDA(cudaFuncSetAttribute(wf_big_kernel<R0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    if (wf->big_clusters <= 0) {
+        cfg.gridDim = dim3((unsigned)(wf->sm_count / CS * CS));
+        int nc = 0;
+        OWRX_CUDA(cudaOccupancyMaxActiveClusters(&nc, wf_big_kernel<R0>, &cfg));
+        if (nc <= 0) return fail(OWRX_E_CUDA, "no resident cluster of %d CTAs for the fused four-step FFT", CS);
+        wf->big_clusters = nc;
+    }
+    const int n_clusters = (int)std::min<long long>(wf->big_clusters, p.units);
+    const size_t y_need = (size_t)wf->big_clusters * 2 * R0 * 4096;
+    if (y_need > wf->ybig_cap) {
+        OWRX_CUDA(cudaStreamSynchronize(st));
+        cudaFree(wf->d_ybig); wf->d_ybig = nullptr; wf->ybig_cap = 0;
+        OWRX_CUDA(cudaMalloc((void**)&wf->d_ybig, y_need * sizeof(float4)));
+        wf->ybig_cap = y_need;
+    }
+    p.y = wf->d_ybig;
+    cfg.gridDim = dim3((unsigned)(n_clusters * CS));
+    OWRX_CUDA(cudaLaunchKernelEx(&cfg, wf_big_kernel<R0>, p));
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+// OWRX_WF_FUSED=0 keeps the two-kernel four-step path (column pass to an HBM scratch, then the row kernel) for A/B runs
+static bool wf_use_fused()
+{
+    static const bool off = getenv("OWRX_WF_FUSED") && atoi(getenv("OWRX_WF_FUSED")) == 0;
+    return !off && wf_use_packed();
+}
+
 static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame, size_t lines, uint8_t* out_dev,
                         float* db_dev, int16_t* s16_dev, cudaStream_t st)
 {
@@ -638,6 +848,11 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
     if (wf->m == 4096 && wf_use_packed() && base_units < (size_t)16 * wf->sm_count)
         subsets = (int)std::max<size_t>(subsets, std::min<size_t>((size_t)std::max(1, std::min(fpl / 16, 8)),
                                                                   ((size_t)16 * wf->sm_count + base_units - 1) / base_units));
+    if (wf->r0 > 1 && wf_use_fused()) {
+        // fused four-step kernel: units are (line, subset), dealt round-robin to ~sm_count / (r0 / 2) clusters
+        const size_t clusters = std::max<size_t>(1, (size_t)wf->sm_count / (size_t)std::max(1, wf->r0 / 2));
+        subsets = (int)std::min<size_t>((size_t)std::max(1, std::min(fpl / 12, 8)), std::max<size_t>(1, (8 * clusters + lines - 1) / lines));
+    }
     int rc;
     if ((rc = grow(&wf->d_partial, &wf->partial_cap, lines * (size_t)subsets * (size_t)n)) != OWRX_OK) return rc;
 
@@ -656,6 +871,19 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
         case 10: rc = launch_fft<10, true>(p, units, st); break;
         case 11: rc = launch_fft<11, true>(p, units, st); break;
         case 12: rc = wf_use_packed() ? launch_fft2<true>(p, units, wf->sm_count, st) : launch_fft<12, true>(p, units, st); break;
+        default: return fail(OWRX_E_INVALID, "unsupported fft size");
+        }
+        if (rc != OWRX_OK) return rc;
+    } else if (wf_use_fused()) {
+        WfBigParams b;
+        b.iq = iq_dev; b.window = wf->d_window; b.twn = wf->d_twn; b.tw2 = wf->d_tw2; b.tw3 = wf->d_tw3; b.y = nullptr;
+        b.partial = wf->d_partial; b.every_n = wf->every_n; b.frames_per_line = fpl; b.subsets = subsets; b.n = n;
+        b.units = (int)(lines * (size_t)subsets); b.first_frame = first_frame;
+        switch (wf->r0) {
+        case 2:  rc = launch_big<2>(wf, b, st); break;
+        case 4:  rc = launch_big<4>(wf, b, st); break;
+        case 8:  rc = launch_big<8>(wf, b, st); break;
+        case 16: rc = launch_big<16>(wf, b, st); break;
         default: return fail(OWRX_E_INVALID, "unsupported fft size");
         }
         if (rc != OWRX_OK) return rc;
@@ -710,7 +938,7 @@ static int wf_process(owrx_wf* wf, const float2* iq_dev, size_t n_samples, uint8
     // chunk so that the four-step scratch stays bounded (<= 256 MiB; measured: an L2-sized scratch is no faster) and
     // grid.y <= 65535
     size_t chunk = lines;
-    if (wf->r0 > 1) {
+    if (wf->r0 > 1 && !wf_use_fused()) {
         const size_t per_line = (size_t)fpl * (size_t)wf->n * sizeof(float2);
         static const size_t y_budget = (size_t)(getenv("OWRX_WF_Y_MB") ? atoi(getenv("OWRX_WF_Y_MB")) : 256) << 20;
         chunk = std::max<size_t>(1, y_budget / per_line);
@@ -841,7 +1069,7 @@ void owrx_wf_destroy(owrx_wf_t* wf)
     if (!wf) return;
     cudaSetDevice(wf->device);
     if (wf->stream) cudaStreamSynchronize(wf->stream);
-    cudaFree(wf->d_window); cudaFree(wf->d_tw2); cudaFree(wf->d_tw3); cudaFree(wf->d_twn); cudaFree(wf->d_counter);
+    cudaFree(wf->d_window); cudaFree(wf->d_tw2); cudaFree(wf->d_tw3); cudaFree(wf->d_twn); cudaFree(wf->d_counter); cudaFree(wf->d_ybig);
     cudaDeviceSynchronize();
     cudaFree(wf->d_partial); cudaFree(wf->d_y); cudaFree(wf->d_s16); cudaFree(wf->d_s16_alt);
     if (wf->fin_done) cudaEventDestroy(wf->fin_done);
