@@ -218,6 +218,7 @@ struct Group {
     float2* d_bp_H = nullptr; float2* d_bp_X = nullptr; float2* d_bp_Y = nullptr;
     size_t bp_blocks_cap = 0;
     ChanCfg* d_cfg = nullptr; ChanState* d_state = nullptr;
+    TailStash* d_stash = nullptr;                    // fused tail: state the next feed starts from (tail_front -> tail_commit)
     std::vector<double> h_rate, h_phase; std::vector<float2> h_w;
     std::vector<int> h_bp_en; std::vector<ChanCfg> h_cfg;
     bool cfg_dirty = true;
@@ -297,6 +298,9 @@ struct owrx_bank {
     bool deferred = false, pending_final = false;
     cudaEvent_t carry_done = nullptr;
     int fir_form_used = 0;                           // form of the latest Shift + FirDecimate pass (owrx_bank_fir_form)
+    // evaluation variants kept for A/B runs and as second opinions in the tests (read from the environment at creation)
+    bool tail_fused = true;                          // OWRX_TAIL_FUSED=0: the seven-kernel low-rate tail
+    bool agc_cta = false;                            // OWRX_AGC_CTA=1: the 8-channel-CTA Agc kernel
     size_t last_consumed = 0;                        // device path: samples of the last block every group is done with
 };
 
@@ -314,7 +318,7 @@ void group_release(Group* g)
 {
     cudaFree(g->d_taps); cudaFree(g->d_deemph); cudaFree(g->d_pre);
     cudaFree(g->d_rate); cudaFree(g->d_phase); cudaFree(g->d_w);
-    cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state);
+    cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state); cudaFree(g->d_stash);
     cudaFree(g->d_bp_H); cudaFree(g->d_bp_X); cudaFree(g->d_bp_Y);
     cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
     cudaFree(g->d_tail_mode); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
@@ -419,7 +423,7 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     if ((rc = dev_alloc(&g->d_rate, S)) || (rc = dev_alloc(&g->d_phase, S)) || (rc = dev_alloc(&g->d_w, S)) ||
         (rc = dev_alloc(&g->d_bp, S * g->Tb)) || (rc = dev_alloc(&g->d_bp_H, S * (size_t)g->bpP * FC_M)) || (rc = dev_alloc(&g->d_bp_en, S)) || (rc = dev_alloc(&g->d_cfg, S)) ||
         (rc = dev_alloc(&g->d_state, S)) || (rc = dev_alloc(&g->d_tail_mode, S)) || (rc = dev_alloc(&g->d_tail, S)) ||
-        (rc = dev_alloc(&g->d_tail_count, S)))
+        (rc = dev_alloc(&g->d_tail_count, S)) || (rc = dev_alloc(&g->d_stash, S)))
         return rc;
     g->h_tail_mode.assign(S, 0);
     g->h_rate.assign(S, 0.0); g->h_phase.assign(S, 0.0); g->h_w.assign(S, make_float2(1.f, 0.f));
@@ -518,7 +522,7 @@ int group_grow(owrx_bank* bank, Group* g)
     if ((rc = regrow(&g->d_rate, 1)) || (rc = regrow(&g->d_phase, 1)) || (rc = regrow(&g->d_w, 1)) ||
         (rc = regrow(&g->d_bp, (size_t)g->Tb)) || (rc = regrow(&g->d_bp_H, (size_t)g->bpP * FC_M)) || (rc = regrow(&g->d_bp_en, 1)) || (rc = regrow(&g->d_cfg, 1)) ||
         (rc = regrow(&g->d_state, 1)) || (rc = regrow(&g->d_tail_mode, 1)) || (rc = regrow(&g->d_tail, 1)) ||
-        (rc = regrow(&g->d_tail_count, 1)))
+        (rc = regrow(&g->d_tail_count, 1)) || (rc = regrow(&g->d_stash, 1)))
         return rc;
     cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
     g->d_tail_s16 = nullptr; g->d_tail_bytes = nullptr; g->tail_rows_cap = 0; g->tail_cap = 0;
@@ -905,12 +909,25 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
         g->feed_blocks += nb;
         const float2* sq_in = reinterpret_cast<const float2*>(g->s3.row_abs(g->sq_abs));
         const int hang_blocks = 2;                                       // hangLength = 2*blockLength, selector.py:124
+        // one launch for Squelch + demodulator front + DcBlock means (tail_front_kernel) unless OWRX_TAIL_FUSED=0 asks for the
+        // seven-kernel evaluation (kept as the second opinion: tests/test_gpu_selector.py runs both)
+        const bool fused = bank->tail_fused && nb <= 65535;
+        if ((rc = g->f1.ensure_new(n4, st)) != OWRX_OK) return rc;
+        if (fused) {
+            const unsigned zsplit = (unsigned)((g->sq_len + TF_ROWS - 1) / TF_ROWS);
+            tail_front_kernel<<<dim3((unsigned)(S / 32), (unsigned)nb, zsplit), 256, 0, st>>>(
+                sq_in, S, (int)nb, g->sq_len, 5, hang_blocks, g->d_cfg, g->d_state, d_power, d_gate, g->f1.append_ptr(), d_dcmean,
+                g->d_dcprev, g->d_stash);
+            OWRX_LAUNCH_CHECK();
+            tail_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, (int)nb, g->d_cfg, d_dcmean, g->d_stash, g->d_state);
+            OWRX_LAUNCH_CHECK();
+            bank->stats.kernel_launches += 2;
+        } else {
         squelch_power_kernel<<<dim3((unsigned)(S / 32), (unsigned)nb), 256, 0, st>>>(sq_in, S, (int)nb, g->sq_len, 5, d_power);
         OWRX_LAUNCH_CHECK();
         squelch_gate_kernel<<<(S + 127) / 128, 128, 0, st>>>(d_power, S, (int)nb, hang_blocks, g->d_cfg, g->d_state, d_gate);
         OWRX_LAUNCH_CHECK();
         // ---- demodulator front -> f1
-        if ((rc = g->f1.ensure_new(n4, st)) != OWRX_OK) return rc;
         {
             // single logical launch split in row chunks that are multiples of sq_len
             const size_t chunk_rows = std::max<size_t>((size_t)g->sq_len, (kRowChunk / (size_t)g->sq_len) * (size_t)g->sq_len);
@@ -932,6 +949,7 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
             OWRX_LAUNCH_CHECK();
         }
         bank->stats.kernel_launches += 3;
+        }
         const long long f1_first = g->f1.abs_end;
         g->f1.appended(n4);
         g->sq_abs += (long long)n4;
@@ -939,10 +957,12 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
         size_t n_audio = 0;
         if (!g->wfm) {
             // ---- demodulator back: NfmDeemphasis / DcBlock / copy -> f2 (pre-AGC)
-            dc_mean_kernel<<<dim3((unsigned)(S / 32), (unsigned)nb), 256, 0, st>>>(g->f1.row_abs(f1_first), S, (int)nb,
-                                                                                        g->sq_len, g->d_cfg, g->d_state,
-                                                                                        d_dcmean, g->d_dcprev);
-            OWRX_LAUNCH_CHECK();
+            if (!fused) {
+                dc_mean_kernel<<<dim3((unsigned)(S / 32), (unsigned)nb), 256, 0, st>>>(g->f1.row_abs(f1_first), S, (int)nb,
+                                                                                            g->sq_len, g->d_cfg, g->d_state,
+                                                                                            d_dcmean, g->d_dcprev);
+                OWRX_LAUNCH_CHECK();
+            }
             if ((rc = g->f2.ensure_new(n4, st)) != OWRX_OK) return rc;
             const size_t chunk_rows = std::max<size_t>((size_t)g->sq_len, (kRowChunk / (size_t)g->sq_len) * (size_t)g->sq_len);
             for (size_t o = 0; o < n4; o += chunk_rows) {
@@ -954,9 +974,11 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
                                                                      g->f2.append_ptr() + o * S);
                 OWRX_LAUNCH_CHECK();
             }
-            dc_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, (int)nb, g->d_cfg, d_dcmean, g->d_state);
-            OWRX_LAUNCH_CHECK();
-            bank->stats.kernel_launches += 3;
+            if (!fused) {
+                dc_commit_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, (int)nb, g->d_cfg, d_dcmean, g->d_state);
+                OWRX_LAUNCH_CHECK();
+            }
+            bank->stats.kernel_launches += fused ? 1 : 3;
             g->f2.appended(n4);
             n_audio = n4;
         } else {
@@ -1029,9 +1051,18 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
                 // that no 177 KB contraction CTA and at most one 68 KB FFT CTA can share their SM (measured inside the
                 // three-stream pipeline, C2: Agc stage 0.32 -> 0.26 ms, step 0.34 -> 0.32 ms).  OWRX_AGC_PAD_KB overrides.
                 static const int agc_pad = (getenv("OWRX_AGC_PAD_KB") ? atoi(getenv("OWRX_AGC_PAD_KB")) : 100) << 10;
-                if (agc_pad) OWRX_CUDA(cudaFuncSetAttribute(agc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, agc_pad));
-                agc_kernel<<<S / AGC_CH, AGC_TL, agc_pad, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+                // one warp per channel with no CTA barrier (agc_warp_kernel) unless OWRX_AGC_CTA=1 asks for the 8-channel CTAs
+                const bool agc_cta = bank->agc_cta;
+                static const int agcw_pad = (getenv("OWRX_AGCW_PAD_KB") ? atoi(getenv("OWRX_AGCW_PAD_KB")) : 0) << 10;
+                if (agc_cta) {
+                    if (agc_pad) OWRX_CUDA(cudaFuncSetAttribute(agc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, agc_pad));
+                    agc_kernel<<<S / AGC_CH, AGC_TL, agc_pad, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
+                                                               g->f3.append_ptr());
+                } else {
+                    if (agcw_pad) OWRX_CUDA(cudaFuncSetAttribute(agc_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, agcw_pad));
+                    agc_warp_kernel<<<S, 32, agcw_pad, st>>>(g->f2.rows(g->f2.fill - n_audio), S, (int)n_audio, g->d_cfg, g->d_state,
                                                            g->f3.append_ptr());
+                }
                 OWRX_LAUNCH_CHECK();
             }
             if ((rc = prof_mark(bank, OWRX_PROF_AGC, st, false)) != OWRX_OK) return rc;
@@ -1221,6 +1252,8 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     b->device = device; b->sm_count = sm; b->input_rate = input_rate;
     if (const char* m = getenv("OWRX_FIR_MODE")) b->fir_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV_TC, atoi(m)));
     b->bp_mode = std::min(b->fir_mode, OWRX_FIR_FASTCONV);
+    if (const char* m = getenv("OWRX_TAIL_FUSED")) b->tail_fused = atoi(m) != 0;
+    if (const char* m = getenv("OWRX_AGC_CTA")) b->agc_cta = atoi(m) != 0;
     if (const char* m = getenv("OWRX_BP_MODE")) b->bp_mode = std::max(OWRX_FIR_AUTO, std::min(OWRX_FIR_FASTCONV, atoi(m)));
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);

@@ -315,6 +315,175 @@ demod_front_commit_kernel(const float2* __restrict__ in, int slots, int n, int l
     st[s].fm_last = x;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tail_front_kernel — Squelch (block power + gate), the demodulator front and the DcBlock block means in ONE launch
+// (squelch_power / squelch_gate / demod_front / demod_front_commit / dc_mean above, kept as the reference evaluation).
+// CTA = (32 slots, squelch block b, row split z).  The gate is a sequential scan over blocks, but its hang counter is at most
+// `hang_blocks` = 2 (hangLength = 2 x blockLength, csdr/chain/selector.py:124), so the gate of block b is a LOCAL function:
+//     open_b = p_b >= L  or  p_{b-1} >= L  or  p_{b-2} >= L           (b >= 2; the carried counter replaces missing blocks)
+// and a CTA evaluates the few block powers it needs itself (each in the oracle's summation order) instead of waiting for a
+// scan kernel.  FmDemod's first row needs the last GATED sample of block b-1, i.e. that block's gate: one more power.
+// In the common case — every slot of blocks b and b-1 above its level — two powers decide everything.
+// The state the next feed starts from (hang counter, FmDemod's last sample) is stashed by the last block's CTA and
+// committed by tail_back_kernel, which runs after every reader of the old state.
+// ------------------------------------------------------------------------------------------------
+struct TailStash {
+    float2 fm_last;
+    int sq_hang;
+    int pad;
+};
+constexpr int TF_ROWS = 1024;            // rows of a block one CTA transforms
+
+__device__ __forceinline__ float tf_block_power(const float2* __restrict__ x, int slots, int length, int decim, int lane, int w,
+                                                float (*tile)[32])
+{
+    // mean |x|^2 over every decim-th sample, added in sample order by warp 0 (the oracle's order); all 8 warps stage
+    const int cnt = (length + decim - 1) / decim;
+    float p = 0.f;
+    for (int j0 = 0; j0 < cnt; j0 += SQ_MAXROWS) {
+        const int nj = min(SQ_MAXROWS, cnt - j0);
+        for (int j = w; j < nj; j += 8) {
+            const float2 v = x[(size_t)((j0 + j) * decim) * slots];
+            tile[j][lane] = v.x * v.x + v.y * v.y;
+        }
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll 8
+            for (int j = 0; j < nj; j++) p += tile[j][lane];
+        }
+        __syncthreads();
+    }
+    return p / (float)cnt;                   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256)
+tail_front_kernel(const float2* __restrict__ in, int slots, int n_blocks, int length, int decim, int hang_blocks,
+                  const ChanCfg* __restrict__ cfg, const ChanState* __restrict__ st, float* __restrict__ power,
+                  unsigned char* __restrict__ gate_out, float* __restrict__ f1, float* __restrict__ dc_mean,
+                  float* __restrict__ dc_prev, TailStash* __restrict__ stash)
+{
+    __shared__ float tile[SQ_MAXROWS][32];
+    __shared__ float s_p[4][32];             // powers of blocks b, b-1, b-2, b-3
+    __shared__ unsigned char s_gate[2][32];  // gate of block b, b-1
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
+    const int b = blockIdx.y, z = blockIdx.z;
+    const ChanCfg c = cfg[s];
+    const float level = c.sq_level;
+    const int h0 = st[s].sq_hang;
+    const bool last_cta = b == n_blocks - 1 && z == gridDim.z - 1;
+    // ---- block powers: b and b-1 always, b-2 and b-3 only if some slot is below its level in b or b-1
+    const float2* xb = in + (size_t)b * length * slots + s;
+    {
+        const float p0 = tf_block_power(xb, slots, length, decim, lane, w, tile);
+        if (w == 0) s_p[0][lane] = p0;
+        const float p1 = b >= 1 ? tf_block_power(xb - (size_t)length * slots, slots, length, decim, lane, w, tile) : 0.f;
+        if (w == 0) s_p[1][lane] = p1;
+    }
+    __syncthreads();
+    const bool below = s_p[0][lane] < level || (b >= 1 && s_p[1][lane] < level);
+    if (__syncthreads_or(below)) {
+        const float p2 = b >= 2 ? tf_block_power(xb - (size_t)2 * length * slots, slots, length, decim, lane, w, tile) : 0.f;
+        const float p3 = b >= 3 ? tf_block_power(xb - (size_t)3 * length * slots, slots, length, decim, lane, w, tile) : 0.f;
+        if (w == 0) { s_p[2][lane] = p2; s_p[3][lane] = p3; }
+    } else if (w == 0) {
+        s_p[2][lane] = level; s_p[3][lane] = level;          // never looked at: everything is open
+    }
+    __syncthreads();
+    if (w == 0) {
+        // hang counter entering block j: h_j = p_{j-1} >= L ? H : (p_{j-2} >= L ? H - 1 : ...) for H = hang_blocks = 2; blocks
+        // before the pass come from the carried counter h0
+        auto hang_before = [&](int j) -> int {                // j = b or b - 1 (>= 0)
+            const int d = b - j;                              // s_p index of block j
+            if (j == 0) return h0;
+            const bool o1 = s_p[d + 1][lane] >= level;        // block j - 1
+            if (o1) return hang_blocks;
+            if (j == 1) return max(h0 - 1, 0);
+            const bool o2 = s_p[d + 2][lane] >= level;        // block j - 2
+            if (hang_blocks >= 2 && o2) return hang_blocks - 1;
+            if (j == 2) return max(h0 - 2, 0);
+            return 0;
+        };
+        const int hb = hang_before(b);
+        const bool open_b = s_p[0][lane] >= level || hb > 0;
+        s_gate[0][lane] = open_b ? 1 : 0;
+        bool open_prev = true;
+        if (b >= 1) open_prev = s_p[1][lane] >= level || hang_before(b - 1) > 0;
+        s_gate[1][lane] = open_prev ? 1 : 0;
+        if (z == 0) {
+            power[(size_t)b * slots + s] = s_p[0][lane];
+            gate_out[(size_t)b * slots + s] = open_b ? 1 : 0;
+        }
+        if (last_cta) stash[s].sq_hang = s_p[0][lane] >= level ? hang_blocks : max(hb - 1, 0);
+    }
+    __syncthreads();
+    const bool open_b = s_gate[0][lane] != 0, open_prev = s_gate[1][lane] != 0;
+    // ---- DcBlock block mean of the gated envelope (AM), in sample order, by warp 0 of the z = 0 CTA; the other warps go on
+    const bool am = c.kind == OWRX_DEMOD_AM;
+    if (z == 0 && w == 0) {
+        if (__any_sync(0xffffffffu, am)) {
+            float acc = 0.f;
+            if (open_b) {
+#pragma unroll 8
+                for (int i = 0; i < length; i++) {
+                    const float2 v = xb[(size_t)i * slots];
+                    acc += sqrtf(v.x * v.x + v.y * v.y);
+                }
+            }
+            dc_mean[(size_t)b * slots + s] = am ? acc / (float)length : 0.f;
+        } else {
+            dc_mean[(size_t)b * slots + s] = 0.f;
+        }
+        if (b == 0) dc_prev[s] = am ? st[s].dc_last : 0.f;
+    }
+    // ---- demodulator front over this CTA's rows of the block
+    const int r0 = z * TF_ROWS, r1 = min(length, r0 + TF_ROWS);
+    const int kind = c.kind;
+    for (int i = r0 + w; i < r1; i += 8) {
+        float2 x = xb[(size_t)i * slots];
+        if (!open_b) x = make_float2(0.f, 0.f);
+        float y = 0.f;
+        if (kind == OWRX_DEMOD_NFM || kind == OWRX_DEMOD_WFM) {
+            float2 pv;
+            if (i > 0) {
+                pv = open_b ? xb[(size_t)(i - 1) * slots] : make_float2(0.f, 0.f);
+            } else if (b > 0) {
+                pv = open_prev ? xb[-(ptrdiff_t)slots] : make_float2(0.f, 0.f);
+            } else {
+                pv = st[s].fm_last;
+            }
+            const float K = 0.340447550238101026565118445432744920253753662109375f;
+            const float num = x.x * (x.y - pv.y) - x.y * (x.x - pv.x);
+            const float den = x.x * x.x + x.y * x.y;
+            y = den != 0.f ? K * num / den : 0.f;
+            y = fminf(1.f, fmaxf(-1.f, y));                       // Limit
+        } else if (kind == OWRX_DEMOD_AM) {
+            y = sqrtf(x.x * x.x + x.y * x.y);
+        } else if (kind == OWRX_DEMOD_SSB) {
+            y = x.x;
+        }
+        f1[((size_t)b * length + i) * slots + s] = y;
+        if (last_cta && i == length - 1) stash[s].fm_last = x;
+    }
+}
+
+// the state hand-over of the fused tail: runs as part of tail_back_kernel's first CTAs, after every reader of the old state
+__device__ __forceinline__ void tail_commit(int s, int n_blocks, const ChanCfg* cfg, const float* dc_mean, int slots,
+                                            const TailStash* stash, ChanState* st)
+{
+    st[s].sq_hang = stash[s].sq_hang;
+    st[s].fm_last = stash[s].fm_last;
+    if (cfg[s].kind == OWRX_DEMOD_AM) st[s].dc_last = dc_mean[(size_t)(n_blocks - 1) * slots + s];
+}
+
+__global__ void __launch_bounds__(128)
+tail_commit_kernel(int slots, int n_blocks, const ChanCfg* __restrict__ cfg, const float* __restrict__ dc_mean,
+                   const TailStash* __restrict__ stash, ChanState* __restrict__ st)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < slots && n_blocks > 0) tail_commit(s, n_blocks, cfg, dc_mean, slots, stash, st);
+}
+
 // Demodulator back (12 kHz-class groups): NFM -> NfmDeemphasis FIR; AM -> DcBlock (block = squelch
 // block); SSB -> copy.  in points at the row of output 0 and has >= T-1 + 2*DB_RB rows of history before it.
 // A thread owns DB_RB consecutive outputs of one channel; the FIR slides a 2*DB_RB-1 sample window through
@@ -860,6 +1029,62 @@ agc_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __rest
         }
         if (tile + 1 < nt) stage(buf ^ 1, lo, hi);
         __syncthreads();                                   // next tile staged, xout free
+    }
+    if (lane == 0 && !bypass) {
+        st[s].agc_gain = a.gain;
+        st[s].agc_hang = a.hang;
+    }
+}
+
+// agc_warp_kernel — the same recurrence, one WARP per CTA and channel, no CTA barrier anywhere.  The 8-channel CTA above stages
+// [256 samples][8 slots] tiles through shared memory behind two __syncthreads per tile: every warp of the CTA then moves at the
+// pace of its slowest channel (a third of the stall samples of the r1 capture sit behind those barriers) and two warps share
+// each scheduler.  Here a warp streams its own channel: the 128 samples of a step arrive through a 4-deep cp.async ring
+// (4-byte gathers `slots` floats apart: 32 sectors per request, all L2 hits — a C2 block of all 64 channels is 5 MB), outputs
+// leave as 4-byte scattered stores, and every channel gets a scheduler — with <= 148 channels an SM — of its own.
+constexpr int AGCW_STAGES = 4;
+__global__ void __launch_bounds__(32)
+agc_warp_kernel(const float* __restrict__ in, int slots, int n, const ChanCfg* __restrict__ cfg, ChanState* __restrict__ st,
+                float* __restrict__ out)
+{
+    __shared__ __align__(16) float ring[AGCW_STAGES][32 * AGC_E];
+    __shared__ __align__(16) float U[32 * AGC_E + 8];
+    if (n <= 0) return;
+    const int lane = threadIdx.x;
+    const int s = blockIdx.x;
+    const ChanCfg c = cfg[s];
+    const bool bypass = c.kind == OWRX_DEMOD_WFM || c.kind == OWRX_DEMOD_NONE;
+    AgcWarp a{st[s].agc_gain, 1.f - c.agc_attack, 1.f + c.agc_decay, c.agc_thr, c.agc_max, st[s].agc_hang, c.agc_hang_time};
+    a.gain = fmaxf(fminf(a.gain, a.gmax), 0.f);
+    constexpr int SL = 32 * AGC_E;                                   // samples per step
+    const int ns = (n + SL - 1) / SL;
+    const float* src = in + s;
+    auto issue = [&](int step) {
+        if (step < ns) {
+            const int i0 = step * SL + AGC_E * lane;
+#pragma unroll
+            for (int e = 0; e < AGC_E; e++) {
+                float* dst = &ring[step % AGCW_STAGES][AGC_E * lane + e];
+                if (i0 + e < n) cp_async4(dst, src + (size_t)(i0 + e) * slots);
+                else *dst = 0.f;                                     // zeros change neither state nor outputs
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int k = 0; k < AGCW_STAGES - 1; k++) issue(k);
+    for (int step = 0; step < ns; step++) {
+        issue(step + AGCW_STAGES - 1);
+        cp_async_wait<AGCW_STAGES - 1>();
+        __syncwarp();
+        const float4 x4 = *reinterpret_cast<const float4*>(&ring[step % AGCW_STAGES][AGC_E * lane]);
+        float v[AGC_E] = {x4.x, x4.y, x4.z, x4.w};
+        if (!bypass) a.step(v, lane, U);
+        const int i0 = step * SL + AGC_E * lane;
+#pragma unroll
+        for (int e = 0; e < AGC_E; e++)
+            if (i0 + e < n) out[(size_t)(i0 + e) * slots + s] = v[e];
+        __syncwarp();                                                // the ring slot is rewritten by the next issue
     }
     if (lane == 0 && !bypass) {
         st[s].agc_gain = a.gain;

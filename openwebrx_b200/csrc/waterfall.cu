@@ -336,15 +336,16 @@ wf_fft2_kernel(WfFftParams p)
 
 // ------------------------------------------------------------------------------------------------
 // wf_big_kernel<R0> — the whole four-step FFT of N = R0 x 4096 points (8192 ... 65536) in ONE persistent kernel.
-// A thread-block CLUSTER of R0 / 2 CTAs (8 for 65536 points) owns a frame pair at a time:
-//   stage A  every CTA takes 4096 / (R0 / 2) columns: windowed loads of both frames, packed radix-R0 column DFT, W_N twiddle,
-//            and writes the R0 rows it produced into the cluster's PRIVATE scratch Y[row][4096] (float4 = both frames);
+// A thread-block CLUSTER of R0 CTAs (16 for 65536 points: the non-portable size, two CTAs per SM) owns a frame pair at a time:
+//   stage A  every CTA takes 4096 / R0 columns (one per thread for R0 = 16): windowed loads of both frames, packed radix-R0
+//            column DFT, W_N twiddle, and writes its columns of all R0 rows into the cluster's PRIVATE scratch
+//            Y[row][4096] (float4 = both frames);
 //   cluster barrier (release / acquire);
-//   stage B  every CTA transforms two rows (one per 256-thread team, each with its own shared-memory buffer and named
-//            barrier): the packed radix 16 x 16 x 16 passes of wf_fft2_kernel, |X|^2 accumulated in registers.
+//   stage B  every CTA transforms ONE row: the packed radix 16 x 16 x 16 passes of wf_fft2_kernel, |X|^2 in registers.
 // The scratch is double-buffered, so one cluster barrier per frame pair orders everything, and it is only 2 x R0 x 64 KB
-// per cluster (36 MB for all 18 clusters of a 65536-point run): it is rewritten every frame pair and stays in L2.  The
-// separate column-pass kernel it replaces wrote every transformed frame to HBM and read it back: 3 x the input bytes.
+// per cluster (~40 MB for all resident clusters of a 65536-point run): it is rewritten every frame pair and stays in L2.
+// The separate column-pass kernel it replaces wrote every transformed frame to HBM and read it back: 3 x the input bytes.
+// Two CTAs of DIFFERENT clusters share an SM, so one cluster's barrier wait is the other's compute time.
 // ------------------------------------------------------------------------------------------------
 template <int R> __device__ __forceinline__ void c2dft(C2* v);
 template <> __device__ __forceinline__ void c2dft<2>(C2* v) { c2dft2(v[0], v[1]); }
@@ -389,23 +390,21 @@ __device__ __forceinline__ float4 ldcg4(const float4* p)
 }
 
 template <int R0>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(256, 2)
 wf_big_kernel(WfBigParams p)
 {
     constexpr int M = 4096;
-    constexpr int CS = R0 / 2;                              // CTAs per cluster
-    constexpr int COLS = M / CS / 512;                      // columns per thread in stage A
-    constexpr int BUF = M + M / 16;
-    extern __shared__ float4 smem4[];                       // [2 teams][BUF]
-    const int tid = threadIdx.x, team = tid >> 8, tt = tid & 255;
+    constexpr int CS = R0;                                  // CTAs per cluster: one row each
+    extern __shared__ float4 smem4[];                       // [M + M / 16]
+    const int tid = threadIdx.x;
     unsigned crank;
     asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
-    float4* const buf = smem4 + team * BUF;
     float4* const ybase = p.y + (size_t)cid * 2 * R0 * M;
-    const int k = tt & 15;
-    const int base2 = (tt >> 4) * 256 + k;
-    const int k1 = 2 * (int)crank + team;                   // the row this team transforms
+    const int k = tid & 15;
+    const int base2 = (tid >> 4) * 256 + k;
+    const int k1 = (int)crank;                              // the row this CTA transforms
+    constexpr int COLS = M / CS / 256;                      // columns a thread transforms in stage A (1 for R0 = 16)
     const int per = (p.frames_per_line + p.subsets - 1) / p.subsets;
     unsigned pc = 0;                                        // frame pairs done by this cluster: scratch parity
 
@@ -421,10 +420,10 @@ wf_big_kernel(WfBigParams p)
             const long long frame = (long long)line * p.frames_per_line + a;
             const float2* x0 = p.iq + (p.first_frame + frame) * (long long)p.every_n;
             const float2* x1 = x0 + p.every_n;
-            // ---- stage A: column pass over this CTA's columns
+            // ---- stage A: column pass over this CTA's M / CS columns
 #pragma unroll 1
             for (int c = 0; c < COLS; c++) {
-                const int n2 = (int)crank * (M / CS) + c * 512 + tid;
+                const int n2 = (int)crank * (M / CS) + c * 256 + tid;
                 C2 u[R0];
 #pragma unroll
                 for (int n1 = 0; n1 < R0; n1++) {
@@ -433,6 +432,17 @@ wf_big_kernel(WfBigParams p)
                     const float w = __ldg(p.window + n2 + M * n1);
                     u[n1].re = __fmul2_rn(make_float2(s0.x, s1.x), OWRX_P2(w));
                     u[n1].im = __fmul2_rn(make_float2(s0.y, s1.y), OWRX_P2(w));
+                }
+                if (a + 2 < a1) {
+                    // the next frame pair's samples of this column go to L2 while this pair is transformed (8 threads share a
+                    // 128-byte line: one request per line)
+                    if ((tid & 15) == 0) {
+#pragma unroll
+                        for (int n1 = 0; n1 < R0; n1++) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(x1 + p.every_n + n2 + M * n1));
+                            if (a + 3 < a1) asm volatile("prefetch.global.L2 [%0];" ::"l"(x1 + 2 * (size_t)p.every_n + n2 + M * n1));
+                        }
+                    }
                 }
                 c2dft<R0>(u);
 #pragma unroll
@@ -447,23 +457,23 @@ wf_big_kernel(WfBigParams p)
                 }
             }
             cluster_sync_all();                             // every row of this frame pair is in the scratch
-            // ---- stage B: this team's row, packed radix 16 x 16 x 16
+            // ---- stage B: this CTA's row, packed radix 16 x 16 x 16
             C2 v[16];
             const float4* yr = y + (size_t)k1 * M;
 #pragma unroll
             for (int r = 0; r < 16; r++) {
-                const float4 t = ldcg4(yr + tt + r * 256);
+                const float4 t = ldcg4(yr + tid + r * 256);
                 v[r].re = make_float2(t.x, t.y);
                 v[r].im = make_float2(t.z, t.w);
             }
             c2dft16(v);
-            team_sync(team);                                // the previous pair's pass-3 reads of this team are done
+            __syncthreads();                                // the previous pair's pass-3 reads are done
 #pragma unroll
-            for (int q = 0; q < 16; q++) buf[pad16(tt * 16 + slot<16>(q))] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
-            team_sync(team);
+            for (int q = 0; q < 16; q++) smem4[pad16(tid * 16 + slot<16>(q))] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
+            __syncthreads();
 #pragma unroll
             for (int r = 0; r < 16; r++) {
-                const float4 t = buf[pad16(tt + r * 256)];
+                const float4 t = smem4[pad16(tid + r * 256)];
                 v[r].re = make_float2(t.x, t.y);
                 v[r].im = make_float2(t.z, t.w);
             }
@@ -473,19 +483,19 @@ wf_big_kernel(WfBigParams p)
                 v[r] = c2mul(v[r], w.x, w.y);
             }
             c2dft16(v);
-            team_sync(team);
+            __syncthreads();
 #pragma unroll
-            for (int q = 0; q < 16; q++) buf[pad16(base2 + slot<16>(q) * 16)] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
-            team_sync(team);
+            for (int q = 0; q < 16; q++) smem4[pad16(base2 + slot<16>(q) * 16)] = make_float4(v[q].re.x, v[q].re.y, v[q].im.x, v[q].im.y);
+            __syncthreads();
 #pragma unroll
             for (int r = 0; r < 16; r++) {
-                const float4 t = buf[pad16(tt + r * 256)];
+                const float4 t = smem4[pad16(tid + r * 256)];
                 v[r].re = make_float2(t.x, t.y);
                 v[r].im = make_float2(t.z, t.w);
             }
 #pragma unroll
             for (int r = 1; r < 16; r++) {
-                const float2 w = __ldg(p.tw3 + r * 256 + tt);
+                const float2 w = __ldg(p.tw3 + r * 256 + tid);
                 v[r] = c2mul(v[r], w.x, w.y);
             }
             c2dft16(v);
@@ -497,7 +507,7 @@ wf_big_kernel(WfBigParams p)
         }
         float* out = p.partial + ((size_t)line * p.subsets + subset) * (size_t)p.n;
 #pragma unroll
-        for (int q = 0; q < 16; q++) out[(size_t)k1 + (size_t)R0 * (tt + slot<16>(q) * 256)] = acc[q];
+        for (int q = 0; q < 16; q++) out[(size_t)k1 + (size_t)R0 * (tid + slot<16>(q) * 256)] = acc[q];
     }
     cluster_sync_all();                                     // no CTA of the cluster exits while another may still arrive
 }
@@ -796,20 +806,22 @@ static bool wf_use_packed()
 // the fused four-step kernel: clusters of R0 / 2 CTAs, as many clusters as the device keeps resident at once
 template <int R0> static int launch_big(owrx_wf* wf, WfBigParams& p, cudaStream_t st)
 {
-    constexpr int CS = R0 / 2;
-    const size_t smem = 2 * (size_t)(4096 + 4096 / 16) * sizeof(float4);
+    constexpr int CS = R0;
+    const size_t smem = (size_t)(4096 + 4096 / 16) * sizeof(float4);
     OWRX_CUDA(cudaFuncSetAttribute(wf_big_kernel<R0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) OWRX_CUDA(cudaFuncSetAttribute(wf_big_kernel<R0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
     if (wf->big_clusters <= 0) {
-        cfg.gridDim = dim3((unsigned)(wf->sm_count / CS * CS));
+        cfg.gridDim = dim3((unsigned)(2 * wf->sm_count / CS * CS));
         int nc = 0;
         OWRX_CUDA(cudaOccupancyMaxActiveClusters(&nc, wf_big_kernel<R0>, &cfg));
         if (nc <= 0) return fail(OWRX_E_CUDA, "no resident cluster of %d CTAs for the fused four-step FFT", CS);
-        wf->big_clusters = nc;
+        static const int cap = getenv("OWRX_WF_CLUSTERS") ? atoi(getenv("OWRX_WF_CLUSTERS")) : 0;
+        wf->big_clusters = cap > 0 ? std::min(cap, nc) : nc;
     }
     const int n_clusters = (int)std::min<long long>(wf->big_clusters, p.units);
     const size_t y_need = (size_t)wf->big_clusters * 2 * R0 * 4096;
@@ -849,8 +861,8 @@ static int wf_run_chunk(owrx_wf* wf, const float2* iq_dev, long long first_frame
         subsets = (int)std::max<size_t>(subsets, std::min<size_t>((size_t)std::max(1, std::min(fpl / 16, 8)),
                                                                   ((size_t)16 * wf->sm_count + base_units - 1) / base_units));
     if (wf->r0 > 1 && wf_use_fused()) {
-        // fused four-step kernel: units are (line, subset), dealt round-robin to ~sm_count / (r0 / 2) clusters
-        const size_t clusters = std::max<size_t>(1, (size_t)wf->sm_count / (size_t)std::max(1, wf->r0 / 2));
+        // fused four-step kernel: units are (line, subset), dealt round-robin to ~2 sm_count / r0 clusters
+        const size_t clusters = std::max<size_t>(1, (size_t)2 * wf->sm_count / (size_t)wf->r0);
         subsets = (int)std::min<size_t>((size_t)std::max(1, std::min(fpl / 12, 8)), std::max<size_t>(1, (8 * clusters + lines - 1) / lines));
     }
     int rc;

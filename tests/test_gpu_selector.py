@@ -382,3 +382,35 @@ def test_deferred_drain_streams_the_same_outputs(gpu):
         assert np.array_equal(got[True][0][i], got[False][0][i]), i
         assert np.array_equal(got[True][1][i], got[False][1][i]), i
     assert got[True][2] == got[False][2] and len(got[True][2]) > 1000
+
+
+def test_fused_tail_and_warp_agc_equal_the_reference_kernels(gpu, monkeypatch):
+    """round 2 kernels against the round 1 evaluation they replace, bit for bit: tail_front_kernel (Squelch + demodulator front +
+    DcBlock means in one launch, gate from local block powers) vs the seven-kernel tail, and agc_warp_kernel (one warp per
+    channel, no CTA barrier) vs the 8-channel-CTA Agc — ragged streaming feeds, a squelched channel, all three demodulators"""
+    fs, out = 2.4e6, 12000
+    cars = carrier_plan(7, fs, seed=61)
+    iq = make_iq(5333 + 200 * (750 * 9 + 123), fs, cars, seed=61)
+    iq[200 * 750 * 3:200 * 750 * 6] *= 1e-4                       # a quiet stretch: squelched channels close and reopen
+
+    def run(tail_fused, agc_cta):
+        monkeypatch.setenv("OWRX_TAIL_FUSED", "1" if tail_fused else "0")
+        monkeypatch.setenv("OWRX_AGC_CTA", "1" if agc_cta else "0")
+        bank = ChannelBank(fs, outputs=N.OUT_AUDIO | N.OUT_DEMOD | N.OUT_POWER)
+        chans = [bank.add_channel(out, demod=c["kind"], offset=c["offset"], bandpass=BANDPASS[c["kind"]]) for c in cars]
+        for ch, c in zip(chans[:4], cars):
+            ch.setSquelchLevel(10 * np.log10(max(0.3 * c["amp"] ** 2, 1e-12)))
+        pos = 0
+        for cut in (200 * 2000 + 17, 200 * 2900, 200 * 5100 + 3, len(iq)):
+            bank.feed(iq[pos:cut])
+            pos = cut
+        res = [(ch.read_demod(), ch.read_audio(), ch.read_power()) for ch in chans]
+        bank.close()
+        return res
+
+    ref = run(False, True)
+    new = run(True, False)
+    assert len(ref[0][0]) >= 750 * 8
+    for (d0, a0, p0), (d1, a1, p1) in zip(ref, new):
+        assert np.array_equal(d0, d1) and np.array_equal(a0, a1) and np.array_equal(p0, p1)
+    assert any((d == 0).any() and (d != 0).any() for d, _, _ in new[:4])      # the gate really closed somewhere
