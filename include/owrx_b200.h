@@ -36,6 +36,14 @@ const char* owrx_version(void);
 uint64_t owrx_launch_count(void);
 int owrx_device_count(int* n);
 
+/* Page-locked host memory for the IQ ingress ring (the reference's TcpSource writes the connector's TCP
+ * stream into the source Buffer, owrx/source/__init__.py:307-330; here that Buffer's storage is a cudaHostAlloc'd ring, so
+ * recv() lands where the copy engine reads and no pageable bounce copy remains between the socket and HBM).
+ * Portable across devices.  owrx_host_is_pinned: 1 if `p` lies in page-locked memory known to CUDA, 0 if not. */
+int owrx_pinned_alloc(size_t bytes, void** out);
+void owrx_pinned_free(void* p);
+int owrx_host_is_pinned(const void* p);
+
 /* Wideband IQ ingress formats.  Sources that do not deliver complex float32 are converted by the reference on
  * the CPU — Chain([Convert(Format.COMPLEX_SHORT, Format.COMPLEX_FLOAT), Gain(Format.COMPLEX_FLOAT, 5.0)]),
  * owrx/source/fifi_sdr.py:27-28 via owrx/source/direct.py:59-71; owrx_*_feed_fmt takes the raw samples (interleaved I, Q)
@@ -81,6 +89,8 @@ int owrx_wf_set_compression(owrx_wf_t* wf, int compression);           /* FftCha
  *   N = first line ? P : min(P, N * (1 + growth));   P' = max(P - alpha * N, beta * P);   dB = 10 log10(P') + corrections */
 int owrx_wf_set_noise_filter(owrx_wf_t* wf, int enable, float alpha, float beta, float growth);
 size_t owrx_wf_line_bytes(const owrx_wf_t* wf);
+/* host-path ingress bytes by source memory kind (see owrx_bank_stats_t) */
+int owrx_wf_get_h2d_bytes(const owrx_wf_t* wf, uint64_t* pinned_bytes, uint64_t* pageable_bytes);
 
 /* Streaming host path (what the pycsdr shim calls): append n_samples of interleaved IQ from HOST
  * memory; every completed line is computed on the GPU and queued. */
@@ -243,6 +253,8 @@ typedef struct {
     uint64_t channel_samples;   /* sum over channels of wideband samples     */
     uint64_t kernel_launches;
     double   device_ms;         /* CUDA-event time of the host-path feeds    */
+    uint64_t h2d_pinned_bytes;   /* host-path feeds whose source was page-locked memory (DMA straight from the ring)   */
+    uint64_t h2d_pageable_bytes; /* ... and whose source was pageable memory (the driver stages it through a bounce buffer) */
 } owrx_bank_stats_t;
 int owrx_bank_get_stats(const owrx_bank_t* bank, owrx_bank_stats_t* st);
 

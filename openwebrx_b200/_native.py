@@ -28,7 +28,7 @@ class ChanSpec(C.Structure):
 
 class BankStats(C.Structure):
     _fields_ = [("input_samples", C.c_uint64), ("channel_samples", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("device_ms", C.c_double)]
+                ("device_ms", C.c_double), ("h2d_pinned_bytes", C.c_uint64), ("h2d_pageable_bytes", C.c_uint64)]
 
 
 if not os.path.exists(SO_PATH):
@@ -47,6 +47,10 @@ SIGNATURES = {
     "owrx_version": (C.c_char_p, []),
     "owrx_launch_count": (C.c_uint64, []),
     "owrx_device_count": (_i, [C.POINTER(_i)]),
+    "owrx_pinned_alloc": (_i, [_sz, _pp]),
+    "owrx_pinned_free": (None, [_vp]),
+    "owrx_host_is_pinned": (_i, [_vp]),
+    "owrx_wf_get_h2d_bytes": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "owrx_iq_multicast_store": (_i, [_vp, _vp, _sz, _vp]),
     "owrx_wf_create": (_i, [_i, _i, _i, _i, _f, _i, _pp]),
     "owrx_wf_destroy": (None, [_vp]),

@@ -185,7 +185,8 @@ class ChannelBank:
         st = N.BankStats()
         N.check(N.lib.owrx_bank_get_stats(self._h, C.byref(st)))
         return dict(input_samples=st.input_samples, channel_samples=st.channel_samples,
-                    kernel_launches=st.kernel_launches, device_ms=st.device_ms)
+                    kernel_launches=st.kernel_launches, device_ms=st.device_ms,
+                    h2d_pinned_bytes=st.h2d_pinned_bytes, h2d_pageable_bytes=st.h2d_pageable_bytes)
 
     def set_pipelined(self, enable=True):
         N.check(N.lib.owrx_bank_set_pipelined(self._h, 1 if enable else 0))

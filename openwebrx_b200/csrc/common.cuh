@@ -43,6 +43,8 @@ inline int fail(int code, const char* fmt, ...)
 
 // Select the device and verify it is a Blackwell-class part; there is no CPU fallback.
 int select_device(int device, int* sm_count);
+// true if `p` lies in page-locked host memory known to CUDA (cudaHostAlloc / cudaHostRegister)
+bool host_is_pinned(const void* p);
 
 // ---- small complex helpers -------------------------------------------------------------------
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }

@@ -24,6 +24,14 @@ int select_device(int device, int* sm_count)
     return OWRX_OK;
 }
 
+bool host_is_pinned(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 }  // namespace owrx
 
 extern "C" {
@@ -31,6 +39,19 @@ extern "C" {
 const char* owrx_last_error(void) { return owrx::g_err; }
 const char* owrx_version(void) { return "owrx_b200 0.1.0 (sm_100a)"; }
 uint64_t owrx_launch_count(void) { return owrx::g_launches.load(); }
+
+int owrx_pinned_alloc(size_t bytes, void** out)
+{
+    if (!out || !bytes) return owrx::fail(OWRX_E_INVALID, "bad argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { *out = nullptr; cudaGetLastError(); return owrx::fail(OWRX_E_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    return OWRX_OK;
+}
+
+void owrx_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+int owrx_host_is_pinned(const void* p) { return owrx::host_is_pinned(p) ? 1 : 0; }
 
 int owrx_device_count(int* n)
 {

@@ -68,11 +68,27 @@ void fft_pow2(std::vector<std::complex<double>>& a)
         j ^= bit;
         if (i < j) std::swap(a[i], a[j]);
     }
+    // twiddles of one size are computed once (setBandpass transforms 25 partitions per call, from websocket threads)
+    static std::mutex tw_mu;
+    static std::map<size_t, std::vector<std::complex<double>>> tw_cache;
+    const std::complex<double>* tw;
+    {
+        std::lock_guard<std::mutex> lk(tw_mu);
+        auto& t = tw_cache[n];
+        if (t.empty()) {
+            t.reserve(n);
+            for (size_t len = 2; len <= n; len <<= 1) {
+                const double ang = -2.0 * M_PI / (double)len;
+                for (size_t k = 0; k < len / 2; k++) t.emplace_back(cos(ang * (double)k), sin(ang * (double)k));
+            }
+        }
+        tw = t.data();
+    }
     for (size_t len = 2; len <= n; len <<= 1) {
-        const double ang = -2.0 * M_PI / (double)len;
+        const std::complex<double>* tl = tw + (len / 2 - 1);               // stages are stored back to back: 1 + 2 + 4 + ...
         for (size_t i = 0; i < n; i += len)
             for (size_t k = 0; k < len / 2; k++) {
-                const std::complex<double> w(cos(ang * (double)k), sin(ang * (double)k));
+                const std::complex<double> w = tl[k];
                 const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
                 a[i + k] = u + v;
                 a[i + k + len / 2] = u - v;
@@ -189,6 +205,8 @@ struct Chan {
     double rate = 0.0, phase = 0.0;        // phase (turns) just before the next unconsumed sample
     bool bp_enabled = false;
     double bp_lo = 0.0, bp_hi = 0.0;
+    bool bp_dirty = false;                 // a designed band-pass waits in bp_stage for the next block boundary
+    std::vector<float2> bp_stage;          // Tb taps followed by the bpP x 256 partition spectra
     ChanCfg cfg{};
     owrx_chan_spec_t spec{};
     float agc_initial = 1.0f;
@@ -212,16 +230,29 @@ struct Group {
     // device tables
     float* d_taps = nullptr; float* d_deemph = nullptr; float* d_pre = nullptr;
     double* d_rate = nullptr; double* d_phase = nullptr; float2* d_w = nullptr;
-    float2* d_bp = nullptr; int* d_bp_en = nullptr;
+    float2* d_bp = nullptr;
+    int* d_bp_en2[2] = {nullptr, nullptr};           // per-slot tables are double-buffered by block parity (see group_begin_feed)
+    int* d_bp_en = nullptr;                          // = d_bp_en2[cur]
     // K4F partitioned-FFT band-pass (fastconv.cuh): H[p][256][slots], scratch spectra
     int bpP = 1;
     float2* d_bp_H = nullptr; float2* d_bp_X = nullptr; float2* d_bp_Y = nullptr;
     size_t bp_blocks_cap = 0;
-    ChanCfg* d_cfg = nullptr; ChanState* d_state = nullptr;
+    ChanCfg* d_cfg2[2] = {nullptr, nullptr};
+    ChanCfg* d_cfg = nullptr;                        // = d_cfg2[cur]
+    ChanState* d_state = nullptr;
     TailStash* d_stash = nullptr;                    // fused tail: state the next feed starts from (tail_front -> tail_commit)
     std::vector<double> h_rate, h_phase; std::vector<float2> h_w;
     std::vector<int> h_bp_en; std::vector<ChanCfg> h_cfg;
-    bool cfg_dirty = true;
+    bool cfg_stale[2] = {true, true};                // host tables changed since that copy was uploaded
+    int cur = 0;                                     // parity of the block being issued
+    std::map<int, SlotPatch> pend;                   // per-slot state patches waiting for the next block boundary
+    bool bp_pending = false;                         // some channel has a staged band-pass
+    SlotPatch* d_patch[2] = {nullptr, nullptr}; int patch_cap = 0;     // device staging: [0] tail stream, [1] serial stream
+    float2* d_bp_stage = nullptr; int* d_bp_stage_slots = nullptr; int bp_stage_cap = 0;
+    // page-locked host staging of the designed band-passes, one per block parity: a pageable source of this size (76 KB per
+    // 3125-tap design) would make cudaMemcpyAsync wait for the stream; the event says the copy that last read it has run
+    unsigned char* h_bp_pin[2] = {nullptr, nullptr}; size_t h_bp_pin_cap[2] = {0, 0};
+    cudaEvent_t bp_pin_ev[2] = {nullptr, nullptr};
     // stream position
     size_t in_off = 0;                               // streaming: offset of the next block in the bank's IQ buffer
     size_t dev_lead = 0;                             // device path: samples at the head of the next block this group has consumed already
@@ -240,7 +271,9 @@ struct Group {
     long long pend_first = 0;
     // client audio tail (Convert / AdpcmEncoder)
     std::vector<int> h_tail_mode;
-    int* d_tail_mode = nullptr; TailState* d_tail = nullptr; int* d_tail_count = nullptr;
+    int* d_tail_mode2[2] = {nullptr, nullptr};
+    int* d_tail_mode = nullptr;                      // = d_tail_mode2[cur]
+    TailState* d_tail = nullptr; int* d_tail_count = nullptr;
     int16_t* d_tail_s16 = nullptr; unsigned char* d_tail_bytes = nullptr;
     size_t tail_rows_cap = 0; int tail_cap = 0;
     bool any_tail = false, tail_ran = false;
@@ -300,8 +333,14 @@ struct owrx_bank {
     int fir_form_used = 0;                           // form of the latest Shift + FirDecimate pass (owrx_bank_fir_form)
     // evaluation variants kept for A/B runs and as second opinions in the tests (read from the environment at creation)
     bool tail_fused = true;                          // OWRX_TAIL_FUSED=0: the seven-kernel low-rate tail
-    bool agc_cta = false;                            // OWRX_AGC_CTA=1: the 8-channel-CTA Agc kernel
+    bool agc_cta = true;                             // OWRX_AGC_CTA=0: one warp per channel (agc_warp_kernel): 0.137 vs 0.219 ms alone,
+                                                     // but stretched to 0.51 ms by the other streams' CTAs on its SMs (C2 step 0.55 vs 0.29 ms)
     size_t last_consumed = 0;                        // device path: samples of the last block every group is done with
+    // groups whose last client left: out of the feed loops at once, their device memory released by a later call once the
+    // event (recorded behind everything issued while the group was live) has completed — no device synchronisation
+    std::vector<std::pair<std::unique_ptr<Group>, cudaEvent_t>> graveyard;
+    cudaStream_t ctl_stream = nullptr;
+    unsigned long long feeds = 0;                    // host-path feeds so far (parity of the per-slot table copies)
 };
 
 namespace {
@@ -318,10 +357,17 @@ void group_release(Group* g)
 {
     cudaFree(g->d_taps); cudaFree(g->d_deemph); cudaFree(g->d_pre);
     cudaFree(g->d_rate); cudaFree(g->d_phase); cudaFree(g->d_w);
-    cudaFree(g->d_bp); cudaFree(g->d_bp_en); cudaFree(g->d_cfg); cudaFree(g->d_state); cudaFree(g->d_stash);
+    cudaFree(g->d_bp); cudaFree(g->d_bp_en2[0]); cudaFree(g->d_bp_en2[1]); cudaFree(g->d_cfg2[0]); cudaFree(g->d_cfg2[1]);
+    cudaFree(g->d_state); cudaFree(g->d_stash); cudaFree(g->d_patch[0]); cudaFree(g->d_patch[1]);
+    cudaFree(g->d_bp_stage); cudaFree(g->d_bp_stage_slots);
+    for (int k = 0; k < 2; k++) {
+        if (g->h_bp_pin[k]) cudaFreeHost(g->h_bp_pin[k]);
+        if (g->bp_pin_ev[k]) cudaEventDestroy(g->bp_pin_ev[k]);
+    }
     cudaFree(g->d_bp_H); cudaFree(g->d_bp_X); cudaFree(g->d_bp_Y);
     cudaFree(g->d_partial); cudaFree(g->d_gate); cudaFree(g->d_power); cudaFree(g->d_dcmean); cudaFree(g->d_dcprev);
-    cudaFree(g->d_tail_mode); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
+    cudaFree(g->d_tail_mode2[0]); cudaFree(g->d_tail_mode2[1]); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16);
+    cudaFree(g->d_tail_bytes);
     cudaFree(g->d_fc_h); cudaFree(g->d_fc_tab); cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates);
     cudaFree(g->d_fc_tabp); cudaFree(g->d_fc_Fp);
     g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1p.release(); g->f1b.release(); g->f2.release(); g->f3.release();
@@ -421,10 +467,13 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     }
     const size_t S = (size_t)g->slots;
     if ((rc = dev_alloc(&g->d_rate, S)) || (rc = dev_alloc(&g->d_phase, S)) || (rc = dev_alloc(&g->d_w, S)) ||
-        (rc = dev_alloc(&g->d_bp, S * g->Tb)) || (rc = dev_alloc(&g->d_bp_H, S * (size_t)g->bpP * FC_M)) || (rc = dev_alloc(&g->d_bp_en, S)) || (rc = dev_alloc(&g->d_cfg, S)) ||
-        (rc = dev_alloc(&g->d_state, S)) || (rc = dev_alloc(&g->d_tail_mode, S)) || (rc = dev_alloc(&g->d_tail, S)) ||
-        (rc = dev_alloc(&g->d_tail_count, S)) || (rc = dev_alloc(&g->d_stash, S)))
+        (rc = dev_alloc(&g->d_bp, S * g->Tb)) || (rc = dev_alloc(&g->d_bp_H, S * (size_t)g->bpP * FC_M)) ||
+        (rc = dev_alloc(&g->d_bp_en2[0], S)) || (rc = dev_alloc(&g->d_bp_en2[1], S)) || (rc = dev_alloc(&g->d_cfg2[0], S)) ||
+        (rc = dev_alloc(&g->d_cfg2[1], S)) || (rc = dev_alloc(&g->d_state, S)) || (rc = dev_alloc(&g->d_tail_mode2[0], S)) ||
+        (rc = dev_alloc(&g->d_tail_mode2[1], S)) || (rc = dev_alloc(&g->d_tail, S)) || (rc = dev_alloc(&g->d_tail_count, S)) ||
+        (rc = dev_alloc(&g->d_stash, S)))
         return rc;
+    g->d_cfg = g->d_cfg2[0]; g->d_bp_en = g->d_bp_en2[0]; g->d_tail_mode = g->d_tail_mode2[0];
     g->h_tail_mode.assign(S, 0);
     g->h_rate.assign(S, 0.0); g->h_phase.assign(S, 0.0); g->h_w.assign(S, make_float2(1.f, 0.f));
     g->h_bp_en.assign(S, 0);
@@ -445,9 +494,42 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     if ((rc = g->f2.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
     if ((rc = g->f3.init(1, g->slots, 0, cap)) != OWRX_OK) return rc;
     g->in_off = bank->iq_fill;          // a new group starts with the next incoming sample
+    for (size_t i = 0; i < bank->groups.size(); i++) {
+        if (!bank->groups[i]) { *index = (int)i; bank->groups[i] = std::move(g); return OWRX_OK; }
+    }
     *index = (int)bank->groups.size();
     bank->groups.push_back(std::move(g));
     return OWRX_OK;
+}
+
+// A group nobody listens to any more leaves the feed loops now; its buffers are freed by reap_groups once everything
+// that was issued while it was live has run (event behind the bank's own streams and the caller's last block).
+int retire_group(owrx_bank* bank, int gi)
+{
+    std::unique_ptr<Group> g = std::move(bank->groups[(size_t)gi]);
+    bank->groups[(size_t)gi].reset();
+    cudaEvent_t ev = nullptr;
+    OWRX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (cudaStream_t s : {bank->stream, bank->side_stream, bank->serial_stream, bank->copy_stream, bank->drain_stream}) {
+        OWRX_CUDA(cudaEventRecord(ev, s));
+        OWRX_CUDA(cudaStreamWaitEvent(bank->ctl_stream, ev, 0));
+    }
+    OWRX_CUDA(cudaStreamWaitEvent(bank->ctl_stream, bank->dev_done, 0));       // the caller's stream (device path)
+    OWRX_CUDA(cudaEventRecord(ev, bank->ctl_stream));
+    bank->graveyard.emplace_back(std::move(g), ev);
+    return OWRX_OK;
+}
+
+void reap_groups(owrx_bank* bank, bool wait)
+{
+    for (size_t i = 0; i < bank->graveyard.size();) {
+        auto& e = bank->graveyard[i];
+        if (wait) cudaEventSynchronize(e.second);
+        if (cudaEventQuery(e.second) != cudaSuccess) { i++; continue; }
+        group_release(e.first.get());
+        cudaEventDestroy(e.second);
+        bank->graveyard.erase(bank->graveyard.begin() + (ptrdiff_t)i);
+    }
 }
 
 int find_group(owrx_bank* bank, const owrx_chan_spec_t& sp)
@@ -476,6 +558,15 @@ void agc_defaults(ChanCfg& c, int kind, int profile)
 
 float agc_initial_gain(int kind) { return kind == OWRX_DEMOD_AM ? 200.0f : 1.0f; }   // Am: setInitialGain(200), analog.py:15
 
+void add_patch(Group* g, int slot, int flags, float agc_gain)
+{
+    SlotPatch& p = g->pend[slot];
+    p.slot = slot;
+    if (flags & (PATCH_AGC_RESET | PATCH_AGC_GAIN)) p.agc_gain = agc_gain;
+    if ((flags & PATCH_AGC_RESET) && (p.flags & PATCH_AGC_GAIN)) p.flags &= ~PATCH_AGC_GAIN;
+    p.flags |= flags;
+}
+
 int place_channel(owrx_bank* bank, Chan* ch, int gi)
 {
     Group* g = bank->groups[(size_t)gi].get();
@@ -484,29 +575,23 @@ int place_channel(owrx_bank* bank, Chan* ch, int gi)
     if (slot < 0) return fail(OWRX_E_STATE, "group full");     // caller grows before placing
     g->slot_chan[(size_t)slot] = ch->id;
     ch->group = gi; ch->slot = slot;
-    // a new client's modules start with empty histories (the reference builds fresh pycsdr modules): clear whatever the
-    // idle slot computed before
-    OWRX_CUDA(cudaDeviceSynchronize());
-    for (StageBuf* b : {&g->s1, &g->s2, &g->s3, &g->f1, &g->f1p, &g->f1b, &g->f2, &g->f3}) {
-        if (!b->d[b->cur] || !b->fill) continue;
-        OWRX_CUDA(cudaMemset2D(b->d[b->cur] + (size_t)slot * b->width, b->row_floats() * sizeof(float), 0, (size_t)b->width * sizeof(float), b->fill));
-    }
-    ChanState st{};
-    st.agc_gain = ch->agc_initial;
-    OWRX_CUDA(cudaMemcpy(g->d_state + slot, &st, sizeof(st), cudaMemcpyHostToDevice));
+    // a new client's modules start with empty histories and fresh state (the reference builds fresh pycsdr modules): recorded
+    // here, applied stream-ordered at the next block boundary (group_begin_feed) — no device synchronisation
+    add_patch(g, slot, PATCH_DEMOD | PATCH_AGC_RESET | PATCH_TAIL | PATCH_SQUELCH | PATCH_HISTORY, ch->agc_initial);
     g->h_cfg[(size_t)slot] = ch->cfg;
     g->h_bp_en[(size_t)slot] = 0;
     g->h_tail_mode[(size_t)slot] = ch->audio_fmt;
-    TailState tl{0, 0, 1001, 0, 0};
-    OWRX_CUDA(cudaMemcpy(g->d_tail + slot, &tl, sizeof(tl), cudaMemcpyHostToDevice));
-    g->cfg_dirty = true;
+    g->cfg_stale[0] = g->cfg_stale[1] = true;
     return OWRX_OK;
 }
 
 // grow a group's slot capacity by K3_CG, re-laying out every per-slot table and stage buffer
 int group_grow(owrx_bank* bank, Group* g)
 {
-    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
+    // re-laying out every table of the group: rare (every 64th client of a class) and the one control operation that
+    // quiesces the device — block kernels on the pipeline's other streams may still read the old arrays
+    (void)bank;
+    OWRX_CUDA(cudaDeviceSynchronize());
     const int os = g->slots, ns = os + K3_CG;
     auto regrow = [&](auto** p, size_t rows) -> int {
         using T = typename std::remove_pointer<typename std::remove_pointer<decltype(p)>::type>::type;
@@ -520,10 +605,13 @@ int group_grow(owrx_bank* bank, Group* g)
     };
     int rc;
     if ((rc = regrow(&g->d_rate, 1)) || (rc = regrow(&g->d_phase, 1)) || (rc = regrow(&g->d_w, 1)) ||
-        (rc = regrow(&g->d_bp, (size_t)g->Tb)) || (rc = regrow(&g->d_bp_H, (size_t)g->bpP * FC_M)) || (rc = regrow(&g->d_bp_en, 1)) || (rc = regrow(&g->d_cfg, 1)) ||
-        (rc = regrow(&g->d_state, 1)) || (rc = regrow(&g->d_tail_mode, 1)) || (rc = regrow(&g->d_tail, 1)) ||
-        (rc = regrow(&g->d_tail_count, 1)) || (rc = regrow(&g->d_stash, 1)))
+        (rc = regrow(&g->d_bp, (size_t)g->Tb)) || (rc = regrow(&g->d_bp_H, (size_t)g->bpP * FC_M)) ||
+        (rc = regrow(&g->d_bp_en2[0], 1)) || (rc = regrow(&g->d_bp_en2[1], 1)) || (rc = regrow(&g->d_cfg2[0], 1)) ||
+        (rc = regrow(&g->d_cfg2[1], 1)) || (rc = regrow(&g->d_state, 1)) || (rc = regrow(&g->d_tail_mode2[0], 1)) ||
+        (rc = regrow(&g->d_tail_mode2[1], 1)) || (rc = regrow(&g->d_tail, 1)) || (rc = regrow(&g->d_tail_count, 1)) ||
+        (rc = regrow(&g->d_stash, 1)))
         return rc;
+    g->d_cfg = g->d_cfg2[g->cur]; g->d_bp_en = g->d_bp_en2[g->cur]; g->d_tail_mode = g->d_tail_mode2[g->cur];
     cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
     g->d_tail_s16 = nullptr; g->d_tail_bytes = nullptr; g->tail_rows_cap = 0; g->tail_cap = 0;
     auto regrow_buf = [&](StageBuf& b) -> int {
@@ -561,34 +649,156 @@ int group_grow(owrx_bank* bank, Group* g)
     g->h_tail_mode.resize((size_t)ns, 0);
     ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f; idle.agc_thr = 0.8f;
     g->h_cfg.resize((size_t)ns, idle);
-    g->cfg_dirty = true;
+    g->cfg_stale[0] = g->cfg_stale[1] = true;
     return OWRX_OK;
 }
 
-int upload_bandpass(owrx_bank* bank, Chan* ch)
+// Bandpass.setBandpass: the taps (and their partition spectra for the K4F form) are designed on the host and staged in the
+// channel; they reach the per-slot tables at the next block boundary (apply_pending), ordered on the stream that reads them
+// pure host arithmetic, no bank state: callers run it WITHOUT the bank mutex (a 3125-tap design is ~0.2 ms of host time)
+void design_bandpass_stage(std::vector<float2>& stage, int Tb, int bpP, double lo, double hi)
+{
+    std::vector<float2> taps;
+    design_bandpass(taps, Tb, lo, hi);                                   // Bandpass.setBandpass, selector.py:159-166
+    const size_t nH = (size_t)bpP * FC_M;
+    stage.resize((size_t)Tb + nH);
+    std::copy(taps.begin(), taps.end(), stage.begin());
+    // partition spectra H[p] = FFT_256([taps[128p .. 128p+127] | 0]) of the SAME float32 taps (double arithmetic, rounded once)
+    std::vector<std::complex<double>> buf((size_t)FC_M);
+    for (int p = 0; p < bpP; p++) {
+        for (int u = 0; u < FC_M; u++) {
+            const int t = p * BPF_H + u;
+            buf[(size_t)u] = (u < BPF_H && t < Tb) ? std::complex<double>(taps[(size_t)t].x, taps[(size_t)t].y) : std::complex<double>(0.0, 0.0);
+        }
+        fft_pow2(buf);
+        for (int q = 0; q < FC_M; q++)
+            stage[(size_t)Tb + (size_t)p * FC_M + q] = make_float2((float)buf[(size_t)q].real(), (float)buf[(size_t)q].imag());
+    }
+}
+
+// `designed` (optional): a stage designed outside the mutex for exactly this group's (Tb, bpP)
+int upload_bandpass(owrx_bank* bank, Chan* ch, std::vector<float2>* designed = nullptr)
 {
     Group* g = bank->groups[(size_t)ch->group].get();
     g->h_bp_en[(size_t)ch->slot] = ch->bp_enabled ? 1 : 0;
-    g->cfg_dirty = true;
+    g->cfg_stale[0] = g->cfg_stale[1] = true;
     if (!ch->bp_enabled) return OWRX_OK;
-    std::vector<float2> taps;
-    design_bandpass(taps, g->Tb, ch->bp_lo, ch->bp_hi);                  // Bandpass.setBandpass, selector.py:159-166
-    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
-    OWRX_CUDA(cudaMemcpy2D(g->d_bp + ch->slot, (size_t)g->slots * sizeof(float2), taps.data(), sizeof(float2), sizeof(float2),
-                           (size_t)g->Tb, cudaMemcpyHostToDevice));
-    // partition spectra H[p] = FFT_256([taps[128p .. 128p+127] | 0]) of the SAME float32 taps (double arithmetic, rounded once)
-    std::vector<float2> H((size_t)g->bpP * FC_M);
-    std::vector<std::complex<double>> buf((size_t)FC_M);
-    for (int p = 0; p < g->bpP; p++) {
-        for (int u = 0; u < FC_M; u++) {
-            const int t = p * BPF_H + u;
-            buf[(size_t)u] = (u < BPF_H && t < g->Tb) ? std::complex<double>(taps[(size_t)t].x, taps[(size_t)t].y) : std::complex<double>(0.0, 0.0);
+    if (designed && designed->size() == (size_t)g->Tb + (size_t)g->bpP * FC_M) ch->bp_stage.swap(*designed);
+    else design_bandpass_stage(ch->bp_stage, g->Tb, g->bpP, ch->bp_lo, ch->bp_hi);
+    ch->bp_dirty = true;
+    g->bp_pending = true;
+    return OWRX_OK;
+}
+
+// Everything the control path recorded since the last block, as stream-ordered device work.  st_fir owns the FirDecimate
+// output history (s1), st_tail every other stage history, the band-pass tables, the squelch / demodulator state and the
+// per-slot tables of this block's parity, st_serial the Agc and audio-tail state.  Called after the history rolls.
+int apply_pending(owrx_bank* bank, Group* g, cudaStream_t st_fir, cudaStream_t st_tail, cudaStream_t st_serial)
+{
+    const int S = g->slots;
+    if (!g->pend.empty()) {
+        std::vector<SlotPatch> v;
+        int any_tail_flags = 0, any_serial_flags = 0;
+        for (auto& kv : g->pend) {
+            v.push_back(kv.second);
+            any_tail_flags |= kv.second.flags & (PATCH_DEMOD | PATCH_SQUELCH);
+            any_serial_flags |= kv.second.flags & (PATCH_AGC_RESET | PATCH_AGC_GAIN | PATCH_TAIL);
         }
-        fft_pow2(buf);
-        for (int q = 0; q < FC_M; q++) H[(size_t)p * FC_M + q] = make_float2((float)buf[(size_t)q].real(), (float)buf[(size_t)q].imag());
+        if ((int)v.size() > g->patch_cap) {
+            // first use / more pending slots than ever before: the staging arrays grow (cudaFree waits for their readers)
+            const int cap = std::max(S, (int)v.size());
+            for (int k = 0; k < 2; k++) {
+                cudaFree(g->d_patch[k]); g->d_patch[k] = nullptr;
+                OWRX_CUDA(cudaMalloc((void**)&g->d_patch[k], (size_t)cap * sizeof(SlotPatch)));
+            }
+            g->patch_cap = cap;
+        }
+        const int n = (int)v.size();
+        // pageable sources: cudaMemcpyAsync stages them before it returns, the vector may go
+        if (any_tail_flags) {
+            OWRX_CUDA(cudaMemcpyAsync(g->d_patch[0], v.data(), (size_t)n * sizeof(SlotPatch), cudaMemcpyHostToDevice, st_tail));
+            slot_patch_kernel<<<(n + 127) / 128, 128, 0, st_tail>>>(g->d_patch[0], n, PATCH_DEMOD | PATCH_SQUELCH, g->d_state, g->d_tail);
+            OWRX_LAUNCH_CHECK();
+            bank->stats.kernel_launches++;
+        }
+        if (any_serial_flags) {
+            OWRX_CUDA(cudaMemcpyAsync(g->d_patch[1], v.data(), (size_t)n * sizeof(SlotPatch), cudaMemcpyHostToDevice, st_serial));
+            slot_patch_kernel<<<(n + 127) / 128, 128, 0, st_serial>>>(g->d_patch[1], n, PATCH_AGC_RESET | PATCH_AGC_GAIN | PATCH_TAIL, g->d_state,
+                                                                     g->d_tail);
+            OWRX_LAUNCH_CHECK();
+            bank->stats.kernel_launches++;
+        }
+        for (const SlotPatch& sp : v) {
+            if (!(sp.flags & PATCH_HISTORY)) continue;
+            struct { StageBuf* b; cudaStream_t st; } bufs[] = {{&g->s1, st_fir}, {&g->s2, st_tail}, {&g->s3, st_tail}, {&g->f1, st_tail},
+                                                              {&g->f1p, st_tail}};
+            for (auto& e : bufs) {
+                StageBuf* b = e.b;
+                if (!b->d[b->cur] || !b->fill) continue;
+                OWRX_CUDA(cudaMemset2DAsync(b->d[b->cur] + (size_t)sp.slot * b->width, b->row_floats() * sizeof(float), 0,
+                                            (size_t)b->width * sizeof(float), b->fill, e.st));
+            }
+        }
+        g->pend.clear();
     }
-    OWRX_CUDA(cudaMemcpy2D(g->d_bp_H + ch->slot, (size_t)g->slots * sizeof(float2), H.data(), sizeof(float2), sizeof(float2),
-                           H.size(), cudaMemcpyHostToDevice));
+    if (g->bp_pending) {
+        const size_t per = (size_t)g->Tb + (size_t)g->bpP * FC_M;
+        std::vector<Chan*> todo;
+        std::vector<int> slots;
+        for (int s = 0; s < S; s++) {
+            const int cid = g->slot_chan[(size_t)s];
+            if (cid < 0) continue;
+            Chan* ch = bank->chans[(size_t)cid].get();
+            if (!ch || !ch->bp_dirty) continue;
+            if (ch->bp_stage.size() == per) { todo.push_back(ch); slots.push_back(s); }
+            ch->bp_dirty = false;
+        }
+        if (!slots.empty()) {
+            const int q = g->cur;
+            const size_t n = slots.size(), bytes = n * per * sizeof(float2) + n * sizeof(int);
+            if (!g->bp_pin_ev[q]) OWRX_CUDA(cudaEventCreateWithFlags(&g->bp_pin_ev[q], cudaEventDisableTiming));
+            OWRX_CUDA(cudaEventSynchronize(g->bp_pin_ev[q]));
+            if (bytes > g->h_bp_pin_cap[q]) {
+                const size_t cap = std::max(bytes, (size_t)16 * (per * sizeof(float2) + sizeof(int)));
+                if (g->h_bp_pin[q]) cudaFreeHost(g->h_bp_pin[q]);
+                g->h_bp_pin[q] = nullptr; g->h_bp_pin_cap[q] = 0;
+                OWRX_CUDA(cudaHostAlloc((void**)&g->h_bp_pin[q], cap, cudaHostAllocDefault));
+                g->h_bp_pin_cap[q] = cap;
+            }
+            if ((int)n > g->bp_stage_cap) {
+                const int cap = std::max((int)n, std::min(S, 16));
+                cudaFree(g->d_bp_stage); cudaFree(g->d_bp_stage_slots);
+                g->d_bp_stage = nullptr; g->d_bp_stage_slots = nullptr; g->bp_stage_cap = 0;
+                OWRX_CUDA(cudaMalloc((void**)&g->d_bp_stage, (size_t)cap * per * sizeof(float2)));
+                OWRX_CUDA(cudaMalloc((void**)&g->d_bp_stage_slots, (size_t)cap * sizeof(int)));
+                g->bp_stage_cap = cap;
+            }
+            float2* hs = reinterpret_cast<float2*>(g->h_bp_pin[q]);
+            int* hi = reinterpret_cast<int*>(g->h_bp_pin[q] + n * per * sizeof(float2));
+            for (size_t i = 0; i < n; i++) {
+                memcpy(hs + i * per, todo[i]->bp_stage.data(), per * sizeof(float2));
+                hi[i] = slots[i];
+            }
+            OWRX_CUDA(cudaMemcpyAsync(g->d_bp_stage, hs, n * per * sizeof(float2), cudaMemcpyHostToDevice, st_tail));
+            OWRX_CUDA(cudaMemcpyAsync(g->d_bp_stage_slots, hi, n * sizeof(int), cudaMemcpyHostToDevice, st_tail));
+            OWRX_CUDA(cudaEventRecord(g->bp_pin_ev[q], st_tail));
+            bp_scatter_kernel<<<dim3((unsigned)((per + 255) / 256), (unsigned)n), 256, 0, st_tail>>>(
+                g->d_bp_stage, g->d_bp_stage_slots, g->Tb, (int)((size_t)g->bpP * FC_M), S, g->d_bp, g->d_bp_H);
+            OWRX_LAUNCH_CHECK();
+            bank->stats.kernel_launches++;
+        }
+        g->bp_pending = false;
+    }
+    // per-slot tables of this block's parity: a block still in flight on the other streams keeps reading the other copy
+    g->d_cfg = g->d_cfg2[g->cur]; g->d_bp_en = g->d_bp_en2[g->cur]; g->d_tail_mode = g->d_tail_mode2[g->cur];
+    if (g->cfg_stale[g->cur]) {
+        OWRX_CUDA(cudaMemcpyAsync(g->d_cfg, g->h_cfg.data(), (size_t)S * sizeof(ChanCfg), cudaMemcpyHostToDevice, st_tail));
+        OWRX_CUDA(cudaMemcpyAsync(g->d_bp_en, g->h_bp_en.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st_tail));
+        OWRX_CUDA(cudaMemcpyAsync(g->d_tail_mode, g->h_tail_mode.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice, st_tail));
+        g->cfg_stale[g->cur] = false;
+    }
+    g->any_tail = false;
+    for (int m : g->h_tail_mode) if (m) g->any_tail = true;
     return OWRX_OK;
 }
 
@@ -663,7 +873,7 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
             // the staging arrays may still be read by an earlier table launch on another stream: order on the device
             OWRX_CUDA(cudaMemcpyAsync(g->d_fc_slots, sl.data(), sl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
             OWRX_CUDA(cudaMemcpyAsync(g->d_fc_rates, rt.data(), rt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-            OWRX_CUDA(cudaStreamSynchronize(st));                     // pageable sources: safe to drop the vectors
+            // (small pageable sources are staged by the runtime before cudaMemcpyAsync returns: no stream wait, the vectors may go)
             rc = tc ? fc_launch_table_tc(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tabp, st)
                     : fc_launch_table(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tab, st);
             if (rc != OWRX_OK) return rc;
@@ -1072,7 +1282,7 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
                 // ---- client audio tail: Convert(FLOAT, SHORT) [+ AdpcmEncoder(sync=True)]; appends behind earlier passes
                 const size_t row0 = g->last_audio - n_audio;
                 if (g->last_audio > g->tail_rows_cap) return fail(OWRX_E_STATE, "audio tail scratch under-provisioned");
-                audio_tail_kernel<<<(S + 63) / 64, 64, 0, st>>>(g->f3.rows(g->f3.fill - n_audio), S, (int)n_audio, g->d_tail_mode,
+                audio_tail_kernel<<<(S + 31) / 32, 32, 0, st>>>(g->f3.rows(g->f3.fill - n_audio), S, (int)n_audio, g->d_tail_mode,
                                                                g->d_tail, g->d_tail_s16 + row0 * (size_t)S, g->d_tail_bytes,
                                                                g->d_tail_count, g->tail_cap);
                 OWRX_LAUNCH_CHECK();
@@ -1087,21 +1297,11 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
 // Start of a feed / device block: drop the previous outputs (histories stay), reset the per-feed counters and
 // provision every buffer for up to `rows` new FirDecimate outputs so that nothing reallocates while the
 // streams overlap.
-int group_begin_feed(owrx_bank* bank, Group* g, size_t rows, cudaStream_t st_fir, cudaStream_t st_tail)
+int group_begin_feed(owrx_bank* bank, Group* g, size_t rows, cudaStream_t st_fir, cudaStream_t st_tail, cudaStream_t st_serial, int parity)
 {
     const int S = g->slots;
     int rc;
-    if (g->cfg_dirty) {
-        // retune / re-filter / mode change since the last block: per-channel tables are consumed by kernels on
-        // both streams, so quiesce the device before replacing them
-        OWRX_CUDA(cudaDeviceSynchronize());
-        OWRX_CUDA(cudaMemcpy(g->d_cfg, g->h_cfg.data(), (size_t)S * sizeof(ChanCfg), cudaMemcpyHostToDevice));
-        OWRX_CUDA(cudaMemcpy(g->d_bp_en, g->h_bp_en.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
-        OWRX_CUDA(cudaMemcpy(g->d_tail_mode, g->h_tail_mode.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
-        g->any_tail = false;
-        for (int m : g->h_tail_mode) if (m) g->any_tail = true;
-        g->cfg_dirty = false;
-    }
+    g->cur = parity & 1;
     const size_t blocks = rows / (size_t)g->sq_len + 2;
     const size_t low = rows + (size_t)g->sq_len + 64;           // rows any low-rate stage can append in one feed
     if ((rc = g->s1.roll(g->s1.hist, st_fir)) != OWRX_OK) return rc;
@@ -1147,7 +1347,20 @@ int group_begin_feed(owrx_bank* bank, Group* g, size_t rows, cudaStream_t st_fir
         }
         OWRX_CUDA(cudaDeviceSynchronize());
     }
-    if (g->any_tail) OWRX_CUDA(cudaMemsetAsync(g->d_tail_count, 0, (size_t)S * sizeof(int), st_tail));
+    if ((rc = apply_pending(bank, g, st_fir, st_tail, st_serial)) != OWRX_OK) return rc;
+    if (g->any_tail) {
+        // the audio tail's scratch follows any_tail, which apply_pending has just refreshed
+        if (low > g->tail_rows_cap) {
+            OWRX_CUDA(cudaDeviceSynchronize());
+            const int cap = (int)(low / 2 + 8 * (low / 2002 + 2) + 16);
+            cudaFree(g->d_tail_s16); cudaFree(g->d_tail_bytes);
+            g->d_tail_s16 = nullptr; g->d_tail_bytes = nullptr; g->tail_rows_cap = 0; g->tail_cap = 0;
+            OWRX_CUDA(cudaMalloc((void**)&g->d_tail_s16, low * (size_t)S * sizeof(int16_t)));
+            OWRX_CUDA(cudaMalloc((void**)&g->d_tail_bytes, (size_t)cap * S));
+            g->tail_rows_cap = low; g->tail_cap = cap;
+        }
+        OWRX_CUDA(cudaMemsetAsync(g->d_tail_count, 0, (size_t)S * sizeof(int), st_serial));
+    }
     return OWRX_OK;
 }
 
@@ -1268,6 +1481,7 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->side_stream, cudaStreamNonBlocking, (tail_prio & 1) ? prio_hi : prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->serial_stream, cudaStreamNonBlocking, (tail_prio & 2) ? prio_hi : prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->drain_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->ctl_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
@@ -1288,6 +1502,8 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     cudaSetDevice(bank->device);
     cudaDeviceSynchronize();
     for (auto& g : bank->groups) if (g) group_release(g.get());
+    reap_groups(bank, true);
+    if (bank->ctl_stream) cudaStreamDestroy(bank->ctl_stream);
     cudaFree(bank->d_iq[0]); cudaFree(bank->d_iq[1]); cudaFree(bank->d_xpose); cudaFree(bank->d_raw);
     if (bank->carry_done) cudaEventDestroy(bank->carry_done);
     for (cudaEvent_t e : bank->chunk_events) cudaEventDestroy(e);
@@ -1316,16 +1532,21 @@ static int add_channel_spec(owrx_bank_t* bank, const owrx_chan_spec_t& sp, int* 
     std::lock_guard<std::mutex> lk(bank->mu);
     OWRX_CUDA(cudaSetDevice(bank->device));
     if (bank->pending_final) { int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
+    reap_groups(bank, false);
     int gi = find_group(bank, sp), rc;
     if (gi < 0 && (rc = group_create(bank, sp, &gi)) != OWRX_OK) return rc;
     Group* g = bank->groups[(size_t)gi].get();
     if (std::find(g->slot_chan.begin(), g->slot_chan.end(), -1) == g->slot_chan.end() && (rc = group_grow(bank, g)) != OWRX_OK) return rc;
     std::unique_ptr<Chan> ch(new Chan());
-    ch->id = (int)bank->chans.size();
+    // ids are handles like file descriptors: the lowest free one is handed out again
+    size_t id = 0;
+    while (id < bank->chans.size() && bank->chans[id]) id++;
+    ch->id = (int)id;
     ch->spec = sp;
     agc_defaults(ch->cfg, sp.wfm ? OWRX_DEMOD_WFM : OWRX_DEMOD_NONE, OWRX_AGC_SLOW);
     Chan* raw = ch.get();
-    bank->chans.push_back(std::move(ch));
+    if (id == bank->chans.size()) bank->chans.push_back(std::move(ch));
+    else bank->chans[id] = std::move(ch);
     if ((rc = place_channel(bank, raw, gi)) != OWRX_OK) return rc;
     *chan = raw->id;
     return OWRX_OK;
@@ -1358,7 +1579,15 @@ int owrx_bank_remove_channel(owrx_bank_t* bank, int chan)
         g->h_cfg[(size_t)ch->slot] = idle;
         g->h_bp_en[(size_t)ch->slot] = 0;
         g->h_tail_mode[(size_t)ch->slot] = 0;
-        g->cfg_dirty = true;
+        g->cfg_stale[0] = g->cfg_stale[1] = true;
+        g->pend.erase(ch->slot);
+        bool live = false;
+        for (int cid : g->slot_chan) if (cid >= 0) live = true;
+        if (!live) {
+            OWRX_CUDA(cudaSetDevice(bank->device));
+            int rcr = retire_group(bank, ch->group);
+            if (rcr != OWRX_OK) return rcr;
+        }
     }
     bank->chans[(size_t)chan].reset();
     return OWRX_OK;
@@ -1386,13 +1615,26 @@ int owrx_chan_set_shift_rate(owrx_bank_t* bank, int chan, double rate)
 int owrx_chan_set_bandpass(owrx_bank_t* bank, int chan, double lo_rate, double hi_rate, int enabled)
 {
     if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    // the filter is designed before the mutex is taken: the DSP thread's next block never waits for a client's trigonometry
+    std::vector<float2> designed;
+    if (enabled) {
+        int Tb = 0, bpP = 0;
+        {
+            std::lock_guard<std::mutex> lk(bank->mu);
+            Chan* ch = get_chan(bank, chan);
+            if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
+            const Group* g = bank->groups[(size_t)ch->group].get();
+            Tb = g->Tb; bpP = g->bpP;
+        }
+        design_bandpass_stage(designed, Tb, bpP, lo_rate, hi_rate);
+    }
     std::lock_guard<std::mutex> lk(bank->mu);
     Chan* ch = get_chan(bank, chan);
     if (!ch) return fail(OWRX_E_INVALID, "no such channel %d", chan);
     if (bank->pending_final) { cudaSetDevice(bank->device); int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
     OWRX_CUDA(cudaSetDevice(bank->device));
     ch->bp_enabled = enabled != 0; ch->bp_lo = lo_rate; ch->bp_hi = hi_rate;
-    return upload_bandpass(bank, ch);
+    return upload_bandpass(bank, ch, &designed);                         // (re-designs under the mutex if the channel changed group meanwhile)
 }
 
 int owrx_chan_set_squelch_level(owrx_bank_t* bank, int chan, float level)
@@ -1405,7 +1647,7 @@ int owrx_chan_set_squelch_level(owrx_bank_t* bank, int chan, float level)
     ch->cfg.sq_level = level;
     Group* g = bank->groups[(size_t)ch->group].get();
     g->h_cfg[(size_t)ch->slot] = ch->cfg;
-    g->cfg_dirty = true;
+    g->cfg_stale[0] = g->cfg_stale[1] = true;
     return OWRX_OK;
 }
 
@@ -1438,9 +1680,18 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
         // move to the matching group (WFM channels keep their own lock-step group)
         int vrc = spec_validate(sp);
         if (vrc != OWRX_OK) return vrc;
-        g->slot_chan[(size_t)ch->slot] = -1;
-        g->cfg_dirty = true;
+        const int old_gi = ch->group, old_slot = ch->slot;
+        g->slot_chan[(size_t)old_slot] = -1;
+        {
+            ChanCfg idle{}; idle.kind = OWRX_DEMOD_NONE; idle.agc_ref = 0.8f; idle.agc_max = 1.f; idle.agc_thr = 0.8f;
+            g->h_cfg[(size_t)old_slot] = idle; g->h_bp_en[(size_t)old_slot] = 0; g->h_tail_mode[(size_t)old_slot] = 0;
+        }
+        g->cfg_stale[0] = g->cfg_stale[1] = true;
+        g->pend.erase(old_slot);
+        bool live = false;
+        for (int cid : g->slot_chan) if (cid >= 0) live = true;
         ch->spec = sp;
+        if (!live) { int rcr = retire_group(bank, old_gi); if (rcr != OWRX_OK) return rcr; }
         int gi = find_group(bank, sp), rc;
         if (gi < 0 && (rc = group_create(bank, sp, &gi)) != OWRX_OK) return rc;
         Group* ng = bank->groups[(size_t)gi].get();
@@ -1448,15 +1699,10 @@ int owrx_chan_set_demod(owrx_bank_t* bank, int chan, int kind, double audio_rate
         if ((rc = place_channel(bank, ch, gi)) != OWRX_OK) return rc;
         return upload_bandpass(bank, ch);
     }
-    // same group: new demodulator chain starts from fresh state (the reference rebuilds the modules)
-    OWRX_CUDA(cudaStreamSynchronize(bank->stream));
-    ChanState stt{};
-    OWRX_CUDA(cudaMemcpy(&stt, g->d_state + ch->slot, sizeof(stt), cudaMemcpyDeviceToHost));
-    stt.fm_last = make_float2(0.f, 0.f); stt.dc_last = 0.f; stt.iir = 0.f; stt.agc_hang = 0;
-    stt.agc_gain = ch->agc_initial;
-    OWRX_CUDA(cudaMemcpy(g->d_state + ch->slot, &stt, sizeof(stt), cudaMemcpyHostToDevice));
+    // same group: new demodulator chain starts from fresh state (the reference rebuilds the modules) at the next block boundary
+    add_patch(g, ch->slot, PATCH_DEMOD | PATCH_AGC_RESET, ch->agc_initial);
     g->h_cfg[(size_t)ch->slot] = ch->cfg;
-    g->cfg_dirty = true;
+    g->cfg_stale[0] = g->cfg_stale[1] = true;
     return OWRX_OK;
 }
 
@@ -1474,14 +1720,10 @@ int owrx_chan_set_agc(owrx_bank_t* bank, int chan, int profile, float initial_ga
     if (max_gain > 0.f) ch->cfg.agc_max = max_gain;
     if (initial_gain > 0.f) {
         ch->agc_initial = initial_gain;
-        OWRX_CUDA(cudaStreamSynchronize(bank->stream));
-        ChanState stt{};
-        OWRX_CUDA(cudaMemcpy(&stt, g->d_state + ch->slot, sizeof(stt), cudaMemcpyDeviceToHost));
-        stt.agc_gain = initial_gain;
-        OWRX_CUDA(cudaMemcpy(g->d_state + ch->slot, &stt, sizeof(stt), cudaMemcpyHostToDevice));
+        add_patch(g, ch->slot, PATCH_AGC_GAIN, initial_gain);
     }
     g->h_cfg[(size_t)ch->slot] = ch->cfg;
-    g->cfg_dirty = true;
+    g->cfg_stale[0] = g->cfg_stale[1] = true;
     return OWRX_OK;
 }
 
@@ -1497,14 +1739,12 @@ int owrx_chan_set_audio_format(owrx_bank_t* bank, int chan, int format)
     Group* g = bank->groups[(size_t)ch->group].get();
     if (format != ch->audio_fmt) {
         // a new AdpcmEncoder starts from reset state and announces it with a SYNC block
-        OWRX_CUDA(cudaStreamSynchronize(bank->stream));
-        TailState tl{0, 0, 1001, 0, 0};
-        OWRX_CUDA(cudaMemcpy(g->d_tail + ch->slot, &tl, sizeof(tl), cudaMemcpyHostToDevice));
+        add_patch(g, ch->slot, PATCH_TAIL, 0.f);
         ch->q_bytes.clear();
     }
     ch->audio_fmt = format;
     g->h_tail_mode[(size_t)ch->slot] = format;
-    g->cfg_dirty = true;
+    g->cfg_stale[0] = g->cfg_stale[1] = true;
     return OWRX_OK;
 }
 
@@ -1624,9 +1864,11 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
     auto lap = [&](const char* what) {
         if (trace) fprintf(stderr, "[owrx feed] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
     };
+    reap_groups(bank, false);
     bool any = false;
     for (auto& g : bank->groups) if (g) any = true;
     if (!any) return OWRX_OK;                         // nobody listening: samples are dropped like an unread ring
+    if (n_samples) (host_is_pinned(iq_raw) ? bank->stats.h2d_pinned_bytes : bank->stats.h2d_pageable_bytes) += n_samples * in_bytes;
     const size_t need = bank->iq_fill + n_samples;
     int rc;
     if (need > bank->iq_cap || (format != OWRX_IQ_CF32 && n_samples * in_bytes > bank->raw_cap)) {
@@ -1700,7 +1942,7 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
         Group* g = gp.get();
         if (!g) continue;
         const size_t rows = (fill0 + n_samples - g->in_off) / (size_t)g->D + 1;
-        if ((rc = group_begin_feed(bank, g, rows, st, tails)) != OWRX_OK) return rc;
+        if ((rc = group_begin_feed(bank, g, rows, st, tails, tails, (int)(bank->feeds & 1))) != OWRX_OK) return rc;
     }
     while (bank->drain_events.size() < n_chunks) {
         cudaEvent_t e;
@@ -1774,6 +2016,7 @@ int owrx_bank_feed_fmt(owrx_bank_t* bank, const void* iq_raw, size_t n_samples, 
     OWRX_CUDA(cudaEventRecord(bank->ev1, st));
     lap("launched");
     bank->stats.input_samples += n_samples;
+    bank->feeds++;
     if (bank->deferred) {
         bank->pending_final = true;                   // drained by the next feed (behind its uploads) or owrx_bank_flush
         return OWRX_OK;
@@ -1820,7 +2063,9 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
     OWRX_CUDA(cudaSetDevice(bank->device));
     cudaStream_t sa = stream ? (cudaStream_t)stream : bank->stream;
     cudaStream_t sb = bank->pipelined ? bank->side_stream : sa;
+    cudaStream_t sc = bank->pipelined ? bank->serial_stream : sa;
     const int par = (int)(bank->calls & 1);
+    reap_groups(bank, false);
     int rc = OWRX_OK;
     if (bank->pipelined) {
         // s1 ping-pong: this block's FirDecimate writes the buffer the parallel stages of two blocks ago were reading
@@ -1835,7 +2080,7 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         size_t consumed = 0;
         // previous block's outputs are dropped; histories stay
         // pipelined: every stage after FirDecimate (rolls of their history buffers included) lives on the side stream
-        if ((rc = group_begin_feed(bank, g, n_samples / (size_t)g->D + 1, sa, sb)) != OWRX_OK) return rc;
+        if ((rc = group_begin_feed(bank, g, n_samples / (size_t)g->D + 1, sa, sb, sc, par)) != OWRX_OK) return rc;
         // groups consume whole decimation steps: a group that got further than the slowest one in the previous block starts
         // `dev_lead` samples into this one (the caller presents [carry | new] from owrx_bank_last_consumed on)
         const size_t lead = std::min(g->dev_lead, n_samples);
@@ -1866,7 +2111,6 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
     // three-deep pipeline: FirDecimate of block i+2 (sa) | parallel low-rate stages of block i+1 (sb) | the sample-serial
     // Agc / audio tail of block i (sc).  Ping-pong stage buffers keep consecutive blocks apart; a buffer is reused two
     // blocks later: s1 after ptail_done[par] (awaited by sa), f2 after tail_done[par] (awaited by sb).
-    cudaStream_t sc = bank->pipelined ? bank->serial_stream : sa;
     if (bank->pipelined) {
         OWRX_CUDA(cudaEventRecord(bank->ptail_done[par], sb));
         OWRX_CUDA(cudaStreamWaitEvent(sc, bank->ptail_done[par], 0));

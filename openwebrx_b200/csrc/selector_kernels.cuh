@@ -11,6 +11,7 @@
 // sample-serial recurrences (AGC, IIR, squelch hang) run one channel per lane.
 #pragma once
 #include "common.cuh"
+#include "adpcm.cuh"
 
 namespace owrx {
 
@@ -362,7 +363,7 @@ tail_front_kernel(const float2* __restrict__ in, int slots, int n_blocks, int le
                   unsigned char* __restrict__ gate_out, float* __restrict__ f1, float* __restrict__ dc_mean,
                   float* __restrict__ dc_prev, TailStash* __restrict__ stash)
 {
-    __shared__ float tile[SQ_MAXROWS][32];
+    __shared__ float tile[2][SQ_MAXROWS][32];
     __shared__ float s_p[4][32];             // powers of blocks b, b-1, b-2, b-3
     __shared__ unsigned char s_gate[2][32];  // gate of block b, b-1
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -375,16 +376,16 @@ tail_front_kernel(const float2* __restrict__ in, int slots, int n_blocks, int le
     // ---- block powers: b and b-1 always, b-2 and b-3 only if some slot is below its level in b or b-1
     const float2* xb = in + (size_t)b * length * slots + s;
     {
-        const float p0 = tf_block_power(xb, slots, length, decim, lane, w, tile);
+        const float p0 = tf_block_power(xb, slots, length, decim, lane, w, tile[0]);
         if (w == 0) s_p[0][lane] = p0;
-        const float p1 = b >= 1 ? tf_block_power(xb - (size_t)length * slots, slots, length, decim, lane, w, tile) : 0.f;
+        const float p1 = b >= 1 ? tf_block_power(xb - (size_t)length * slots, slots, length, decim, lane, w, tile[0]) : 0.f;
         if (w == 0) s_p[1][lane] = p1;
     }
     __syncthreads();
     const bool below = s_p[0][lane] < level || (b >= 1 && s_p[1][lane] < level);
     if (__syncthreads_or(below)) {
-        const float p2 = b >= 2 ? tf_block_power(xb - (size_t)2 * length * slots, slots, length, decim, lane, w, tile) : 0.f;
-        const float p3 = b >= 3 ? tf_block_power(xb - (size_t)3 * length * slots, slots, length, decim, lane, w, tile) : 0.f;
+        const float p2 = b >= 2 ? tf_block_power(xb - (size_t)2 * length * slots, slots, length, decim, lane, w, tile[0]) : 0.f;
+        const float p3 = b >= 3 ? tf_block_power(xb - (size_t)3 * length * slots, slots, length, decim, lane, w, tile[0]) : 0.f;
         if (w == 0) { s_p[2][lane] = p2; s_p[3][lane] = p3; }
     } else if (w == 0) {
         s_p[2][lane] = level; s_p[3][lane] = level;          // never looked at: everything is open
@@ -418,52 +419,71 @@ tail_front_kernel(const float2* __restrict__ in, int slots, int n_blocks, int le
     }
     __syncthreads();
     const bool open_b = s_gate[0][lane] != 0, open_prev = s_gate[1][lane] != 0;
-    // ---- DcBlock block mean of the gated envelope (AM), in sample order, by warp 0 of the z = 0 CTA; the other warps go on
+    // ---- demodulator front over this CTA's rows of the block, in tiles of SQ_MAXROWS rows.  DcBlock's block mean (AM) is
+    // the in-order sum of the gated envelope over the WHOLE block: the z = 0 CTA also walks the rows other CTAs transform,
+    // every warp stages its rows' envelopes in a shared tile, and warp 0 adds tile t in sample order (the oracle's order)
+    // while the other warps already work on tile t + 1 (two tile buffers, one barrier per tile).
     const bool am = c.kind == OWRX_DEMOD_AM;
-    if (z == 0 && w == 0) {
-        if (__any_sync(0xffffffffu, am)) {
-            float acc = 0.f;
-            if (open_b) {
-#pragma unroll 8
-                for (int i = 0; i < length; i++) {
-                    const float2 v = xb[(size_t)i * slots];
-                    acc += sqrtf(v.x * v.x + v.y * v.y);
-                }
-            }
-            dc_mean[(size_t)b * slots + s] = am ? acc / (float)length : 0.f;
-        } else {
-            dc_mean[(size_t)b * slots + s] = 0.f;
-        }
-        if (b == 0) dc_prev[s] = am ? st[s].dc_last : 0.f;
-    }
-    // ---- demodulator front over this CTA's rows of the block
+    const bool do_dc = __syncthreads_or(am) && z == 0;
     const int r0 = z * TF_ROWS, r1 = min(length, r0 + TF_ROWS);
+    const int t_begin = do_dc ? 0 : r0, t_end = do_dc ? length : r1;
     const int kind = c.kind;
-    for (int i = r0 + w; i < r1; i += 8) {
-        float2 x = xb[(size_t)i * slots];
-        if (!open_b) x = make_float2(0.f, 0.f);
-        float y = 0.f;
-        if (kind == OWRX_DEMOD_NFM || kind == OWRX_DEMOD_WFM) {
-            float2 pv;
-            if (i > 0) {
-                pv = open_b ? xb[(size_t)(i - 1) * slots] : make_float2(0.f, 0.f);
-            } else if (b > 0) {
-                pv = open_prev ? xb[-(ptrdiff_t)slots] : make_float2(0.f, 0.f);
-            } else {
-                pv = st[s].fm_last;
+    float acc = 0.f;
+    int buf = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += SQ_MAXROWS, buf ^= 1) {
+        const int nt = min(SQ_MAXROWS, t_end - t0);
+        // a warp takes TF_WR consecutive rows of the tile and fetches them (and the row before) in one go: one memory latency per
+        // tile and warp instead of one per row (54 CTAs cannot hide latency by occupancy)
+        constexpr int TF_WR = SQ_MAXROWS / 8;
+        const int j0 = w * TF_WR;
+        float2 xr[TF_WR + 1];                               // xr[k + 1] = row t0 + j0 + k, xr[0] = the row before (gated)
+#pragma unroll
+        for (int k = 0; k <= TF_WR; k++) {
+            const int i = t0 + j0 + k - 1;
+            float2 v = make_float2(0.f, 0.f);
+            if (k == 0) {
+                if (i >= 0) { if (open_b) v = xb[(size_t)i * slots]; }
+                else if (b > 0) { if (open_prev) v = xb[-(ptrdiff_t)slots]; }
+                else v = st[s].fm_last;
+            } else if (j0 + k - 1 < nt && open_b) {
+                v = xb[(size_t)i * slots];
             }
-            const float K = 0.340447550238101026565118445432744920253753662109375f;
-            const float num = x.x * (x.y - pv.y) - x.y * (x.x - pv.x);
-            const float den = x.x * x.x + x.y * x.y;
-            y = den != 0.f ? K * num / den : 0.f;
-            y = fminf(1.f, fmaxf(-1.f, y));                       // Limit
-        } else if (kind == OWRX_DEMOD_AM) {
-            y = sqrtf(x.x * x.x + x.y * x.y);
-        } else if (kind == OWRX_DEMOD_SSB) {
-            y = x.x;
+            xr[k] = v;
         }
-        f1[((size_t)b * length + i) * slots + s] = y;
-        if (last_cta && i == length - 1) stash[s].fm_last = x;
+#pragma unroll
+        for (int k = 0; k < TF_WR; k++) {
+            const int j = j0 + k, i = t0 + j;
+            if (j >= nt) break;
+            const float2 x = xr[k + 1], pv = xr[k];
+            float y = 0.f;
+            if (kind == OWRX_DEMOD_NFM || kind == OWRX_DEMOD_WFM) {
+                const float K = 0.340447550238101026565118445432744920253753662109375f;
+                const float num = x.x * (x.y - pv.y) - x.y * (x.x - pv.x);
+                const float den = x.x * x.x + x.y * x.y;
+                y = den != 0.f ? K * num / den : 0.f;
+                y = fminf(1.f, fmaxf(-1.f, y));                       // Limit
+            } else if (kind == OWRX_DEMOD_AM) {
+                y = sqrtf(x.x * x.x + x.y * x.y);
+            } else if (kind == OWRX_DEMOD_SSB) {
+                y = x.x;
+            }
+            if (do_dc) tile[buf][j][lane] = am ? y : 0.f;
+            if (i >= r0 && i < r1) {
+                f1[((size_t)b * length + i) * slots + s] = y;
+                if (last_cta && i == length - 1) stash[s].fm_last = x;
+            }
+        }
+        if (do_dc) {
+            __syncthreads();
+            if (w == 0) {
+#pragma unroll 8
+                for (int j = 0; j < nt; j++) acc += tile[buf][j][lane];
+            }
+        }
+    }
+    if (z == 0 && w == 0) {
+        dc_mean[(size_t)b * slots + s] = am ? acc / (float)length : 0.f;
+        if (b == 0) dc_prev[s] = am ? st[s].dc_last : 0.f;
     }
 }
 
@@ -1122,72 +1142,167 @@ struct TailState {
     int index, pred, since_sync, have_lo, lo;
 };
 
-__constant__ int16_t c_ima_step_audio[89] = {
-    7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45,
-    50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130, 143, 157, 173, 190, 209, 230, 253, 279, 307,
-    337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411, 1552, 1707, 1878, 2066,
-    2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899,
-    15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
-
-__device__ __forceinline__ int ima_encode_audio(int sample, int& index, int& pred, const int* steps)
-{
-    const int st = steps[index];
-    int diff = sample - pred;
-    int code = 0;
-    if (diff < 0) { code = 8; diff = -diff; }
-    int d = st >> 3;
-    if (diff >= st) { code |= 4; diff -= st; d += st; }
-    const int s1 = st >> 1;
-    if (diff >= s1) { code |= 2; diff -= s1; d += s1; }
-    const int s2 = st >> 2;
-    if (diff >= s2) { code |= 1; d += s2; }
-    pred = (code & 8) ? pred - d : pred + d;
-    pred = max(-32768, min(32767, pred));
-    const int c3 = code & 7;
-    index += (c3 < 4) ? -1 : (2 * c3 - 6);
-    index = max(0, min(88, index));
-    return code;
-}
-
-// mode[s]: 0 = float only, 1 = int16, 2 = int16 + ADPCM with SYNC framing
-__global__ void __launch_bounds__(64)
+// mode[s]: 0 = float only, 1 = int16, 2 = int16 + ADPCM with SYNC framing.
+// One warp per 32 channels (lane = channel: the codec state is sample-serial per channel).  The warp stages AT_R rows of its
+// 32 channels through shared memory with cp.async, one tile ahead of the encoder, so the sample chain never waits for
+// global memory (the first version, one dependent global load per sample, ran the C2 block of 20 141 samples per channel in
+// 11.6 ms: ~1150 cycles per sample; the quantiser itself is ~114, adpcm.cuh).
+constexpr int AT_R = 32;
+constexpr int AT_OB = 36;
+__global__ void __launch_bounds__(32)
 audio_tail_kernel(const float* __restrict__ in, int slots, int n, const int* __restrict__ mode, TailState* __restrict__ ts,
                   int16_t* __restrict__ s16_out, unsigned char* __restrict__ bytes_out, int* __restrict__ count_out, int cap)
 {
-    __shared__ int steps[89];
-    for (int i = threadIdx.x; i < 89; i += blockDim.x) steps[i] = c_ima_step_audio[i];
-    __syncthreads();
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= slots) return;
-    const int md = mode[s];
-    if (md == 0) return;
-    TailState t = ts[s];
-    unsigned char* o = bytes_out + (size_t)s * cap;
-    int cnt = count_out[s];            // append behind earlier passes of the same feed (host zeroes it per feed)
-    for (int i = 0; i < n; i++) {
-        float v = in[(size_t)i * slots + s] * 32767.0f;                  // Convert(FLOAT, SHORT), SURVEY A.12
-        const int q = v > 32767.0f ? 32767 : (v < -32768.0f ? -32768 : __float2int_rz(v));
-        s16_out[(size_t)i * slots + s] = (int16_t)q;
-        if (md == 2) {
-            if (!t.have_lo) {
-                if (t.since_sync == 1001) {
-                    o[cnt++] = 'S'; o[cnt++] = 'Y'; o[cnt++] = 'N'; o[cnt++] = 'C';
-                    o[cnt++] = (unsigned char)(t.index & 0xff); o[cnt++] = (unsigned char)((t.index >> 8) & 0xff);
-                    o[cnt++] = (unsigned char)(t.pred & 0xff);  o[cnt++] = (unsigned char)((t.pred >> 8) & 0xff);
-                    t.since_sync = 0;
+    __shared__ uint4 cand[89];
+    __shared__ float tile[2][AT_R][32];
+    __shared__ unsigned char obuf[32][AT_OB];       // a tile's output bytes per channel (<= AT_R / 2 data + 8 SYNC), padded rows
+    const int lane = threadIdx.x;
+    ima_build_table(cand, lane, 32);
+    const int s = blockIdx.x * 32 + lane;
+    const bool live = s < slots;
+    const int sc = live ? s : slots - 1;
+    const int md = live ? mode[sc] : 0;
+    if (__all_sync(0xffffffffu, md == 0)) return;
+    TailState t = ts[sc];
+    ImaState cs = ima_state(t.index, t.pred);
+    unsigned char* o = bytes_out + (size_t)sc * cap;
+    int cnt = count_out[sc];           // append behind earlier passes of the same feed (host zeroes it per feed)
+    const int n_tiles = (n + AT_R - 1) / AT_R;
+    auto stage = [&](int tl, int buf) {
+        if (tl < n_tiles) {
+            const int r0 = tl * AT_R;
+#pragma unroll
+            for (int k = 0; k < AT_R; k++) {
+                if (r0 + k < n) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[buf][k][lane]);
+                    const float* src = in + (size_t)(r0 + k) * slots + sc;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src));
                 }
-                t.lo = ima_encode_audio(q, t.index, t.pred, steps);
-                t.have_lo = 1;
-            } else {
-                const int hi = ima_encode_audio(q, t.index, t.pred, steps);
-                o[cnt++] = (unsigned char)(t.lo | (hi << 4));
-                t.have_lo = 0;
-                t.since_sync++;
             }
         }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    stage(0, 0);
+    __syncwarp();
+    for (int tl = 0; tl < n_tiles; tl++) {
+        const int buf = tl & 1, r0 = tl * AT_R;
+        const int valid = min(AT_R, n - r0);
+        stage(tl + 1, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;\n" ::);
+        __syncwarp();
+        int nb = 0;                                   // bytes this channel produced in this tile
+        if (md != 0) {
+            unsigned char* ob = obuf[lane];
+            // Convert(FLOAT, SHORT) of the lane's 32 samples first (independent: the loads and conversions overlap), written back
+            // into the tile as integers, so the serial encoder below starts each sample from a ready int16
+            int* qt = reinterpret_cast<int*>(&tile[buf][0][0]);
+#pragma unroll 8
+            for (int k = 0; k < valid; k++) {
+                const float x = tile[buf][k][lane] * 32767.0f;
+                const int q = x > 32767.0f ? 32767 : (x < -32768.0f ? -32768 : __float2int_rz(x));
+                qt[k * 32 + lane] = q;
+                s16_out[(size_t)(r0 + k) * slots + sc] = (int16_t)q;
+            }
+            if (md == 2) {
+                auto sync_block = [&]() {
+                    if (t.since_sync == 1001) {
+                        ob[nb++] = 'S'; ob[nb++] = 'Y'; ob[nb++] = 'N'; ob[nb++] = 'C';
+                        ob[nb++] = (unsigned char)(cs.index & 0xff); ob[nb++] = (unsigned char)((cs.index >> 8) & 0xff);
+                        ob[nb++] = (unsigned char)(cs.pred & 0xff);  ob[nb++] = (unsigned char)((cs.pred >> 8) & 0xff);
+                        t.since_sync = 0;
+                    }
+                };
+                int k = 0;
+                if (t.have_lo && valid > 0) {                                    // an odd sample left over from the previous tile
+                    const unsigned hi = ima_encode(qt[lane], cs, cand);
+                    ob[nb++] = (unsigned char)((unsigned)t.lo | (hi << 4));
+                    t.have_lo = 0; t.since_sync++;
+                    k = 1;
+                }
+#pragma unroll 2
+                for (; k + 1 < valid; k += 2) {                                  // whole bytes: low nibble first
+                    sync_block();
+                    const unsigned lo = ima_encode(qt[k * 32 + lane], cs, cand);
+                    const unsigned hi = ima_encode(qt[(k + 1) * 32 + lane], cs, cand);
+                    ob[nb++] = (unsigned char)(lo | (hi << 4));
+                    t.since_sync++;
+                }
+                if (k < valid) {
+                    sync_block();
+                    t.lo = (int)ima_encode(qt[k * 32 + lane], cs, cand);
+                    t.have_lo = 1;
+                }
+            }
+        }
+        __syncwarp();
+        // the tile's bytes leave channel by channel as one contiguous run each (a lane-per-channel byte store would be 32
+        // separate sectors per instruction)
+        if (__any_sync(0xffffffffu, nb > 0)) {
+            const unsigned long long dst = (unsigned long long)(o + cnt);
+            for (int l = 0; l < 32; l++) {
+                const int nl = __shfl_sync(0xffffffffu, nb, l);
+                if (nl == 0) continue;
+                unsigned char* d = (unsigned char*)__shfl_sync(0xffffffffu, dst, l);
+                if (lane < nl) d[lane] = obuf[l][lane];
+            }
+            cnt += nb;
+        }
+        __syncwarp();
     }
-    ts[s] = t;
-    count_out[s] = cnt;
+    if (live && md != 0) {
+        t.index = cs.index; t.pred = cs.pred;
+        ts[s] = t;
+        count_out[s] = cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Control path (csdr/chain/selector.py:132-166: setFrequencyOffset / setBandpass / setSquelchLevel from websocket threads;
+// owrx/dsp.py:96-148: demodulator swaps): nothing a client does may stall the device.  Host setters only record what
+// changed; at the next block boundary the changes reach the device as stream-ordered work on the stream that owns the
+// state they touch — per-slot state patches (slot_patch_kernel), staged band-pass columns (bp_scatter_kernel), and the
+// per-slot tables, which are double-buffered by block parity so that a block still in flight keeps reading its own copy.
+// ------------------------------------------------------------------------------------------------
+enum : int {
+    PATCH_DEMOD = 1,       // fresh demodulator modules: FmDemod's last sample, DcBlock's mean, the de-emphasis IIR
+    PATCH_AGC_RESET = 2,   // fresh Agc: gain = agc_gain, hang counter 0
+    PATCH_TAIL = 4,        // fresh AdpcmEncoder(sync=True): reset codec, SYNC block first
+    PATCH_SQUELCH = 8,     // fresh Squelch: hang counter 0
+    PATCH_HISTORY = 16,    // fresh modules everywhere: the slot's column of every stage history is zeroed (host: memset2D)
+    PATCH_AGC_GAIN = 32,   // Agc.setInitialGain on a live Agc: gain only
+};
+struct SlotPatch {
+    int slot, flags;
+    float agc_gain;
+    int pad;
+};
+
+__global__ void __launch_bounds__(128)
+slot_patch_kernel(const SlotPatch* __restrict__ patches, int n, int mask, ChanState* __restrict__ st, TailState* __restrict__ tail)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SlotPatch p = patches[i];
+    const int f = p.flags & mask, s = p.slot;
+    if (f & PATCH_DEMOD) { st[s].fm_last = make_float2(0.f, 0.f); st[s].dc_last = 0.f; st[s].iir = 0.f; }
+    if (f & PATCH_SQUELCH) st[s].sq_hang = 0;
+    if (f & PATCH_AGC_RESET) { st[s].agc_gain = p.agc_gain; st[s].agc_hang = 0; }
+    else if (f & PATCH_AGC_GAIN) st[s].agc_gain = p.agc_gain;
+    if (f & PATCH_TAIL) tail[s] = TailState{0, 0, 1001, 0, 0};
+}
+
+// staged band-pass columns -> the per-slot tables: stage[i] = Tb taps followed by nH partition-spectrum entries of slot slots[i]
+__global__ void __launch_bounds__(256)
+bp_scatter_kernel(const float2* __restrict__ stage, const int* __restrict__ slots_list, int Tb, int nH, int S,
+                  float2* __restrict__ d_bp, float2* __restrict__ d_bp_H)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (e >= Tb + nH) return;
+    const int slot = slots_list[i];
+    const float2 v = stage[(size_t)i * (Tb + nH) + e];
+    if (e < Tb) d_bp[(size_t)e * S + slot] = v;
+    else d_bp_H[(size_t)(e - Tb) * S + slot] = v;
 }
 
 #endif  // OWRX_K3_ONLY

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "fft_small.cuh"
 #include "ingress.cuh"
+#include "adpcm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -599,40 +600,6 @@ wf_finalize_kernel(const float* __restrict__ partial, int subsets, int n, float 
     }
 }
 
-// IMA-ADPCM tables — values pinned by the browser decoder, reference htdocs/lib/AudioEngine.js:426-438.
-__constant__ int16_t c_ima_step[89] = {
-    7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45,
-    50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130, 143, 157, 173, 190, 209, 230, 253, 279, 307,
-    337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411, 1552, 1707, 1878, 2066,
-    2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899,
-    15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
-
-// One IMA-ADPCM step.  `st` is the step of the current index (carried in a register).  The steps
-// of the five possible successor indices come from ONE 16-byte shared-memory entry per index, fetched while
-// the quantiser's compare chain resolves, so no table lookup sits on the sample-to-sample dependency chain.
-//   cand[i] = { step[max(i-1,0)] | step[min(i+2,88)] << 16,  step[min(i+4,88)] | step[min(i+6,88)] << 16,  step[min(i+8,88)], - }
-__device__ __forceinline__ int ima_encode(int sample, int& index, int& pred, int& st, const uint4* cand)
-{
-    const uint4 c = cand[index];
-    int diff = sample - pred;
-    const int neg = diff < 0;
-    diff = abs(diff);
-    int code = 0;
-    int d = st >> 3;
-    if (diff >= st) { code = 4; diff -= st; d += st; }
-    const int s1 = st >> 1;
-    if (diff >= s1) { code |= 2; diff -= s1; d += s1; }
-    const int s2 = st >> 2;
-    if (diff >= s2) { code |= 1; d += s2; }
-    pred = max(-32768, min(32767, neg ? pred - d : pred + d));
-    // successor: index-1 for code < 4, else index + 2*(code-3); the matching step is field f of the entry
-    const int f = max(code - 3, 0);
-    index = max(0, min(88, index + (code < 4 ? -1 : 2 * code - 6)));
-    const unsigned w = f < 2 ? c.x : (f < 4 ? c.y : c.z);
-    st = (int)((w >> ((f & 1) << 4)) & 0xffffu);
-    return code | (neg << 3);
-}
-
 // FftAdpcm encoder, warp-cooperative: a warp owns 32 lines (one per lane: the codec state is strictly
 // sequential within a line, lines are independent and reset per line).  Each iteration the warp stages a
 // 64-sample chunk of all 32 lines through shared memory with coalesced 128-byte row loads (cp.async, one chunk
@@ -646,11 +613,7 @@ wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int 
     __shared__ unsigned tile[2][32][ADPCM_CH / 2 + 1];
     __shared__ unsigned otile[32][ADPCM_CH / 8 + 1];
     const int lane = threadIdx.x;
-    for (int i = lane; i < 89; i += 32) {
-        const unsigned c0 = c_ima_step[max(i - 1, 0)], c1 = c_ima_step[min(i + 2, 88)], c2 = c_ima_step[min(i + 4, 88)];
-        const unsigned c3 = c_ima_step[min(i + 6, 88)], c4 = c_ima_step[min(i + 8, 88)];
-        cand[i] = make_uint4(c0 | (c1 << 16), c2 | (c3 << 16), c4, 0u);
-    }
+    ima_build_table(cand, lane, 32);
     const size_t line0 = (size_t)blockIdx.x * 32;
     const int nl = (int)min((size_t)32, n_lines - line0);
     const int n_chunks = (n_samples + ADPCM_CH - 1) / ADPCM_CH;
@@ -667,7 +630,7 @@ wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int 
     };
     stage(0, 0);
     __syncwarp();
-    int index = 0, pred = 0, st = 7;
+    ImaState cs = ima_state(0, 0);
     for (int chunk = 0; chunk < n_chunks; chunk++) {
         const int buf = chunk & 1;
         const int c0 = chunk * ADPCM_CH;
@@ -681,9 +644,9 @@ wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int 
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const unsigned v = tile[buf][lane][4 * w4 + k];
-                    const int lo = ima_encode((int)(short)(v & 0xffffu), index, pred, st, cand);
-                    const int hi = ima_encode((int)(short)(v >> 16), index, pred, st, cand);
-                    packed |= (unsigned)(lo | (hi << 4)) << (8 * k);
+                    const unsigned lo = ima_encode((int)(short)(v & 0xffffu), cs, cand);
+                    const unsigned hi = ima_encode((int)(short)(v >> 16), cs, cand);
+                    packed |= (lo | (hi << 4)) << (8 * k);
                 }
                 otile[lane][w4] = packed;
             }
@@ -693,9 +656,9 @@ wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int 
                 unsigned packed = 0;
                 for (int k = 0; k < (valid - done) / 2; k++) {
                     const unsigned v = tile[buf][lane][done / 2 + k];
-                    const int lo = ima_encode((int)(short)(v & 0xffffu), index, pred, st, cand);
-                    const int hi = ima_encode((int)(short)(v >> 16), index, pred, st, cand);
-                    packed |= (unsigned)(lo | (hi << 4)) << (8 * k);
+                    const unsigned lo = ima_encode((int)(short)(v & 0xffffu), cs, cand);
+                    const unsigned hi = ima_encode((int)(short)(v >> 16), cs, cand);
+                    packed |= (lo | (hi << 4)) << (8 * k);
                 }
                 otile[lane][valid / 8] = packed;
             }
@@ -717,6 +680,7 @@ using namespace owrx;
 
 struct owrx_wf {
     int device = 0, sm_count = 0;
+    uint64_t h2d_pinned = 0, h2d_pageable = 0;                 // host-path ingress bytes by source memory kind
     int n = 0, every_n = 0, avg = 0, compression = 0;
     float add_db = 0.0f;
     int m = 0, log2m = 0, r0 = 1;
@@ -822,6 +786,7 @@ template <int R0> static int launch_big(owrx_wf* wf, WfBigParams& p, cudaStream_
         if (nc <= 0) return fail(OWRX_E_CUDA, "no resident cluster of %d CTAs for the fused four-step FFT", CS);
         static const int cap = getenv("OWRX_WF_CLUSTERS") ? atoi(getenv("OWRX_WF_CLUSTERS")) : 0;
         wf->big_clusters = cap > 0 ? std::min(cap, nc) : nc;
+        if (getenv("OWRX_TRACE")) fprintf(stderr, "[owrx wf] fused four-step kernel: clusters of %d CTAs, %d resident at once (%d SMs)\n", CS, nc, wf->sm_count);
     }
     const int n_clusters = (int)std::min<long long>(wf->big_clusters, p.units);
     const size_t y_need = (size_t)wf->big_clusters * 2 * R0 * 4096;
@@ -1166,6 +1131,7 @@ int owrx_wf_feed_fmt(owrx_wf_t* wf, const void* iq_raw, size_t n_samples, int fo
         iq_raw = static_cast<const unsigned char*>(iq_raw) + d * in_bytes; n_samples -= d; wf->skip -= d;
     }
     if (!n_samples) return OWRX_OK;
+    (host_is_pinned(iq_raw) ? wf->h2d_pinned : wf->h2d_pageable) += n_samples * in_bytes;
     const size_t need = wf->in_fill + n_samples;
     if (need > wf->in_cap) {
         const size_t cap = std::max(need, wf->in_cap * 2);
@@ -1224,6 +1190,13 @@ int owrx_wf_feed_fmt(owrx_wf_t* wf, const void* iq_raw, size_t n_samples, int fo
     }
     OWRX_CUDA(cudaStreamSynchronize(wf->stream));
     for (size_t l = 0; l < got; l++) wf->queue.emplace_back(wf->h_out + l * lb, wf->h_out + (l + 1) * lb);
+    return OWRX_OK;
+}
+
+int owrx_wf_get_h2d_bytes(const owrx_wf_t* wf, uint64_t* pinned_bytes, uint64_t* pageable_bytes)
+{
+    if (!wf || !pinned_bytes || !pageable_bytes) return fail(OWRX_E_INVALID, "NULL argument");
+    *pinned_bytes = wf->h2d_pinned; *pageable_bytes = wf->h2d_pageable;
     return OWRX_OK;
 }
 

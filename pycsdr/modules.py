@@ -19,6 +19,7 @@ receives the result bytes, and the selector output is materialised only when som
 """
 import ctypes as C
 import logging
+import os
 import threading
 import weakref
 from collections import deque
@@ -41,6 +42,42 @@ _BUFFER_CAP_BYTES = 1 << 28
 def _native():
     from openwebrx_b200 import _native as N      # raises ImportError if the CUDA library is not built
     return N
+
+
+# ================================================================================================
+# page-locked ingress ring (owrx/source/__init__.py:307-330)
+# ================================================================================================
+class _PinnedRing:
+    """cudaHostAlloc'd arena behind a SOURCE Buffer (one that a GPU runner reads): TcpSource recv()s straight into it and the
+    runner hands the copy engine pointers into it, so no pageable bounce copy sits between the socket and HBM.  Chunks are
+    never split across the wrap (the allocator skips to offset 0 when the end is too short)."""
+
+    def __init__(self, nbytes):
+        N = _native()
+        p = C.c_void_p()
+        N.check(N.lib.owrx_pinned_alloc(nbytes, C.byref(p)))
+        self._free = N.lib.owrx_pinned_free
+        self.ptr, self.size, self.head = p.value, int(nbytes), 0
+        self.view = memoryview((C.c_ubyte * nbytes).from_address(self.ptr)).cast("B")
+
+    def close(self):
+        if self.ptr:
+            self.view = None
+            self._free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_RING_WAIT_S = 5.0      # how long a writer holds back for a runner that has not consumed the oldest ring chunk
+
+
+def _ring_bytes():
+    return max(1, int(os.environ.get("OWRX_RING_MB", "64"))) << 20
 
 
 # ================================================================================================
@@ -116,10 +153,50 @@ class Reader:
             else:
                 chunks = [b._chunks[first]]
                 self._pos += 1
+            # a Python reader gets its own copy of ring-backed chunks (the ring region is overwritten later)
+            chunks = [c if isinstance(c, bytes) else bytes(b._ring.view[c[0]:c[0] + c[1]]) for c in chunks]
             b._trim()
         if len(chunks) == 1:
             return memoryview(chunks[0])
         return memoryview(b"".join(chunks))
+
+    def _read_views(self):
+        """the GPU runner's read: everything that has arrived, as a list of buffers to feed in order — views INTO the page-locked
+        ring where the Buffer has one (adjacent chunks merged; zero copy), bytes otherwise.  Ring regions stay reserved
+        (the writer will not overwrite them) until _release()."""
+        b = self._buffer
+        with b._cond:
+            while not self._stopped and self._pos >= b._end:
+                b._cond.wait()
+            if self._stopped:
+                return None
+            if self._pos < b._start:
+                self._pos = b._start
+            first = self._pos - b._start
+            chunks = [b._chunks[i] for i in range(first, len(b._chunks))]
+            self._pos = b._end
+            out, runs = [], []
+            for c in chunks:
+                if isinstance(c, bytes):
+                    out.append(memoryview(c))
+                elif runs and out and runs[-1] is not None and runs[-1][0] + runs[-1][1] == c[0]:
+                    runs[-1][1] += c[1]
+                    out[-1] = b._ring.view[runs[-1][0]:runs[-1][0] + runs[-1][1]]
+                    continue
+                else:
+                    out.append(b._ring.view[c[0]:c[0] + c[1]])
+                runs.append(None if isinstance(c, bytes) else [c[0], c[1]])
+            b._inflight = [tuple(r) for r in runs if r is not None]
+            b._trim()
+            b._cond.notify_all()
+        return out
+
+    def _release(self):
+        b = self._buffer
+        with b._cond:
+            if b._inflight:
+                b._inflight = []
+                b._cond.notify_all()
 
     def stop(self):
         with self._buffer._cond:
@@ -151,6 +228,9 @@ class Buffer(Writer):
         # set by the source-side Convert (+ Gain) pump: this COMPLEX_FLOAT buffer physically carries the source's raw
         # samples ("cs16" / "cu8") and the gain to apply; the GPU does the conversion (owrx_*_feed_fmt)
         self._raw = None
+        # page-locked storage, enabled when a GPU runner attaches (None: not tried, False: no CUDA device here)
+        self._ring = None
+        self._inflight = []         # ring regions (offset, length) the runner is feeding from: not to be overwritten
 
     def getFormat(self):
         return self._format
@@ -167,6 +247,15 @@ class Buffer(Writer):
         return r
 
     def write(self, data):
+        if self._ring:
+            mv = memoryview(data).cast("B")
+            step = self._ring.size // 4
+            for o in range(0, len(mv), step):
+                part = mv[o:o + step]
+                off = self._reserve(len(part))
+                self._ring.view[off:off + len(part)] = part
+                self._commit(off, len(part))
+            return
         data = bytes(data)
         if not data:
             return
@@ -177,11 +266,66 @@ class Buffer(Writer):
             self._trim()
             self._cond.notify_all()
 
+    # ---- page-locked ring (single writer) --------------------------------------------------------
+    def _enable_ring(self):
+        """called when a GPU runner attaches to this Buffer; without a CUDA device the Buffer stays a plain byte queue"""
+        with self._cond:
+            if self._ring is None:
+                try:
+                    self._ring = _PinnedRing(_ring_bytes())
+                except Exception as e:        # no device (build container) / out of lockable memory
+                    logger.debug("pycsdr-b200: no page-locked ring for this Buffer: %s", e)
+                    self._ring = False
+        return bool(self._ring)
+
+    def _reserve(self, nbytes):
+        """offset of a contiguous writable region of nbytes (<= size / 2) in the ring.  Unread chunks in the way are dropped
+        (a slow reader loses the oldest data, as with the reference's ring); regions the runner is feeding from are waited
+        for (back-pressure on the socket)."""
+        r = self._ring
+        if nbytes > r.size // 2:
+            raise ValueError("chunk larger than half the ring")
+        with self._cond:
+            if r.head + nbytes > r.size:
+                r.head = 0
+            lo, hi = r.head, r.head + nbytes
+            while any(a < hi and lo < a + n for a, n in self._inflight):
+                self._cond.wait(0.5)
+            waited = 0.0
+            while self._chunks:
+                c = self._chunks[0]
+                if isinstance(c, bytes) or not (c[0] < hi and lo < c[0] + c[1]):
+                    break
+                # the oldest chunk is in the way.  If the GPU runner has not taken it yet, hold the socket back for a moment
+                # (TCP back-pressure is gentler than a gap in the stream: the first block also pays CUDA start-up); a consumer
+                # that stays away loses the data, as with the reference's ring.
+                r = self._runner
+                if r is not None and r.is_alive() and not r.reader._stopped and r.reader._pos <= self._start and waited < _RING_WAIT_S:
+                    self._cond.wait(0.05)
+                    waited += 0.05
+                    continue
+                self._chunks.popleft()
+                self._bytes -= c[1]
+                self._start += 1
+            return lo
+
+    def _commit(self, off, nbytes):
+        if not nbytes:
+            return
+        with self._cond:
+            self._ring.head = off + nbytes
+            self._chunks.append((off, nbytes))
+            self._end += 1
+            self._bytes += nbytes
+            self._trim()
+            self._cond.notify_all()
+
     def _trim(self):
         live = [r._pos for r in self._readers if not r._stopped and not r._virtual]
         low = min(live) if live else self._end
         while self._chunks and (self._start < low or self._bytes > _BUFFER_CAP_BYTES):
-            self._bytes -= len(self._chunks.popleft())
+            c = self._chunks.popleft()
+            self._bytes -= len(c) if isinstance(c, bytes) else c[1]
             self._start += 1
 
     def _extra_readers(self, used):
@@ -600,7 +744,8 @@ class Afc(_Unfused):
 
 class TcpSource(Module):
     """TcpSource(port, Format) — owrx/source/__init__.py:310-314: reads the connector's TCP stream into
-    its writer.  IQ ingress is outside the accelerated path; this is plain socket glue."""
+    its writer.  When the writer is a source Buffer with a page-locked ring (a GPU runner reads it) the socket is
+    received straight into the ring: TcpSource -> pinned host ring -> H2D."""
 
     def __init__(self, port, format):
         import socket
@@ -623,6 +768,25 @@ class TcpSource(Module):
         item = self._format.size
         pending = b""
         while not self._stop:
+            w = self._writer
+            ring = getattr(w, "_ring", None)
+            if ring:
+                # the writer is a source Buffer with a page-locked ring: the kernel copies the TCP payload straight into it
+                want = min(1 << 20, ring.size // 4)
+                off = w._reserve(want)
+                k = len(pending)
+                ring.view[off:off + k] = pending
+                try:
+                    got = self._sock.recv_into(ring.view[off + k:off + want])
+                except OSError:
+                    break
+                if not got:
+                    break
+                n = (k + got) - (k + got) % item
+                pending = bytes(ring.view[off + n:off + k + got])       # at most item - 1 bytes of a split sample
+                w._commit(off, n)
+                self.bytes_direct = getattr(self, "bytes_direct", 0) + n
+                continue
             try:
                 data = self._sock.recv(1 << 20)
             except OSError:
@@ -631,8 +795,8 @@ class TcpSource(Module):
                 break
             pending += data
             n = len(pending) - len(pending) % item
-            if n and self._writer is not None:
-                self._writer.write(pending[:n])
+            if n and w is not None:
+                w.write(pending[:n])
                 pending = pending[n:]
 
     def stop(self):
@@ -849,6 +1013,7 @@ class _SourceRunner(threading.Thread):
         with cls._lock:
             r = buffer._runner
             if r is None or not r.is_alive():
+                buffer._enable_ring()
                 r = cls(buffer)
                 buffer._runner = r
                 r.start()
@@ -985,8 +1150,8 @@ class _SourceRunner(threading.Thread):
         idle = 0
         while True:
             self.processed = self.reader._pos
-            data = self.reader._read(True)      # the runner batches everything that has arrived into one GPU pass
-            if data is None:
+            views = self.reader._read_views()   # the runner batches everything that has arrived (views into the pinned ring)
+            if views is None:
                 break
             try:
                 if N is None:
@@ -1004,10 +1169,11 @@ class _SourceRunner(threading.Thread):
                     continue
                 idle = 0
                 raw = self.buffer._raw          # source-side Convert (+ Gain): the buffer carries raw samples
-                for plan in list(self.wf_plans.values()):
-                    plan.feed(data, raw)
-                if self.channels:
-                    self._feed_bank(N, data, raw)
+                for data in views:
+                    for plan in list(self.wf_plans.values()):
+                        plan.feed(data, raw)
+                    if self.channels:
+                        self._feed_bank(N, data, raw)
             except (ValueError, BufferError):
                 # a bad argument on one plan: logged, the source keeps feeding (only CUDA / memory failures are fatal)
                 logger.exception("pycsdr-b200 runner: block dropped")

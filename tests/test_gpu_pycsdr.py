@@ -147,29 +147,9 @@ def test_audio_tail_convert_and_adpcm_bit_exact(gpu):
         assert len(dec) == 4500
 
 
-@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present (GPU box)")
-def test_unmodified_reference_fftchain_on_gpu(gpu):
-    sys.path.insert(0, REF)
-    try:
-        from csdr.chain.fft import FftChain
-        fs, n = 2400000, 4096
-        fc = FftChain(fs, n, 0.3, 9, "adpcm")
-        src, out = M.Buffer(Format.COMPLEX_FLOAT), M.Buffer(Format.CHAR)
-        fc.setWriter(out)
-        rd = out.getReader()
-        fc.setReader(src.getReader())
-        iq = make_iq(2867 * 93 * 2 + n, fs, carrier_plan(6, fs, seed=34), seed=34)
-        src.write(iq.tobytes())
-        msgs = _collect(rd, 2 * 2053)
-        ref = oracle.fftchain_run(iq, n, 2867, 93)
-        assert [len(m) for m in msgs] == [2053, 2053]
-        for m, db in zip(msgs, ref["db"]):
-            assert np.median(np.abs(browser_fft_decode(np.frombuffer(m, np.uint8)) - db)) < 0.6
-        fc.stop()
-    finally:
-        sys.path.remove(REF)
-        for k in [k for k in sys.modules if k == "csdr" or k.startswith("csdr.") or k == "owrx" or k.startswith("owrx.")]:
-            sys.modules.pop(k)
+# (The reference's own FftChain / SpectrumThread / DspManager classes cannot be imported on the GPU box — /root/reference does not
+# travel.  Their recorded call traces are replayed with data in tests/test_gpu_trace_replay.py; the classes themselves run
+# unmodified on the shim, without a device, in tests/test_pycsdr_shim.py.)
 
 
 def test_raw_ingress_formats_equal_cpu_side_convert(gpu):

@@ -244,3 +244,55 @@ def test_fused_stage_readers_do_not_pin_the_source_buffer():
     src.write(b"\x01" * 8)
     assert bytes(r.read()) == b"\x01" * 8
     fft.stop()
+
+
+class _FakeRing:
+    """stands in for the cudaHostAlloc'd arena (no CUDA device in the build container): same fields as pycsdr.modules._PinnedRing"""
+
+    def __init__(self, nbytes):
+        self.store = bytearray(nbytes)
+        self.view = memoryview(self.store)
+        self.size, self.head, self.ptr = nbytes, 0, 1
+
+
+def test_ring_backed_source_buffer_logic():
+    """the page-locked ingress ring's bookkeeping (chunks never split across the wrap, adjacent chunks merge into one
+    feed, a Python reader gets copies, regions being fed are not overwritten, unread data in the way is dropped oldest-first)"""
+    import threading
+    import time
+    import pycsdr.modules as M
+    from pycsdr.types import Format
+    buf = M.Buffer(Format.COMPLEX_FLOAT)
+    buf._ring = _FakeRing(1024)
+    runner_rd, py_rd = buf.getReader(), buf.getReader()
+    a, b = bytes(range(200)), bytes(range(50, 250))
+    buf.write(a); buf.write(b)
+    views = runner_rd._read_views()
+    assert len(views) == 1 and bytes(views[0]) == a + b            # adjacent ring chunks merge into ONE view (one feed, zero copy)
+    assert views[0].obj is buf._ring.store                          # ... into the ring itself
+    assert buf._inflight == [(0, 400)]
+    got = py_rd.read()
+    assert isinstance(got.obj, bytes) and bytes(got) == a           # a Python pump gets its own copy, one write = one read
+    assert bytes(py_rd.read()) == b
+    # the next 400 bytes fit behind (400..800); the one after would wrap onto the region the runner is still feeding from
+    buf.write(bytes(400))
+    done = []
+    th = threading.Thread(target=lambda: (buf.write(b"\x07" * 300), done.append(1)), daemon=True)
+    th.start()
+    time.sleep(0.3)
+    assert not done, "the writer overwrote a region the runner is feeding from"
+    assert bytes(views[0]) == a + b
+    runner_rd._release()
+    th.join(5)
+    assert done and buf._ring.head == 300                          # wrapped to offset 0, never split
+    # unread chunks in the way are dropped oldest-first (ring semantics), whole chunks only
+    v2 = runner_rd._read_views()
+    assert [len(v) for v in v2] == [400, 300]                       # not adjacent across the wrap: two feeds
+    runner_rd._release()
+    big = M.Buffer(Format.CHAR); big._ring = _FakeRing(1024)
+    rd = big.getReader()
+    for k in range(6):
+        big.write(bytes([k]) * 256)                                 # 6 x 256 through 1024 bytes with nobody reading
+    vs = rd._read_views()
+    assert b"".join(bytes(v) for v in vs) == b"".join(bytes([k]) * 256 for k in (2, 3, 4, 5))
+    rd._release()
