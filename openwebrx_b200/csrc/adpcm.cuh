@@ -1,10 +1,11 @@
 // adpcm.cuh — the IMA-ADPCM quantiser step shared by FftAdpcm (waterfall.cu) and the client audio tail (selector_kernels.cuh).
 //
 // The codec is strictly sample-serial per stream (predictor and step index feed back): one warp, one stream per lane, and the
-// speed is what ONE warp can issue per sample.  Measured on B200 (profiles/r2_adpcm_notes.md): this compare/subtract cascade is
-// 43 instructions and 114 cycles per sample; a variant with seven independent threshold compares and IADD3 trees (8 dependent
-// levels instead of 16) needs 50 instructions and ran SLOWER (142 cycles) — the warp is bound by ALU-pipe issue
-// (~2.8 cycles per instruction for a lone warp), not by the dependency chain, so the form with the fewest instructions wins.
+// speed is what ONE warp can issue per sample.  Measured on B200 (profiles/r2_adpcm_notes.md): the compare/subtract cascade with
+// the successor steps selected from a 16-byte candidate entry was 43 instructions and 114 cycles per sample; a variant with
+// seven independent threshold compares and IADD3 trees (8 dependent levels instead of 16) needed 50 instructions and ran
+// SLOWER (142 cycles) — a lone warp is bound by ALU-pipe issue (~2.8 cycles per instruction), not by the dependency chain,
+// so neither a shorter chain bought with more instructions nor fewer instructions bought with a load on the chain wins.
 // Values of the step table are pinned by the browser decoder, reference htdocs/lib/AudioEngine.js:426-438.
 #pragma once
 
@@ -26,7 +27,10 @@ struct ImaState {
 // cand[i] = { step[max(i-1,0)] | step[min(i+2,88)] << 16,  step[min(i+4,88)] | step[min(i+6,88)] << 16,  step[min(i+8,88)], - }:
 // the steps of the five possible successor indices in ONE 16-byte shared-memory entry per index, fetched while the
 // quantiser's compare chain resolves, so no table lookup sits on the sample-to-sample dependency chain.
-// Fills `cand` (89 entries of shared memory) cooperatively; the caller synchronises afterwards.
+// (A single word succ[index * 8 + code] = next index << 16 | next step saves ten instructions but puts a shared-memory load
+// between the code and the next sample's first compare: 126 instead of 114 cycles per sample, measured.)
+// Fills `cand` (IMA_TABLE_ENTRIES entries of shared memory) cooperatively; the caller synchronises afterwards.
+constexpr int IMA_TABLE_ENTRIES = 89;
 __device__ __forceinline__ void ima_build_table(uint4* cand, int tid, int nthreads)
 {
     for (int i = tid; i < 89; i += nthreads) {

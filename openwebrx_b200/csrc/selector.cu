@@ -1282,7 +1282,7 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
                 // ---- client audio tail: Convert(FLOAT, SHORT) [+ AdpcmEncoder(sync=True)]; appends behind earlier passes
                 const size_t row0 = g->last_audio - n_audio;
                 if (g->last_audio > g->tail_rows_cap) return fail(OWRX_E_STATE, "audio tail scratch under-provisioned");
-                audio_tail_kernel<<<(S + 31) / 32, 32, 0, st>>>(g->f3.rows(g->f3.fill - n_audio), S, (int)n_audio, g->d_tail_mode,
+                audio_tail_kernel<<<(S + 31) / 32, 128, 0, st>>>(g->f3.rows(g->f3.fill - n_audio), S, (int)n_audio, g->d_tail_mode,
                                                                g->d_tail, g->d_tail_s16 + row0 * (size_t)S, g->d_tail_bytes,
                                                                g->d_tail_count, g->tail_cap);
                 OWRX_LAUNCH_CHECK();

@@ -1143,67 +1143,49 @@ struct TailState {
 };
 
 // mode[s]: 0 = float only, 1 = int16, 2 = int16 + ADPCM with SYNC framing.
-// One warp per 32 channels (lane = channel: the codec state is sample-serial per channel).  The warp stages AT_R rows of its
-// 32 channels through shared memory with cp.async, one tile ahead of the encoder, so the sample chain never waits for
-// global memory (the first version, one dependent global load per sample, ran the C2 block of 20 141 samples per channel in
-// 11.6 ms: ~1150 cycles per sample; the quantiser itself is ~114, adpcm.cuh).
+// One CTA of four warps per 32 channels, specialised: the codec state is sample-serial per channel (lane = channel) and a lone
+// warp issues one instruction every ~2.8 cycles, so everything that is NOT the quantiser recurrence is taken off the encoder
+// warp's instruction stream:
+//   warps 1..3  fetch tiles of AT_R rows (coalesced 128-byte rows), do Convert(FLOAT, SHORT), store the int16 rows, leave the
+//               integers in shared memory; warp 1 also moves the finished tiles' bytes to global memory, one contiguous run
+//               per channel;
+//   warp 0      only runs ima_encode over the staged integers and drops bytes into shared memory.
+// Two tile buffers, named barriers full[b] / empty[b] between the roles.  History: one dependent global load per sample
+// (first version) 11.6 ms per C2 block of 20 141 samples per channel; cp.async staging in a single warp 3.1 ms; this form
+// see profiles/r2_adpcm_notes.md.
 constexpr int AT_R = 32;
 constexpr int AT_OB = 36;
-__global__ void __launch_bounds__(32)
+__device__ __forceinline__ void at_bar_sync(int id) { asm volatile("barrier.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void at_bar_arrive(int id) { asm volatile("barrier.arrive %0, 128;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(128)
 audio_tail_kernel(const float* __restrict__ in, int slots, int n, const int* __restrict__ mode, TailState* __restrict__ ts,
                   int16_t* __restrict__ s16_out, unsigned char* __restrict__ bytes_out, int* __restrict__ count_out, int cap)
 {
-    __shared__ uint4 cand[89];
-    __shared__ float tile[2][AT_R][32];
-    __shared__ unsigned char obuf[32][AT_OB];       // a tile's output bytes per channel (<= AT_R / 2 data + 8 SYNC), padded rows
-    const int lane = threadIdx.x;
-    ima_build_table(cand, lane, 32);
+    __shared__ uint4 succ[IMA_TABLE_ENTRIES];
+    __shared__ int qt[2][AT_R][32];                  // converted samples of a tile
+    __shared__ unsigned char obuf[2][32][AT_OB];     // a tile's output bytes per channel (<= AT_R / 2 data + 8 SYNC), padded rows
+    __shared__ int onb[2][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    ima_build_table(succ, threadIdx.x, 128);
     const int s = blockIdx.x * 32 + lane;
     const bool live = s < slots;
     const int sc = live ? s : slots - 1;
     const int md = live ? mode[sc] : 0;
-    if (__all_sync(0xffffffffu, md == 0)) return;
-    TailState t = ts[sc];
-    ImaState cs = ima_state(t.index, t.pred);
-    unsigned char* o = bytes_out + (size_t)sc * cap;
-    int cnt = count_out[sc];           // append behind earlier passes of the same feed (host zeroes it per feed)
+    if (__syncthreads_and(md == 0)) return;          // (also publishes the table)
     const int n_tiles = (n + AT_R - 1) / AT_R;
-    auto stage = [&](int tl, int buf) {
-        if (tl < n_tiles) {
-            const int r0 = tl * AT_R;
-#pragma unroll
-            for (int k = 0; k < AT_R; k++) {
-                if (r0 + k < n) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[buf][k][lane]);
-                    const float* src = in + (size_t)(r0 + k) * slots + sc;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src));
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    stage(0, 0);
-    __syncwarp();
-    for (int tl = 0; tl < n_tiles; tl++) {
-        const int buf = tl & 1, r0 = tl * AT_R;
-        const int valid = min(AT_R, n - r0);
-        stage(tl + 1, buf ^ 1);
-        asm volatile("cp.async.wait_group 1;\n" ::);
-        __syncwarp();
-        int nb = 0;                                   // bytes this channel produced in this tile
-        if (md != 0) {
-            unsigned char* ob = obuf[lane];
-            // Convert(FLOAT, SHORT) of the lane's 32 samples first (independent: the loads and conversions overlap), written back
-            // into the tile as integers, so the serial encoder below starts each sample from a ready int16
-            int* qt = reinterpret_cast<int*>(&tile[buf][0][0]);
-#pragma unroll 8
-            for (int k = 0; k < valid; k++) {
-                const float x = tile[buf][k][lane] * 32767.0f;
-                const int q = x > 32767.0f ? 32767 : (x < -32768.0f ? -32768 : __float2int_rz(x));
-                qt[k * 32 + lane] = q;
-                s16_out[(size_t)(r0 + k) * slots + sc] = (int16_t)q;
-            }
+    constexpr int FULL = 1, EMPTY = 3;               // barrier ids FULL + b, EMPTY + b
+    if (w == 0) {
+        // ---------------------------------------------------------------- encoder
+        TailState t = ts[sc];
+        ImaState cs = ima_state(t.index, t.pred);
+        for (int tl = 0; tl < n_tiles; tl++) {
+            const int b = tl & 1, valid = min(AT_R, n - tl * AT_R);
+            at_bar_sync(FULL + b);
+            int nb = 0;
             if (md == 2) {
+                unsigned char* ob = obuf[b][lane];
+                const int* q = &qt[b][0][lane];
                 auto sync_block = [&]() {
                     if (t.since_sync == 1001) {
                         ob[nb++] = 'S'; ob[nb++] = 'Y'; ob[nb++] = 'N'; ob[nb++] = 'C';
@@ -1214,7 +1196,7 @@ audio_tail_kernel(const float* __restrict__ in, int slots, int n, const int* __r
                 };
                 int k = 0;
                 if (t.have_lo && valid > 0) {                                    // an odd sample left over from the previous tile
-                    const unsigned hi = ima_encode(qt[lane], cs, cand);
+                    const unsigned hi = ima_encode(q[0], cs, succ);
                     ob[nb++] = (unsigned char)((unsigned)t.lo | (hi << 4));
                     t.have_lo = 0; t.since_sync++;
                     k = 1;
@@ -1222,37 +1204,69 @@ audio_tail_kernel(const float* __restrict__ in, int slots, int n, const int* __r
 #pragma unroll 2
                 for (; k + 1 < valid; k += 2) {                                  // whole bytes: low nibble first
                     sync_block();
-                    const unsigned lo = ima_encode(qt[k * 32 + lane], cs, cand);
-                    const unsigned hi = ima_encode(qt[(k + 1) * 32 + lane], cs, cand);
+                    const unsigned lo = ima_encode(q[k * 32], cs, succ);
+                    const unsigned hi = ima_encode(q[(k + 1) * 32], cs, succ);
                     ob[nb++] = (unsigned char)(lo | (hi << 4));
                     t.since_sync++;
                 }
                 if (k < valid) {
                     sync_block();
-                    t.lo = (int)ima_encode(qt[k * 32 + lane], cs, cand);
+                    t.lo = (int)ima_encode(q[k * 32], cs, succ);
                     t.have_lo = 1;
                 }
             }
+            onb[b][lane] = nb;
+            at_bar_arrive(EMPTY + b);
         }
-        __syncwarp();
-        // the tile's bytes leave channel by channel as one contiguous run each (a lane-per-channel byte store would be 32
-        // separate sectors per instruction)
-        if (__any_sync(0xffffffffu, nb > 0)) {
-            const unsigned long long dst = (unsigned long long)(o + cnt);
-            for (int l = 0; l < 32; l++) {
-                const int nl = __shfl_sync(0xffffffffu, nb, l);
-                if (nl == 0) continue;
-                unsigned char* d = (unsigned char*)__shfl_sync(0xffffffffu, dst, l);
-                if (lane < nl) d[lane] = obuf[l][lane];
+        if (live && md != 0) {
+            t.index = cs.index; t.pred = cs.pred;
+            ts[s] = t;
+        }
+    } else {
+        // ---------------------------------------------------------------- loaders / converters / flusher
+        unsigned char* o = bytes_out + (size_t)sc * cap;
+        int cnt = count_out[sc];       // append behind earlier passes of the same feed (host zeroes it per feed); warp 1 keeps it
+        auto flush = [&](int b) {
+            if (w != 1) return;
+            const int nb = onb[b][lane];
+            if (__any_sync(0xffffffffu, nb > 0)) {
+                const unsigned long long dst = (unsigned long long)(o + cnt);
+                for (int l = 0; l < 32; l++) {
+                    const int nl = __shfl_sync(0xffffffffu, nb, l);
+                    if (nl == 0) continue;
+                    unsigned char* d = (unsigned char*)__shfl_sync(0xffffffffu, dst, l);
+                    if (lane < nl) d[lane] = obuf[b][l][lane];
+                }
+                cnt += nb;
             }
-            cnt += nb;
+        };
+        for (int tl = 0; tl < n_tiles; tl++) {
+            const int b = tl & 1, r0 = tl * AT_R, valid = min(AT_R, n - r0);
+            if (tl >= 2) { at_bar_sync(EMPTY + b); flush(b); }
+            float v[(AT_R + 2) / 3];
+#pragma unroll
+            for (int j = 0; j < (AT_R + 2) / 3; j++) {
+                const int k = (w - 1) + 3 * j;
+                v[j] = k < valid ? in[(size_t)(r0 + k) * slots + sc] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < (AT_R + 2) / 3; j++) {
+                const int k = (w - 1) + 3 * j;
+                if (k < valid) {
+                    const float x = v[j] * 32767.0f;                             // Convert(FLOAT, SHORT), SURVEY A.12
+                    const int q = x > 32767.0f ? 32767 : (x < -32768.0f ? -32768 : __float2int_rz(x));
+                    qt[b][k][lane] = q;
+                    if (md != 0) s16_out[(size_t)(r0 + k) * slots + sc] = (int16_t)q;
+                }
+            }
+            at_bar_arrive(FULL + b);
         }
-        __syncwarp();
-    }
-    if (live && md != 0) {
-        t.index = cs.index; t.pred = cs.pred;
-        ts[s] = t;
-        count_out[s] = cnt;
+        for (int tl = max(0, n_tiles - 2); tl < n_tiles; tl++) {
+            const int b = tl & 1;
+            at_bar_sync(EMPTY + b);
+            flush(b);
+        }
+        if (w == 1 && live && md != 0) count_out[s] = cnt;
     }
 }
 

@@ -605,16 +605,24 @@ wf_finalize_kernel(const float* __restrict__ partial, int subsets, int n, float 
 // 64-sample chunk of all 32 lines through shared memory with coalesced 128-byte row loads (cp.async, one chunk
 // ahead of the encoder), every lane encodes its own line's chunk from padded (conflict-free) shared memory, and
 // the 32 output bytes per line leave through shared memory as one 32-byte sector per line.
+// Four such warps per CTA, one per scheduler of the SM (a lone warp issues at ~0.35 IPC, so they do not slow each other down):
+// the encoder then holds a quarter of the SMs it would with one warp per CTA — every SM it holds is one the FFT pass of the
+// next batch does not get (C1: 5 SMs instead of 19 for 592 lines).
 constexpr int ADPCM_CH = 64;
-__global__ void __launch_bounds__(32)
+constexpr int ADPCM_WARPS = 4;
+__global__ void __launch_bounds__(32 * ADPCM_WARPS)
 wf_adpcm_kernel(const int16_t* __restrict__ s16, uint8_t* __restrict__ out, int n_samples, size_t n_lines)
 {
-    __shared__ uint4 cand[89];
-    __shared__ unsigned tile[2][32][ADPCM_CH / 2 + 1];
-    __shared__ unsigned otile[32][ADPCM_CH / 8 + 1];
-    const int lane = threadIdx.x;
-    ima_build_table(cand, lane, 32);
-    const size_t line0 = (size_t)blockIdx.x * 32;
+    __shared__ uint4 cand[IMA_TABLE_ENTRIES];
+    __shared__ unsigned tile_all[ADPCM_WARPS][2][32][ADPCM_CH / 2 + 1];
+    __shared__ unsigned otile_all[ADPCM_WARPS][32][ADPCM_CH / 8 + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ima_build_table(cand, threadIdx.x, 32 * ADPCM_WARPS);
+    __syncthreads();
+    unsigned (*tile)[32][ADPCM_CH / 2 + 1] = tile_all[wid];
+    unsigned (*otile)[ADPCM_CH / 8 + 1] = otile_all[wid];
+    const size_t line0 = ((size_t)blockIdx.x * ADPCM_WARPS + wid) * 32;
+    if (line0 >= n_lines) return;
     const int nl = (int)min((size_t)32, n_lines - line0);
     const int n_chunks = (n_samples + ADPCM_CH - 1) / ADPCM_CH;
     auto stage = [&](int chunk, int buf) {
@@ -958,7 +966,8 @@ static int wf_process(owrx_wf* wf, const float2* iq_dev, size_t n_samples, uint8
         // OWRX_WF_ADPCM_PAD_KB overrides)
         static const int adpcm_pad = (getenv("OWRX_WF_ADPCM_PAD_KB") ? atoi(getenv("OWRX_WF_ADPCM_PAD_KB")) : 150) << 10;
         if (adpcm_pad) OWRX_CUDA(cudaFuncSetAttribute(wf_adpcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, adpcm_pad));
-        wf_adpcm_kernel<<<(unsigned)((lines + 31) / 32), 32, side_adpcm ? adpcm_pad : 0, sa>>>(s16, out_dev, n + 10, lines);
+        wf_adpcm_kernel<<<(unsigned)((lines + 32 * ADPCM_WARPS - 1) / (32 * ADPCM_WARPS)), 32 * ADPCM_WARPS, side_adpcm ? adpcm_pad : 0, sa>>>(
+            s16, out_dev, n + 10, lines);
         OWRX_LAUNCH_CHECK();
         if (side_adpcm) {
             OWRX_CUDA(cudaEventRecord(wf->adpcm_done[wf->s16_cur], sa));
@@ -1258,8 +1267,8 @@ int owrx_fft_adpcm_encode_device(int device, const void* s16_dev, int fft_size, 
     int rc = select_device(device, nullptr);
     if (rc != OWRX_OK) return rc;
     if (!n_lines) return OWRX_OK;
-    wf_adpcm_kernel<<<(unsigned)((n_lines + 31) / 32), 32, 0, (cudaStream_t)stream>>>((const int16_t*)s16_dev, (uint8_t*)out_dev,
-                                                                                   fft_size + 10, n_lines);
+    wf_adpcm_kernel<<<(unsigned)((n_lines + 32 * ADPCM_WARPS - 1) / (32 * ADPCM_WARPS)), 32 * ADPCM_WARPS, 0, (cudaStream_t)stream>>>(
+        (const int16_t*)s16_dev, (uint8_t*)out_dev, fft_size + 10, n_lines);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }

@@ -171,7 +171,14 @@ class PullGatherHop(_HopBase):
         self.handle = symm.rendezvous(self.mem, group if group is not None else dist.group.WORLD)
         self.peer = [self.handle.get_buffer(r, (2 * self.block_floats,), torch.float32, 0) for r in range(world)]
         self.bufs = [self.mem[:self.block_floats].view(-1, 2), self.mem[self.block_floats:].view(-1, 2)]
-        self.kind = "copy-engine pull all-gather over symmetric memory (peer cudaMemcpyAsync, signal-ordered)"
+        # the N - 1 pulls go out on several streams: one peer copy keeps ONE copy engine busy (~200 GB/s over NVLink 5 measured,
+        # 1.19 ms for the 235 MB a rank pulls of a 2^25-sample block at N = 8), several run on different engines side by side
+        import os
+        self.lanes = max(1, min(world - 1, int(os.environ.get("OWRX_HOP_LANES", "4"))))
+        self.side = [torch.cuda.Stream(device=device) for _ in range(self.lanes - 1)]
+        self.fork = torch.cuda.Event()
+        self.joined = [torch.cuda.Event() for _ in self.side]
+        self.kind = ("copy-engine pull all-gather over symmetric memory (peer cudaMemcpyAsync on %d streams, signal-ordered)" % self.lanes)
         self.calls = [0, 0]
 
     def gather(self, j, my_slice):
@@ -189,25 +196,78 @@ class PullGatherHop(_HopBase):
             self.mem[base + self.rank * S: base + (self.rank + 1) * S].copy_(my_slice.reshape(-1), non_blocking=True)
             for k in range(1, self.world):
                 h.put_signal((self.rank + k) % self.world, channel=b, timeout_ms=self.TIMEOUT_MS)
+            self.fork.record(self.stream)
+            lanes = [self.stream] + self.side
             for k in range(1, self.world):                       # staggered: rank r starts with r + 1, so the sources differ at any moment
                 p = (self.rank + k) % self.world
-                h.wait_signal(p, channel=b, timeout_ms=self.TIMEOUT_MS)
-                self.mem[base + p * S: base + (p + 1) * S].copy_(self.peer[p][base + p * S: base + (p + 1) * S], non_blocking=True)
+                st = lanes[(k - 1) % self.lanes]
+                with torch.cuda.stream(st):
+                    if st is not self.stream and k - 1 < self.lanes:
+                        st.wait_event(self.fork)
+                    h.wait_signal(p, channel=b, timeout_ms=self.TIMEOUT_MS)
+                    self.mem[base + p * S: base + (p + 1) * S].copy_(self.peer[p][base + p * S: base + (p + 1) * S], non_blocking=True)
+            for st, ev in zip(self.side, self.joined):
+                ev.record(st)
+                self.stream.wait_event(ev)
             for k in range(1, self.world):
                 h.put_signal((self.rank + k) % self.world, channel=2 + b, timeout_ms=self.TIMEOUT_MS)
             e1.record(self.stream)
             self.landed[b].record(self.stream)
 
 
+class PushGatherHop(PullGatherHop):
+    """the same all-gather with the copies turned round: a rank WRITES its slice into the N - 1 peers' buffers (posted writes over
+    NVLink: no read round trip per request).  Signals: "my buffer b may be overwritten" (channel 2 + b) to every peer before,
+    "my slice has landed in your buffer" (channel b) after each copy."""
+
+    def __init__(self, block_samples, world, rank, device, group=None):
+        super().__init__(block_samples, world, rank, device, group)
+        self.kind = "copy-engine push all-gather over symmetric memory (peer cudaMemcpyAsync on %d streams, signal-ordered)" % self.lanes
+
+    def gather(self, j, my_slice):
+        b = j & 1
+        torch, h, S = self._torch, self.handle, self.shard_floats
+        base = b * self.block_floats
+        mine = my_slice.reshape(-1)
+        self.stream.wait_event(self.free[b])                     # this rank's consumer is done with buffer b
+        with torch.cuda.stream(self.stream):
+            e0, e1 = self._timed()
+            e0.record(self.stream)
+            for k in range(1, self.world):
+                h.put_signal((self.rank + k) % self.world, channel=2 + b, timeout_ms=self.TIMEOUT_MS)
+            self.mem[base + self.rank * S: base + (self.rank + 1) * S].copy_(mine, non_blocking=True)
+            self.fork.record(self.stream)
+            lanes = [self.stream] + self.side
+            for k in range(1, self.world):                       # staggered: the destinations differ at any moment
+                p = (self.rank + k) % self.world
+                st = lanes[(k - 1) % self.lanes]
+                with torch.cuda.stream(st):
+                    if st is not self.stream and k - 1 < self.lanes:
+                        st.wait_event(self.fork)
+                    h.wait_signal(p, channel=2 + b, timeout_ms=self.TIMEOUT_MS)
+                    self.peer[p][base + self.rank * S: base + (self.rank + 1) * S].copy_(mine, non_blocking=True)
+                    h.put_signal(p, channel=b, timeout_ms=self.TIMEOUT_MS)
+            for st, ev in zip(self.side, self.joined):
+                ev.record(st)
+                self.stream.wait_event(ev)
+            for k in range(1, self.world):
+                h.wait_signal((self.rank + k) % self.world, channel=b, timeout_ms=self.TIMEOUT_MS)
+            e1.record(self.stream)
+            self.landed[b].record(self.stream)
+
+
 def make_hop(kind, block_samples, world, rank, device, group=None):
-    """kind: "nccl" | "pull" | "auto" (pull when the GPUs offer symmetric memory, else nccl; every rank takes the same branch)"""
+    """kind: "nccl" | "pull" | "push" | "auto".  auto = nccl: measured on 8 x B200 with 2^25-sample blocks (profiles/r2_hop.md), alone
+    ncclAllGather needs 0.41 ms per block, the copy-engine all-gathers 0.62-0.78 ms (pull) / 0.69-0.71 ms (push) whatever the number
+    of copy streams; beside the DSP pass all three stretch to 1.0-1.2 ms and the step is 1.08 ms with NCCL, 1.19-1.25 ms with the
+    copy engines — the SM-free transports do not pay for themselves here.  Every rank takes the same branch."""
     import sys
     import torch
     import torch.distributed as dist
-    if kind in ("pull", "auto"):
+    if kind in ("pull", "push"):
         hop, ok = None, 1
         try:
-            hop = PullGatherHop(block_samples, world, rank, device, group)
+            hop = (PushGatherHop if kind == "push" else PullGatherHop)(block_samples, world, rank, device, group)
         except Exception as e:                               # no symmetric memory on this box / torch build
             print("[hop] pull all-gather unavailable (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
             ok = 0
@@ -215,6 +275,6 @@ def make_hop(kind, block_samples, world, rank, device, group=None):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         if int(flag.item()) == 1:
             return hop
-        if kind == "pull":
-            raise RuntimeError("OWRX_HOP=pull but symmetric memory is not available on every rank")
+        if kind in ("pull", "push"):
+            raise RuntimeError("OWRX_HOP=%s but symmetric memory is not available on every rank" % kind)
     return NcclGatherHop(block_samples, world, rank, device, group)

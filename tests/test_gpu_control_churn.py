@@ -98,6 +98,7 @@ def _live(torch, cars, blocks, n, n_blocks, events, drain_every, fire=True):
     st = torch.cuda.Stream()
     rig.bank.set_pipelined(True)
     lock = threading.Lock()
+    tick = threading.Condition()
     state = dict(issued=0, fired=0)
     stamps = []
 
@@ -106,8 +107,9 @@ def _live(torch, cars, blocks, n, n_blocks, events, drain_every, fire=True):
     def fire_all():
         for k, e in enumerate(events):
             # paced: `per_block` events per block of the stream (a Python lock is not fair: an unpaced loop would starve the feeder)
-            while state["issued"] < k // per_block:
-                time.sleep(0)
+            with tick:
+                while state["issued"] < k // per_block:
+                    tick.wait(0.05)                    # (no spinning: a busy Python thread would take the GIL from the feeder)
             with lock:
                 rig.apply(e)
                 stamps.append(state["issued"])
@@ -131,6 +133,8 @@ def _live(torch, cars, blocks, n, n_blocks, events, drain_every, fire=True):
             state["issued"] += 1
             if (b + 1) % drain_every == 0:
                 out[b] = rig.collect()                     # same lock hold: no event between a block and its drain
+        with tick:
+            tick.notify_all()
         ev = torch.cuda.Event(); ev.record(st); marks.append(ev)
         if len(marks) > 4:
             marks[-5].synchronize()                        # run at most four blocks ahead of the device, as a paced source would
