@@ -256,6 +256,43 @@ class PushGatherHop(PullGatherHop):
             self.landed[b].record(self.stream)
 
 
+class MulticastGatherHop(_HopBase):
+    """the all-gather over NVSwitch multicast (NVLS): every rank streams ITS slice through the multicast address of the symmetric
+    allocation (libowrx_b200's owrx_iq_multicast_store: multimem.st, a few dozen CTAs) — the slice leaves its NVLink port ONCE and
+    the switch replicates it into every rank's buffer, so a rank sends 1/N of the block instead of (N-1)/N.  Two cross-GPU barriers
+    on the hop stream per block: "every rank's consumer has finished with buffer b" before, "every slice has landed" after."""
+
+    def __init__(self, block_samples, world, rank, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        self._N = N
+        self._init_common(block_samples, world, rank, device)
+        self.mem = symm.empty(2 * self.block_floats, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.mem, group if group is not None else dist.group.WORLD)
+        self.mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if not self.mc:
+            raise RuntimeError("no NVSwitch multicast support for this group")
+        self.bufs = [self.mem[:self.block_floats].view(-1, 2), self.mem[self.block_floats:].view(-1, 2)]
+        self.kind = "NVSwitch multicast all-gather (multimem.st of each rank's slice, two cross-GPU barriers per block)"
+
+    def gather(self, j, my_slice):
+        b = j & 1
+        torch, S = self._torch, self.shard_floats
+        mine = my_slice.reshape(-1)
+        self.stream.wait_event(self.free[b])                     # this rank's consumer is done with buffer b
+        with torch.cuda.stream(self.stream):
+            e0, e1 = self._timed()
+            e0.record(self.stream)
+            self.handle.barrier(channel=0)                       # ... and so is every other rank's
+            dst = self.mc + 4 * (b * self.block_floats + self.rank * S)
+            self._N.check(self._N.lib.owrx_iq_multicast_store(mine.data_ptr(), dst, 4 * S, self.stream.cuda_stream))
+            self.handle.barrier(channel=1)                       # every slice has landed in every rank's buffer b
+            e1.record(self.stream)
+            self.landed[b].record(self.stream)
+
+
 def make_hop(kind, block_samples, world, rank, device, group=None):
     """kind: "nccl" | "pull" | "push" | "auto".  auto = nccl: measured on 8 x B200 with 2^25-sample blocks (profiles/r2_hop.md), alone
     ncclAllGather needs 0.41 ms per block, the copy-engine all-gathers 0.62-0.78 ms (pull) / 0.69-0.71 ms (push) whatever the number
@@ -264,10 +301,10 @@ def make_hop(kind, block_samples, world, rank, device, group=None):
     import sys
     import torch
     import torch.distributed as dist
-    if kind in ("pull", "push"):
+    if kind in ("pull", "push", "multicast"):
         hop, ok = None, 1
         try:
-            hop = (PushGatherHop if kind == "push" else PullGatherHop)(block_samples, world, rank, device, group)
+            hop = {"push": PushGatherHop, "pull": PullGatherHop, "multicast": MulticastGatherHop}[kind](block_samples, world, rank, device, group)
         except Exception as e:                               # no symmetric memory on this box / torch build
             print("[hop] pull all-gather unavailable (%s: %s)" % (type(e).__name__, e), file=sys.stderr)
             ok = 0
@@ -275,6 +312,6 @@ def make_hop(kind, block_samples, world, rank, device, group=None):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         if int(flag.item()) == 1:
             return hop
-        if kind in ("pull", "push"):
+        if kind in ("pull", "push", "multicast"):
             raise RuntimeError("OWRX_HOP=%s but symmetric memory is not available on every rank" % kind)
     return NcclGatherHop(block_samples, world, rank, device, group)

@@ -76,6 +76,22 @@ def test_fft_chain_through_module_api(gpu):
         assert np.median(np.abs(shown - db)) < 0.6
     same = sum(m == l.tobytes() for m, l in zip(msgs, ref["lines"]))
     assert same >= 4                                                 # byte-identical unless an int16 sits on a rounding edge
+    # the same chain without FftAdpcm (compression "none", csdr/chain/fft.py:87-96): the float32 dB lines themselves, held to the
+    # north-star tolerance through the module API
+    ws = [M.Fft(size=n, every_n_samples=0), M.LogAveragePower(add_db=-70, fft_size=n, avg_number=avg), M.FftSwap(fft_size=n)]
+    ws[0].setEveryNSamples(every_n)
+    _connect(ws)
+    src, out = M.Buffer(Format.COMPLEX_FLOAT), M.Buffer(Format.FLOAT)
+    ws[-1].setWriter(out)
+    rd = out.getReader()
+    ws[0].setReader(src.getReader())
+    for o in range(0, len(raw), 8 * 1000):
+        src.write(raw[o:o + 8 * 1000])
+    msgs = _collect(rd, 6 * 4 * n)
+    assert len(msgs) == 6 and all(len(m) == 4 * n for m in msgs)
+    from test_gpu_waterfall import _assert_db_parity, _truth_db
+    got = np.stack([np.frombuffer(m, np.float32) for m in msgs])
+    _assert_db_parity(got, ref["db"], _truth_db(iq, n, every_n, avg))   # 0.01 dB, as in test_gpu_waterfall
 
 
 def test_two_clients_share_one_source_buffer(gpu):

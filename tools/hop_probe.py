@@ -23,7 +23,9 @@ def main():
     mine = torch.randn(shard, 2, device=dev)
     st = torch.cuda.Stream(device=dev)
     out = []
-    for kind, lanes in (("pull", 1), ("pull", 4), ("pull", 7), ("push", 1), ("push", 7), ("nccl", 0)):
+    kinds = (("multicast", 0), ("nccl", 0)) if os.environ.get("OWRX_HOP_PROBE") == "mc" else (
+        ("pull", 1), ("pull", 4), ("pull", 7), ("push", 1), ("push", 7), ("multicast", 0), ("nccl", 0))
+    for kind, lanes in kinds:
         os.environ["OWRX_HOP_LANES"] = str(max(lanes, 1))
         hop = make_hop(kind, block, world, rank, dev)
         for j in range(25):

@@ -14,7 +14,7 @@ import bench                                                             # noqa:
 
 def run(pipelined, blocks, cars, steps=30):
     bank, _ = bench.make_bank(bench.C2, cars, 0)
-    st = torch.cuda.Stream()
+    st = torch.cuda.Stream(priority=int(os.environ.get("PROBE_STREAM_PRIORITY", "0")))
     torch.cuda.set_stream(st)
     bank.set_pipelined(pipelined)
     for i in range(3):
@@ -39,5 +39,5 @@ if __name__ == "__main__":
     cars = bench.channel_plan(0, 64)
     iq = bench.synth_iq_torch(bench.BLOCK, bench.C2["fs"], cars, dev)
     blocks = [iq, iq.clone()]
-    env = {k: v for k, v in os.environ.items() if k.startswith("OWRX_")}
+    env = {k: v for k, v in os.environ.items() if k.startswith("OWRX_") or k.startswith("PROBE_")}
     print(json.dumps({"env": env, "alone": run(False, blocks, cars), "pipelined": run(True, blocks, cars)}))
