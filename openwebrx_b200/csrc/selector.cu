@@ -1121,7 +1121,9 @@ int group_tail(owrx_bank* bank, Group* g, cudaStream_t st)
         const int hang_blocks = 2;                                       // hangLength = 2*blockLength, selector.py:124
         // one launch for Squelch + demodulator front + DcBlock means (tail_front_kernel) unless OWRX_TAIL_FUSED=0 asks for the
         // seven-kernel evaluation (kept as the second opinion: tests/test_gpu_selector.py runs both)
-        const bool fused = bank->tail_fused && nb <= 65535;
+        // the fused front re-derives the block powers its gate needs in EVERY CTA of a block: fine while a squelch block is one or
+        // two CTAs long (12 kHz: 750 rows), 7x redundant reads for the 15 625-row blocks of a 250 kHz WFM IF (C5: 190 us vs 60 us)
+        const bool fused = bank->tail_fused && nb <= 65535 && g->sq_len <= 2 * TF_ROWS;
         if ((rc = g->f1.ensure_new(n4, st)) != OWRX_OK) return rc;
         if (fused) {
             const unsigned zsplit = (unsigned)((g->sq_len + TF_ROWS - 1) / TF_ROWS);
