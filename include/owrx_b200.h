@@ -141,6 +141,15 @@ typedef struct owrx_bank owrx_bank_t;
 int owrx_bank_create(int device, double input_rate, owrx_bank_t** out);
 void owrx_bank_destroy(owrx_bank_t* bank);
 
+/* Threading and ordering of the control calls below (the reference calls the setters from websocket threads while the DSP
+ * thread pumps the chain: csdr/chain/selector.py:132-166, owrx/dsp.py:96-148,835-839).  Every owrx_bank_add_channel* /
+ * owrx_bank_remove_channel / owrx_chan_set_* call is thread-safe against the feed calls and only RECORDS the change: it takes
+ * effect at the next block boundary (the next owrx_bank_feed* / owrx_bank_process_device), applied on the device in stream
+ * order, so blocks already in flight are not touched and no call synchronises the device (the one exception: adding the 65th,
+ * 129th, ... client of a parameter class re-lays that class's tables).  A new or re-moded client starts from fresh module state
+ * (empty filter histories, reset Agc / codec), as the reference's freshly built pycsdr modules do; a retune keeps the NCO phase
+ * continuous.  Channel ids are handles: the lowest free id is handed out again after owrx_bank_remove_channel. */
+
 /* Selector(inputRate, outputRate): csdr/chain/selector.py:89-113 (Decimator math :21-26,37-51). */
 int owrx_bank_add_channel(owrx_bank_t* bank, double output_rate, int* chan);
 
