@@ -29,11 +29,11 @@ __device__ __forceinline__ void split_bf16x3(float x, __nv_bfloat16& h, __nv_bfl
 // TC = false: tab[q][r][slot] complex float32.  TC = true: bf16 planes Tp[2 level + part][q * slots + slot][r].
 template <bool TC>
 __global__ void __launch_bounds__(256)
-fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int slots, const int* __restrict__ slot_list,
+fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int slots, int M, const int* __restrict__ slot_list,
                 const double* __restrict__ rate_list, void* __restrict__ tab_out)
 {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= (long long)FC_M * D) return;
+    if (idx >= (long long)M * D) return;
     const int q = (int)(idx / D), r = (int)(idx % D);
     const double rate = rate_list[blockIdx.y];
     const int slot = slot_list[blockIdx.y];
@@ -41,7 +41,7 @@ fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int sl
     a0 -= floor(a0);
     double aw = rate * (double)D;
     aw -= floor(aw);
-    aw += (double)q / FC_M;
+    aw += (double)q / M;
     double c0, s0, cw, sw;
     sincospi(2.0 * a0, &s0, &c0);
     sincospi(2.0 * aw, &sw, &cw);
@@ -60,7 +60,7 @@ fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int sl
         reinterpret_cast<float2*>(tab_out)[((size_t)q * Dp + r) * slots + slot] = make_float2((float)ar, (float)ai);
     } else {
         __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(tab_out);
-        const size_t plane = (size_t)FC_M * slots * Dp, at = ((size_t)q * slots + slot) * Dp + r;
+        const size_t plane = (size_t)M * slots * Dp, at = ((size_t)q * slots + slot) * Dp + r;
         __nv_bfloat16 a[3], b[3];
         split_bf16x3((float)ar, a[0], a[1], a[2]);
         split_bf16x3((float)ai, b[0], b[1], b[2]);
@@ -91,50 +91,65 @@ __device__ __forceinline__ void fc_fill_twiddles(float2* tw)
     }
 }
 
-// in: v[n1] = x[16 n1 + g];  out: v[q] = X[g + 16 slot<16>(q)]
-__device__ __forceinline__ void fc_fft256(float2* v, float2* seq, const float2* tw, int g)
+// V x V-point FFT (V = 16: 256 points, V = 8: 64 points), V threads per sequence, V points per thread.
+// tw[r * V + k] = e^{-2 pi i r k / V^2};  in: v[n1] = x[V n1 + g];  out: v[q] = X[g + V slot<V>(q)]
+template <int V>
+__device__ __forceinline__ void fc_fill_twiddles_v(float2* tw)
 {
-    dft<16>(v);
+    for (int i = threadIdx.x; i < V * V; i += blockDim.x) {
+        const int e = ((i / V) * (i % V)) & (V * V - 1);
+        float s, c;
+        sincospif(-(float)e / (float)(V * V / 2), &s, &c);
+        tw[i] = make_float2(c, s);
+    }
+}
+template <int V>
+__device__ __forceinline__ void fc_fft_vv(float2* v, float2* seq, const float2* tw, int g)
+{
+    dft<V>(v);
 #pragma unroll
-    for (int q = 0; q < 16; q++) seq[g * 16 + slot<16>(q)] = v[q];
+    for (int q = 0; q < V; q++) seq[g * V + slot<V>(q)] = v[q];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; r++) v[r] = seq[r * 16 + g];
+    for (int r = 0; r < V; r++) v[r] = seq[r * V + g];
 #pragma unroll
-    for (int r = 1; r < 16; r++) v[r] = cmul(v[r], tw[r * 16 + g]);
-    dft<16>(v);
+    for (int r = 1; r < V; r++) v[r] = cmul(v[r], tw[r * V + g]);
+    dft<V>(v);
 }
+__device__ __forceinline__ void fc_fft256(float2* v, float2* seq, const float2* tw, int g) { fc_fft_vv<16>(v, seq, tw, g); }
 
 // TC = false: F[q][b][r] as (re, re, -im, im).  TC = true: bf16 planes Fp[2 level + part][q * B + b][r].
-template <bool TC>
-__global__ void __launch_bounds__(16 * FC_SEQ)
+// V = 16: 256-point FFTs (16 threads x 16 points per sequence), V = 8: 64-point FFTs (8 x 8).
+template <bool TC, int V>
+__global__ void __launch_bounds__(V * FC_SEQ)
 fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp, int Kb, int B, void* __restrict__ F_out)
 {
+    constexpr int M = V * V;
     extern __shared__ float2 fc_smem[];
-    float2* tw = fc_smem;                       // [256]
-    float2* seqs = fc_smem + 256;               // [32][257]
+    float2* tw = fc_smem;                       // [M]
+    float2* seqs = fc_smem + M;                 // [32][M + 1]
     const int tid = threadIdx.x, j = tid & 31, g = tid >> 5;
     const int b = blockIdx.y;
     const int r = blockIdx.x * FC_SEQ + j;
-    fc_fill_twiddles(tw);
-    float2 v[16];
+    fc_fill_twiddles_v<V>(tw);
+    float2 v[V];
     const long long s0 = (long long)b * Kb * D + r;
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        const long long s = s0 + (long long)(16 * n1 + g) * D;
+    for (int n1 = 0; n1 < V; n1++) {
+        const long long s = s0 + (long long)(V * n1 + g) * D;
         v[n1] = (r < D && s < n_lim) ? __ldg(iq + s) : make_float2(0.f, 0.f);
     }
     __syncthreads();                            // twiddles visible
-    fc_fft256(v, seqs + j * FC_STR, tw, g);
+    fc_fft_vv<V>(v, seqs + j * (M + 1), tw, g);
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-        const int bin = g + 16 * slot<16>(q);
+    for (int q = 0; q < V; q++) {
+        const int bin = g + V * slot<V>(q);
         if (!TC) {
             // operand layout of the contraction's packed FMAs: (re, re) and (-im, im)
             reinterpret_cast<float4*>(F_out)[((size_t)bin * B + b) * Dp + r] = make_float4(v[q].x, v[q].x, -v[q].y, v[q].y);
         } else {
             __nv_bfloat16* fp = reinterpret_cast<__nv_bfloat16*>(F_out);
-            const size_t plane = (size_t)FC_M * B * Dp, at = ((size_t)bin * B + b) * Dp + r;
+            const size_t plane = (size_t)M * B * Dp, at = ((size_t)bin * B + b) * Dp + r;
             __nv_bfloat16 a[3], c[3];
             split_bf16x3(v[q].x, a[0], a[1], a[2]);
             split_bf16x3(v[q].y, c[0], c[1], c[2]);
@@ -222,7 +237,7 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
 template <int NW>
 __global__ void __launch_bounds__(NW * 64 + 32, 1)
 fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT, float2* __restrict__ Z, int B, int Dp,
-                   int slots, int nbt, int nsplit)
+                   int slots, int nbt, int nsplit, int M)
 {
     constexpr int BT = 16 * NW;
     constexpr unsigned F_STAGE = BT * FC_KC * sizeof(float4), T_STAGE = FC_KC * FC_CG * sizeof(float2);
@@ -244,7 +259,7 @@ fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_consta
     const int all_chunks = Dp / FC_KC;
     const int ch0 = (int)(((long long)all_chunks * blockIdx.z) / nsplit);
     const int nchunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / nsplit) - ch0;
-    Z += (size_t)blockIdx.z * FC_M * B * slots;
+    Z += (size_t)blockIdx.z * M * B * slots;
     // rows 16w + 2i + lr of this warp that exist: i < ni (the lr = 1 half of a last odd row reads a stale row; not stored)
     const int ni = min(8, max(0, (rows - warp * 16 + 1) / 2));
 
@@ -349,47 +364,50 @@ fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_consta
 // z[m] = (1/M) IFFT_M over q of Z[q][b][c]; valid m < Kb; post-rotation e^{j 2 pi (ph + rate (kD + 1))}; store s1.
 // IFFT(x) = conj(FFT(conj(x))).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(16 * FC_SEQ)
+template <int V>
+__global__ void __launch_bounds__(V * FC_SEQ)
 fc_inverse_kernel(const float2* __restrict__ Z, int nsplit, int B, int slots, int D, int Kb, const double* __restrict__ ch_rate,
                   const double* __restrict__ ch_phase, long long k0, long long n_k, float2* __restrict__ out)
 {
+    constexpr int M = V * V;
     extern __shared__ float2 fc_smem[];
     float2* tw = fc_smem;
-    float2* seqs = fc_smem + 256;
+    float2* seqs = fc_smem + M;
     const int tid = threadIdx.x, j = tid & 31, g = tid >> 5;
     const int b = blockIdx.y;
     const int c = blockIdx.x * FC_SEQ + j;
-    fc_fill_twiddles(tw);
-    float2 v[16];
+    fc_fill_twiddles_v<V>(tw);
+    float2 v[V];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        const size_t at = ((size_t)(16 * n1 + g) * B + b) * slots + c;
+    for (int n1 = 0; n1 < V; n1++) {
+        const size_t at = ((size_t)(V * n1 + g) * B + b) * slots + c;
         float2 z = __ldg(Z + at);
         for (int sp = 1; sp < nsplit; sp++) {                      // split-K partial sums of the contraction
-            const float2 zz = __ldg(Z + (size_t)sp * FC_M * B * slots + at);
+            const float2 zz = __ldg(Z + (size_t)sp * M * B * slots + at);
             z.x += zz.x; z.y += zz.y;
         }
         v[n1] = make_float2(z.x, -z.y);
     }
     __syncthreads();
-    fc_fft256(v, seqs + j * FC_STR, tw, g);
+    fc_fft_vv<V>(v, seqs + j * (M + 1), tw, g);
     const double rate = ch_rate[c], ph = ch_phase[c];
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-        const int m = g + 16 * slot<16>(q);
+    for (int q = 0; q < V; q++) {
+        const int m = g + V * slot<V>(q);
         const long long k = k0 + (long long)b * Kb + m;
         if (m < Kb && k < n_k) {
             double t = ph + rate * (double)(k * D + 1);
             t -= floor(t);
             float sn, cs;
             sincospif(2.0f * (float)t, &sn, &cs);
-            const float2 z = make_float2(v[q].x * (1.0f / FC_M), -v[q].y * (1.0f / FC_M));
+            const float2 z = make_float2(v[q].x * (1.0f / M), -v[q].y * (1.0f / M));
             out[(size_t)k * slots + c] = cmul(z, make_float2(cs, sn));
         }
     }
 }
 
 constexpr size_t kFftSmem = (256 + FC_SEQ * FC_STR) * sizeof(float2);
+constexpr size_t kFftSmemSmall = (FC_M_SMALL + FC_SEQ * (FC_M_SMALL + 1)) * sizeof(float2);
 
 // ------------------------------------------------------------------------------------------------
 // K4F band-pass kernels (see fastconv.cuh).  Streams are channel-minor ([row][slot]), so a warp's 32 lanes are 32
@@ -545,22 +563,31 @@ int launch_contract_nw(const FcShape& sh, const float4* F, const float2* tab, in
     const int nbt = (B + BT - 1) / BT;
     CUtensorMap mapF, mapT;
     int rc;
-    if ((rc = make_map(&mapF, F, (size_t)sh.Dp * 4, (size_t)FC_M * B, FC_KC * 4, BT)) != OWRX_OK) return rc;
-    if ((rc = make_map(&mapT, tab, (size_t)sh.slots * 2, (size_t)FC_M * sh.Dp, FC_CG * 2, FC_KC)) != OWRX_OK) return rc;
-    fc_contract_kernel<NW><<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG), (unsigned)nsplit), NW * 64 + 32, smem, st>>>(mapF, mapT, Z, B, sh.Dp,
-                                                                                                                                     sh.slots, nbt, nsplit);
+    if ((rc = make_map(&mapF, F, (size_t)sh.Dp * 4, (size_t)sh.M * B, FC_KC * 4, BT)) != OWRX_OK) return rc;
+    if ((rc = make_map(&mapT, tab, (size_t)sh.slots * 2, (size_t)sh.M * sh.Dp, FC_CG * 2, FC_KC)) != OWRX_OK) return rc;
+    fc_contract_kernel<NW><<<dim3((unsigned)(sh.M * nbt), (unsigned)(sh.slots / FC_CG), (unsigned)nsplit), NW * 64 + 32, smem, st>>>(mapF, mapT, Z, B, sh.Dp,
+                                                                                                                                     sh.slots, nbt, nsplit, sh.M);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
 
 }  // namespace
 
+int fc_pick_fft_size(int D, int P)
+{
+    if (const char* m = getenv("OWRX_FC_M")) {
+        const int v = atoi(m);
+        if ((v == FC_M || v == FC_M_SMALL) && P <= v / 2) return v;
+    }
+    return (D >= 2048 && P <= FC_M_SMALL / 2) ? FC_M_SMALL : FC_M;
+}
+
 int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, float2* d_tab,
                     cudaStream_t st)
 {
     if (n <= 0) return OWRX_OK;
-    const long long total = (long long)FC_M * sh.D;
-    fc_table_kernel<false><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, d_slot_list,
+    const long long total = (long long)sh.M * sh.D;
+    fc_table_kernel<false><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, sh.M, d_slot_list,
                                                                                               d_rate_list, d_tab);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
@@ -570,8 +597,8 @@ int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_li
                        cudaStream_t st)
 {
     if (n <= 0) return OWRX_OK;
-    const long long total = (long long)FC_M * sh.D;
-    fc_table_kernel<true><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, d_slot_list,
+    const long long total = (long long)sh.M * sh.D;
+    fc_table_kernel<true><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, sh.M, d_slot_list,
                                                                                              d_rate_list, d_tabp);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
@@ -579,16 +606,24 @@ int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_li
 
 int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float4* d_F, cudaStream_t st)
 {
-    OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-    fc_forward_kernel<false><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
+    if (sh.M == FC_M_SMALL) {
+        fc_forward_kernel<false, 8><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 8 * FC_SEQ, kFftSmemSmall, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
+    } else {
+        OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+        fc_forward_kernel<false, 16><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
+    }
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
 
 int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, cudaStream_t st)
 {
-    OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-    fc_forward_kernel<true><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp);
+    if (sh.M == FC_M_SMALL) {
+        fc_forward_kernel<true, 8><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 8 * FC_SEQ, kFftSmemSmall, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp);
+    } else {
+        OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+        fc_forward_kernel<true, 16><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp);
+    }
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
@@ -604,7 +639,7 @@ void fc_contract_plan(const FcShape& sh, int B, int sm_count, int* nw_out, int* 
     const int nbt = (B + 16 * nw - 1) / (16 * nw);
     const size_t smem = (size_t)FC_ST * (16 * nw * FC_KC * sizeof(float4) + FC_KC * FC_CG * sizeof(float2));
     const int per_sm = std::max(1, std::min((int)((size_t)(220 << 10) / smem), 2048 / (nw * 64 + 32)));
-    const long long tiles = (long long)FC_M * nbt * (sh.slots / FC_CG), slots = (long long)sm_count * per_sm;
+    const long long tiles = (long long)sh.M * nbt * (sh.slots / FC_CG), slots = (long long)sm_count * per_sm;
     const int chunks = sh.Dp / FC_KC;
     int best = 1;
     double best_cost = 1e30;
@@ -670,9 +705,14 @@ int bpf_launch_inverse(const float2* Y, const float2* in, const int* enabled, in
 int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
                       float2* out, cudaStream_t st)
 {
-    OWRX_CUDA(cudaFuncSetAttribute(fc_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-    fc_inverse_kernel<<<dim3((unsigned)(sh.slots / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb, d_rate,
-                                                                                                    d_phase, k0, n_k, out);
+    if (sh.M == FC_M_SMALL) {
+        fc_inverse_kernel<8><<<dim3((unsigned)(sh.slots / FC_SEQ), (unsigned)B), 8 * FC_SEQ, kFftSmemSmall, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb,
+                                                                                                               d_rate, d_phase, k0, n_k, out);
+    } else {
+        OWRX_CUDA(cudaFuncSetAttribute(fc_inverse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+        fc_inverse_kernel<16><<<dim3((unsigned)(sh.slots / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb,
+                                                                                                            d_rate, d_phase, k0, n_k, out);
+    }
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }

@@ -18,7 +18,8 @@
 
 namespace owrx {
 
-constexpr int FC_M = 256;        // branch FFT size
+constexpr int FC_M = 256;        // branch FFT size (default; also the block size of the K4F band-pass)
+constexpr int FC_M_SMALL = 64;   // branch FFT size of groups with a large decimation (fc_pick_fft_size)
 constexpr int FC_KC = 32;        // contraction chunk (branches per pipeline stage)
 constexpr int FC_DPAD = 32;      // D is padded to a multiple of this (forward pass: 32 branches per CTA)
 constexpr int FC_CG = 64;        // channel slots per contraction CTA
@@ -26,7 +27,15 @@ constexpr int FC_MAXSPLIT = 4;   // split-K planes of Z (scratch is sized for th
 
 struct FcShape {
     int D, T, P, Kb, Dp, slots;
+    int M;                       // branch FFT size: FC_M or FC_M_SMALL; Kb = M - P + 1
 };
+
+// Branch FFT size of a group.  Bytes a pass moves ~ 12 M Dp (S + 2 n_k / (M - P + 1)): the per-channel table (M Dp S entries,
+// read once per pass) against the branch spectra (written and read once, M / Kb times the input).  With D in the thousands
+// a pass holds few outputs n_k per channel slot S and the table dominates: 64-point FFTs (Kb = 38 at P = 27) cut the table
+// to a quarter for 1.5 times the spectra (C3, D = 5120, 2^25 samples: 16.4 -> 5.3 GB at 1024 slots, 2.9 -> 1.9 GB at 128).
+// Short decimations keep 256 points (C2, D = 833, 64 slots: 61 vs 90 k per unit).  OWRX_FC_M = 64 / 256 overrides.
+int fc_pick_fft_size(int D, int P);
 
 // rebuild the table columns of `n` slots: slot_list[i], rate_list[i] (device arrays)
 int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, float2* d_tab,

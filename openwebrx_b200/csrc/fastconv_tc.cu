@@ -104,20 +104,24 @@ __constant__ int kTcProd[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}
 
 __global__ void __launch_bounds__(192, 1)
 fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float2* __restrict__ Z, int B, int Dp,
-                      int slots, int nbt, int mrows, int nsplit)
+                      int slots, int nbt, int mrows, int nsplit, int M)
 {
     extern __shared__ unsigned char tc_smem_raw[];
     __shared__ unsigned long long bars[2 * TC_ST + 1];               // full[ST], empty[ST], accumulators ready
     __shared__ unsigned tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int q = blockIdx.x / nbt, bt = blockIdx.x % nbt;
-    const int cg = blockIdx.y;
+    // channel groups fastest: the CTAs that share a spectra tile (same bin and row tile, different 64-slot groups) are launched
+    // side by side, so the tile is read from DRAM once and from L2 by the others (C3, 1024 slots: 16 groups re-read 0.47 GB of
+    // spectra each — a third of the kernel's DRAM traffic when the launch order kept them 256 CTAs apart)
+    const int ngroups = slots / FC_CG;
+    const int cg = blockIdx.x % ngroups;
+    const int q = (blockIdx.x / ngroups) / nbt, bt = (blockIdx.x / ngroups) % nbt;
     const int b0 = bt * mrows;
     const int rows = min(mrows, B - b0);
     const int all_chunks = Dp / TC_KC;
     const int ch0 = (int)(((long long)all_chunks * blockIdx.z) / nsplit);
     const int nchunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / nsplit) - ch0;
-    Z += (size_t)blockIdx.z * FC_M * B * slots;
+    Z += (size_t)blockIdx.z * M * B * slots;
 
     const unsigned a_plane = (unsigned)mrows * TC_ROWB;              // mrows is a multiple of 8: every plane starts 512-aligned
     const unsigned a_stage = TC_NPL * a_plane;
@@ -215,6 +219,154 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same contraction with the operand roles exchanged ("slots in M"): A = table tile of 128 channel slots, B = the
+// spectra rows of a tile of <= 128 overlap-save blocks, re and im planes stacked along N (they are adjacent in the stage):
+//   D1 = T_re . [F_re | F_im]^T  (TMEM columns 0 .. 2 mrows)        D2 = T_im . [F_re | F_im]^T  (columns 2 mrows .. 4 mrows)
+//   Z_re[c][b] = D1[c][b] - D2[c][mrows + b]                         Z_im[c][b] = D1[c][mrows + b] + D2[c][b]
+// A tcgen05.mma of M = 128 costs max(M, 128) N / 256 cycles whatever its rows hold, so the block rows belong on the N side
+// when a pass has few of them: C3 (D = 5120: 29 blocks per 2^25-sample step) issues M128 x N64 instead of M128 x N128 with
+// 29 of 128 rows used, for twice the slots — a quarter of the tensor-pipe time per slot — and reads every spectra tile once per
+// 128 slots instead of once per 64.  TMEM lane = channel slot: an epilogue warp stores 32 adjacent slots of one block per
+// instruction (256-byte rows of Z[q][b][slots]).  Row tiles of up to 64 blocks run a 3-stage operand ring (<= 72 KB per
+// stage); 65..128 blocks (N up to 256, all 512 TMEM columns) a 2-stage ring of <= 96 KB stages — the table, which is what
+// such a pass is bound by, is then streamed once per 128 blocks (row tiles of one table tile start whenever an SM frees up:
+// measured at C3, three 64-block tiles re-read most of the table from DRAM, not from L2).
+// ------------------------------------------------------------------------------------------------
+constexpr int TT_SLOTS = 128;                               // channel slots per CTA (the MMA's M)
+constexpr unsigned TT_A_PLANE = TT_SLOTS * TC_ROWB;         // 8192
+constexpr unsigned TT_A_STAGE = TC_NPL * TT_A_PLANE;        // 49152
+
+__device__ __forceinline__ void umma_desc(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <unsigned COLS, int ST>
+__global__ void __launch_bounds__(192, 1)
+fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT, float2* __restrict__ Z, int B, int Dp,
+                       int slots, int nbt, int mrows, int nsplit, int M)
+{
+    extern __shared__ unsigned char tc_smem_raw[];
+    __shared__ unsigned long long bars[2 * ST + 1];               // full[ST], empty[ST], accumulators ready
+    __shared__ unsigned tmem_slot;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // slot groups fastest: the CTAs that share a spectra tile run side by side (one DRAM read, L2 hits for the others); row
+    // tiles next, so that a table tile needed by several row tiles is still in L2
+    const int ngroups = (slots + TT_SLOTS - 1) / TT_SLOTS;
+    const int cg = blockIdx.x % ngroups;
+    const int q = (blockIdx.x / ngroups) / nbt, bt = (blockIdx.x / ngroups) % nbt;
+    const int b0 = bt * mrows;
+    const int rows = min(mrows, B - b0);
+    const int all_chunks = Dp / TC_KC;
+    const int ch0 = (int)(((long long)all_chunks * blockIdx.z) / nsplit);
+    const int nchunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / nsplit) - ch0;
+    Z += (size_t)blockIdx.z * M * B * slots;
+
+    const unsigned f_plane = (unsigned)mrows * TC_ROWB;              // mrows is a multiple of 16: planes stay 512-aligned
+    const unsigned stage_bytes = TT_A_STAGE + TC_NPL * f_plane;
+    const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    const unsigned bar_acc = bar0 + 8 * (2 * ST);
+    const unsigned ncols = 2u * (unsigned)mrows;                     // N of one MMA = width of D1 (and of D2)
+
+    if (tid == 0) {
+        for (int s = 0; s < ST; s++) {
+            mbar_init(bar0 + 8 * s, 1);
+            mbar_init(bar0 + 8 * (ST + s), 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (wid == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_slot)),
+                     "r"(COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem = tmem_slot;
+
+    if (wid == 0) {
+        if (lane == 0) {
+            for (int ch = 0; ch < nchunks; ch++) {
+                const int stage = ch % ST, use = ch / ST;
+                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (ST + stage);
+                mbar_wait(empty, (use & 1) ^ 1);
+                mbar_expect_tx(full, stage_bytes);
+                const unsigned sa = smem0 + stage * stage_bytes;
+                // slot rows past the group's last slot / block rows past the tile's last block come from the next bin (or are
+                // zero-filled past the tensor): they only feed accumulator lanes / columns that are never stored
+                tma_load_3d(sa, &mapT, (ch0 + ch) * TC_KC, q * slots + cg * TT_SLOTS, 0, full);
+                tma_load_3d(sa + TT_A_STAGE, &mapF, (ch0 + ch) * TC_KC, q * B + b0, 0, full);
+            }
+        }
+        __syncwarp();
+    } else if (wid == 1) {
+        if (lane == 0) {
+            // D = F32, A = B = BF16, both K-major, N = 2 mrows, M = 128
+            const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
+            for (int ch = 0; ch < nchunks; ch++) {
+                const int stage = ch % ST, use = ch / ST;
+                mbar_wait(bar0 + 8 * stage, use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const unsigned sa = smem0 + stage * stage_bytes, sf = sa + TT_A_STAGE;
+#pragma unroll
+                for (int kk = 0; kk < TC_KC / 16; kk++) {
+#pragma unroll
+                    for (int p = 0; p < 6; p++) {
+                        const int lt = kTcProd[p][0], lf = kTcProd[p][1];
+                        const unsigned long long d_re = smem_desc(sa + (unsigned)(2 * lt) * TT_A_PLANE + kk * 32);
+                        const unsigned long long d_im = smem_desc(sa + (unsigned)(2 * lt + 1) * TT_A_PLANE + kk * 32);
+                        const unsigned long long d_f = smem_desc(sf + (unsigned)(2 * lf) * f_plane + kk * 32);   // [F_re ; F_im] of level lf
+                        const unsigned acc = (ch | kk | p) != 0;
+                        umma_desc(tmem, d_re, d_f, idesc, acc);           // D1 += T_re . [F_re | F_im]^T
+                        umma_desc(tmem + ncols, d_im, d_f, idesc, acc);   // D2 += T_im . [F_re | F_im]^T
+                    }
+                }
+                umma_commit(bar0 + 8 * (ST + stage));
+            }
+            umma_commit(bar_acc);
+        }
+        __syncwarp();
+    } else {
+        // epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31; thread <-> channel slot, columns <-> blocks
+        const int quarter = wid & 3;
+        const int c = cg * TT_SLOTS + quarter * 32 + lane;
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const unsigned trow = tmem + ((unsigned)(quarter * 32) << 16);
+        float2* zc = Z + ((size_t)q * B + b0) * slots + c;
+#pragma unroll 1
+        for (int bb = 0; bb < rows; bb += 16) {
+            float d1r[16], d1i[16], d2r[16], d2i[16];
+            tmem_ld16(trow + bb, d1r);                                 // T_re . F_re
+            tmem_ld16(trow + mrows + bb, d1i);                         // T_re . F_im
+            tmem_ld16(trow + ncols + bb, d2r);                         // T_im . F_re
+            tmem_ld16(trow + ncols + mrows + bb, d2i);                 // T_im . F_im
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (c < slots) {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (bb + i < rows) zc[(size_t)(bb + i) * slots] = make_float2(d1r[i] - d2i[i], d1i[i] + d2r[i]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (wid == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -240,35 +392,82 @@ int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows,
     return OWRX_OK;
 }
 
+// split-K factor (one CTA per SM): waves of CTAs, each 1/sp of a tile plus a fixed prologue / epilogue worth about three chunks;
+// the split that wastes the least of the last wave (192 tiles of 160 chunks on 148 SMs: 3 -> 4 waves of a third instead of 2 whole)
+int tc_plan_split(long long tiles, int chunks, int sm_count)
+{
+    int best = 1;
+    double best_cost = 1e30;
+    for (int sp = 1; sp <= std::min(FC_MAXSPLIT, chunks); sp++) {
+        const double cost = (double)((tiles * sp + sm_count - 1) / sm_count) * (1.0 / sp + 3.0 / chunks);
+        if (cost < best_cost * 0.97) { best_cost = cost; best = sp; }
+    }
+    return best;
+}
+
 }  // namespace
 
-size_t fc_tc_plane_elems_F(const FcShape& sh, int B) { return (size_t)FC_M * B * sh.Dp; }
-size_t fc_tc_plane_elems_tab(const FcShape& sh) { return (size_t)FC_M * sh.slots * sh.Dp; }
+size_t fc_tc_plane_elems_F(const FcShape& sh, int B) { return (size_t)sh.M * B * sh.Dp; }
+size_t fc_tc_plane_elems_tab(const FcShape& sh) { return (size_t)sh.M * sh.slots * sh.Dp; }
 
 int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tabp, int B, float2* d_Z, int sm_count, int* nsplit_out,
                           cudaStream_t st)
 {
     static const int force_split = getenv("OWRX_FC_SPLIT") ? atoi(getenv("OWRX_FC_SPLIT")) : 0;
-    // row tiles of <= 128 blocks, balanced, a multiple of 8 rows (the swizzle atom)
-    const int nbt = (B + 127) / 128;
-    const int mrows = std::min(128, (((B + nbt - 1) / nbt) + 7) / 8 * 8);
-    const unsigned stage_bytes = TC_NPL * (unsigned)mrows * TC_ROWB + TC_B_STAGE;
-    const size_t smem = (size_t)TC_ST * stage_bytes + 1024;
-    const long long tiles = (long long)FC_M * nbt * (sh.slots / FC_CG);
+    // 0: blocks in M, 1: slots in M; read per launch (a host-side lookup) so that one process can exercise both forms
+    const char* ff = getenv("OWRX_FC_TC_FORM");
+    const int force_form = ff ? atoi(ff) : -1;
     const int chunks = sh.Dp / TC_KC;
     CUtensorMap mapA, mapB;
     int rc;
-    if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)FC_M * B, (unsigned)mrows)) != OWRX_OK) return rc;
-    if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)FC_M * sh.slots, (unsigned)FC_CG)) != OWRX_OK) return rc;
+    // ---- blocks in M: row tiles of <= 128 blocks, balanced, a multiple of 8 rows (the swizzle atom); 64 slots per CTA
+    const int nbt = (B + 127) / 128;
+    const int mrows = std::min(128, (((B + nbt - 1) / nbt) + 7) / 8 * 8);
+    // ---- slots in M: row tiles of <= 128 blocks (a multiple of 16: the epilogue reads 16 TMEM columns at a time); 128 slots per CTA
+    const int nbt_t = (B + 127) / 128;
+    const int mrows_t = std::min(128, (((B + nbt_t - 1) / nbt_t) + 15) / 16 * 16);
+    // tensor-pipe cycles per 32-branch chunk and 64 slots: 24 MMAs of max(M, 128) N / 256 cycles each
+    const long long cyc_m = 24ll * 64 * nbt, cyc_t = 24ll * mrows_t * nbt_t / 2;
+    const bool slots_in_m = force_form >= 0 ? (force_form == 1 && sh.slots >= FC_CG) : (sh.slots >= TT_SLOTS && cyc_t < cyc_m);
 
-    // ---- one tile per CTA (split-K only when the tiles alone cannot occupy the machine)
-    int nsplit = tiles >= sm_count ? 1 : (int)std::min<long long>(FC_MAXSPLIT, (sm_count + tiles - 1) / tiles);
-    nsplit = std::max(1, std::min(nsplit, chunks));
+    if (slots_in_m) {
+        const int ngroups = (sh.slots + TT_SLOTS - 1) / TT_SLOTS;
+        const unsigned stage_bytes = TT_A_STAGE + TC_NPL * (unsigned)mrows_t * TC_ROWB;
+        const int stages = mrows_t <= 64 ? 3 : 2;
+        const size_t smem = (size_t)stages * stage_bytes + 1024;
+        const long long tiles = (long long)sh.M * nbt_t * ngroups;
+        if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows_t)) != OWRX_OK) return rc;
+        if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)TT_SLOTS)) != OWRX_OK) return rc;
+        int nsplit = tc_plan_split(tiles, chunks, sm_count);
+        if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks}));
+        *nsplit_out = nsplit;
+        const dim3 grid((unsigned)tiles, 1, (unsigned)nsplit);
+        // TMEM columns: D1 | D2, each 2 mrows wide; the allocation is a power of two >= 32
+#define OWRX_TCT_LAUNCH(COLS, ST)                                                                                                        \
+        do {                                                                                                                             \
+            OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tct_kernel<COLS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+            fc_contract_tct_kernel<COLS, ST><<<grid, 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt_t, mrows_t, nsplit, sh.M); \
+        } while (0)
+        if (mrows_t <= 16) OWRX_TCT_LAUNCH(64, 3);
+        else if (mrows_t <= 32) OWRX_TCT_LAUNCH(128, 3);
+        else if (mrows_t <= 64) OWRX_TCT_LAUNCH(256, 3);
+        else OWRX_TCT_LAUNCH(512, 2);
+#undef OWRX_TCT_LAUNCH
+        OWRX_LAUNCH_CHECK();
+        return OWRX_OK;
+    }
+
+    const unsigned stage_bytes = TC_NPL * (unsigned)mrows * TC_ROWB + TC_B_STAGE;
+    const size_t smem = (size_t)TC_ST * stage_bytes + 1024;
+    const long long tiles = (long long)sh.M * nbt * (sh.slots / FC_CG);
+    if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows)) != OWRX_OK) return rc;
+    if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)FC_CG)) != OWRX_OK) return rc;
+
+    int nsplit = tc_plan_split(tiles, chunks, sm_count);
     if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks}));
     *nsplit_out = nsplit;
     OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fc_contract_tc_kernel<<<dim3((unsigned)(FC_M * nbt), (unsigned)(sh.slots / FC_CG), (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp,
-                                                                                                                          sh.slots, nbt, mrows, nsplit);
+    fc_contract_tc_kernel<<<dim3((unsigned)tiles, 1, (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt, mrows, nsplit, sh.M);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }

@@ -443,8 +443,9 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     }
     g->fc_taps.resize((size_t)g->T);
     for (int t = 0; t < g->T; t++) g->fc_taps[(size_t)t] = (float)h[t];
-    g->fc = FcShape{g->D, g->T, P, FC_M - P + 1, (g->D + FC_DPAD - 1) / FC_DPAD * FC_DPAD, g->slots};
-    g->fc_ok = g->D >= 8 && P <= FC_M / 4;
+    const int fcM = fc_pick_fft_size(g->D, P);
+    g->fc = FcShape{g->D, g->T, P, fcM - P + 1, (g->D + FC_DPAD - 1) / FC_DPAD * FC_DPAD, g->slots, fcM};
+    g->fc_ok = g->D >= 8 && P <= fcM / 2;
     int rc;
     if ((rc = dev_alloc(&g->d_taps, ht.size())) != OWRX_OK) return rc;
     OWRX_CUDA(cudaMemcpy(g->d_taps, ht.data(), ht.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -844,7 +845,7 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
     }
     // zero-fill on `st` (a non-blocking stream: a legacy-stream cudaMemset would not be ordered before the table kernel)
     if (!tc && !g->d_fc_tab) {
-        const size_t tab_bytes = (size_t)FC_M * sh.Dp * S * sizeof(float2);
+        const size_t tab_bytes = (size_t)sh.M * sh.Dp * S * sizeof(float2);
         OWRX_CUDA(cudaMalloc((void**)&g->d_fc_tab, tab_bytes));
         OWRX_CUDA(cudaMemsetAsync(g->d_fc_tab, 0, tab_bytes, st));
         g->fc_tab_rate.assign((size_t)S, NAN);
@@ -882,8 +883,9 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
     }
     // ---- scratch for up to Bmax blocks per pass (branch spectra: 16 B per complex as packed-FMA operands, 12 B as bf16 planes)
     const size_t blocks_total = (n_k + (size_t)sh.Kb - 1) / (size_t)sh.Kb;
-    const size_t per_block = (size_t)FC_M * sh.Dp * (tc ? (size_t)FC_TC_PLANES * 2 : sizeof(float4));
-    const size_t Bmax = std::max<size_t>(1, std::min<size_t>(4096, ((size_t)512 << 20) / per_block));
+    const size_t per_block = (size_t)sh.M * sh.Dp * (tc ? (size_t)FC_TC_PLANES * 2 : sizeof(float4));
+    // (a pass is cut when its spectra exceed 1 GB: every cut re-reads the table)
+    const size_t Bmax = std::max<size_t>(1, std::min<size_t>(4096, ((size_t)1 << 30) / per_block));
     const size_t need = std::min(blocks_total, Bmax);
     const size_t z_cap = std::max(g->fc_blocks_cap, g->fc_blocks_cap_tc);
     if (need > z_cap || (!tc && need > g->fc_blocks_cap) || (tc && need > g->fc_blocks_cap_tc)) {
@@ -901,7 +903,7 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
     }
     if (!g->d_fc_Z) {
         const size_t cap = std::max(g->fc_blocks_cap, g->fc_blocks_cap_tc);
-        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * cap * (size_t)FC_M * S * sizeof(float2)));
+        OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * cap * (size_t)sh.M * S * sizeof(float2)));
     }
     float2* out = reinterpret_cast<float2*>(g->s1.append_ptr());
     for (size_t b0 = 0; b0 < blocks_total; b0 += Bmax) {

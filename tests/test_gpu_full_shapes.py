@@ -1,7 +1,7 @@
 """GPU parity at the BASELINE configurations' OWN shapes, against the CPU oracle (task 1a):
 
   C2  10 MS/s, the full 2^24-sample bench block, 64 channels resident, 6 of them compared with the oracle per form
-  C3  61.44 MS/s -> 12 kHz (D = 5120, T = 136533), 64 channels in ONE group, the form OWRX_FIR_AUTO picks for that pass
+  C3  61.44 MS/s -> 12 kHz (D = 5120, T = 136533), 128 channels in ONE group: the form OWRX_FIR_AUTO picks and every other one
   C5  20 MS/s -> 250 kHz IF (D = 80, T = 2133) -> band-pass 3125 taps -> WFM -> 48 kHz, 8 channels
 
 Every case records its worst relative RMS per form in gpurun_out/parity_margins.json (copied to profiles/ per round), so the
@@ -107,22 +107,61 @@ def test_c2_full_block_against_the_oracle(gpu):
             assert form == "fastconv_tc"          # 88 overlap-save blocks: the tensor-core contraction
 
 
-def test_c3_shape_64_channels_in_one_group_auto_form(gpu):
-    """61.44 MS/s -> 12 kHz: D = 5120, T = 136533, no fractional stage; 64 channels share one group and one pass"""
+def _if_float64(iq, fs, out, offset_hz, bandpass_hz):
+    """Shift + FirDecimate + Bandpass of one channel in float64 (the oracle's float32 taps, exact phases; integer decimation
+    only): the yardstick for the float32 noise of BOTH implementations when the channel sits 70 dB below the wideband power"""
+    D, frac, transition, cutoff = oracle.decimator_params(fs, out)
+    assert frac == 1.0
+    T = oracle.filter_len(transition)
+    h = oracle.firdes_lowpass(T, cutoff / D).astype(np.float64)
+    rate = -offset_hz / fs
+    n_k = (len(iq) - T) // D + 1
+    x = iq.astype(np.complex128)
+    ph = rate * (np.arange(len(iq), dtype=np.float64) + 1.0)
+    x *= np.exp(2j * np.pi * (ph - np.floor(ph)))
+    y = np.empty(n_k, np.complex128)
+    for k in range(n_k):
+        y[k] = np.dot(x[k * D:k * D + T], h)
+    bt = oracle.firdes_bandpass(oracle.filter_len(320.0 / out), bandpass_hz[0] / out, bandpass_hz[1] / out).astype(np.complex128)
+    return np.convolve(y, bt)[:n_k]                                # causal, zero initial history (oc_bandpass)
+
+
+def test_c3_shape_128_channels_in_one_group_every_form(gpu, monkeypatch):
+    """61.44 MS/s -> 12 kHz: D = 5120, T = 136533, no fractional stage; 128 channels (one GPU's share of BASELINE config 3 on
+    8 GPUs) share one group and one pass.  AUTO here = 64-point branch FFTs + the slots-in-M tensor-core contraction; the other
+    arrangements (blocks in M, 256-point FFTs, the FP32-pipe contraction) run beside it.  The wideband signal is the 64-carrier
+    plan of round 1 (weakest carrier 67 dB below full scale); channels 64..127 tune 1 Hz beside channels 0..63.  At this depth
+    the float32 noise of ANY evaluation — the oracle's 136 533-term float32 sums included — is a few 1e-5 of the channel level,
+    so the three weakest channels are also measured against a float64 evaluation: GPU and oracle each against the yardstick"""
     fs, out = 61.44e6, 12000
-    cars = carrier_plan(64, fs, seed=31)
+    cars64 = carrier_plan(64, fs, seed=31)
+    cars = cars64 + [dict(c, offset=c["offset"] + 1) for c in cars64]
     n = 136533 + 5120 * (750 * 2 + 40)
-    iq = _gpu_iq(n, fs, cars, seed=31)
+    iq = _gpu_iq(n, fs, cars64, seed=31)
     refs = _oracle_many(iq, fs, out, cars, fast_shift=False)
-    for mode in ("auto", "fastconv_tc"):
-        form, res = _run_bank(iq, fs, out, cars, mode)
+    weakest = [int(i) for i in np.argsort([c["amp"] for c in cars64])[:3]]
+    with ThreadPoolExecutor(max_workers=3) as ex:
+        truth = dict(zip(weakest, ex.map(lambda i: _if_float64(iq, fs, out, cars[i]["offset"], BANDPASS[cars[i]["kind"]]), weakest)))
+    oracle_vs_f64 = max(rel_rms(refs[i]["if_"], truth[i]) for i in weakest)
+    monkeypatch.delenv("OWRX_FC_M", raising=False)
+    monkeypatch.delenv("OWRX_FC_TC_FORM", raising=False)
+    for mode, env in (("auto", {}), ("fastconv_tc", {"OWRX_FC_TC_FORM": "0"}), ("fastconv_tc", {"OWRX_FC_M": "256"}),
+                      ("fastconv_tc", {"OWRX_FC_M": "256", "OWRX_FC_TC_FORM": "0"}), ("fastconv", {})):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            form, res = _run_bank(iq, fs, out, cars, mode)
         worst_if, worst_dm = 0.0, 0.0
         for (if_, dm), ref in zip(res, refs):
             assert len(if_) == len(ref["if_"]) >= 1500 and len(dm) == len(ref["demod"]) >= 1500
             worst_if, worst_dm = max(worst_if, rel_rms(if_, ref["if_"])), max(worst_dm, rel_rms(dm, ref["demod"]))
-        _record("C3 shape (61.44 MS/s, 64 ch in one group)", "%s->%s" % (mode, form), worst_if_rel_rms=worst_if,
-                worst_demod_rel_rms=worst_dm, tolerance=TOL)
-        assert worst_if <= TOL and worst_dm <= TOL, (mode, form, worst_if, worst_dm)
+        gpu_vs_f64 = max(rel_rms(res[i][0], truth[i]) for i in weakest)
+        tag = "%s->%s%s" % (mode, form, "".join(" %s=%s" % (k[5:], v) for k, v in sorted(env.items())))
+        _record("C3 shape (61.44 MS/s, 128 ch in one group)", tag, worst_if_rel_rms=worst_if, worst_demod_rel_rms=worst_dm,
+                weakest3_if_vs_float64=gpu_vs_f64, oracle_weakest3_if_vs_float64=oracle_vs_f64, tolerance=TOL)
+        assert worst_if <= TOL and worst_dm <= TOL and gpu_vs_f64 <= TOL, (tag, worst_if, worst_dm, gpu_vs_f64)
+        if mode == "auto":
+            assert form == "fastconv_tc"
 
 
 def test_c5_shape_wfm_from_20msps(gpu):

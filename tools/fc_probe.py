@@ -54,6 +54,8 @@ def main():
     shapes = {
         "C2": dict(fs=10e6, out_rate=12000, n_ch=64, block=1 << 24),
         "C3/8": dict(fs=61.44e6, out_rate=12000, n_ch=128, block=1 << 24),
+        "C3/8L": dict(fs=61.44e6, out_rate=12000, n_ch=128, block=1 << 25, steps=8),
+        "C3": dict(fs=61.44e6, out_rate=12000, n_ch=1024, block=1 << 25, steps=3),
         "C5": dict(fs=20e6, out_rate=250000, n_ch=128, block=1 << 23, wfm=True, audio_rate=48000.0, tau=50e-6),
     }
     pick = [a for a in sys.argv[1:] if a in shapes] or list(shapes)
