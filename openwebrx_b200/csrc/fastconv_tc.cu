@@ -228,14 +228,12 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 // when a pass has few of them: C3 (D = 5120: 29 blocks per 2^25-sample step) issues M128 x N64 instead of M128 x N128 with
 // 29 of 128 rows used, for twice the slots — a quarter of the tensor-pipe time per slot — and reads every spectra tile once per
 // 128 slots instead of once per 64.  TMEM lane = channel slot: an epilogue warp stores 32 adjacent slots of one block per
-// instruction (256-byte rows of Z[q][b][slots]).  Row tiles of up to 64 blocks run a 3-stage operand ring (<= 72 KB per
-// stage); 65..128 blocks (N up to 256, all 512 TMEM columns) a 2-stage ring of <= 96 KB stages — the table, which is what
-// such a pass is bound by, is then streamed once per 128 blocks (row tiles of one table tile start whenever an SM frees up:
-// measured at C3, three 64-block tiles re-read most of the table from DRAM, not from L2).
+// instruction (256-byte rows of Z[q][b][slots]).  Row tiles hold up to 128 blocks (N up to 256, all 512 TMEM columns), so the
+// table — what such a pass is bound by — is streamed once per 128 blocks (row tiles of one table tile start whenever an SM
+// frees up: measured at C3, three 64-block tiles re-read most of the table from DRAM, not from L2).
 // ------------------------------------------------------------------------------------------------
 constexpr int TT_SLOTS = 128;                               // channel slots per CTA (the MMA's M)
-constexpr unsigned TT_A_PLANE = TT_SLOTS * TC_ROWB;         // 8192
-constexpr unsigned TT_A_STAGE = TC_NPL * TT_A_PLANE;        // 49152
+constexpr int TT_MAXST = 8;                                 // most ring stages (mbarrier slots)
 
 __device__ __forceinline__ void umma_desc(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
 {
@@ -247,14 +245,24 @@ __device__ __forceinline__ void umma_desc(unsigned tmem_d, unsigned long long da
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// K-major shared-memory matrix descriptor for rows of `rowb` bytes (64: SWIZZLE_64B, 32: SWIZZLE_32B), SBO = 8 rows
+__device__ __forceinline__ unsigned long long smem_desc_rows(unsigned addr, unsigned rowb)
+{
+    const unsigned long long layout = rowb == 64 ? 4ull : 6ull;
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)((8u * rowb) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
 
-template <unsigned COLS, int ST>
+// kc = branches per ring stage: 32 (64-byte operand rows, two K = 16 steps per stage) or 16 (32-byte rows, one step).  What a
+// table-bound pass needs is bytes in flight: an SM streams (stages x stage bytes) per (load latency + MMA time of a stage).  With
+// 128-slot table tiles a 32-branch stage is 48 KB + 6 x 64 B per block row — only two fit beside 96 block rows, and the ring then
+// delivers 2 stages per (2.0 + 1.2) us: 52 GB/s per SM, below the SM's share of DRAM.  16-branch stages halve the granule: five of
+// 42 KB fit, 5 per (2.0 + 0.6) us.
 __global__ void __launch_bounds__(192, 1)
 fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT, float2* __restrict__ Z, int B, int Dp,
-                       int slots, int nbt, int mrows, int nsplit, int M)
+                       int slots, int nbt, int mrows, int nsplit, int M, int kc, int nst, unsigned tmem_cols)
 {
     extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ unsigned long long bars[2 * ST + 1];               // full[ST], empty[ST], accumulators ready
+    __shared__ unsigned long long bars[2 * TT_MAXST + 1];            // full[nst], empty[nst], accumulators ready
     __shared__ unsigned tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // slot groups fastest: the CTAs that share a spectra tile run side by side (one DRAM read, L2 hits for the others); row
@@ -264,29 +272,31 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
     const int q = (blockIdx.x / ngroups) / nbt, bt = (blockIdx.x / ngroups) % nbt;
     const int b0 = bt * mrows;
     const int rows = min(mrows, B - b0);
-    const int all_chunks = Dp / TC_KC;
+    const int all_chunks = Dp / kc;
     const int ch0 = (int)(((long long)all_chunks * blockIdx.z) / nsplit);
     const int nchunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / nsplit) - ch0;
     Z += (size_t)blockIdx.z * M * B * slots;
 
-    const unsigned f_plane = (unsigned)mrows * TC_ROWB;              // mrows is a multiple of 16: planes stay 512-aligned
-    const unsigned stage_bytes = TT_A_STAGE + TC_NPL * f_plane;
+    const unsigned rowb = (unsigned)kc * 2;                          // bytes per operand row of a stage
+    const unsigned t_plane = TT_SLOTS * rowb, t_stage = TC_NPL * t_plane;
+    const unsigned f_plane = (unsigned)mrows * rowb;                 // mrows is a multiple of 16: planes stay 256-byte aligned
+    const unsigned stage_bytes = t_stage + TC_NPL * f_plane;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
-    const unsigned bar_acc = bar0 + 8 * (2 * ST);
+    const unsigned bar_acc = bar0 + 8 * (2 * TT_MAXST);
     const unsigned ncols = 2u * (unsigned)mrows;                     // N of one MMA = width of D1 (and of D2)
 
     if (tid == 0) {
-        for (int s = 0; s < ST; s++) {
+        for (int s = 0; s < nst; s++) {
             mbar_init(bar0 + 8 * s, 1);
-            mbar_init(bar0 + 8 * (ST + s), 1);
+            mbar_init(bar0 + 8 * (TT_MAXST + s), 1);
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (wid == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tmem_slot)),
-                     "r"(COLS)
+                     "r"(tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -297,16 +307,18 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
 
     if (wid == 0) {
         if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
             for (int ch = 0; ch < nchunks; ch++) {
-                const int stage = ch % ST, use = ch / ST;
-                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (ST + stage);
-                mbar_wait(empty, (use & 1) ^ 1);
+                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (TT_MAXST + stage);
+                mbar_wait(empty, phase ^ 1);
                 mbar_expect_tx(full, stage_bytes);
                 const unsigned sa = smem0 + stage * stage_bytes;
                 // slot rows past the group's last slot / block rows past the tile's last block come from the next bin (or are
                 // zero-filled past the tensor): they only feed accumulator lanes / columns that are never stored
-                tma_load_3d(sa, &mapT, (ch0 + ch) * TC_KC, q * slots + cg * TT_SLOTS, 0, full);
-                tma_load_3d(sa + TT_A_STAGE, &mapF, (ch0 + ch) * TC_KC, q * B + b0, 0, full);
+                tma_load_3d(sa, &mapT, (ch0 + ch) * kc, q * slots + cg * TT_SLOTS, 0, full);
+                tma_load_3d(sa + t_stage, &mapF, (ch0 + ch) * kc, q * B + b0, 0, full);
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
         }
         __syncwarp();
@@ -314,25 +326,27 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
         if (lane == 0) {
             // D = F32, A = B = BF16, both K-major, N = 2 mrows, M = 128
             const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
+            const int ksteps = kc / 16;
+            int stage = 0;
+            unsigned phase = 0;
             for (int ch = 0; ch < nchunks; ch++) {
-                const int stage = ch % ST, use = ch / ST;
-                mbar_wait(bar0 + 8 * stage, use & 1);
+                mbar_wait(bar0 + 8 * stage, phase);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const unsigned sa = smem0 + stage * stage_bytes, sf = sa + TT_A_STAGE;
-#pragma unroll
-                for (int kk = 0; kk < TC_KC / 16; kk++) {
+                const unsigned sa = smem0 + stage * stage_bytes, sf = sa + t_stage;
+                for (int kk = 0; kk < ksteps; kk++) {
 #pragma unroll
                     for (int p = 0; p < 6; p++) {
                         const int lt = kTcProd[p][0], lf = kTcProd[p][1];
-                        const unsigned long long d_re = smem_desc(sa + (unsigned)(2 * lt) * TT_A_PLANE + kk * 32);
-                        const unsigned long long d_im = smem_desc(sa + (unsigned)(2 * lt + 1) * TT_A_PLANE + kk * 32);
-                        const unsigned long long d_f = smem_desc(sf + (unsigned)(2 * lf) * f_plane + kk * 32);   // [F_re ; F_im] of level lf
+                        const unsigned long long d_re = smem_desc_rows(sa + (unsigned)(2 * lt) * t_plane + kk * 32, rowb);
+                        const unsigned long long d_im = smem_desc_rows(sa + (unsigned)(2 * lt + 1) * t_plane + kk * 32, rowb);
+                        const unsigned long long d_f = smem_desc_rows(sf + (unsigned)(2 * lf) * f_plane + kk * 32, rowb);   // [F_re ; F_im] of level lf
                         const unsigned acc = (ch | kk | p) != 0;
                         umma_desc(tmem, d_re, d_f, idesc, acc);           // D1 += T_re . [F_re | F_im]^T
                         umma_desc(tmem + ncols, d_im, d_f, idesc, acc);   // D2 += T_im . [F_re | F_im]^T
                     }
                 }
-                umma_commit(bar0 + 8 * (ST + stage));
+                umma_commit(bar0 + 8 * (TT_MAXST + stage));
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
             umma_commit(bar_acc);
         }
@@ -363,7 +377,7 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (wid == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -371,7 +385,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // bf16 tensor [6 planes][rows][cols] (cols contiguous) with a (32 cols x box_rows x 6 planes) box, SWIZZLE_64B
-int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_rows)
+int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_rows, unsigned kc = TC_KC)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -383,11 +397,11 @@ int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows,
     }
     const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)TC_NPL};
     const cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * rows * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)TC_KC, box_rows, (cuuint32_t)TC_NPL};
+    const cuuint32_t box[3] = {(cuuint32_t)kc, box_rows, (cuuint32_t)TC_NPL};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled (bf16 planes) failed (%d)", (int)r);
     return OWRX_OK;
 }
@@ -431,28 +445,26 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
     const bool slots_in_m = force_form >= 0 ? (force_form == 1 && sh.slots >= FC_CG) : (sh.slots >= TT_SLOTS && cyc_t < cyc_m);
 
     if (slots_in_m) {
+        // OWRX_FC_TCT_KC = 32: the 64-byte-row stages of the first version (A/B runs)
+        const char* kce = getenv("OWRX_FC_TCT_KC");
+        const int kc = kce && atoi(kce) == 32 ? 32 : 16;
+        const int chunks_t = sh.Dp / kc;
         const int ngroups = (sh.slots + TT_SLOTS - 1) / TT_SLOTS;
-        const unsigned stage_bytes = TT_A_STAGE + TC_NPL * (unsigned)mrows_t * TC_ROWB;
-        const int stages = mrows_t <= 64 ? 3 : 2;
+        const unsigned stage_bytes = TC_NPL * (unsigned)(TT_SLOTS + mrows_t) * (unsigned)kc * 2;
+        const int stages = std::max(2, std::min(TT_MAXST, (int)(((size_t)(220 << 10)) / stage_bytes)));
         const size_t smem = (size_t)stages * stage_bytes + 1024;
         const long long tiles = (long long)sh.M * nbt_t * ngroups;
-        if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows_t)) != OWRX_OK) return rc;
-        if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)TT_SLOTS)) != OWRX_OK) return rc;
-        int nsplit = tc_plan_split(tiles, chunks, sm_count);
-        if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks}));
+        if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows_t, (unsigned)kc)) != OWRX_OK) return rc;
+        if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)TT_SLOTS, (unsigned)kc)) != OWRX_OK) return rc;
+        int nsplit = tc_plan_split(tiles, chunks_t, sm_count);
+        if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks_t}));
         *nsplit_out = nsplit;
-        const dim3 grid((unsigned)tiles, 1, (unsigned)nsplit);
         // TMEM columns: D1 | D2, each 2 mrows wide; the allocation is a power of two >= 32
-#define OWRX_TCT_LAUNCH(COLS, ST)                                                                                                        \
-        do {                                                                                                                             \
-            OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tct_kernel<COLS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-            fc_contract_tct_kernel<COLS, ST><<<grid, 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt_t, mrows_t, nsplit, sh.M); \
-        } while (0)
-        if (mrows_t <= 16) OWRX_TCT_LAUNCH(64, 3);
-        else if (mrows_t <= 32) OWRX_TCT_LAUNCH(128, 3);
-        else if (mrows_t <= 64) OWRX_TCT_LAUNCH(256, 3);
-        else OWRX_TCT_LAUNCH(512, 2);
-#undef OWRX_TCT_LAUNCH
+        unsigned cols = 32;
+        while (cols < 4u * (unsigned)mrows_t) cols *= 2;
+        OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fc_contract_tct_kernel<<<dim3((unsigned)tiles, 1, (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt_t, mrows_t,
+                                                                                               nsplit, sh.M, kc, stages, cols);
         OWRX_LAUNCH_CHECK();
         return OWRX_OK;
     }

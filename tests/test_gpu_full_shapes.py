@@ -145,8 +145,10 @@ def test_c3_shape_128_channels_in_one_group_every_form(gpu, monkeypatch):
     oracle_vs_f64 = max(rel_rms(refs[i]["if_"], truth[i]) for i in weakest)
     monkeypatch.delenv("OWRX_FC_M", raising=False)
     monkeypatch.delenv("OWRX_FC_TC_FORM", raising=False)
+    monkeypatch.delenv("OWRX_FC_TCT_KC", raising=False)
     for mode, env in (("auto", {}), ("fastconv_tc", {"OWRX_FC_TC_FORM": "0"}), ("fastconv_tc", {"OWRX_FC_M": "256"}),
-                      ("fastconv_tc", {"OWRX_FC_M": "256", "OWRX_FC_TC_FORM": "0"}), ("fastconv", {})):
+                      ("fastconv_tc", {"OWRX_FC_M": "256", "OWRX_FC_TC_FORM": "0"}), ("fastconv_tc", {"OWRX_FC_TCT_KC": "32"}),
+                      ("fastconv", {})):
         with monkeypatch.context() as mp:
             for k, v in env.items():
                 mp.setenv(k, v)

@@ -15,6 +15,7 @@ from openwebrx_b200.synth import BANDPASS, carrier_plan                 # noqa: 
 
 
 def run(fs, out_rate, n_ch, block, mode, steps=20, wfm=False, **kw):
+    steps = int(os.environ.get("FC_PROBE_STEPS", steps))                # short runs under ncu
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev); g.manual_seed(1)
     iq = 1e-3 * torch.randn(block, 2, device=dev, generator=g)
