@@ -29,12 +29,7 @@ namespace owrx {
 
 namespace {
 
-constexpr int TC_KC = 32;                                   // branches per stage = one 64-byte swizzle row of bf16
-constexpr int TC_ST = 3;                                    // pipeline stages
 constexpr int TC_NPL = 6;                                   // planes: 3 levels x (re, im)
-constexpr unsigned TC_ROWB = TC_KC * 2;                     // bytes per tile row
-constexpr unsigned TC_B_PLANE = FC_CG * TC_ROWB;            // 4096
-constexpr unsigned TC_B_STAGE = TC_NPL * TC_B_PLANE;        // 24576
 constexpr unsigned TC_COLS = 256;                           // TMEM columns: D1 | D2
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
@@ -63,12 +58,6 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
                  "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
-}
-// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in [0,14), LBO unused (one
-// swizzle atom along K), SBO = 8 rows x 64 B = 512 >> 4 in [32,46), version 1 in [46,48), layout type 4 (SWIZZLE_64B) in [61,64)
-__device__ __forceinline__ unsigned long long smem_desc(unsigned addr)
-{
-    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major,
 // N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
@@ -99,41 +88,67 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float* v)
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+constexpr int TT_MAXST = 8;                                 // most ring stages (mbarrier slots)
+
+__device__ __forceinline__ void umma_desc(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor) for operand rows of `rowb` bytes — one swizzle atom
+// along K (64: SWIZZLE_64B, layout type 4; 32: SWIZZLE_32B, type 6): start >> 4 in [0,14), LBO unused, SBO = 8 rows >> 4 in
+// [32,46), version 1 in [46,48), layout type in [61,64)
+__device__ __forceinline__ unsigned long long smem_desc_rows(unsigned addr, unsigned rowb)
+{
+    const unsigned long long layout = rowb == 64 ? 4ull : 6ull;
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)((8u * rowb) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
 // the six partial products (A level, B level), smallest first
 __constant__ int kTcProd[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
 
-__global__ void __launch_bounds__(192, 1)
+// kc = branches per ring stage: 32 (64-byte operand rows, SWIZZLE_64B, two K = 16 steps per stage: round 1's form, OWRX_FC_TC_KC=32)
+// or 16 (32-byte rows, SWIZZLE_32B, one step; default).  With 16-branch stages three stages of a 64-slot x 88-block tile are
+// 88 KB, so TWO CTAs share an SM (256 TMEM columns each): C2's 256 tiles are all resident at once — no second, 73 %-full wave —
+// and an SM keeps two operand streams in flight.
+__global__ void __launch_bounds__(192, 2)
 fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float2* __restrict__ Z, int B, int Dp,
-                      int slots, int nbt, int mrows, int nsplit, int M)
+                      int slots, int nbt, int mrows, int nsplit, int M, int kc, int nst)
 {
     extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ unsigned long long bars[2 * TC_ST + 1];               // full[ST], empty[ST], accumulators ready
+    __shared__ unsigned long long bars[2 * TT_MAXST + 1];            // full[nst], empty[nst], accumulators ready
     __shared__ unsigned tmem_slot;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // channel groups fastest: the CTAs that share a spectra tile (same bin and row tile, different 64-slot groups) are launched
-    // side by side, so the tile is read from DRAM once and from L2 by the others (C3, 1024 slots: 16 groups re-read 0.47 GB of
-    // spectra each — a third of the kernel's DRAM traffic when the launch order kept them 256 CTAs apart)
+    // side by side, so the tile is read from DRAM once and from L2 by the others
     const int ngroups = slots / FC_CG;
     const int cg = blockIdx.x % ngroups;
     const int q = (blockIdx.x / ngroups) / nbt, bt = (blockIdx.x / ngroups) % nbt;
     const int b0 = bt * mrows;
     const int rows = min(mrows, B - b0);
-    const int all_chunks = Dp / TC_KC;
+    const int all_chunks = Dp / kc;
     const int ch0 = (int)(((long long)all_chunks * blockIdx.z) / nsplit);
     const int nchunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / nsplit) - ch0;
     Z += (size_t)blockIdx.z * M * B * slots;
 
-    const unsigned a_plane = (unsigned)mrows * TC_ROWB;              // mrows is a multiple of 8: every plane starts 512-aligned
+    const unsigned rowb = (unsigned)kc * 2;                          // bytes per operand row of a stage
+    const unsigned a_plane = (unsigned)mrows * rowb;                 // mrows is a multiple of 8: every plane starts on a swizzle atom
     const unsigned a_stage = TC_NPL * a_plane;
-    const unsigned stage_bytes = a_stage + TC_B_STAGE;
+    const unsigned b_plane = FC_CG * rowb;
+    const unsigned stage_bytes = a_stage + TC_NPL * b_plane;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
-    const unsigned bar_acc = bar0 + 8 * (2 * TC_ST);
+    const unsigned bar_acc = bar0 + 8 * (2 * TT_MAXST);
 
     if (tid == 0) {
-        for (int s = 0; s < TC_ST; s++) {
+        for (int s = 0; s < nst; s++) {
             mbar_init(bar0 + 8 * s, 1);                               // full: the producer's expect_tx arrival
-            mbar_init(bar0 + 8 * (TC_ST + s), 1);                     // empty: one tcgen05.commit arrival
+            mbar_init(bar0 + 8 * (TT_MAXST + s), 1);                  // empty: one tcgen05.commit arrival
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -151,40 +166,44 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
     if (wid == 0) {
         if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
             for (int ch = 0; ch < nchunks; ch++) {
-                const int stage = ch % TC_ST, use = ch / TC_ST;
-                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (TC_ST + stage);
-                mbar_wait(empty, (use & 1) ^ 1);                      // the MMAs that read this slot have completed
+                const unsigned full = bar0 + 8 * stage, empty = bar0 + 8 * (TT_MAXST + stage);
+                mbar_wait(empty, phase ^ 1);                          // the MMAs that read this slot have completed
                 mbar_expect_tx(full, stage_bytes);
                 const unsigned sa = smem0 + stage * stage_bytes;
                 // rows past the tile's last block come from the next bin (or are zero-filled past the tensor): they only
                 // feed accumulator rows that are never stored
-                tma_load_3d(sa, &mapA, (ch0 + ch) * TC_KC, q * B + b0, 0, full);
-                tma_load_3d(sa + a_stage, &mapB, (ch0 + ch) * TC_KC, q * slots + cg * FC_CG, 0, full);
+                tma_load_3d(sa, &mapA, (ch0 + ch) * kc, q * B + b0, 0, full);
+                tma_load_3d(sa + a_stage, &mapB, (ch0 + ch) * kc, q * slots + cg * FC_CG, 0, full);
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
         }
         __syncwarp();
     } else if (wid == 1) {
         if (lane == 0) {
+            const int ksteps = kc / 16;
+            int stage = 0;
+            unsigned phase = 0;
             for (int ch = 0; ch < nchunks; ch++) {
-                const int stage = ch % TC_ST, use = ch / TC_ST;
-                mbar_wait(bar0 + 8 * stage, use & 1);                 // the stage's bytes have landed
+                mbar_wait(bar0 + 8 * stage, phase);                   // the stage's bytes have landed
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned sa = smem0 + stage * stage_bytes, sb = sa + a_stage;
-#pragma unroll
-                for (int kk = 0; kk < TC_KC / 16; kk++) {
+                for (int kk = 0; kk < ksteps; kk++) {
 #pragma unroll
                     for (int p = 0; p < 6; p++) {
                         const int la = kTcProd[p][0], lb = kTcProd[p][1];
-                        const unsigned long long d_re = smem_desc(sa + (unsigned)(2 * la) * a_plane + kk * 32);
-                        const unsigned long long d_im = smem_desc(sa + (unsigned)(2 * la + 1) * a_plane + kk * 32);
-                        const unsigned long long d_b = smem_desc(sb + (unsigned)(2 * lb) * TC_B_PLANE + kk * 32);
+                        const unsigned long long d_re = smem_desc_rows(sa + (unsigned)(2 * la) * a_plane + kk * 32, rowb);
+                        const unsigned long long d_im = smem_desc_rows(sa + (unsigned)(2 * la + 1) * a_plane + kk * 32, rowb);
+                        const unsigned long long d_b = smem_desc_rows(sb + (unsigned)(2 * lb) * b_plane + kk * 32, rowb);
                         const unsigned acc = (ch | kk | p) != 0;
                         umma(tmem, d_re, d_b, acc);                   // D1 += F_re . [T_re | T_im]
                         umma(tmem + 128, d_im, d_b, acc);             // D2 += F_im . [T_re | T_im]
                     }
                 }
-                umma_commit(bar0 + 8 * (TC_ST + stage));              // slot free once these MMAs have read it
+                umma_commit(bar0 + 8 * (TT_MAXST + stage));           // slot free once these MMAs have read it
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
             umma_commit(bar_acc);                                     // accumulators complete
         }
@@ -233,25 +252,6 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 // frees up: measured at C3, three 64-block tiles re-read most of the table from DRAM, not from L2).
 // ------------------------------------------------------------------------------------------------
 constexpr int TT_SLOTS = 128;                               // channel slots per CTA (the MMA's M)
-constexpr int TT_MAXST = 8;                                 // most ring stages (mbarrier slots)
-
-__device__ __forceinline__ void umma_desc(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major shared-memory matrix descriptor for rows of `rowb` bytes (64: SWIZZLE_64B, 32: SWIZZLE_32B), SBO = 8 rows
-__device__ __forceinline__ unsigned long long smem_desc_rows(unsigned addr, unsigned rowb)
-{
-    const unsigned long long layout = rowb == 64 ? 4ull : 6ull;
-    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)((8u * rowb) >> 4) << 32) | (1ull << 46) | (layout << 61);
-}
-
 // kc = branches per ring stage: 32 (64-byte operand rows, two K = 16 steps per stage) or 16 (32-byte rows, one step).  What a
 // table-bound pass needs is bytes in flight: an SM streams (stages x stage bytes) per (load latency + MMA time of a stage).  With
 // 128-slot table tiles a 32-branch stage is 48 KB + 6 x 64 B per block row — only two fit beside 96 block rows, and the ring then
@@ -385,7 +385,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // bf16 tensor [6 planes][rows][cols] (cols contiguous) with a (32 cols x box_rows x 6 planes) box, SWIZZLE_64B
-int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_rows, unsigned kc = TC_KC)
+int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_rows, unsigned kc)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -431,7 +431,6 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
     // 0: blocks in M, 1: slots in M; read per launch (a host-side lookup) so that one process can exercise both forms
     const char* ff = getenv("OWRX_FC_TC_FORM");
     const int force_form = ff ? atoi(ff) : -1;
-    const int chunks = sh.Dp / TC_KC;
     CUtensorMap mapA, mapB;
     int rc;
     // ---- blocks in M: row tiles of <= 128 blocks, balanced, a multiple of 8 rows (the swizzle atom); 64 slots per CTA
@@ -469,17 +468,24 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
         return OWRX_OK;
     }
 
-    const unsigned stage_bytes = TC_NPL * (unsigned)mrows * TC_ROWB + TC_B_STAGE;
-    const size_t smem = (size_t)TC_ST * stage_bytes + 1024;
+    // OWRX_FC_TC_KC = 32: round 1's 64-byte-row stages, three of them, one CTA per SM (A/B runs)
+    const char* kce = getenv("OWRX_FC_TC_KC");
+    const int kc = kce && atoi(kce) == 32 ? 32 : 16;
+    const int chunks_m = sh.Dp / kc;
+    const unsigned stage_bytes = TC_NPL * (unsigned)(mrows + FC_CG) * (unsigned)kc * 2;
+    // kc = 16: three stages, two CTAs per SM when they fit (<= 110 KB each); kc = 32: three stages
+    const int stages = 3;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
     const long long tiles = (long long)sh.M * nbt * (sh.slots / FC_CG);
-    if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows)) != OWRX_OK) return rc;
-    if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)FC_CG)) != OWRX_OK) return rc;
-
-    int nsplit = tc_plan_split(tiles, chunks, sm_count);
-    if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks}));
+    if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows, (unsigned)kc)) != OWRX_OK) return rc;
+    if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)FC_CG, (unsigned)kc)) != OWRX_OK) return rc;
+    const int per_sm = smem <= (size_t)(113 << 10) ? 2 : 1;
+    int nsplit = tc_plan_split(tiles, chunks_m, sm_count * per_sm);
+    if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks_m}));
     *nsplit_out = nsplit;
     OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fc_contract_tc_kernel<<<dim3((unsigned)tiles, 1, (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt, mrows, nsplit, sh.M);
+    fc_contract_tc_kernel<<<dim3((unsigned)tiles, 1, (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt, mrows, nsplit, sh.M,
+                                                                                          kc, stages);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }

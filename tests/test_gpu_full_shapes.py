@@ -79,7 +79,7 @@ def _run_bank(iq, fs, out, cars, mode, **kw):
     return form, res
 
 
-def test_c2_full_block_against_the_oracle(gpu):
+def test_c2_full_block_against_the_oracle(gpu, monkeypatch):
     """the bench's own block: 2^24 samples at 10 MS/s (D = 833, fraction 1.0004, T = 22223), all 64 channels resident; six
     of them — the two weakest, the two strongest and two in between — are compared with the oracle, per evaluation form"""
     import bench
@@ -89,8 +89,11 @@ def test_c2_full_block_against_the_oracle(gpu):
     order = np.argsort([c["amp"] for c in cars])
     pick = sorted({int(order[0]), int(order[1]), int(order[31]), int(order[32]), int(order[-2]), int(order[-1])})
     refs = dict(zip(pick, _oracle_many(iq, fs, out, [cars[i] for i in pick])))
-    for mode in ("auto", "fastconv", "direct"):
-        form, res = _run_bank(iq, fs, out, cars, mode)
+    for mode, env in (("auto", {}), ("auto", {"OWRX_FC_TC_KC": "32"}), ("fastconv", {}), ("direct", {})):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            form, res = _run_bank(iq, fs, out, cars, mode)
         worst_if, worst_dm, at = 0.0, 0.0, None
         for i in pick:
             if_, dm = res[i]
@@ -100,7 +103,7 @@ def test_c2_full_block_against_the_oracle(gpu):
             if e_dm > worst_dm:
                 at = dict(channel=i, kind=cars[i]["kind"], amp_db=round(20 * np.log10(cars[i]["amp"]), 1))
             worst_if, worst_dm = max(worst_if, e_if), max(worst_dm, e_dm)
-        _record("C2 full block (2^24 x 64 ch, 6 compared)", "%s->%s" % (mode, form), worst_if_rel_rms=worst_if,
+        _record("C2 full block (2^24 x 64 ch, 6 compared)", "%s->%s%s" % (mode, form, " TC_KC=32" if env else ""), worst_if_rel_rms=worst_if,
                 worst_demod_rel_rms=worst_dm, worst_at=at, tolerance=TOL)
         assert worst_if <= TOL and worst_dm <= TOL, (mode, form, worst_if, worst_dm)
         if mode == "auto":
