@@ -279,7 +279,7 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
 
     const unsigned rowb = (unsigned)kc * 2;                          // bytes per operand row of a stage
     const unsigned t_plane = TT_SLOTS * rowb, t_stage = TC_NPL * t_plane;
-    const unsigned f_plane = (unsigned)mrows * rowb;                 // mrows is a multiple of 16: planes stay 256-byte aligned
+    const unsigned f_plane = (unsigned)mrows * rowb;                 // mrows is a multiple of 8: every plane starts on a swizzle atom
     const unsigned stage_bytes = t_stage + TC_NPL * f_plane;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
@@ -436,9 +436,10 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
     // ---- blocks in M: row tiles of <= 128 blocks, balanced, a multiple of 8 rows (the swizzle atom); 64 slots per CTA
     const int nbt = (B + 127) / 128;
     const int mrows = std::min(128, (((B + nbt - 1) / nbt) + 7) / 8 * 8);
-    // ---- slots in M: row tiles of <= 128 blocks (a multiple of 16: the epilogue reads 16 TMEM columns at a time); 128 slots per CTA
+    // ---- slots in M: row tiles of <= 128 blocks, balanced, a multiple of 8 (the swizzle atom; N = 2 mrows is then a multiple
+    // of 16) and at least 16 (the epilogue reads 16 TMEM columns at a time and must stay inside the allocation); 128 slots per CTA
     const int nbt_t = (B + 127) / 128;
-    const int mrows_t = std::min(128, (((B + nbt_t - 1) / nbt_t) + 15) / 16 * 16);
+    const int mrows_t = std::max(16, std::min(128, (((B + nbt_t - 1) / nbt_t) + 7) / 8 * 8));
     // tensor-pipe cycles per 32-branch chunk and 64 slots: 24 MMAs of max(M, 128) N / 256 cycles each
     const long long cyc_m = 24ll * 64 * nbt, cyc_t = 24ll * mrows_t * nbt_t / 2;
     const bool slots_in_m = force_form >= 0 ? (force_form == 1 && sh.slots >= FC_CG) : (sh.slots >= TT_SLOTS && cyc_t < cyc_m);
