@@ -594,12 +594,15 @@ def run_single(args, torch, local, dev):
         M, P = 256, -(-T // D)
         Kb, Dp = M - P + 1, -(-D // 32) * 32
         B = -(-m["n_k"] // Kb)
-        op_bytes = 12.0 * M * B * Dp + 12.0 * M * Dp * n_ch + 8.0 * M * B * n_ch
+        lv = 3 if os.environ.get("OWRX_FC_TC_FMT") == "bf16x3" else 2          # operand split: fp16 x 2 (default) or bf16 x 3
+        eb = 4.0 * lv                                                          # bytes per complex operand entry
+        op_bytes = eb * M * B * Dp + eb * M * Dp * n_ch + 8.0 * M * B * n_ch
         ks = stages["fc_contract"] * 1e-3
-        rk = {"kernel": "fc_contract_tc_kernel (tcgen05 bf16x3 -> FP32 in TMEM; %d blocks x %d branches x %d ch)" % (B, D, n_ch),
+        fmt = "fp16x2, block-scaled" if lv == 2 else "bf16x3"
+        rk = {"kernel": "fc_contract_tc_kernel (tcgen05 %s -> FP32 in TMEM; %d blocks x %d branches x %d ch)" % (fmt, B, D, n_ch),
               "bound": "hbm", "achieved": op_bytes / ks / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": op_bytes / ks / 1e9 / hbm_peak,
               "operand_bytes": op_bytes, "kernel_ms": stages["fc_contract"], "kernel_share_of_step": stages["fc_contract"] / ms_step,
-              "note": "the kernel's OWN operand bytes (bf16x3 spectra + table + Z), not SURVEY 8(d)'s algorithmic bytes"}
+              "note": "the kernel's OWN operand bytes (%s spectra + table + Z), not SURVEY 8(d)'s algorithmic bytes" % fmt}
 
     line = {
         "metric": METRIC, "value": value, "unit": "channel-MS/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

@@ -6,8 +6,11 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 
 namespace owrx {
 
@@ -26,11 +29,19 @@ __device__ __forceinline__ void split_bf16x3(float x, __nv_bfloat16& h, __nv_bfl
     l = __float2bfloat16_rn(r1 - __bfloat162float(m));
 }
 
-// TC = false: tab[q][r][slot] complex float32.  TC = true: bf16 planes Tp[2 level + part][q * slots + slot][r].
-template <bool TC>
+// x 2^k = h + m with two fp16 terms (the block-scaled operand planes of the tensor-core contraction's default form)
+__device__ __forceinline__ void split_f16x2(float x, __half& h, __half& m)
+{
+    h = __float2half_rn(x);
+    m = __float2half_rn(x - __half2float(h));
+}
+
+// TC = 0: tab[q][r][slot] complex float32.  TC = 3: bf16 planes Tp[2 level + part][q * slots + slot][r].  TC = 2: fp16 planes of
+// the entries times tab_scale (a power of two).
+template <int TC>
 __global__ void __launch_bounds__(256)
 fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int slots, int M, const int* __restrict__ slot_list,
-                const double* __restrict__ rate_list, void* __restrict__ tab_out)
+                const double* __restrict__ rate_list, void* __restrict__ tab_out, float tab_scale)
 {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= (long long)M * D) return;
@@ -56,8 +67,19 @@ fc_table_kernel(const float* __restrict__ h, int T, int D, int Dp, int P, int sl
         const double nc = c0 * cw - s0 * sw, ns = c0 * sw + s0 * cw;
         c0 = nc; s0 = ns;
     }
-    if (!TC) {
+    if (TC == 0) {
         reinterpret_cast<float2*>(tab_out)[((size_t)q * Dp + r) * slots + slot] = make_float2((float)ar, (float)ai);
+    } else if (TC == 2) {
+        __half* tp = reinterpret_cast<__half*>(tab_out);
+        const size_t plane = (size_t)M * slots * Dp, at = ((size_t)q * slots + slot) * Dp + r;
+        __half a[2], b[2];
+        split_f16x2((float)ar * tab_scale, a[0], a[1]);
+        split_f16x2((float)ai * tab_scale, b[0], b[1]);
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+            tp[(size_t)(2 * l) * plane + at] = a[l];
+            tp[(size_t)(2 * l + 1) * plane + at] = b[l];
+        }
     } else {
         __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(tab_out);
         const size_t plane = (size_t)M * slots * Dp, at = ((size_t)q * slots + slot) * Dp + r;
@@ -118,11 +140,13 @@ __device__ __forceinline__ void fc_fft_vv(float2* v, float2* seq, const float2* 
 }
 __device__ __forceinline__ void fc_fft256(float2* v, float2* seq, const float2* tw, int g) { fc_fft_vv<16>(v, seq, tw, g); }
 
-// TC = false: F[q][b][r] as (re, re, -im, im).  TC = true: bf16 planes Fp[2 level + part][q * B + b][r].
+// TC = 0: F[q][b][r] as (re, re, -im, im).  TC = 3: bf16 planes Fp[2 level + part][q * B + b][r].  TC = 2: fp16 planes of the
+// spectra times *scale (the pass's power of two, fc_scale_kernel).
 // V = 16: 256-point FFTs (16 threads x 16 points per sequence), V = 8: 64-point FFTs (8 x 8).
-template <bool TC, int V>
+template <int TC, int V>
 __global__ void __launch_bounds__(V * FC_SEQ)
-fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp, int Kb, int B, void* __restrict__ F_out)
+fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp, int Kb, int B, void* __restrict__ F_out,
+                  const float* __restrict__ scale)
 {
     constexpr int M = V * V;
     extern __shared__ float2 fc_smem[];
@@ -144,9 +168,21 @@ fc_forward_kernel(const float2* __restrict__ iq, long long n_lim, int D, int Dp,
 #pragma unroll
     for (int q = 0; q < V; q++) {
         const int bin = g + V * slot<V>(q);
-        if (!TC) {
+        if (TC == 0) {
             // operand layout of the contraction's packed FMAs: (re, re) and (-im, im)
             reinterpret_cast<float4*>(F_out)[((size_t)bin * B + b) * Dp + r] = make_float4(v[q].x, v[q].x, -v[q].y, v[q].y);
+        } else if (TC == 2) {
+            __half* fp = reinterpret_cast<__half*>(F_out);
+            const size_t plane = (size_t)M * B * Dp, at = ((size_t)bin * B + b) * Dp + r;
+            const float sc = __ldg(scale);
+            __half a[2], c[2];
+            split_f16x2(v[q].x * sc, a[0], a[1]);
+            split_f16x2(v[q].y * sc, c[0], c[1]);
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                fp[(size_t)(2 * l) * plane + at] = a[l];
+                fp[(size_t)(2 * l + 1) * plane + at] = c[l];
+            }
         } else {
             __nv_bfloat16* fp = reinterpret_cast<__nv_bfloat16*>(F_out);
             const size_t plane = (size_t)M * B * Dp, at = ((size_t)bin * B + b) * Dp + r;
@@ -367,9 +403,11 @@ fc_contract_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_consta
 template <int V>
 __global__ void __launch_bounds__(V * FC_SEQ)
 fc_inverse_kernel(const float2* __restrict__ Z, int nsplit, int B, int slots, int D, int Kb, const double* __restrict__ ch_rate,
-                  const double* __restrict__ ch_phase, long long k0, long long n_k, float2* __restrict__ out)
+                  const double* __restrict__ ch_phase, long long k0, long long n_k, float2* __restrict__ out,
+                  const float* __restrict__ out_scale)
 {
     constexpr int M = V * V;
+    const float osc = out_scale ? __ldg(out_scale) : 1.0f / M;       // a power of two either way
     extern __shared__ float2 fc_smem[];
     float2* tw = fc_smem;
     float2* seqs = fc_smem + M;
@@ -400,10 +438,41 @@ fc_inverse_kernel(const float2* __restrict__ Z, int nsplit, int B, int slots, in
             t -= floor(t);
             float sn, cs;
             sincospif(2.0f * (float)t, &sn, &cs);
-            const float2 z = make_float2(v[q].x * (1.0f / M), -v[q].y * (1.0f / M));
+            const float2 z = make_float2(v[q].x * osc, -v[q].y * osc);
             out[(size_t)k * slots + c] = cmul(z, make_float2(cs, sn));
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block scaling of the fp16 x 2 operand form: the largest |re|, |im| of the pass's input, then the two powers of two.
+// Non-negative floats order like their bit patterns, so the running maximum is an atomicMax on unsigned.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fc_absmax_kernel(const float2* __restrict__ iq, long long n, unsigned* __restrict__ out)
+{
+    float m = 0.0f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float2 v = __ldg(iq + i);
+        m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+
+__global__ void fc_scale_kernel(const unsigned* __restrict__ absmax_bits, int M, float tab_scale, float* __restrict__ scale)
+{
+    const float a = __uint_as_float(*absmax_bits);
+    int kf = 0;
+    if (a > 0.0f && a < 3.0e38f) {
+        // |F| <= M sqrt(2) max|x|;  2^kf = the largest power of two with M sqrt(2) max|x| 2^kf <= 2^15
+        int e;
+        frexpf(a * (float)M * 1.41421356f, &e);                       // a M sqrt2 = f 2^e, 0.5 <= f < 1  =>  < 2^e
+        kf = max(-100, min(100, 15 - e));
+    }
+    scale[0] = ldexpf(1.0f, kf);
+    scale[1] = ldexpf(1.0f / ((float)M * tab_scale), -kf);            // M and tab_scale are powers of two
 }
 
 constexpr size_t kFftSmem = (256 + FC_SEQ * FC_STR) * sizeof(float2);
@@ -587,19 +656,58 @@ int fc_launch_table(const FcShape& sh, const float* d_h, const int* d_slot_list,
 {
     if (n <= 0) return OWRX_OK;
     const long long total = (long long)sh.M * sh.D;
-    fc_table_kernel<false><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, sh.M, d_slot_list,
-                                                                                              d_rate_list, d_tab);
+    fc_table_kernel<0><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, sh.M, d_slot_list,
+                                                                                          d_rate_list, d_tab, 1.0f);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
 
 int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, void* d_tabp,
-                       cudaStream_t st)
+                       float tab_scale, cudaStream_t st)
 {
     if (n <= 0) return OWRX_OK;
     const long long total = (long long)sh.M * sh.D;
-    fc_table_kernel<true><<<dim3((unsigned)((total + 255) / 256), (unsigned)n), 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, sh.M, d_slot_list,
-                                                                                             d_rate_list, d_tabp);
+    const dim3 grid((unsigned)((total + 255) / 256), (unsigned)n);
+    if (sh.tc_levels == 2)
+        fc_table_kernel<2><<<grid, 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, sh.M, d_slot_list, d_rate_list, d_tabp, tab_scale);
+    else
+        fc_table_kernel<3><<<grid, 256, 0, st>>>(d_h, sh.T, sh.D, sh.Dp, sh.P, sh.slots, sh.M, d_slot_list, d_rate_list, d_tabp, 1.0f);
+    OWRX_LAUNCH_CHECK();
+    return OWRX_OK;
+}
+
+int fc_pick_tc_levels()
+{
+    const char* f = getenv("OWRX_FC_TC_FMT");
+    return f && !strcmp(f, "bf16x3") ? 3 : 2;
+}
+
+float fc_tab_scale(const FcShape& sh, const float* h_taps)
+{
+    if (sh.tc_levels != 2) return 1.0f;
+    // |Tab[q][r]| <= sum_s |h[D s + r]|
+    double bound = 0.0;
+    for (int r = 0; r < sh.D; r++) {
+        double a = 0.0;
+        for (int t = r; t < sh.T; t += sh.D) a += fabs((double)h_taps[t]);
+        bound = std::max(bound, a);
+    }
+    if (!(bound > 0.0) || !std::isfinite(bound)) return 1.0f;
+    int e;
+    frexp(bound, &e);                                                 // bound < 2^e
+    return ldexpf(1.0f, std::max(-100, std::min(100, 14 - e)));
+}
+
+int fc_launch_scale(const FcShape& sh, const float2* iq, long long n, float tab_scale, unsigned* d_work, float* d_scale, cudaStream_t st)
+{
+    OWRX_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned), st));
+    if (sh.tc_levels == 2 && n > 0) {
+        const unsigned blocks = (unsigned)std::min<long long>(148 * 8, (n + 255) / 256);
+        fc_absmax_kernel<<<blocks, 256, 0, st>>>(iq, n, d_work);
+        OWRX_LAUNCH_CHECK();
+    }
+    // levels = 3: the maximum stays 0 => scale (1, 1 / M)
+    fc_scale_kernel<<<1, 1, 0, st>>>(d_work, sh.M, sh.tc_levels == 2 ? tab_scale : 1.0f, d_scale);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
@@ -607,25 +715,34 @@ int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_li
 int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int B, float4* d_F, cudaStream_t st)
 {
     if (sh.M == FC_M_SMALL) {
-        fc_forward_kernel<false, 8><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 8 * FC_SEQ, kFftSmemSmall, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
+        fc_forward_kernel<0, 8><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 8 * FC_SEQ, kFftSmemSmall, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F,
+                                                                                                             nullptr);
     } else {
-        OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-        fc_forward_kernel<false, 16><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F);
+        OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+        fc_forward_kernel<0, 16><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_F,
+                                                                                                            nullptr);
     }
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }
 
-int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, cudaStream_t st)
+template <int TC>
+static int launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, const float* d_scale, cudaStream_t st)
 {
+    const dim3 grid((unsigned)(sh.Dp / FC_SEQ), (unsigned)B);
     if (sh.M == FC_M_SMALL) {
-        fc_forward_kernel<true, 8><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 8 * FC_SEQ, kFftSmemSmall, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp);
+        fc_forward_kernel<TC, 8><<<grid, 8 * FC_SEQ, kFftSmemSmall, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp, d_scale);
     } else {
-        OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-        fc_forward_kernel<true, 16><<<dim3((unsigned)(sh.Dp / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp);
+        OWRX_CUDA(cudaFuncSetAttribute(fc_forward_kernel<TC, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
+        fc_forward_kernel<TC, 16><<<grid, 16 * FC_SEQ, kFftSmem, st>>>(iq, n_lim, sh.D, sh.Dp, sh.Kb, B, d_Fp, d_scale);
     }
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
+}
+
+int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, const float* d_scale, cudaStream_t st)
+{
+    return sh.tc_levels == 2 ? launch_forward_tc<2>(sh, iq, n_lim, B, d_Fp, d_scale, st) : launch_forward_tc<3>(sh, iq, n_lim, B, d_Fp, d_scale, st);
 }
 
 // CTA shape and split-K factor for B blocks: as few row tiles as 96-row CTAs allow, the smallest CTA that covers them, and
@@ -703,15 +820,14 @@ int bpf_launch_inverse(const float2* Y, const float2* in, const int* enabled, in
 }
 
 int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, const double* d_rate, const double* d_phase, long long k0, long long n_k,
-                      float2* out, cudaStream_t st)
+                      float2* out, const float* d_out_scale, cudaStream_t st)
 {
+    const dim3 grid((unsigned)(sh.slots / FC_SEQ), (unsigned)B);
     if (sh.M == FC_M_SMALL) {
-        fc_inverse_kernel<8><<<dim3((unsigned)(sh.slots / FC_SEQ), (unsigned)B), 8 * FC_SEQ, kFftSmemSmall, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb,
-                                                                                                               d_rate, d_phase, k0, n_k, out);
+        fc_inverse_kernel<8><<<grid, 8 * FC_SEQ, kFftSmemSmall, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb, d_rate, d_phase, k0, n_k, out, d_out_scale);
     } else {
         OWRX_CUDA(cudaFuncSetAttribute(fc_inverse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmem));
-        fc_inverse_kernel<16><<<dim3((unsigned)(sh.slots / FC_SEQ), (unsigned)B), 16 * FC_SEQ, kFftSmem, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb,
-                                                                                                            d_rate, d_phase, k0, n_k, out);
+        fc_inverse_kernel<16><<<grid, 16 * FC_SEQ, kFftSmem, st>>>(d_Z, nsplit, B, sh.slots, sh.D, sh.Kb, d_rate, d_phase, k0, n_k, out, d_out_scale);
     }
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;

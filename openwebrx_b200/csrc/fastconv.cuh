@@ -28,6 +28,7 @@ constexpr int FC_MAXSPLIT = 4;   // split-K planes of Z (scratch is sized for th
 struct FcShape {
     int D, T, P, Kb, Dp, slots;
     int M;                       // branch FFT size: FC_M or FC_M_SMALL; Kb = M - P + 1
+    int tc_levels;               // operand split of the tensor-core form: 2 = fp16 x 2 (block-scaled), 3 = bf16 x 3
 };
 
 // Branch FFT size of a group.  Bytes a pass moves ~ 12 M Dp (S + 2 n_k / (M - P + 1)): the per-channel table (M Dp S entries,
@@ -45,18 +46,34 @@ int fc_launch_forward(const FcShape& sh, const float2* iq, long long n_lim, int 
 // d_Z holds FC_MAXSPLIT planes of [M][B][slots]; *nsplit = how many partial-sum planes this launch wrote
 int fc_launch_contract(const FcShape& sh, const float4* d_F, const float2* d_tab, int B, float2* d_Z, int sm_count, int* nsplit, cudaStream_t st);
 // out[(k0 + b Kb + m) * slots + c] for k0 + b Kb + m < n_k; phases are relative to iq[-1] of the whole call
+// d_out_scale: device float the result is multiplied by instead of 1 / M (fc_launch_scale's d_scale + 1), or nullptr
 int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, const double* d_rate, const double* d_phase, long long k0,
-                      long long n_k, float2* out, cudaStream_t st);
+                      long long n_k, float2* out, const float* d_out_scale, cudaStream_t st);
 
-// ---- tensor-core form of the contraction (fastconv_tc.cu): operands as three bf16 terms per float (x = h + m + l),
-// real and imaginary parts in separate K-major planes, plane p = 2 * level + part:
-//   Fp[p][q * B + b][r]  (fc_tc_plane_elems_F bf16 per plane)      Tp[p][q * slots + c][r]  (fc_tc_plane_elems_tab per plane)
-constexpr int FC_TC_PLANES = 6;
+// ---- tensor-core form of the contraction (fastconv_tc.cu): every float operand as `levels` 16-bit terms, real and imaginary
+// parts in separate K-major planes, plane p = 2 * level + part:
+//   Fp[p][q * B + b][r]  (fc_tc_plane_elems_F 16-bit words per plane)      Tp[p][q * slots + c][r]  (fc_tc_plane_elems_tab per plane)
+//   levels = 3: x = h + m + l in bf16 (float's exponent range, no scaling), six partial products;
+//   levels = 2 (default): x = h + m in fp16 (11 + 11 significand bits), three partial products hh + hm + mh — half the tensor-pipe
+//     work and two thirds of the operand bytes.  fp16 has 5 exponent bits, so both operands are scaled by exact powers of two:
+//     the table by 2^kt with max_r sum_s |h[D s + r]| * 2^kt <= 2^14 (fc_tab_scale, host, from the taps), the spectra of a pass by
+//     2^kf with M * sqrt(2) * max|x| * 2^kf <= 2^15, max|x| measured over the pass's input by fc_launch_scale (one extra read
+//     of the block); the inverse FFT multiplies by 2^-(kf + kt) / M.  Powers of two commute with every rounding in between,
+//     so the result does not depend on the scale and IF(x / 2) == IF(x) / 2 stays exact.
+constexpr int FC_TC_MAXPLANES = 6;
+inline int fc_tc_planes(const FcShape& sh) { return 2 * sh.tc_levels; }
+// operand split of new groups: OWRX_FC_TC_FMT = bf16x3 | f16x2 (default f16x2)
+int fc_pick_tc_levels();
+// exact power of two 2^kt for the table of a group with these taps (1 for levels = 3)
+float fc_tab_scale(const FcShape& sh, const float* h_taps);
 size_t fc_tc_plane_elems_F(const FcShape& sh, int B);
 size_t fc_tc_plane_elems_tab(const FcShape& sh);
 int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, void* d_tabp,
-                       cudaStream_t st);
-int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, cudaStream_t st);
+                       float tab_scale, cudaStream_t st);
+// d_scale[0] = 2^kf (what the forward pass multiplies by), d_scale[1] = 2^-(kf + kt) / M (the inverse pass); levels = 3: (1, 1 / M).
+// d_work: 4 bytes of device scratch (the running maximum)
+int fc_launch_scale(const FcShape& sh, const float2* iq, long long n, float tab_scale, unsigned* d_work, float* d_scale, cudaStream_t st);
+int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, const float* d_scale, cudaStream_t st);
 int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tabp, int B, float2* d_Z, int sm_count, int* nsplit,
                           cudaStream_t st);
 

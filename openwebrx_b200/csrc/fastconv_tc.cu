@@ -29,7 +29,6 @@ namespace owrx {
 
 namespace {
 
-constexpr int TC_NPL = 6;                                   // planes: 3 levels x (re, im)
 constexpr unsigned TC_COLS = 256;                           // TMEM columns: D1 | D2
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
@@ -58,20 +57,6 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
                  "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major,
-// N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
-constexpr unsigned TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void umma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
-        : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned bar)
 {
@@ -109,8 +94,17 @@ __device__ __forceinline__ unsigned long long smem_desc_rows(unsigned addr, unsi
     return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)((8u * rowb) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-// the six partial products (A level, B level), smallest first
-__constant__ int kTcProd[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
+// the partial products (A level, B level), smallest first: three levels (bf16) keep the six of weight > 2^-24, two levels (fp16)
+// the three of weight > 2^-22
+__constant__ int kTcProd3[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
+__constant__ int kTcProd2[3][2] = {{1, 0}, {0, 1}, {0, 0}};
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A and B formats at bits 7 and 10 (0 = F16, 1 = BF16),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ unsigned tc_idesc(int levels, unsigned n)
+{
+    const unsigned fmt = levels == 3 ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 // kc = branches per ring stage: 32 (64-byte operand rows, SWIZZLE_64B, two K = 16 steps per stage: round 1's form, OWRX_FC_TC_KC=32)
 // or 16 (32-byte rows, SWIZZLE_32B, one step; default).  With 16-branch stages three stages of a 64-slot x 88-block tile are
@@ -118,7 +112,7 @@ __constant__ int kTcProd[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}
 // and an SM keeps two operand streams in flight.
 __global__ void __launch_bounds__(192, 2)
 fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, float2* __restrict__ Z, int B, int Dp,
-                      int slots, int nbt, int mrows, int nsplit, int M, int kc, int nst)
+                      int slots, int nbt, int mrows, int nsplit, int M, int kc, int nst, int levels)
 {
     extern __shared__ unsigned char tc_smem_raw[];
     __shared__ unsigned long long bars[2 * TT_MAXST + 1];            // full[nst], empty[nst], accumulators ready
@@ -137,10 +131,11 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     Z += (size_t)blockIdx.z * M * B * slots;
 
     const unsigned rowb = (unsigned)kc * 2;                          // bytes per operand row of a stage
+    const unsigned npl = 2u * (unsigned)levels;                      // operand planes: levels x (re, im)
     const unsigned a_plane = (unsigned)mrows * rowb;                 // mrows is a multiple of 8: every plane starts on a swizzle atom
-    const unsigned a_stage = TC_NPL * a_plane;
+    const unsigned a_stage = npl * a_plane;
     const unsigned b_plane = FC_CG * rowb;
-    const unsigned stage_bytes = a_stage + TC_NPL * b_plane;
+    const unsigned stage_bytes = a_stage + npl * b_plane;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
     const unsigned bar_acc = bar0 + 8 * (2 * TT_MAXST);
@@ -184,6 +179,8 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     } else if (wid == 1) {
         if (lane == 0) {
             const int ksteps = kc / 16;
+            const unsigned idesc = tc_idesc(levels, 128u);
+            const int nprod = levels == 3 ? 6 : 3;
             int stage = 0;
             unsigned phase = 0;
             for (int ch = 0; ch < nchunks; ch++) {
@@ -191,15 +188,14 @@ fc_contract_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned sa = smem0 + stage * stage_bytes, sb = sa + a_stage;
                 for (int kk = 0; kk < ksteps; kk++) {
-#pragma unroll
-                    for (int p = 0; p < 6; p++) {
-                        const int la = kTcProd[p][0], lb = kTcProd[p][1];
+                    for (int p = 0; p < nprod; p++) {
+                        const int la = levels == 3 ? kTcProd3[p][0] : kTcProd2[p][0], lb = levels == 3 ? kTcProd3[p][1] : kTcProd2[p][1];
                         const unsigned long long d_re = smem_desc_rows(sa + (unsigned)(2 * la) * a_plane + kk * 32, rowb);
                         const unsigned long long d_im = smem_desc_rows(sa + (unsigned)(2 * la + 1) * a_plane + kk * 32, rowb);
                         const unsigned long long d_b = smem_desc_rows(sb + (unsigned)(2 * lb) * b_plane + kk * 32, rowb);
                         const unsigned acc = (ch | kk | p) != 0;
-                        umma(tmem, d_re, d_b, acc);                   // D1 += F_re . [T_re | T_im]
-                        umma(tmem + 128, d_im, d_b, acc);             // D2 += F_im . [T_re | T_im]
+                        umma_desc(tmem, d_re, d_b, idesc, acc);       // D1 += F_re . [T_re | T_im]
+                        umma_desc(tmem + 128, d_im, d_b, idesc, acc); // D2 += F_im . [T_re | T_im]
                     }
                 }
                 umma_commit(bar0 + 8 * (TT_MAXST + stage));           // slot free once these MMAs have read it
@@ -259,7 +255,7 @@ constexpr int TT_SLOTS = 128;                               // channel slots per
 // 42 KB fit, 5 per (2.0 + 0.6) us.
 __global__ void __launch_bounds__(192, 1)
 fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT, float2* __restrict__ Z, int B, int Dp,
-                       int slots, int nbt, int mrows, int nsplit, int M, int kc, int nst, unsigned tmem_cols)
+                       int slots, int nbt, int mrows, int nsplit, int M, int kc, int nst, unsigned tmem_cols, int levels)
 {
     extern __shared__ unsigned char tc_smem_raw[];
     __shared__ unsigned long long bars[2 * TT_MAXST + 1];            // full[nst], empty[nst], accumulators ready
@@ -278,9 +274,10 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
     Z += (size_t)blockIdx.z * M * B * slots;
 
     const unsigned rowb = (unsigned)kc * 2;                          // bytes per operand row of a stage
-    const unsigned t_plane = TT_SLOTS * rowb, t_stage = TC_NPL * t_plane;
+    const unsigned npl = 2u * (unsigned)levels;                      // operand planes: levels x (re, im)
+    const unsigned t_plane = TT_SLOTS * rowb, t_stage = npl * t_plane;
     const unsigned f_plane = (unsigned)mrows * rowb;                 // mrows is a multiple of 8: every plane starts on a swizzle atom
-    const unsigned stage_bytes = t_stage + TC_NPL * f_plane;
+    const unsigned stage_bytes = t_stage + npl * f_plane;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(tc_smem_raw) + 1023u) & ~1023u;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
     const unsigned bar_acc = bar0 + 8 * (2 * TT_MAXST);
@@ -324,8 +321,8 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
         __syncwarp();
     } else if (wid == 1) {
         if (lane == 0) {
-            // D = F32, A = B = BF16, both K-major, N = 2 mrows, M = 128
-            const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((ncols >> 3) << 17) | ((128u >> 4) << 24);
+            const unsigned idesc = tc_idesc(levels, ncols);          // N = 2 mrows, M = 128
+            const int nprod = levels == 3 ? 6 : 3;
             const int ksteps = kc / 16;
             int stage = 0;
             unsigned phase = 0;
@@ -334,9 +331,8 @@ fc_contract_tct_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned sa = smem0 + stage * stage_bytes, sf = sa + t_stage;
                 for (int kk = 0; kk < ksteps; kk++) {
-#pragma unroll
-                    for (int p = 0; p < 6; p++) {
-                        const int lt = kTcProd[p][0], lf = kTcProd[p][1];
+                    for (int p = 0; p < nprod; p++) {
+                        const int lt = levels == 3 ? kTcProd3[p][0] : kTcProd2[p][0], lf = levels == 3 ? kTcProd3[p][1] : kTcProd2[p][1];
                         const unsigned long long d_re = smem_desc_rows(sa + (unsigned)(2 * lt) * t_plane + kk * 32, rowb);
                         const unsigned long long d_im = smem_desc_rows(sa + (unsigned)(2 * lt + 1) * t_plane + kk * 32, rowb);
                         const unsigned long long d_f = smem_desc_rows(sf + (unsigned)(2 * lf) * f_plane + kk * 32, rowb);   // [F_re ; F_im] of level lf
@@ -385,7 +381,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // bf16 tensor [6 planes][rows][cols] (cols contiguous) with a (32 cols x box_rows x 6 planes) box, SWIZZLE_64B
-int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_rows, unsigned kc)
+int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows, unsigned box_rows, unsigned kc, int levels)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -395,14 +391,14 @@ int make_plane_map(CUtensorMap* map, const void* base, size_t cols, size_t rows,
         if (!fn || qr != cudaDriverEntryPointSuccess) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled is not available");
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)TC_NPL};
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(2 * levels)};
     const cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * rows * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)kc, box_rows, (cuuint32_t)TC_NPL};
+    const cuuint32_t box[3] = {(cuuint32_t)kc, box_rows, (cuuint32_t)(2 * levels)};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    const CUresult r = encode(map, levels == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled (bf16 planes) failed (%d)", (int)r);
+    if (r != CUDA_SUCCESS) return fail(OWRX_E_CUDA, "cuTensorMapEncodeTiled (operand planes) failed (%d)", (int)r);
     return OWRX_OK;
 }
 
@@ -441,7 +437,9 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
     const int nbt_t = (B + 127) / 128;
     const int mrows_t = std::max(16, std::min(128, (((B + nbt_t - 1) / nbt_t) + 7) / 8 * 8));
     // tensor-pipe cycles per 32-branch chunk and 64 slots: 24 MMAs of max(M, 128) N / 256 cycles each
-    const long long cyc_m = 24ll * 64 * nbt, cyc_t = 24ll * mrows_t * nbt_t / 2;
+    const long long cyc_m = 24ll * 64 * nbt, cyc_t = 24ll * mrows_t * nbt_t / 2;   // (the same factor for either operand split)
+    const int lv = sh.tc_levels;
+    const unsigned npl = 2u * (unsigned)lv;
     const bool slots_in_m = force_form >= 0 ? (force_form == 1 && sh.slots >= FC_CG) : (sh.slots >= TT_SLOTS && cyc_t < cyc_m);
 
     if (slots_in_m) {
@@ -450,12 +448,12 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
         const int kc = kce && atoi(kce) == 32 ? 32 : 16;
         const int chunks_t = sh.Dp / kc;
         const int ngroups = (sh.slots + TT_SLOTS - 1) / TT_SLOTS;
-        const unsigned stage_bytes = TC_NPL * (unsigned)(TT_SLOTS + mrows_t) * (unsigned)kc * 2;
+        const unsigned stage_bytes = npl * (unsigned)(TT_SLOTS + mrows_t) * (unsigned)kc * 2;
         const int stages = std::max(2, std::min(TT_MAXST, (int)(((size_t)(220 << 10)) / stage_bytes)));
         const size_t smem = (size_t)stages * stage_bytes + 1024;
         const long long tiles = (long long)sh.M * nbt_t * ngroups;
-        if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows_t, (unsigned)kc)) != OWRX_OK) return rc;
-        if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)TT_SLOTS, (unsigned)kc)) != OWRX_OK) return rc;
+        if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows_t, (unsigned)kc, lv)) != OWRX_OK) return rc;
+        if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)TT_SLOTS, (unsigned)kc, lv)) != OWRX_OK) return rc;
         int nsplit = tc_plan_split(tiles, chunks_t, sm_count);
         if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks_t}));
         *nsplit_out = nsplit;
@@ -464,7 +462,7 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
         while (cols < 4u * (unsigned)mrows_t) cols *= 2;
         OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fc_contract_tct_kernel<<<dim3((unsigned)tiles, 1, (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt_t, mrows_t,
-                                                                                               nsplit, sh.M, kc, stages, cols);
+                                                                                               nsplit, sh.M, kc, stages, cols, lv);
         OWRX_LAUNCH_CHECK();
         return OWRX_OK;
     }
@@ -473,20 +471,20 @@ int fc_launch_contract_tc(const FcShape& sh, const void* d_Fp, const void* d_tab
     const char* kce = getenv("OWRX_FC_TC_KC");
     const int kc = kce && atoi(kce) == 32 ? 32 : 16;
     const int chunks_m = sh.Dp / kc;
-    const unsigned stage_bytes = TC_NPL * (unsigned)(mrows + FC_CG) * (unsigned)kc * 2;
-    // kc = 16: three stages, two CTAs per SM when they fit (<= 110 KB each); kc = 32: three stages
-    const int stages = 3;
+    const unsigned stage_bytes = npl * (unsigned)(mrows + FC_CG) * (unsigned)kc * 2;
+    // kc = 16: as many stages as leave room for two CTAs per SM (<= 110 KB each), at least three; kc = 32: three stages
+    const int stages = kc == 16 ? std::max(3, std::min(TT_MAXST, (int)(((size_t)(108 << 10)) / stage_bytes))) : 3;
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     const long long tiles = (long long)sh.M * nbt * (sh.slots / FC_CG);
-    if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows, (unsigned)kc)) != OWRX_OK) return rc;
-    if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)FC_CG, (unsigned)kc)) != OWRX_OK) return rc;
+    if ((rc = make_plane_map(&mapA, d_Fp, (size_t)sh.Dp, (size_t)sh.M * B, (unsigned)mrows, (unsigned)kc, lv)) != OWRX_OK) return rc;
+    if ((rc = make_plane_map(&mapB, d_tabp, (size_t)sh.Dp, (size_t)sh.M * sh.slots, (unsigned)FC_CG, (unsigned)kc, lv)) != OWRX_OK) return rc;
     const int per_sm = smem <= (size_t)(113 << 10) ? 2 : 1;
     int nsplit = tc_plan_split(tiles, chunks_m, sm_count * per_sm);
     if (force_split) nsplit = std::max(1, std::min({FC_MAXSPLIT, force_split, chunks_m}));
     *nsplit_out = nsplit;
     OWRX_CUDA(cudaFuncSetAttribute(fc_contract_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fc_contract_tc_kernel<<<dim3((unsigned)tiles, 1, (unsigned)nsplit), 192, smem, st>>>(mapA, mapB, d_Z, B, sh.Dp, sh.slots, nbt, mrows, nsplit, sh.M,
-                                                                                          kc, stages);
+                                                                                          kc, stages, lv);
     OWRX_LAUNCH_CHECK();
     return OWRX_OK;
 }

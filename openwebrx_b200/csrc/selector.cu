@@ -281,6 +281,8 @@ struct Group {
     bool fc_ok = false;
     FcShape fc{};
     float* d_fc_h = nullptr; float2* d_fc_tab = nullptr; float4* d_fc_F = nullptr; float2* d_fc_Z = nullptr;
+    float fc_tab_scale = 1.0f;                                 // fp16 x 2 operand form: the table's power of two
+    float* d_fc_scale = nullptr;                               // [0] spectra scale of the pass, [1] output scale, [2] running max (bits)
     int* d_fc_slots = nullptr; double* d_fc_rates = nullptr;
     size_t fc_blocks_cap = 0;
     std::vector<double> fc_tab_rate;                 // per slot: Shift rate its table column was built for (NaN = none)
@@ -369,6 +371,7 @@ void group_release(Group* g)
     cudaFree(g->d_tail_mode2[0]); cudaFree(g->d_tail_mode2[1]); cudaFree(g->d_tail); cudaFree(g->d_tail_count); cudaFree(g->d_tail_s16);
     cudaFree(g->d_tail_bytes);
     cudaFree(g->d_fc_h); cudaFree(g->d_fc_tab); cudaFree(g->d_fc_F); cudaFree(g->d_fc_Z); cudaFree(g->d_fc_slots); cudaFree(g->d_fc_rates);
+    cudaFree(g->d_fc_scale);
     cudaFree(g->d_fc_tabp); cudaFree(g->d_fc_Fp);
     g->s1.release(); g->s2.release(); g->s3.release(); g->f1.release(); g->f1p.release(); g->f1b.release(); g->f2.release(); g->f3.release();
 }
@@ -444,7 +447,8 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     g->fc_taps.resize((size_t)g->T);
     for (int t = 0; t < g->T; t++) g->fc_taps[(size_t)t] = (float)h[t];
     const int fcM = fc_pick_fft_size(g->D, P);
-    g->fc = FcShape{g->D, g->T, P, fcM - P + 1, (g->D + FC_DPAD - 1) / FC_DPAD * FC_DPAD, g->slots, fcM};
+    g->fc = FcShape{g->D, g->T, P, fcM - P + 1, (g->D + FC_DPAD - 1) / FC_DPAD * FC_DPAD, g->slots, fcM, fc_pick_tc_levels()};
+    g->fc_tab_scale = fc_tab_scale(g->fc, g->fc_taps.data());
     g->fc_ok = g->D >= 8 && P <= fcM / 2;
     int rc;
     if ((rc = dev_alloc(&g->d_taps, ht.size())) != OWRX_OK) return rc;
@@ -851,7 +855,7 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         g->fc_tab_rate.assign((size_t)S, NAN);
     }
     if (tc && !g->d_fc_tabp) {
-        const size_t tab_bytes = (size_t)FC_TC_PLANES * fc_tc_plane_elems_tab(sh) * 2;
+        const size_t tab_bytes = (size_t)fc_tc_planes(sh) * fc_tc_plane_elems_tab(sh) * 2;
         OWRX_CUDA(cudaMalloc(&g->d_fc_tabp, tab_bytes));
         OWRX_CUDA(cudaMemsetAsync(g->d_fc_tabp, 0, tab_bytes, st));
         g->fc_tabp_rate.assign((size_t)S, NAN);
@@ -875,7 +879,7 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
             OWRX_CUDA(cudaMemcpyAsync(g->d_fc_slots, sl.data(), sl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
             OWRX_CUDA(cudaMemcpyAsync(g->d_fc_rates, rt.data(), rt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
             // (small pageable sources are staged by the runtime before cudaMemcpyAsync returns: no stream wait, the vectors may go)
-            rc = tc ? fc_launch_table_tc(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tabp, st)
+            rc = tc ? fc_launch_table_tc(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tabp, g->fc_tab_scale, st)
                     : fc_launch_table(sh, g->d_fc_h, g->d_fc_slots, g->d_fc_rates, (int)sl.size(), g->d_fc_tab, st);
             if (rc != OWRX_OK) return rc;
             bank->stats.kernel_launches++;
@@ -883,7 +887,7 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
     }
     // ---- scratch for up to Bmax blocks per pass (branch spectra: 16 B per complex as packed-FMA operands, 12 B as bf16 planes)
     const size_t blocks_total = (n_k + (size_t)sh.Kb - 1) / (size_t)sh.Kb;
-    const size_t per_block = (size_t)sh.M * sh.Dp * (tc ? (size_t)FC_TC_PLANES * 2 : sizeof(float4));
+    const size_t per_block = (size_t)sh.M * sh.Dp * (tc ? (size_t)fc_tc_planes(sh) * 2 : sizeof(float4));
     // (a pass is cut when its spectra exceed 1 GB: every cut re-reads the table)
     const size_t Bmax = std::max<size_t>(1, std::min<size_t>(4096, ((size_t)1 << 30) / per_block));
     const size_t need = std::min(blocks_total, Bmax);
@@ -906,11 +910,18 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * cap * (size_t)sh.M * S * sizeof(float2)));
     }
     float2* out = reinterpret_cast<float2*>(g->s1.append_ptr());
+    if (tc) {
+        // operand scaling of the pass (fp16 x 2 form: one read of the input for its largest magnitude; bf16 x 3: constants)
+        if (!g->d_fc_scale) OWRX_CUDA(cudaMalloc((void**)&g->d_fc_scale, 4 * sizeof(float)));
+        if ((rc = fc_launch_scale(sh, iq, (long long)n_avail, g->fc_tab_scale, reinterpret_cast<unsigned*>(g->d_fc_scale + 2), g->d_fc_scale, st)) != OWRX_OK)
+            return rc;
+        bank->stats.kernel_launches += sh.tc_levels == 2 ? 2 : 1;
+    }
     for (size_t b0 = 0; b0 < blocks_total; b0 += Bmax) {
         const int B = (int)std::min(Bmax, blocks_total - b0);
         const size_t s_off = b0 * (size_t)sh.Kb * (size_t)sh.D;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, true)) != OWRX_OK) return rc;
-        rc = tc ? fc_launch_forward_tc(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_Fp, st)
+        rc = tc ? fc_launch_forward_tc(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_Fp, g->d_fc_scale, st)
                 : fc_launch_forward(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_F, st);
         if (rc != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, false)) != OWRX_OK) return rc;
@@ -921,7 +932,8 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         if (rc != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, false)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, true)) != OWRX_OK) return rc;
-        if ((rc = fc_launch_inverse(sh, g->d_fc_Z, nsplit, B, g->d_rate, g->d_phase, (long long)(b0 * (size_t)sh.Kb), (long long)n_k, out, st)) != OWRX_OK)
+        if ((rc = fc_launch_inverse(sh, g->d_fc_Z, nsplit, B, g->d_rate, g->d_phase, (long long)(b0 * (size_t)sh.Kb), (long long)n_k, out,
+                                    tc ? g->d_fc_scale + 1 : nullptr, st)) != OWRX_OK)
             return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, false)) != OWRX_OK) return rc;
         bank->stats.kernel_launches += 3;
@@ -964,7 +976,7 @@ int group_fir(owrx_bank* bank, Group* g, const float2* iq, size_t n_avail, size_
         // pass): tensor cores win for B > ~21 at 64 slots and B > ~18 at 128.  Measured: C3 (128 slots, B = 15) 0.57 ms on
         // the FP32 pipe vs 0.69 ms on the tensor cores; C2 (64 slots, B = 88) 0.29 vs 0.10 ms.
         const size_t fc_blocks = (n_k + (size_t)g->fc.Kb - 1) / (size_t)g->fc.Kb;
-        const double fp32_cost = 8.0 * (double)fc_blocks * S / 35e12, tc_cost = 12.0 * ((double)fc_blocks + S) / 3.3e12;
+        const double fp32_cost = 8.0 * (double)fc_blocks * S / 35e12, tc_cost = 4.0 * g->fc.tc_levels * ((double)fc_blocks + S) / 3.3e12;
         const bool tc = bank->fir_mode == OWRX_FIR_FASTCONV_TC || (bank->fir_mode == OWRX_FIR_AUTO && fp32_cost > tc_cost);
         bank->fir_form_used = tc ? OWRX_FIR_FASTCONV_TC : OWRX_FIR_FASTCONV;
         if ((rc = g->s1.ensure_new(n_k, st)) != OWRX_OK) return rc;

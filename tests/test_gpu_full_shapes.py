@@ -89,7 +89,8 @@ def test_c2_full_block_against_the_oracle(gpu, monkeypatch):
     order = np.argsort([c["amp"] for c in cars])
     pick = sorted({int(order[0]), int(order[1]), int(order[31]), int(order[32]), int(order[-2]), int(order[-1])})
     refs = dict(zip(pick, _oracle_many(iq, fs, out, [cars[i] for i in pick])))
-    for mode, env in (("auto", {}), ("auto", {"OWRX_FC_TC_KC": "32"}), ("fastconv", {}), ("direct", {})):
+    monkeypatch.delenv("OWRX_FC_TC_FMT", raising=False)
+    for mode, env in (("auto", {}), ("auto", {"OWRX_FC_TC_KC": "32"}), ("auto", {"OWRX_FC_TC_FMT": "bf16x3"}), ("fastconv", {}), ("direct", {})):
         with monkeypatch.context() as mp:
             for k, v in env.items():
                 mp.setenv(k, v)
@@ -103,7 +104,7 @@ def test_c2_full_block_against_the_oracle(gpu, monkeypatch):
             if e_dm > worst_dm:
                 at = dict(channel=i, kind=cars[i]["kind"], amp_db=round(20 * np.log10(cars[i]["amp"]), 1))
             worst_if, worst_dm = max(worst_if, e_if), max(worst_dm, e_dm)
-        _record("C2 full block (2^24 x 64 ch, 6 compared)", "%s->%s%s" % (mode, form, " TC_KC=32" if env else ""), worst_if_rel_rms=worst_if,
+        _record("C2 full block (2^24 x 64 ch, 6 compared)", "%s->%s%s" % (mode, form, "".join(" %s=%s" % (k[5:], v) for k, v in sorted(env.items()))), worst_if_rel_rms=worst_if,
                 worst_demod_rel_rms=worst_dm, worst_at=at, tolerance=TOL)
         assert worst_if <= TOL and worst_dm <= TOL, (mode, form, worst_if, worst_dm)
         if mode == "auto":
@@ -149,9 +150,10 @@ def test_c3_shape_128_channels_in_one_group_every_form(gpu, monkeypatch):
     monkeypatch.delenv("OWRX_FC_M", raising=False)
     monkeypatch.delenv("OWRX_FC_TC_FORM", raising=False)
     monkeypatch.delenv("OWRX_FC_TCT_KC", raising=False)
+    monkeypatch.delenv("OWRX_FC_TC_FMT", raising=False)
     for mode, env in (("auto", {}), ("fastconv_tc", {"OWRX_FC_TC_FORM": "0"}), ("fastconv_tc", {"OWRX_FC_M": "256"}),
                       ("fastconv_tc", {"OWRX_FC_M": "256", "OWRX_FC_TC_FORM": "0"}), ("fastconv_tc", {"OWRX_FC_TCT_KC": "32"}),
-                      ("fastconv", {})):
+                      ("fastconv_tc", {"OWRX_FC_TC_FMT": "bf16x3"}), ("fastconv", {})):
         with monkeypatch.context() as mp:
             for k, v in env.items():
                 mp.setenv(k, v)

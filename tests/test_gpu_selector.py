@@ -11,13 +11,15 @@ pytestmark = pytest.mark.gpu
 
 
 _FORMS = {
-    # name: (OWRX_FIR_MODE, OWRX_FC_TC_FORM, OWRX_FC_M)
-    "direct": ("direct", "0", "256"),
-    "fastconv": ("fastconv", "0", "256"),
-    "fastconv_tc": ("fastconv_tc", "0", "256"),
-    "fastconv_tct": ("fastconv_tc", "1", "256"),
-    "fastconv_m64": ("fastconv", "0", "64"),
-    "fastconv_tct_m64": ("fastconv_tc", "1", "64"),
+    # name: (OWRX_FIR_MODE, OWRX_FC_TC_FORM, OWRX_FC_M, OWRX_FC_TC_FMT)
+    "direct": ("direct", "0", "256", "f16x2"),
+    "fastconv": ("fastconv", "0", "256", "f16x2"),
+    "fastconv_tc": ("fastconv_tc", "0", "256", "f16x2"),
+    "fastconv_tct": ("fastconv_tc", "1", "256", "f16x2"),
+    "fastconv_m64": ("fastconv", "0", "64", "f16x2"),
+    "fastconv_tct_m64": ("fastconv_tc", "1", "64", "f16x2"),
+    "fastconv_tc_bf16x3": ("fastconv_tc", "0", "256", "bf16x3"),
+    "fastconv_tct_m64_bf16x3": ("fastconv_tc", "1", "64", "bf16x3"),
 }
 
 
@@ -25,14 +27,16 @@ _FORMS = {
 def fir_mode(request, monkeypatch):
     """every parity case runs through all evaluations of Shift + FirDecimate: the direct-form K3 kernel, the polyphase
     fast-convolution path K3F with its contraction on the FP32 pipe, and K3F with the contraction on the tensor cores
-    (tcgen05, bf16x3 operands) in both operand arrangements — overlap-save blocks in the MMA's M (fc_contract_tc_kernel) and
-    channel slots in M (fc_contract_tct_kernel: what the cost model picks for groups of >= 128 slots and short passes) —
-    and with both branch FFT sizes (256 points; 64 points: the default of groups with D >= 2048)
-    (owrx_bank_create reads OWRX_FIR_MODE, a new group OWRX_FC_M, fc_launch_contract_tc OWRX_FC_TC_FORM per launch)"""
-    mode, form, m = _FORMS[request.param]
+    (tcgen05) in both operand arrangements — overlap-save blocks in the MMA's M (fc_contract_tc_kernel) and channel slots in
+    M (fc_contract_tct_kernel: what the cost model picks for groups of >= 128 slots and short passes) — with both branch FFT
+    sizes (256 points; 64 points: the default of groups with D >= 2048) and both operand splits (block-scaled fp16 x 2: the
+    default; bf16 x 3)
+    (owrx_bank_create reads OWRX_FIR_MODE, a new group OWRX_FC_M and OWRX_FC_TC_FMT, fc_launch_contract_tc OWRX_FC_TC_FORM per launch)"""
+    mode, form, m, fmt = _FORMS[request.param]
     monkeypatch.setenv("OWRX_FIR_MODE", str(N.FIR_MODES[mode]))
     monkeypatch.setenv("OWRX_FC_TC_FORM", form)
     monkeypatch.setenv("OWRX_FC_M", m)
+    monkeypatch.setenv("OWRX_FC_TC_FMT", fmt)
     return request.param
 
 AUDIO_TOL = 1e-4       # north_star: demodulated audio within 1e-4 relative RMS (float32), pre-AGC
@@ -332,7 +336,7 @@ def test_full_size_block_properties(gpu, fir_mode):
         # the noise floor of the evaluation itself (block partition differs between the two feeds): FP32-pipe forms 1e-5,
         # bf16x3 tensor-core contraction 3e-5 on the weakest channels (50 dB below the wideband power), 4e-5 with 64-point
         # branch FFTs (six times the overlap-save blocks: measured 3.1e-5; not the size AUTO uses at D = 833); the spec is 1e-4
-        floor = 4e-5 if fir_mode == "fastconv_tct_m64" else 3e-5 if fir_mode.startswith("fastconv_tc") else 1e-5
+        floor = 4e-5 if fir_mode.startswith("fastconv_tct_m64") else 3e-5 if fir_mode.startswith("fastconv_tc") else 1e-5
         assert rel_rms(two[c][0], one[c][0]) <= floor, c
         assert rel_rms(two[c][1], one[c][1]) <= AUDIO_TOL, c
         assert np.array_equal(half[c][0], one[c][0] * np.complex64(0.5)), c
