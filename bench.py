@@ -364,7 +364,7 @@ def time_bank_device(torch, bank, blocks, n, stream, steps, warmup):
     ms = e0.elapsed_time(e1) / steps
     prof = bank.profile_read_ex(reset=True)
     bank.profile(False)
-    stages = {k: v[0] / v[1] for k, v in prof.items() if v[1]}
+    stages = {k: v[0] / steps for k, v in prof.items() if v[1]}          # device time per step (a stage may be several brackets)
     return ms, stages, (N.lib.owrx_launch_count() - l0) / steps
 
 
@@ -594,7 +594,8 @@ def run_single(args, torch, local, dev):
         M, P = 256, -(-T // D)
         Kb, Dp = M - P + 1, -(-D // 32) * 32
         B = -(-m["n_k"] // Kb)
-        lv = 3 if os.environ.get("OWRX_FC_TC_FMT") == "bf16x3" else 2          # operand split: fp16 x 2 (default) or bf16 x 3
+        fmt_env = os.environ.get("OWRX_FC_TC_FMT")                             # operand split (fc_pick_tc_levels): fp16 x 2 for D >= 2048
+        lv = 3 if fmt_env == "bf16x3" else 2 if fmt_env == "f16x2" else (2 if D >= 2048 else 3)
         eb = 4.0 * lv                                                          # bytes per complex operand entry
         op_bytes = eb * M * B * Dp + eb * M * Dp * n_ch + 8.0 * M * B * n_ch
         ks = stages["fc_contract"] * 1e-3
@@ -701,7 +702,7 @@ def run_sharded(args, torch, dist, world, rank, local, dev):
     launches = N.lib.owrx_launch_count() - l0
     prof = bank.profile_read_ex(reset=True)
     bank.profile(False)
-    stages = {k: v[0] / v[1] for k, v in prof.items() if v[1]}
+    stages = {k: v[0] / args.steps for k, v in prof.items() if v[1]}     # device time per step (a stage may be several brackets)
     hop_ms = hop.mean_ms()
     t = torch.tensor([ms_total, hop_ms or 0.0], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -448,17 +448,43 @@ fc_inverse_kernel(const float2* __restrict__ Z, int nsplit, int B, int slots, in
 // Block scaling of the fp16 x 2 operand form: the largest |re|, |im| of the pass's input, then the two powers of two.
 // Non-negative floats order like their bit patterns, so the running maximum is an atomicMax on unsigned.
 // ------------------------------------------------------------------------------------------------
+// CTA = 8192 consecutive samples (64 KB), CTAs in REVERSE order of the block: the forward FFTs that follow read the block
+// from its start, so what this pass read last is what they need first and the 126 MB L2 still holds it.  Small fixed-size CTAs
+// rather than a grid-stride loop: beside the other streams' kernels not every CTA of a persistent grid finds a slot at once,
+// and a late one would run the whole duration again.
+constexpr int FC_AMAX_CHUNK = 8192;
 __global__ void __launch_bounds__(256)
 fc_absmax_kernel(const float2* __restrict__ iq, long long n, unsigned* __restrict__ out)
 {
+    __shared__ float wmax[8];
     float m = 0.0f;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        const float2 v = __ldg(iq + i);
-        m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+    const long long c0 = (long long)(gridDim.x - 1 - blockIdx.x) * FC_AMAX_CHUNK;
+    const float2* p = iq + c0 + threadIdx.x;
+    const int left = (int)min((long long)FC_AMAX_CHUNK, n - c0);
+    if (left == FC_AMAX_CHUNK) {
+#pragma unroll
+        for (int k = 0; k < FC_AMAX_CHUNK / 256; k += 8) {          // eight independent loads in flight per thread
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldg(p + (k + u) * 256);
+#pragma unroll
+            for (int u = 0; u < 8; u++) m = fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y)));
+        }
+    } else {
+        for (int i = threadIdx.x; i < left; i += 256) {
+            const float2 v = __ldg(iq + c0 + i);
+            m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {                                 // one atomic per CTA: same-address atomics serialise in L2
+#pragma unroll
+        for (int w = 1; w < 8; w++) m = fmaxf(m, wmax[w]);
+        if (m > 0.0f) atomicMax(out, __float_as_uint(m));
+    }
 }
 
 __global__ void fc_scale_kernel(const unsigned* __restrict__ absmax_bits, int M, float tab_scale, float* __restrict__ scale)
@@ -676,10 +702,16 @@ int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_li
     return OWRX_OK;
 }
 
-int fc_pick_tc_levels()
+int fc_pick_tc_levels(int D)
 {
-    const char* f = getenv("OWRX_FC_TC_FMT");
-    return f && !strcmp(f, "bf16x3") ? 3 : 2;
+    if (const char* f = getenv("OWRX_FC_TC_FMT")) {
+        if (!strcmp(f, "bf16x3")) return 3;
+        if (!strcmp(f, "f16x2")) return 2;
+    }
+    // fp16 x 2 pays where the contraction is what a pass costs — large decimations: few outputs per table entry (C3: 2.83 ->
+    // 2.05 ms per step).  With a short decimation (C2, C5) the contraction is a third of the FIR chain, the chain is not what
+    // bounds the step, and the extra read of the input for max|x| costs the other streams what the smaller operands save.
+    return D >= 2048 ? 2 : 3;
 }
 
 float fc_tab_scale(const FcShape& sh, const float* h_taps)
@@ -702,7 +734,7 @@ int fc_launch_scale(const FcShape& sh, const float2* iq, long long n, float tab_
 {
     OWRX_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned), st));
     if (sh.tc_levels == 2 && n > 0) {
-        const unsigned blocks = (unsigned)std::min<long long>(148 * 8, (n + 255) / 256);
+        const unsigned blocks = (unsigned)((n + FC_AMAX_CHUNK - 1) / FC_AMAX_CHUNK);
         fc_absmax_kernel<<<blocks, 256, 0, st>>>(iq, n, d_work);
         OWRX_LAUNCH_CHECK();
     }

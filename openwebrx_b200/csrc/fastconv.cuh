@@ -54,7 +54,7 @@ int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, c
 // parts in separate K-major planes, plane p = 2 * level + part:
 //   Fp[p][q * B + b][r]  (fc_tc_plane_elems_F 16-bit words per plane)      Tp[p][q * slots + c][r]  (fc_tc_plane_elems_tab per plane)
 //   levels = 3: x = h + m + l in bf16 (float's exponent range, no scaling), six partial products;
-//   levels = 2 (default): x = h + m in fp16 (11 + 11 significand bits), three partial products hh + hm + mh — half the tensor-pipe
+//   levels = 2 (default of groups with a large decimation): x = h + m in fp16 (11 + 11 significand bits), three partial products hh + hm + mh — half the tensor-pipe
 //     work and two thirds of the operand bytes.  fp16 has 5 exponent bits, so both operands are scaled by exact powers of two:
 //     the table by 2^kt with max_r sum_s |h[D s + r]| * 2^kt <= 2^14 (fc_tab_scale, host, from the taps), the spectra of a pass by
 //     2^kf with M * sqrt(2) * max|x| * 2^kf <= 2^15, max|x| measured over the pass's input by fc_launch_scale (one extra read
@@ -62,15 +62,15 @@ int fc_launch_inverse(const FcShape& sh, const float2* d_Z, int nsplit, int B, c
 //     so the result does not depend on the scale and IF(x / 2) == IF(x) / 2 stays exact.
 constexpr int FC_TC_MAXPLANES = 6;
 inline int fc_tc_planes(const FcShape& sh) { return 2 * sh.tc_levels; }
-// operand split of new groups: OWRX_FC_TC_FMT = bf16x3 | f16x2 (default f16x2)
-int fc_pick_tc_levels();
+// operand split of a new group: fp16 x 2 for D >= 2048, else bf16 x 3; OWRX_FC_TC_FMT = bf16x3 | f16x2 overrides
+int fc_pick_tc_levels(int D);
 // exact power of two 2^kt for the table of a group with these taps (1 for levels = 3)
 float fc_tab_scale(const FcShape& sh, const float* h_taps);
 size_t fc_tc_plane_elems_F(const FcShape& sh, int B);
 size_t fc_tc_plane_elems_tab(const FcShape& sh);
 int fc_launch_table_tc(const FcShape& sh, const float* d_h, const int* d_slot_list, const double* d_rate_list, int n, void* d_tabp,
                        float tab_scale, cudaStream_t st);
-// d_scale[0] = 2^kf (what the forward pass multiplies by), d_scale[1] = 2^-(kf + kt) / M (the inverse pass); levels = 3: (1, 1 / M).
+// levels = 2 only: d_scale[0] = 2^kf (what the forward pass multiplies by), d_scale[1] = 2^-(kf + kt) / M (the inverse pass).
 // d_work: 4 bytes of device scratch (the running maximum)
 int fc_launch_scale(const FcShape& sh, const float2* iq, long long n, float tab_scale, unsigned* d_work, float* d_scale, cudaStream_t st);
 int fc_launch_forward_tc(const FcShape& sh, const float2* iq, long long n_lim, int B, void* d_Fp, const float* d_scale, cudaStream_t st);

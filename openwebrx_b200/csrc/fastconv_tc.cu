@@ -2,22 +2,26 @@
 //
 // Same contraction as fc_contract_kernel (fastconv.cu): Z[q][b][c] = sum_{r<Dp} F[q][b][r] * Tab[q][r][c], complex, the
 // per-channel half of pycsdr Shift + FirDecimate (reference call sites csdr/chain/selector.py:29,57,95,140).  Per bin q it
-// is a dense GEMM [B blocks x Dp branches] . [Dp x 64 slots] — the "true dense contraction" north_star asks for before
+// is a dense GEMM [B blocks x Dp branches] . [Dp x slots] — the "true dense contraction" north_star asks for before
 // tensor cores may be used.  FP32 results are required (1e-4 relative RMS on channels up to 50 dB below the wideband
-// power), so every FP32 operand is carried as THREE bf16 terms x = h + m + l (8 + 8 + 8 significand bits; same exponent
-// range as float, no scaling needed) and the product is assembled from the six partial products whose weight is above
-// 2^-24:  hh, hm, mh, hl, lh, mm  (the "bf16x9" scheme minus its three smallest terms), accumulated in FP32 in TMEM.
+// power), so every FP32 operand is carried as several 16-bit terms and the product is assembled from the partial products
+// that matter, accumulated in FP32 in TMEM (fastconv.cuh, FcShape::tc_levels):
+//   2 levels (default): block-scaled fp16, x 2^k = h + m (11 + 11 significand bits), products hh + hm + mh;
+//   3 levels: bf16, x = h + m + l (8 + 8 + 8 bits, float's exponent range, no scaling), products hh, hm, mh, hl, lh, mm
+//             (the "bf16x9" scheme minus its three smallest terms) — twice the tensor-pipe work, 1.5 x the bytes.
 //
 // Complex arithmetic without duplicating an operand in HBM: real and imaginary parts are separate planes,
 //   D1 = F_re . [T_re | T_im]   (TMEM columns   0..127)         D2 = F_im . [T_re | T_im]   (TMEM columns 128..255)
 //   Z_re = D1[:, c] - D2[:, 64 + c]        Z_im = D1[:, 64 + c] + D2[:, c]        (combined by the epilogue warps)
-// so both MMAs of a product share one B descriptor and every instruction is M128 x N128 x K16.
+// so both MMAs of a product share one B descriptor and every instruction is M128 x N128 x K16 (fc_contract_tc_kernel:
+// overlap-save blocks in the MMA's M, 64 slots per CTA); fc_contract_tct_kernel exchanges the roles (128 channel slots in M,
+// the blocks in N) for passes with few blocks — see there.
 //
-// Operand planes (bf16, K-major, written by fc_forward_tc_kernel / fc_table_tc_kernel), plane p = 2 * level + part:
+// Operand planes (K-major, written by fc_forward_kernel<TC> / fc_table_kernel<TC>), plane p = 2 * level + part:
 //   Fp[p][q * B + b][r]        Tp[p][q * slots + c][r]            r < Dp contiguous
-// CTA = (bin q, row tile of <= 128 blocks, 64 channel slots, split-K plane).  Warp 0: TMA producer (one 3D box per operand
-// and stage: 32 branches x rows x 6 planes, SWIZZLE_64B).  Warp 1: TMEM allocation + MMA issue (one thread; 24
-// tcgen05.mma per stage; tcgen05.commit releases the stage).  Warps 2-5: epilogue (tcgen05.ld -> combine -> Z).
+// CTA = (bin q, row tile of <= 128 blocks, 64 or 128 channel slots, split-K plane).  Warp 0: TMA producer (one 3D box per
+// operand and stage: 16 branches x rows x planes, SWIZZLE_32B).  Warp 1: TMEM allocation + MMA issue (one thread;
+// tcgen05.commit releases the stage).  Warps 2-5: epilogue (tcgen05.ld -> combine -> Z).
 #include "fastconv.cuh"
 
 #include <cuda.h>

@@ -447,7 +447,7 @@ int group_create(owrx_bank* bank, const owrx_chan_spec_t& sp, int* index)
     g->fc_taps.resize((size_t)g->T);
     for (int t = 0; t < g->T; t++) g->fc_taps[(size_t)t] = (float)h[t];
     const int fcM = fc_pick_fft_size(g->D, P);
-    g->fc = FcShape{g->D, g->T, P, fcM - P + 1, (g->D + FC_DPAD - 1) / FC_DPAD * FC_DPAD, g->slots, fcM, fc_pick_tc_levels()};
+    g->fc = FcShape{g->D, g->T, P, fcM - P + 1, (g->D + FC_DPAD - 1) / FC_DPAD * FC_DPAD, g->slots, fcM, fc_pick_tc_levels(g->D)};
     g->fc_tab_scale = fc_tab_scale(g->fc, g->fc_taps.data());
     g->fc_ok = g->D >= 8 && P <= fcM / 2;
     int rc;
@@ -910,18 +910,22 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         OWRX_CUDA(cudaMalloc((void**)&g->d_fc_Z, (size_t)FC_MAXSPLIT * cap * (size_t)sh.M * S * sizeof(float2)));
     }
     float2* out = reinterpret_cast<float2*>(g->s1.append_ptr());
-    if (tc) {
-        // operand scaling of the pass (fp16 x 2 form: one read of the input for its largest magnitude; bf16 x 3: constants)
+    const bool scaled = tc && sh.tc_levels == 2;
+    if (scaled) {
+        // operand scaling of the pass (fp16 x 2 form: one read of the input for its largest magnitude; bf16 x 3 needs none)
         if (!g->d_fc_scale) OWRX_CUDA(cudaMalloc((void**)&g->d_fc_scale, 4 * sizeof(float)));
+        // (timed with the forward FFTs: the scaling pass is part of what the shared front costs)
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, true)) != OWRX_OK) return rc;
         if ((rc = fc_launch_scale(sh, iq, (long long)n_avail, g->fc_tab_scale, reinterpret_cast<unsigned*>(g->d_fc_scale + 2), g->d_fc_scale, st)) != OWRX_OK)
             return rc;
-        bank->stats.kernel_launches += sh.tc_levels == 2 ? 2 : 1;
+        if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, false)) != OWRX_OK) return rc;
+        bank->stats.kernel_launches += 2;
     }
     for (size_t b0 = 0; b0 < blocks_total; b0 += Bmax) {
         const int B = (int)std::min(Bmax, blocks_total - b0);
         const size_t s_off = b0 * (size_t)sh.Kb * (size_t)sh.D;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, true)) != OWRX_OK) return rc;
-        rc = tc ? fc_launch_forward_tc(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_Fp, g->d_fc_scale, st)
+        rc = tc ? fc_launch_forward_tc(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_Fp, scaled ? g->d_fc_scale : nullptr, st)
                 : fc_launch_forward(sh, iq + s_off, (long long)(n_avail - s_off), B, g->d_fc_F, st);
         if (rc != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_FORWARD, st, false)) != OWRX_OK) return rc;
@@ -933,7 +937,7 @@ int group_fir_fastconv(owrx_bank* bank, Group* g, const float2* iq, size_t n_ava
         if ((rc = prof_mark(bank, OWRX_PROF_FC_CONTRACT, st, false)) != OWRX_OK) return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, true)) != OWRX_OK) return rc;
         if ((rc = fc_launch_inverse(sh, g->d_fc_Z, nsplit, B, g->d_rate, g->d_phase, (long long)(b0 * (size_t)sh.Kb), (long long)n_k, out,
-                                    tc ? g->d_fc_scale + 1 : nullptr, st)) != OWRX_OK)
+                                    scaled ? g->d_fc_scale + 1 : nullptr, st)) != OWRX_OK)
             return rc;
         if ((rc = prof_mark(bank, OWRX_PROF_FC_INVERSE, st, false)) != OWRX_OK) return rc;
         bank->stats.kernel_launches += 3;
@@ -1273,10 +1277,11 @@ int group_tail_serial(owrx_bank* bank, Group* g, cudaStream_t st)
                                           cudaMemcpyDeviceToDevice, st));
             } else {
                 // The Agc is a latency-bound dependent chain (one warp per channel): every cycle another kernel's warps take
-                // on its scheduler stretches it.  Its CTAs therefore claim 100 KB of dynamic shared memory they do not use, so
-                // that no 177 KB contraction CTA and at most one 68 KB FFT CTA can share their SM (measured inside the
-                // three-stream pipeline, C2: Agc stage 0.32 -> 0.26 ms, step 0.34 -> 0.32 ms).  OWRX_AGC_PAD_KB overrides.
-                static const int agc_pad = (getenv("OWRX_AGC_PAD_KB") ? atoi(getenv("OWRX_AGC_PAD_KB")) : 100) << 10;
+                // on its scheduler stretches it.  Its CTAs therefore claim 160 KB of dynamic shared memory they do not use
+                // (189 KB with their own buffers), so that neither a contraction CTA (>= 58 KB since the 16-branch stages) nor
+                // a 66 KB FFT CTA can share their SM (measured inside the three-stream pipeline, C2, with a 100 KB claim while
+                // the contraction needed 177 KB: Agc stage 0.32 -> 0.26 ms, step 0.34 -> 0.32 ms).  OWRX_AGC_PAD_KB overrides.
+                static const int agc_pad = (getenv("OWRX_AGC_PAD_KB") ? atoi(getenv("OWRX_AGC_PAD_KB")) : 160) << 10;
                 // one warp per channel with no CTA barrier (agc_warp_kernel) unless OWRX_AGC_CTA=1 asks for the 8-channel CTAs
                 const bool agc_cta = bank->agc_cta;
                 static const int agcw_pad = (getenv("OWRX_AGCW_PAD_KB") ? atoi(getenv("OWRX_AGCW_PAD_KB")) : 0) << 10;

@@ -41,12 +41,12 @@ def run(fs, out_rate, n_ch, block, mode, steps=20, wfm=False, **kw):
     bank.join(st.cuda_stream)
     e1.record(st); st.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    prof = {k: (v[0] / max(v[1], 1), v[1] // steps) for k, v in bank.profile_read_ex().items() if v[1]}
+    prof = {k: (v[0] / steps, v[1] // steps) for k, v in bank.profile_read_ex().items() if v[1]}   # ms per block, brackets per block
     bank.profile(False)
     bank.drain()
     outs = [chans[i].read_if() for i in (0, n_ch // 2, n_ch - 1)]
     res = dict(mode=mode, ms_per_block=round(ms, 4), channel_MSps=round(n_ch * block / (ms * 1e-3) / 1e6, 1),
-               kernels_ms_per_launch={k: round(v[0], 4) for k, v in prof.items()}, launches_per_block={k: v[1] for k, v in prof.items()})
+               stages_ms_per_block={k: round(v[0], 4) for k, v in prof.items()}, brackets_per_block={k: v[1] for k, v in prof.items()})
     bank.close()
     return res, outs
 
