@@ -725,25 +725,32 @@ def run_sharded(args, torch, dist, world, rank, local, dev):
         hop.gather(j, up[j & 1])
 
     def e2e_step():
-        # one block ahead: block j + 1 is uploaded and all-gathered (copy engines only) under the DSP pass and the drain of block j
+        # one block ahead on the way in (block j + 1 is uploaded and all-gathered under block j's DSP pass) and one block behind
+        # on the way out (split-phase drain: block j - 1's audio crosses PCIe and is read on the host while block j is processed)
         j = cnt[0]
         cnt[0] += 1
         ingest(j + 1)
         buf = hop.recv(j, stream)
         bank.process_device(buf, BLOCK, stream=sp)
         hop.release(j, stream)
-        bank.drain()
-        return sum(bank.read_audio_all(chans, audio_buf))
+        bank.drain_end()                                             # block j - 1 (no-op for the first block)
+        got = sum(bank.read_audio_all(chans, audio_buf))
+        bank.drain_begin()                                           # block j: copied behind its kernels
+        return got
 
     ingest(cnt[0])
     for _ in range(3):
         e2e_step()
+    bank.drain_end()                                                 # the warm-up's last block: outside the timed region
+    bank.read_audio_all(chans, audio_buf)
     barrier()
     e2e_steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     n_audio = 0
     for _ in range(e2e_steps):
         n_audio += e2e_step()
+    bank.drain_end()                                                 # the last block's audio, inside the timed region
+    n_audio += sum(bank.read_audio_all(chans, audio_buf))
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     t = torch.tensor([e2e_ms, float(n_audio)], device=dev, dtype=torch.float64)
@@ -784,7 +791,8 @@ def run_sharded(args, torch, dist, world, rank, local, dev):
         "e2e": {"value": e2e_value, "unit": "channel-MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                 "mode": "sharded ingest: every rank uploads 1/N of the block from pinned host memory over its own PCIe link (%d bytes per rank "
                         "and step), all-gather over NVLink, owrx_bank_process_device + owrx_bank_drain + the audio of every channel read on "
-                        "the host, on every rank; block j + 1's upload and all-gather run under block j's DSP pass and drain" % (shard * 8)},
+                        "the host, on every rank; block j + 1's upload and all-gather run under block j's DSP pass, block j - 1's audio is "
+                        "drained (owrx_bank_drain_begin / _end) and read under it too" % (shard * 8)},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": rl,

@@ -251,6 +251,13 @@ int owrx_bank_join(owrx_bank_t* bank, void* stream);
 /* Copy the outputs of the last owrx_bank_process_device call into the per-channel host queues (D2H), so that
  * owrx_chan_read_* pops them exactly as after owrx_bank_feed.  Synchronous. */
 int owrx_bank_drain(owrx_bank_t* bank);
+/* Split-phase form for hosts that stream blocks through the device path: _begin enqueues the D2H of the last
+ * owrx_bank_process_device block behind that block's kernels and returns; the caller may issue the NEXT
+ * owrx_bank_process_device before _end, which waits for the copies and fills the queues exactly as owrx_bank_drain would
+ * have.  One drain in flight at a time (_begin before the previous _end is OWRX_E_INVALID); _end without _begin is a
+ * no-op.  When S-meter power reports (OWRX_OUT_POWER) or a client-audio format are enabled, _begin drains synchronously. */
+int owrx_bank_drain_begin(owrx_bank_t* bank);
+int owrx_bank_drain_end(owrx_bank_t* bank);
 /* samples of audio produced per channel by the last owrx_bank_process_device call */
 int owrx_bank_last_audio_count(const owrx_bank_t* bank, int chan, size_t* n);
 /* device pointer + layout of the last block's audio: element (k, slot) at base[k*stride + slot] */

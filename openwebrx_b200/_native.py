@@ -95,6 +95,8 @@ SIGNATURES = {
     "owrx_bank_set_pipelined": (_i, [_vp, _i]),
     "owrx_bank_join": (_i, [_vp, _vp]),
     "owrx_bank_drain": (_i, [_vp]),
+    "owrx_bank_drain_begin": (_i, [_vp]),
+    "owrx_bank_drain_end": (_i, [_vp]),
     "owrx_bank_last_consumed": (_i, [_vp, _psz]),
     "owrx_bank_last_audio_count": (_i, [_vp, _i, _psz]),
     "owrx_bank_last_audio_device": (_i, [_vp, _i, _pp, _psz, _psz]),

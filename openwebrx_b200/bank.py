@@ -198,6 +198,14 @@ class ChannelBank:
         """D2H of the last process_device block into the host queues (then read_audio etc. pop it)"""
         N.check(N.lib.owrx_bank_drain(self._h))
 
+    def drain_begin(self):
+        """split-phase drain: enqueue the D2H of the last process_device block; the next block may be issued before drain_end"""
+        N.check(N.lib.owrx_bank_drain_begin(self._h))
+
+    def drain_end(self):
+        """wait for drain_begin's copies and fill the host queues (no-op without a pending drain_begin)"""
+        N.check(N.lib.owrx_bank_drain_end(self._h))
+
     def profile(self, enable=True):
         N.check(N.lib.owrx_bank_profile(self._h, 1 if enable else 0))
 

@@ -310,6 +310,15 @@ struct owrx_bank {
     // pinned staging + device transpose scratch for the output drain
     float* h_stage = nullptr; size_t h_stage_cap = 0;
     float* d_xpose = nullptr; size_t d_xpose_cap = 0;
+    // split-phase drain of the device path (owrx_bank_drain_begin / _end): its own staging, so a synchronous drain in between
+    // cannot clobber it; one item per (group, output) that is in flight
+    struct AsyncDrainItem { int which, width; size_t n, off; std::vector<int> chans; };
+    float* h_adrain = nullptr; size_t h_adrain_cap = 0;
+    float* d_adrain = nullptr; size_t d_adrain_cap = 0;
+    std::vector<AsyncDrainItem> adrain_items;
+    bool adrain_pending = false;
+    cudaEvent_t adrain_read[2] = {nullptr, nullptr};           // the transposes have read the stage buffers of that block parity
+    cudaEvent_t adrain_done = nullptr;                         // the D2H copies have landed
     owrx_bank_stats_t stats{};
     // H2D copy stream for the chunked host path; side stream + events for the pipelined device path
     cudaStream_t copy_stream = nullptr, side_stream = nullptr, serial_stream = nullptr;
@@ -1502,6 +1511,8 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->side_stream, cudaStreamNonBlocking, (tail_prio & 1) ? prio_hi : prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->serial_stream, cudaStreamNonBlocking, (tail_prio & 2) ? prio_hi : prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->drain_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->adrain_read[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->adrain_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->ctl_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[1], cudaEventDisableTiming);
@@ -1531,6 +1542,9 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     for (cudaEvent_t e : bank->fir_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->drain_events) cudaEventDestroy(e);
     if (bank->drain_stream) cudaStreamDestroy(bank->drain_stream);
+    for (cudaEvent_t e : {bank->adrain_read[0], bank->adrain_read[1], bank->adrain_done}) if (e) cudaEventDestroy(e);
+    cudaFree(bank->d_adrain);
+    if (bank->h_adrain) cudaFreeHost(bank->h_adrain);
     if (bank->fir_done) cudaEventDestroy(bank->fir_done);
     if (bank->dev_done) cudaEventDestroy(bank->dev_done);
     if (bank->tail_done[0]) cudaEventDestroy(bank->tail_done[0]);
@@ -2094,6 +2108,9 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         // f2 ping-pong: this block's parallel stages write the buffer the Agc of two blocks ago was reading
         OWRX_CUDA(cudaStreamWaitEvent(sb, bank->tail_done[par], 0));
     }
+    // a split-phase drain of the block two calls ago has read these stage buffers (no-op when there was none)
+    OWRX_CUDA(cudaStreamWaitEvent(sb, bank->adrain_read[par], 0));
+    if (sc != sb) OWRX_CUDA(cudaStreamWaitEvent(sc, bank->adrain_read[par], 0));
     bank->reserve_sm = bank->pipelined;
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
@@ -2169,6 +2186,115 @@ int owrx_bank_drain(owrx_bank_t* bank)
         if ((rc = group_drain(bank, g, st, DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks}, true)) != OWRX_OK) return rc;
     }
     OWRX_CUDA(cudaStreamSynchronize(st));
+    return OWRX_OK;
+}
+
+// Split-phase drain (streaming hosts of the device path): _begin enqueues, on the drain stream, the transposes and D2H copies of
+// what the last owrx_bank_process_device call produced, behind that block's kernels; the caller may issue the NEXT block
+// before _end, which waits for the copies and hands the samples to the per-channel queues.  The stage buffers are
+// double-buffered by block parity, so the next block does not touch what is being drained; the block after that waits for
+// the transposes (adrain_read).  Outputs the asynchronous form does not cover (S-meter power reports, the client-audio
+// tail) make _begin fall back to the synchronous drain.
+static int adrain_sync_fallback(owrx_bank* bank)
+{
+    cudaStream_t st = bank->stream;
+    OWRX_CUDA(cudaStreamWaitEvent(st, bank->dev_done, 0));
+    OWRX_CUDA(cudaStreamWaitEvent(st, bank->tail_done[0], 0));
+    OWRX_CUDA(cudaStreamWaitEvent(st, bank->tail_done[1], 0));
+    int rc;
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        g->sq_block_abs -= (long long)g->last_blocks;
+        if ((rc = group_drain(bank, g, st, DrainMark{g->last_audio, g->last_demod, g->last_if, g->last_blocks}, true)) != OWRX_OK) return rc;
+    }
+    OWRX_CUDA(cudaStreamSynchronize(st));
+    return OWRX_OK;
+}
+
+int owrx_bank_drain_begin(owrx_bank_t* bank)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    if (bank->adrain_pending) return fail(OWRX_E_INVALID, "owrx_bank_drain_begin: the previous split-phase drain has not been ended");
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    if (bank->pending_final) { int rcp = finish_pending(bank); if (rcp != OWRX_OK) return rcp; }
+    if (bank->calls == 0) return OWRX_OK;
+    bool fallback = (bank->out_mask & OWRX_OUT_POWER) != 0;
+    for (auto& gp : bank->groups) if (gp && gp->any_tail && gp->tail_ran && gp->last_audio) fallback = true;
+    if (fallback) return adrain_sync_fallback(bank);
+    // ---- what is to move: one item per (group, output)
+    bank->adrain_items.clear();
+    size_t total = 0;
+    struct Src { const float* rows; int slots; };
+    std::vector<Src> srcs;
+    for (auto& gp : bank->groups) {
+        Group* g = gp.get();
+        if (!g) continue;
+        const struct { int bit; int which; int width; size_t n; const float* rows; } outs[3] = {
+            {OWRX_OUT_AUDIO, 0, 1, g->last_audio, g->last_audio ? g->f3.rows(g->f3.fill - g->last_audio) : nullptr},
+            {OWRX_OUT_DEMOD, 1, 1, g->last_demod, g->last_demod ? g->f2.rows(g->f2.fill - g->last_demod) : nullptr},
+            {OWRX_OUT_IF, 2, 2, g->last_if, g->last_if ? g->s3.rows(g->s3.fill - g->last_if) : nullptr}};
+        for (const auto& o : outs) {
+            if (!(bank->out_mask & o.bit) || !o.n) continue;
+            owrx_bank::AsyncDrainItem it;
+            it.which = o.which; it.width = o.width; it.n = o.n; it.off = total;
+            it.chans.assign(g->slot_chan.begin(), g->slot_chan.end());
+            total += o.n * (size_t)g->slots * o.width;
+            bank->adrain_items.push_back(std::move(it));
+            srcs.push_back(Src{o.rows, g->slots});
+        }
+    }
+    if (bank->adrain_items.empty()) return OWRX_OK;
+    if (total > bank->h_adrain_cap) {
+        // (the previous drain has been ended: nothing is in flight on these buffers)
+        OWRX_CUDA(cudaStreamSynchronize(bank->drain_stream));
+        if (bank->h_adrain) cudaFreeHost(bank->h_adrain);
+        cudaFree(bank->d_adrain);
+        bank->h_adrain = nullptr; bank->d_adrain = nullptr; bank->h_adrain_cap = bank->d_adrain_cap = 0;
+        OWRX_CUDA(cudaMallocHost((void**)&bank->h_adrain, total * sizeof(float)));
+        OWRX_CUDA(cudaMalloc((void**)&bank->d_adrain, total * sizeof(float)));
+        bank->h_adrain_cap = bank->d_adrain_cap = total;
+    }
+    cudaStream_t ds = bank->drain_stream;
+    OWRX_CUDA(cudaStreamWaitEvent(ds, bank->dev_done, 0));
+    OWRX_CUDA(cudaStreamWaitEvent(ds, bank->tail_done[0], 0));
+    OWRX_CUDA(cudaStreamWaitEvent(ds, bank->tail_done[1], 0));
+    for (size_t i = 0; i < bank->adrain_items.size(); i++) {
+        const auto& it = bank->adrain_items[i];
+        const dim3 grid((unsigned)((srcs[i].slots + 31) / 32), (unsigned)((it.n + 31) / 32));
+        if (it.width == 1) transpose_kernel<float><<<grid, dim3(32, 8), 0, ds>>>(srcs[i].rows, srcs[i].slots, it.n, bank->d_adrain + it.off);
+        else transpose_kernel<float2><<<grid, dim3(32, 8), 0, ds>>>(reinterpret_cast<const float2*>(srcs[i].rows), srcs[i].slots, it.n,
+                                                                     reinterpret_cast<float2*>(bank->d_adrain + it.off));
+        OWRX_LAUNCH_CHECK();
+        bank->stats.kernel_launches++;
+    }
+    // the block just processed ran with parity (calls - 1) & 1: the block after next writes the same stage buffers
+    OWRX_CUDA(cudaEventRecord(bank->adrain_read[(bank->calls - 1) & 1], ds));
+    OWRX_CUDA(cudaMemcpyAsync(bank->h_adrain, bank->d_adrain, total * sizeof(float), cudaMemcpyDeviceToHost, ds));
+    OWRX_CUDA(cudaEventRecord(bank->adrain_done, ds));
+    bank->adrain_pending = true;
+    return OWRX_OK;
+}
+
+int owrx_bank_drain_end(owrx_bank_t* bank)
+{
+    if (!bank) return fail(OWRX_E_INVALID, "NULL bank");
+    std::lock_guard<std::mutex> lk(bank->mu);
+    if (!bank->adrain_pending) return OWRX_OK;
+    OWRX_CUDA(cudaSetDevice(bank->device));
+    OWRX_CUDA(cudaEventSynchronize(bank->adrain_done));
+    bank->adrain_pending = false;
+    for (const auto& it : bank->adrain_items) {
+        for (size_t s = 0; s < it.chans.size(); s++) {
+            const int cid = it.chans[s];
+            if (cid < 0 || (size_t)cid >= bank->chans.size() || !bank->chans[(size_t)cid]) continue;   // the client left in between
+            Chan* ch = bank->chans[(size_t)cid].get();
+            FQ& q = it.which == 0 ? ch->q_audio : (it.which == 1 ? ch->q_demod : ch->q_if);
+            q.push(bank->h_adrain + it.off + s * it.n * (size_t)it.width, it.n * (size_t)it.width);
+        }
+    }
+    bank->adrain_items.clear();
     return OWRX_OK;
 }
 
