@@ -719,10 +719,21 @@ def run_sharded(args, torch, dist, world, rank, local, dev):
     audio_buf = np.empty((len(chans), 1 << 15), np.float32)
     cnt = [sent[0]]
 
+    up_stream = torch.cuda.Stream(device=dev)
+    ev_up = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_read = [torch.cuda.Event(), torch.cuda.Event()]
+
     def ingest(j):
-        with torch.cuda.stream(hop.stream):
-            up[j & 1].copy_(h_slice, non_blocking=True)          # H2D of this rank's 1/N of the block (ordered before the gather's read)
-        hop.gather(j, up[j & 1])
+        # H2D of this rank's 1/N of the block on its own stream: the upload of block j + 1 runs beside the all-gather of block j
+        # instead of behind it (events: the gather of block j - 1 has read this upload buffer; the gather waits for the upload)
+        b = j & 1
+        up_stream.wait_event(ev_read[b])
+        with torch.cuda.stream(up_stream):
+            up[b].copy_(h_slice, non_blocking=True)
+            ev_up[b].record(up_stream)
+        hop.stream.wait_event(ev_up[b])
+        hop.gather(j, up[b])
+        ev_read[b].record(hop.stream)
 
     def e2e_step():
         # one block ahead on the way in (block j + 1 is uploaded and all-gathered under block j's DSP pass) and one block behind
