@@ -123,6 +123,9 @@ void design_nfm_deemphasis(std::vector<float>& out, int sample_rate)
 // rows of `slots * width` floats; rows [0, fill) hold absolute indices [abs_end - fill, abs_end).
 struct StageBuf {
     float* d[2] = {nullptr, nullptr};
+    // split-phase drain (owrx_bank_drain_begin): recorded after the transpose that read buffer b; the next writer of that
+    // buffer waits for it.  Created on first use; an event that was never recorded does not block.
+    cudaEvent_t drained[2] = {nullptr, nullptr};
     int cur = 0, width = 1, slots = 0;
     size_t hist = 0, cap_rows = 0, fill = 0;
     long long abs_end = 0;
@@ -173,7 +176,21 @@ struct StageBuf {
     void release()
     {
         for (int b = 0; b < 2; b++) { if (d[b]) cudaFree(d[b]); d[b] = nullptr; }
+        for (int b = 0; b < 2; b++) { if (drained[b]) cudaEventDestroy(drained[b]); drained[b] = nullptr; }
         cap_rows = fill = 0;
+    }
+    // the current buffer has been read by work enqueued on `st` so far
+    int mark_drained(cudaStream_t st)
+    {
+        if (!drained[cur]) OWRX_CUDA(cudaEventCreateWithFlags(&drained[cur], cudaEventDisableTiming));
+        OWRX_CUDA(cudaEventRecord(drained[cur], st));
+        return OWRX_OK;
+    }
+    // `st` is about to write the current buffer
+    int wait_drained(cudaStream_t st) const
+    {
+        if (drained[cur]) OWRX_CUDA(cudaStreamWaitEvent(st, drained[cur], 0));
+        return OWRX_OK;
     }
 };
 
@@ -317,7 +334,6 @@ struct owrx_bank {
     float* d_adrain = nullptr; size_t d_adrain_cap = 0;
     std::vector<AsyncDrainItem> adrain_items;
     bool adrain_pending = false;
-    cudaEvent_t adrain_read[2] = {nullptr, nullptr};           // the transposes have read the stage buffers of that block parity
     cudaEvent_t adrain_done = nullptr;                         // the D2H copies have landed
     owrx_bank_stats_t stats{};
     // H2D copy stream for the chunked host path; side stream + events for the pipelined device path
@@ -1511,7 +1527,6 @@ int owrx_bank_create(int device, double input_rate, owrx_bank_t** out)
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->side_stream, cudaStreamNonBlocking, (tail_prio & 1) ? prio_hi : prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->serial_stream, cudaStreamNonBlocking, (tail_prio & 2) ? prio_hi : prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->drain_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->adrain_read[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->adrain_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->ctl_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ptail_done[0], cudaEventDisableTiming);
@@ -1542,7 +1557,7 @@ void owrx_bank_destroy(owrx_bank_t* bank)
     for (cudaEvent_t e : bank->fir_events) cudaEventDestroy(e);
     for (cudaEvent_t e : bank->drain_events) cudaEventDestroy(e);
     if (bank->drain_stream) cudaStreamDestroy(bank->drain_stream);
-    for (cudaEvent_t e : {bank->adrain_read[0], bank->adrain_read[1], bank->adrain_done}) if (e) cudaEventDestroy(e);
+    if (bank->adrain_done) cudaEventDestroy(bank->adrain_done);
     cudaFree(bank->d_adrain);
     if (bank->h_adrain) cudaFreeHost(bank->h_adrain);
     if (bank->fir_done) cudaEventDestroy(bank->fir_done);
@@ -2108,9 +2123,6 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         // f2 ping-pong: this block's parallel stages write the buffer the Agc of two blocks ago was reading
         OWRX_CUDA(cudaStreamWaitEvent(sb, bank->tail_done[par], 0));
     }
-    // a split-phase drain of the block two calls ago has read these stage buffers (no-op when there was none)
-    OWRX_CUDA(cudaStreamWaitEvent(sb, bank->adrain_read[par], 0));
-    if (sc != sb) OWRX_CUDA(cudaStreamWaitEvent(sc, bank->adrain_read[par], 0));
     bank->reserve_sm = bank->pipelined;
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
@@ -2119,6 +2131,12 @@ int owrx_bank_process_device(owrx_bank_t* bank, const void* iq_dev, size_t n_sam
         // previous block's outputs are dropped; histories stay
         // pipelined: every stage after FirDecimate (rolls of their history buffers included) lives on the side stream
         if ((rc = group_begin_feed(bank, g, n_samples / (size_t)g->D + 1, sa, sb, sc, par)) != OWRX_OK) return rc;
+        // the output buffers this block writes (the rolls above have just selected them) may still be read by a split-phase
+        // drain of an earlier block that used the same buffer: both low-rate streams wait for that transpose (none: no-op)
+        for (const StageBuf* sbuf : {&g->f3, &g->f2, &g->s3}) {
+            if ((rc = sbuf->wait_drained(sb)) != OWRX_OK) return rc;
+            if (sc != sb && (rc = sbuf->wait_drained(sc)) != OWRX_OK) return rc;
+        }
         // groups consume whole decimation steps: a group that got further than the slowest one in the previous block starts
         // `dev_lead` samples into this one (the caller presents [carry | new] from owrx_bank_last_consumed on)
         const size_t lead = std::min(g->dev_lead, n_samples);
@@ -2192,8 +2210,8 @@ int owrx_bank_drain(owrx_bank_t* bank)
 // Split-phase drain (streaming hosts of the device path): _begin enqueues, on the drain stream, the transposes and D2H copies of
 // what the last owrx_bank_process_device call produced, behind that block's kernels; the caller may issue the NEXT block
 // before _end, which waits for the copies and hands the samples to the per-channel queues.  The stage buffers are
-// double-buffered by block parity, so the next block does not touch what is being drained; the block after that waits for
-// the transposes (adrain_read).  Outputs the asynchronous form does not cover (S-meter power reports, the client-audio
+// double-buffered, so the next block does not touch what is being drained; whichever later block writes such a buffer again
+// waits for the transpose that read it (StageBuf::drained).  Outputs the asynchronous form does not cover (S-meter power reports, the client-audio
 // tail) make _begin fall back to the synchronous drain.
 static int adrain_sync_fallback(owrx_bank* bank)
 {
@@ -2226,15 +2244,15 @@ int owrx_bank_drain_begin(owrx_bank_t* bank)
     // ---- what is to move: one item per (group, output)
     bank->adrain_items.clear();
     size_t total = 0;
-    struct Src { const float* rows; int slots; };
+    struct Src { const float* rows; int slots; StageBuf* buf; };
     std::vector<Src> srcs;
     for (auto& gp : bank->groups) {
         Group* g = gp.get();
         if (!g) continue;
-        const struct { int bit; int which; int width; size_t n; const float* rows; } outs[3] = {
-            {OWRX_OUT_AUDIO, 0, 1, g->last_audio, g->last_audio ? g->f3.rows(g->f3.fill - g->last_audio) : nullptr},
-            {OWRX_OUT_DEMOD, 1, 1, g->last_demod, g->last_demod ? g->f2.rows(g->f2.fill - g->last_demod) : nullptr},
-            {OWRX_OUT_IF, 2, 2, g->last_if, g->last_if ? g->s3.rows(g->s3.fill - g->last_if) : nullptr}};
+        const struct { int bit; int which; int width; size_t n; const float* rows; StageBuf* buf; } outs[3] = {
+            {OWRX_OUT_AUDIO, 0, 1, g->last_audio, g->last_audio ? g->f3.rows(g->f3.fill - g->last_audio) : nullptr, &g->f3},
+            {OWRX_OUT_DEMOD, 1, 1, g->last_demod, g->last_demod ? g->f2.rows(g->f2.fill - g->last_demod) : nullptr, &g->f2},
+            {OWRX_OUT_IF, 2, 2, g->last_if, g->last_if ? g->s3.rows(g->s3.fill - g->last_if) : nullptr, &g->s3}};
         for (const auto& o : outs) {
             if (!(bank->out_mask & o.bit) || !o.n) continue;
             owrx_bank::AsyncDrainItem it;
@@ -2242,7 +2260,7 @@ int owrx_bank_drain_begin(owrx_bank_t* bank)
             it.chans.assign(g->slot_chan.begin(), g->slot_chan.end());
             total += o.n * (size_t)g->slots * o.width;
             bank->adrain_items.push_back(std::move(it));
-            srcs.push_back(Src{o.rows, g->slots});
+            srcs.push_back(Src{o.rows, g->slots, o.buf});
         }
     }
     if (bank->adrain_items.empty()) return OWRX_OK;
@@ -2268,9 +2286,9 @@ int owrx_bank_drain_begin(owrx_bank_t* bank)
                                                                      reinterpret_cast<float2*>(bank->d_adrain + it.off));
         OWRX_LAUNCH_CHECK();
         bank->stats.kernel_launches++;
+        int rcm = srcs[i].buf->mark_drained(ds);                      // the next writer of THIS buffer waits for the transpose
+        if (rcm != OWRX_OK) return rcm;
     }
-    // the block just processed ran with parity (calls - 1) & 1: the block after next writes the same stage buffers
-    OWRX_CUDA(cudaEventRecord(bank->adrain_read[(bank->calls - 1) & 1], ds));
     OWRX_CUDA(cudaMemcpyAsync(bank->h_adrain, bank->d_adrain, total * sizeof(float), cudaMemcpyDeviceToHost, ds));
     OWRX_CUDA(cudaEventRecord(bank->adrain_done, ds));
     bank->adrain_pending = true;
